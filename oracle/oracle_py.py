@@ -61,13 +61,13 @@ def _out(*shape):
 
 
 def x1():
-    a, p = _out(22)
+    a, p = _out(23)
     lib().orc_x1(p)
     return a
 
 
 VP_NAMES = ["L", "a", "b", "h", "G", "m", "Izz", "mu", "Caf", "Car", "Cd0", "Cd1", "Cd2", "fwd_frac", "rwd_frac", "fwb_frac",
-            "rwb_frac", "Fx_max", "Fx_min", "Px_max", "delta_max", "kappa_max"]
+            "rwb_frac", "Fx_max", "Fx_min", "Px_max", "delta_max", "kappa_max", "inv_fiala_corrected"]
 CP_NAMES = ["V_min", "V_max", "k_V", "k_s", "delta_dot_max", "Q_ds", "Q_dpsi", "Q_e", "W_beta", "W_r", "W_HJI", "N_HJI", "R_delta",
             "R_ddelta", "R_Fx", "R_dFx"]
 ST_NAMES = ["rho", "sigma", "alpha", "eps_abs", "eps_rel", "eps_prim_inf", "eps_dual_inf", "max_iter", "scaling",

@@ -20,8 +20,11 @@ struct VehicleParams {
     double fwd_frac, rwd_frac, fwb_frac, rwb_frac;
     // ControlLimits
     double Fx_max, Fx_min, Px_max, delta_max, kappa_max;
+    // 0 (default): _invfialatiremodel restated literally (vehicle_dynamics.jl:56-62 returns the slip *ratio* in its
+    // unsaturated branch); 1: multiply by tan(alpha_slide) = 3 Fy_max / C_alpha (the evident intent). See DESIGN.md.
+    double inv_fiala_corrected;
 };
-static const int VEHICLE_PARAMS_LEN = 22;
+static const int VEHICLE_PARAMS_LEN = 23;
 
 // vehicles.jl:1-59
 inline VehicleParams X1() {
@@ -52,6 +55,7 @@ inline VehicleParams X1() {
     P.Fx_min = f1 > f2 ? f1 : f2;
     P.delta_max = 18 * M_PI / 180;
     P.kappa_max = std::tan(P.delta_max) / P.L;
+    P.inv_fiala_corrected = 0.0;
     return P;
 }
 
@@ -72,10 +76,11 @@ inline T fialatiremodel(const T& alpha, double Ca, double mu, const T& Fx, const
     if (value(absd(Fx)) >= value(F_max)) return T(0.0);
     return _fialatiremodel(tan(alpha), Ca, sqrt(F_max * F_max - Fx * Fx));
 }
-inline double _invfialatiremodel(double Fy, double Ca, double Fy_max) {  // returns tan(alpha)
+inline double _invfialatiremodel(double Fy, double Ca, double Fy_max, bool corrected = false) {  // returns tan(alpha)
     if (std::fabs(Fy) >= Fy_max) return -(3 * Fy_max / Ca) * signd(Fy);
     // NB restated literally: the reference returns the slip *ratio* here (no 3*Fy_max/Ca factor), vehicle_dynamics.jl:60
-    return -(1 + std::cbrt(std::fabs(Fy) / Fy_max - 1)) * signd(Fy);
+    double r = -(1 + std::cbrt(std::fabs(Fy) / Fy_max - 1)) * signd(Fy);
+    return corrected ? r * (3 * Fy_max / Ca) : r;
 }
 
 // lateral_tire_forces (vehicle_dynamics.jl:64-76)
@@ -272,14 +277,14 @@ inline SteadyState steady_state_estimates(const VehicleParams& P, double V, doub
         double Fyr_max = std::sqrt(Fr_max * Fr_max - Fxr * Fxr);
         double Fyr = (Ay * m - Fy_grade - rdot * Izz / a) / (1 + b / a);
         Fyr = clampd(Fyr, -Fyr_max, Fyr_max);
-        double tanar = _invfialatiremodel(Fyr, P.Car, Fyr_max);
+        double tanar = _invfialatiremodel(Fyr, P.Car, Fyr_max, P.inv_fiala_corrected != 0);
         double Fxf_t = clampd(Fx - Fxr, -Ff_max, Ff_max);
         double Fyf_tmax = std::sqrt(Ff_max * Ff_max - Fxf_t * Fxf_t);
         double Fyf_t = clampd((b * Fyr + rdot * Izz) / a, -Fyf_tmax, Fyf_tmax);
         Fxf = Fxf_t * cd + Fyf_t * sd;
         Fyf = Fyf_t * cd - Fxf_t * sd;
         double Fyf_max = std::sqrt(Ff_max * Ff_max - Fxf * Fxf);
-        double af = std::atan(_invfialatiremodel(Fyf, P.Caf, Fyf_max));
+        double af = std::atan(_invfialatiremodel(Fyf, P.Caf, Fyf_max, P.inv_fiala_corrected != 0));
         delta = std::atan2(Uy + a * r, Ux) - af;
         if (i == num_iters) {
             Ax = (Fxf * cd - Fyf * sd + Fxr + Fx_drag + Fx_grade) / m;
