@@ -1,0 +1,148 @@
+/* pigeon_b200.h — C ABI of the B200-native batched MPC engine (libpigeon_b200.so).
+ *
+ * Drop-in boundary for the per-time-step hot path of StanfordASL/Pigeon.jl.  The reference has no FFI boundary of its
+ * own on this path (its only native hop is OSQP.jl's ccall into libosqp); the de-facto operator interface is the 5-call
+ * step API on `TrajectoryTrackingMPC` (reference src/model_predictive_control.jl:70-78) with inputs written as struct
+ * fields (:32-58).  Each entry point below names the reference interface it replaces.  A Julia host binds these with
+ * one-line `ccall`s (julia/PigeonB200.jl); the Python mirror used by the tests binds the same symbols
+ * with ctypes (pigeon.jl_b200/_lib.py).
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative pgn_status; pgn_last_error() gives a thread-local message.
+ *  - host arrays are caller-owned, vehicle-major ("[B][k]" = Julia Matrix{Float64}(k, B)), read/written only during the call.
+ *  - all device memory, the CUDA stream and the static factorisation schedules are owned by the opaque handle.
+ *  - a handle is bound to one CUDA device and must be driven by one host thread at a time.
+ *  - there is NO CPU fallback: pgn_create fails with PGN_ECUDA when no sm_100 device is usable.
+ */
+#ifndef PIGEON_B200_H
+#define PIGEON_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PGN_API __attribute__((visibility("default")))
+#else
+#define PGN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgn_handle pgn_handle;
+
+typedef enum pgn_status {
+    PGN_OK = 0,
+    PGN_EINVAL = -1,   /* bad argument / call order */
+    PGN_ECUDA = -2,    /* CUDA runtime error (message in pgn_last_error) */
+    PGN_ENOMEM = -3,
+    PGN_ESTATE = -4    /* required input (trajectories, state, ...) not set */
+} pgn_status;
+
+enum { PGN_COUPLED = 0, PGN_DECOUPLED = 1 };
+
+/* per-QP solver status, same codes as libosqp */
+enum {
+    PGN_QP_SOLVED = 1, PGN_QP_SOLVED_INACCURATE = 2, PGN_QP_PRIMAL_INFEASIBLE_INACCURATE = 3, PGN_QP_DUAL_INFEASIBLE_INACCURATE = 4,
+    PGN_QP_MAX_ITER_REACHED = -2, PGN_QP_PRIMAL_INFEASIBLE = -3, PGN_QP_DUAL_INFEASIBLE = -4, PGN_QP_UNSOLVED = -10
+};
+
+/* Mirrors the keyword arguments of CoupledTrajectoryTrackingMPC / DecoupledTrajectoryTrackingMPC
+ * (reference src/coupled_lat_long.jl:42-43, src/decoupled_lat_long.jl:32-33) plus the OSQP settings the reference leaves at
+ * their defaults (src/coupled_lat_long.jl:201-204). */
+typedef struct pgn_config {
+    int32_t kind;                 /* PGN_COUPLED | PGN_DECOUPLED */
+    int32_t batch;                /* B: number of independent vehicles / scenarios on this device */
+    int32_t N_short, N_long;      /* 10, 20 */
+    double dt_short, dt_long;     /* 0.01, 0.2 */
+    int32_t use_correction_step;  /* 1 */
+    int32_t device;               /* CUDA ordinal, -1 = current device */
+    /* OSQP-style ADMM settings */
+    double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+    int32_t max_iter, scaling, check_termination, adaptive_rho, adaptive_rho_interval;
+    double adaptive_rho_tolerance;
+    int32_t warm_start;
+    /* flow integrator used by the coupled linearisation and the plant rollout: RK4 sub-steps per control interval */
+    int32_t rk4_substeps;         /* 10 */
+    double hji_eps;               /* HJI_ϵ, 0.05 (model_predictive_control.jl:67) */
+    int32_t kkt_ordering;         /* 0 = nested dissection over stages (default), 1 = minimum degree */
+    int32_t reserved;
+} pgn_config;
+
+#define PGN_VEHICLE_PARAMS_LEN 23   /* L,a,b,h,G,m,Izz,mu,Caf,Car,Cd0,Cd1,Cd2,fwd,rwd,fwb,rwb,Fx_max,Fx_min,Px_max,delta_max,kappa_max,inv_fiala_corrected */
+#define PGN_CONTROL_PARAMS_LEN 16   /* V_min,V_max,k_V,k_s,ddelta_max,Q_ds,Q_dpsi,Q_e,W_beta,W_r,W_HJI,N_HJI,R_delta,R_ddelta,R_Fx,R_dFx */
+
+/* --- construction --------------------------------------------------------------------------------------------- */
+/* defaults of the reference constructors + OSQP defaults */
+PGN_API int pgn_default_config(pgn_config* cfg, int32_t kind);
+/* X1() (reference src/vehicles.jl:1-59) and Coupled/DecoupledControlParams() defaults (coupled_lat_long.jl:23-38, decoupled_lat_long.jl:18-28) */
+PGN_API int pgn_x1_vehicle_params(double* vp /*[23]*/);
+PGN_API int pgn_default_control_params(int32_t kind, double* cp /*[16]*/);
+/* replaces Coupled/DecoupledTrajectoryTrackingMPC(vehicle, trajectory; ...) incl. construct_*_QP + Parametron.initialize! */
+PGN_API int pgn_create(const pgn_config* cfg, pgn_handle** out);
+PGN_API int pgn_destroy(pgn_handle* h);
+PGN_API const char* pgn_last_error(void);
+/* run all work of this handle on an externally owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+PGN_API int pgn_set_stream(pgn_handle* h, void* cuda_stream);
+PGN_API int pgn_synchronize(pgn_handle* h);
+
+/* --- inputs (fields of TrajectoryTrackingMPC, model_predictive_control.jl:32-58) --------------------------------- */
+PGN_API int pgn_set_vehicle_params(pgn_handle* h, const double* vp /*[23]*/);          /* mpc.vehicle / dynamics */
+PGN_API int pgn_set_control_params(pgn_handle* h, const double* cp /*[16]*/);          /* mpc.control_params */
+/* mpc.trajectory: n_traj TrajectoryTubes of n_nodes nodes each; fields[k] is [n_traj][n_nodes] in the order
+ * t,s,V,A,E,N,psi,kappa,theta,phi,edge_L,edge_R (trajectories.jl:8-20) */
+PGN_API int pgn_set_trajectories(pgn_handle* h, int32_t n_traj, int32_t n_nodes, const double* const fields[12]);
+PGN_API int pgn_assign_trajectories(pgn_handle* h, const int32_t* traj_id /*[B]*/);
+/* mpc.HJI_cache (HJI_computation.jl:26-57): knots concatenated, V column-major (dim 1 fastest), gradV with the 7 components fastest */
+PGN_API int pgn_set_hji_cache(pgn_handle* h, const int32_t dims[7], const float* knots, const float* V, const float* gradV);
+/* mpc.current_state [B][6], mpc.current_control [B][3], mpc.other_car_state [B][4] (NULL = keep), mpc.time_offset [B] (NULL = keep; NaN = path mode) */
+PGN_API int pgn_set_state(pgn_handle* h, const double* q, const double* u, const double* other_car, const double* time_offset);
+/* mpc.solved = false for the masked vehicles (mask NULL = all): next node generation is the cold steady-state rollout */
+PGN_API int pgn_reset_solved(pgn_handle* h, const uint8_t* mask /*[B]*/);
+/* Parametron.initialize!(mpc.model) (ros_integration.jl:146): cold ADMM iterates, rho back to its setting */
+PGN_API int pgn_reset_solver(pgn_handle* h, const uint8_t* mask /*[B]*/);
+
+/* --- the 5-call step API (model_predictive_control.jl:70-78) ------------------------------------------------------ */
+PGN_API int pgn_compute_time_steps(pgn_handle* h, const double* t0 /*[B]*/);           /* compute_time_steps!(mpc, t0) */
+PGN_API int pgn_compute_linearization_nodes(pgn_handle* h);                            /* compute_linearization_nodes!(mpc) */
+PGN_API int pgn_update_qp(pgn_handle* h);                                              /* update_QP!(mpc) */
+PGN_API int pgn_solve(pgn_handle* h);                                                  /* solve!(mpc) */
+PGN_API int pgn_get_next_control(pgn_handle* h, double* out /*[B][3] = (delta, Fxf, Fxr)*/);  /* get_next_control(mpc) */
+/* the five calls fused (host buffers; copies inside) */
+PGN_API int pgn_step(pgn_handle* h, const double* t0 /*[B]*/, double* out /*[B][3]*/);
+/* same with inputs already resident: t0 and out are DEVICE pointers ([B] and [3][B] field-major); out may be NULL */
+PGN_API int pgn_step_device(pgn_handle* h, const double* d_t0, double* d_out);
+/* simulate (model_predictive_control.jl:80-100): n_steps closed-loop steps fully on the device:
+ * step at t0 + k*dt, plant rollout propagate(dynamics, state, StepControl(dt, control)), apply the new control */
+PGN_API int pgn_simulate(pgn_handle* h, const double* t0 /*[B]*/, double dt, int32_t n_steps);
+/* one plant rollout + control application (the tail of the simulate loop) */
+PGN_API int pgn_rollout(pgn_handle* h, double dt);
+
+/* --- outputs / introspection (used by the parity tests) ----------------------------------------------------------- */
+PGN_API int pgn_qp_dims(pgn_handle* h, int32_t* out /*[8] = N, nx, nu, n, m, nnz(A), nnz(L), n_levels*/);
+PGN_API int pgn_get_state(pgn_handle* h, double* q /*[B][6]*/, double* u /*[B][3]*/);
+PGN_API int pgn_get_time_steps(pgn_handle* h, double* ts /*[B][N]*/, double* dt /*[B][N-1]*/, double* prev_ts /*[B][N]*/);
+PGN_API int pgn_get_nodes(pgn_handle* h, double* qs /*[B][N][nx]*/, double* us /*[B][N][2]*/, double* ps /*[B][N][4]*/);
+PGN_API int pgn_set_nodes(pgn_handle* h, const double* qs, const double* us, const double* ps);
+/* A [B][T][nx][nx], B0/Bf [B][T][nx][nu] (already multiplied by u_normalization for the coupled QP), c [B][T][nx],
+ * H [B][T][4][2], G [B][T][4], dmin/dmax/fxmax [B][T], hji [B][3] = (M1*un1, M2*un2, b) */
+PGN_API int pgn_get_qp_data(pgn_handle* h, double* A, double* B0, double* Bf, double* c, double* H, double* G, double* dmin, double* dmax,
+                    double* fxmax, double* hji);
+PGN_API int pgn_get_solution(pgn_handle* h, double* x /*[B][n]*/, double* y /*[B][m]*/);
+PGN_API int pgn_get_stats(pgn_handle* h, int32_t* iters, int32_t* status, double* pri_res, double* dua_res, double* rho, int32_t* rho_updates);
+/* stand-alone HJI lookup cache[x] (HJI_computation.jl:66-72); x [M][7] host, V [M], gradV [M][7] */
+PGN_API int pgn_hji_lookup(pgn_handle* h, int32_t M, const double* x, double* V, double* gradV);
+/* device variant for the HBM roofline micro-benchmark: d_x [7][M] field-major, d_V [M], d_gradV [7][M] */
+PGN_API int pgn_hji_lookup_device(pgn_handle* h, int32_t M, const double* d_x, double* d_V, double* d_gradV);
+/* device pointers of library-owned buffers (for zero-copy gathers through torch.distributed / NCCL) */
+PGN_API int pgn_device_controls(pgn_handle* h, double** d_out /* [3][B] */);
+PGN_API int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_status);
+/* per-stage device time accumulated with CUDA events since the last reset, milliseconds:
+ * [0] time steps + nodes, [1] linearisation + envelope, [2] HJI, [3] ADMM, [4] controls, [5] rollout, [6] launches counted */
+PGN_API int pgn_set_profiling(pgn_handle* h, int32_t on);
+PGN_API int pgn_get_stage_ms(pgn_handle* h, double* out /*[8]*/, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIGEON_B200_H */

@@ -1,0 +1,9 @@
+"""pigeon.jl_b200 — B200-native batched MPC engine for the per-time-step hot path of StanfordASL/Pigeon.jl.
+
+Host-side mirror of the reference's MPC API over the C ABI of libpigeon_b200.so (include/pigeon_b200.h).
+"""
+from . import synthetic  # noqa: F401
+from ._lib import LIB_PATH, PGN_COUPLED, PGN_DECOUPLED, STATUS_NAMES, SYMBOLS, PigeonError, load  # noqa: F401
+from .mpc import (BatchedCoupledTrajectoryTrackingMPC, BatchedDecoupledTrajectoryTrackingMPC, BatchedTrajectoryTrackingMPC,  # noqa: F401
+                  CoupledControlParams, DecoupledControlParams, HJICache, TrajectoryTube, X1, compute_linearization_nodes, compute_time_steps,
+                  get_next_control, placeholder_HJICache, simulate, solve, straight_trajectory, update_QP)

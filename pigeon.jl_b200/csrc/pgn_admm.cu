@@ -1,0 +1,512 @@
+// pgn_admm.cu — solve!: batched OSQP-style ADMM, one QP per CTA, persistent CTAs pulling vehicles from an atomic ticket.
+//
+// Replaces Parametron.solve! -> OSQP.update!/osqp_solve (reference src/model_predictive_control.jl:76 with the settings of
+// src/coupled_lat_long.jl:201-204; libosqp 0.4.x is not vendored — algorithm per Stellato et al. 2020 and restated on the
+// CPU in oracle/osqp_port.hpp).  Per vehicle and per MPC step the CTA
+//   1. gathers the QP values (P, q, A, l, u) from the vehicle's piece record through the static source tables,
+//   2. re-equilibrates them (modified Ruiz, `scaling` passes, cost scaling) — osqp_update_P_A rescales from scratch,
+//   3. factors the quasi-definite KKT matrix [P+sigma I, A'; A, -1/rho] = L D L' with a static elimination order
+//      (nested dissection over the horizon stages) and a level-scheduled gather program computed once on the host,
+//   4. iterates  (x~,nu) = K^-1 rhs;  x,z,y update with relaxation alpha;  every `check_termination` iterations the unscaled
+//      residuals, tolerances and infeasibility certificates; every `adaptive_rho_interval` the rho estimate with refactorisation,
+//   5. stores the unscaled solution, the (scaled) warm-start iterates and rho for the next step, and the per-QP statistics.
+// Everything the iteration touches lives in shared memory (~180 KB for the coupled N=31 QP): L values, 1/D, the scaled A
+// values, seven KKT-length work vectors and the 16-bit index tables of the triangular solves.  All vectors are indexed by KKT
+// *position* (elimination order), so no permutation gathers happen inside the loop.  FP64 throughout: the KKT matrix mixes
+// sigma = 1e-6 with 1/rho up to 1e6 and the parity target (1e-4 on controls at eps = 1e-3) does not survive an FP32 factor.
+#include "pgn_internal.h"
+
+namespace pgn {
+
+#define ADMM_THREADS 256
+#define NW (ADMM_THREADS / 32)
+
+static const double OSQP_INFTY = 1e20;
+
+struct AdmmArgs {
+    QpDev q;
+    AdmmSettings st;
+    int B;
+    const double* rec;
+    double *ws_xz, *ws_y, *rho;
+    double *sol_x, *sol_y;
+    int32_t *iters, *status, *rho_updates;
+    double *pri_res, *dua_res;
+    uint8_t* solved;
+    int* counter;
+};
+
+struct Smem {
+    double *Lval, *Dinv, *Aval, *xz, *sol, *yq, *lo, *hi, *sc, *dxy, *red;
+    uint16_t *lrow_col, *lcol_row, *lcol_val, *lrow_ptr, *lcol_ptr, *lvl_ptr;
+    uint8_t* flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t admm_smem_bytes(const QpTables& t) {
+    size_t d = (size_t)t.nnzL + t.Nk + t.nnzA + 7 * (size_t)t.Nk + 16 * NW + 8;
+    size_t u16 = 3 * (size_t)t.nnzL + 2 * (size_t)(t.Nk + 1) + (t.nlev + 1) + 8;
+    return d * 8 + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + 64;
+}
+
+__device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem& s) {
+    double* d = reinterpret_cast<double*>(base);
+    s.Lval = d; d += q.nnzL;
+    s.Dinv = d; d += q.Nk;
+    s.Aval = d; d += q.nnzA;
+    s.xz = d; d += q.Nk;
+    s.sol = d; d += q.Nk;
+    s.yq = d; d += q.Nk;
+    s.lo = d; d += q.Nk;
+    s.hi = d; d += q.Nk;
+    s.sc = d; d += q.Nk;
+    s.dxy = d; d += q.Nk;
+    s.red = d; d += 16 * NW + 8;
+    uint16_t* u = reinterpret_cast<uint16_t*>(d);
+    s.lrow_col = u; u += q.nnzL;
+    s.lcol_row = u; u += q.nnzL;
+    s.lcol_val = u; u += q.nnzL;
+    s.lrow_ptr = u; u += q.Nk + 1;
+    s.lcol_ptr = u; u += q.Nk + 1;
+    s.lvl_ptr = u; u += q.nlev + 1;
+    size_t off = align_up((size_t)(reinterpret_cast<unsigned char*>(u) - base), 8);
+    s.flag = base + off;
+}
+
+// block-wide max / sum of NV values per thread; every thread returns with the results in v[]
+template <int NV, bool IS_MAX>
+__device__ __forceinline__ void block_reduce(double* v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double a = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double b = __shfl_xor_sync(0xffffffffu, a, o);
+            a = IS_MAX ? fmax(a, b) : a + b;
+        }
+        v[k] = a;
+    }
+    __syncthreads();   // red[] free
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) red[w * NV + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double a = red[k];
+#pragma unroll
+        for (int ww = 1; ww < NW; ww++) a = IS_MAX ? fmax(a, red[ww * NV + k]) : a + red[ww * NV + k];
+        v[k] = a;
+    }
+}
+
+__device__ __forceinline__ double limit_scaling(double a) {
+    a = a < 1e-4 ? 1.0 : a;
+    return a > 1e4 ? 1e4 : a;
+}
+__device__ __forceinline__ double rho_of(uint8_t flag, double rho) { return flag == 2 ? 1e3 * rho : (flag == 3 ? 1e-6 : rho); }
+// rho_inv_vec of OSQP: reciprocals are formed once per rho value and multiplied in
+struct RhoInv { double in, eq, loose; };
+__device__ __forceinline__ RhoInv make_rho_inv(double rho) { RhoInv r; r.in = 1.0 / rho; r.eq = 1.0 / (1e3 * rho); r.loose = 1.0 / 1e-6; return r; }
+__device__ __forceinline__ double rinv_of(uint8_t flag, const RhoInv& r) { return flag == 2 ? r.eq : (flag == 3 ? r.loose : r.in); }
+
+// numeric LDL' of K = [P + sigma I, A'; A, -1/rho] (position space) with the static gather program
+__device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) {
+    const int tid = threadIdx.x;
+    const RhoInv ri = make_rho_inv(rho);
+    for (int e = tid; e < q.nnzL; e += ADMM_THREADS) s.Lval[e] = 0.0;
+    // D workspace lives in s.sol during the factorisation
+    for (int p = tid; p < q.Nk; p += ADMM_THREADS) s.sol[p] = s.flag[p] ? -rinv_of(s.flag[p], ri) : s.lo[p] + sigma;
+    __syncthreads();
+    for (int e = tid; e < q.nnzA; e += ADMM_THREADS) s.Lval[__ldg(q.a_lpos + e)] = s.Aval[e];
+    __syncthreads();
+    double* D = s.sol;
+    for (int l = 0; l < q.nlev; l++) {
+        const uint32_t t0 = __ldg(q.ftgt_ptr + l), t1 = __ldg(q.ftgt_ptr + l + 1);
+        for (uint32_t t = t0 + tid; t < t1; t += ADMM_THREADS) {
+            const int id = __ldg(q.ftgt_id + t);
+            const uint32_t x0 = __ldg(q.fac_ptr + t), x1 = __ldg(q.fac_ptr + t + 1);
+            if (id >= q.nnzL) {
+                const int j = id - q.nnzL;
+                double acc = D[j];
+                for (uint32_t x = x0; x < x1; x++) { const double v = s.Lval[__ldg(q.fac_a + x)]; acc -= v * v * D[__ldg(q.fac_k + x)]; }
+                D[j] = acc;
+                s.Dinv[j] = 1.0 / acc;
+            } else {
+                double acc = s.Lval[id];
+                for (uint32_t x = x0; x < x1; x++) acc -= s.Lval[__ldg(q.fac_a + x)] * s.Lval[__ldg(q.fac_b + x)] * D[__ldg(q.fac_k + x)];
+                s.Lval[id] = acc;
+            }
+        }
+        __syncthreads();
+        for (uint32_t t = t0 + tid; t < t1; t += ADMM_THREADS) {
+            const int id = __ldg(q.ftgt_id + t);
+            if (id < q.nnzL) s.Lval[id] *= s.Dinv[__ldg(q.ftgt_col + t)];
+        }
+        __syncthreads();
+    }
+}
+
+// sol <- K^-1 sol   (level-scheduled forward, diagonal, backward substitution)
+__device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
+    const int tid = threadIdx.x;
+    for (int l = 1; l < q.nlev; l++) {
+        const int r0 = s.lvl_ptr[l], r1 = s.lvl_ptr[l + 1];
+        for (int r = r0 + tid; r < r1; r += ADMM_THREADS) {
+            double acc = s.sol[r];
+            const int e1 = s.lrow_ptr[r + 1];
+            for (int e = s.lrow_ptr[r]; e < e1; e++) acc -= s.Lval[e] * s.sol[s.lrow_col[e]];
+            s.sol[r] = acc;
+        }
+        __syncthreads();
+    }
+    for (int l = q.nlev - 1; l >= 0; l--) {
+        const int r0 = s.lvl_ptr[l], r1 = s.lvl_ptr[l + 1];
+        for (int r = r0 + tid; r < r1; r += ADMM_THREADS) {
+            double acc = s.sol[r] * s.Dinv[r];
+            const int e1 = s.lcol_ptr[r + 1];
+            for (int e = s.lcol_ptr[r]; e < e1; e++) acc -= s.Lval[s.lcol_val[e]] * s.sol[s.lcol_row[e]];
+            s.sol[r] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// out[p] = sum over the off-diagonal KKT entries of row p:  constraints get (A x)_i, variables get (A' y)_j
+__device__ __forceinline__ void kadj_product(const QpDev& q, const Smem& s, const double* vin_var, const double* vin_con, double* out) {
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS) {
+        const bool con = s.flag[p] != 0;
+        const double* in = con ? vin_var : vin_con;
+        double acc = 0.0;
+        const int e1 = __ldg(q.kadj_ptr + p + 1);
+        for (int e = __ldg(q.kadj_ptr + p); e < e1; e++) acc += s.Aval[__ldg(q.kadj_e + e)] * in[__ldg(q.kadj_nb + e)];
+        out[p] = acc;
+    }
+}
+
+struct Resid { double pri_res, dua_res, eps_pri_n, eps_dua_n, s_pri, s_dua, s_pn, s_dn; };
+
+// residuals in unscaled norms (termination) and scaled norms (rho estimate). s.sol receives [A'y ; Ax] by position.
+__device__ __forceinline__ Resid residuals(const QpDev& q, const Smem& s, double cinv) {
+    kadj_product(q, s, s.xz, s.yq, s.sol);
+    double v[14];
+#pragma unroll
+    for (int k = 0; k < 14; k++) v[k] = 0.0;
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS) {
+        const double t = s.sol[p], sc = s.sc[p], isc = 1.0 / sc;
+        if (s.flag[p]) {
+            const double z = s.xz[p], r = t - z;
+            v[0] = fmax(v[0], fabs(r * isc)); v[1] = fmax(v[1], fabs(z * isc)); v[2] = fmax(v[2], fabs(t * isc));
+            v[7] = fmax(v[7], fabs(r)); v[8] = fmax(v[8], fabs(z)); v[9] = fmax(v[9], fabs(t));
+        } else {
+            const double px = s.lo[p] * s.xz[p], qq = s.yq[p], r = px + qq + t;
+            v[3] = fmax(v[3], fabs(r * isc)); v[4] = fmax(v[4], fabs(px * isc)); v[5] = fmax(v[5], fabs(t * isc)); v[6] = fmax(v[6], fabs(qq * isc));
+            v[10] = fmax(v[10], fabs(r)); v[11] = fmax(v[11], fabs(px)); v[12] = fmax(v[12], fabs(t)); v[13] = fmax(v[13], fabs(qq));
+        }
+    }
+    block_reduce<14, true>(v, s.red);
+    Resid R;
+    R.pri_res = v[0]; R.eps_pri_n = fmax(v[1], v[2]);
+    R.dua_res = cinv * v[3]; R.eps_dua_n = cinv * fmax(v[6], fmax(v[5], v[4]));
+    R.s_pri = v[7]; R.s_pn = fmax(v[8], v[9]);
+    R.s_dua = v[10]; R.s_dn = fmax(v[13], fmax(v[12], v[11]));
+    return R;
+}
+
+// is_primal_infeasible / is_dual_infeasible of OSQP on the increments stored in s.dxy (delta_x at variables, delta_y at constraints)
+__device__ bool primal_infeasible(const QpDev& q, const Smem& s, double eps) {
+    const double thr = OSQP_INFTY * 1e-4;
+    double v[1] = {0.0};
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS)
+        if (s.flag[p]) {
+            double dy = s.dxy[p];
+            const double l = s.lo[p], u = s.hi[p];
+            if (u > thr) { dy = (l < -thr) ? 0.0 : fmin(dy, 0.0); }
+            else if (l < -thr) dy = fmax(dy, 0.0);
+            s.dxy[p] = dy;
+            v[0] = fmax(v[0], fabs(s.sc[p] * dy));
+        }
+    block_reduce<1, true>(v, s.red);
+    const double norm_dy = v[0];
+    if (!(norm_dy > eps)) return false;
+    double w[1] = {0.0};
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS)
+        if (s.flag[p]) { const double dy = s.dxy[p]; w[0] += s.hi[p] * fmax(dy, 0.0) + s.lo[p] * fmin(dy, 0.0); }
+    block_reduce<1, false>(w, s.red);
+    if (!(w[0] < -eps * norm_dy)) return false;
+    // ||Dinv A' dy||
+    kadj_product(q, s, s.dxy, s.dxy, s.sol);
+    double n2[1] = {0.0};
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS)
+        if (!s.flag[p]) n2[0] = fmax(n2[0], fabs(s.sol[p] / s.sc[p]));
+    block_reduce<1, true>(n2, s.red);
+    return n2[0] < eps * norm_dy;
+}
+__device__ bool dual_infeasible(const QpDev& q, const Smem& s, double eps, double c) {
+    const double thr = OSQP_INFTY * 1e-4;
+    double v[2] = {0.0, 0.0};
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS)
+        if (!s.flag[p]) { v[0] = fmax(v[0], fabs(s.sc[p] * s.dxy[p])); }
+    block_reduce<1, true>(v, s.red);
+    const double norm_dx = v[0];
+    if (!(norm_dx > eps)) return false;
+    double w[1] = {0.0};
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS)
+        if (!s.flag[p]) w[0] += s.yq[p] * s.dxy[p];
+    block_reduce<1, false>(w, s.red);
+    if (!(w[0] < -c * eps * norm_dx)) return false;
+    double n2[1] = {0.0};
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS)
+        if (!s.flag[p]) n2[0] = fmax(n2[0], fabs(s.lo[p] * s.dxy[p] / s.sc[p]));
+    block_reduce<1, true>(n2, s.red);
+    if (!(n2[0] < c * eps * norm_dx)) return false;
+    kadj_product(q, s, s.dxy, s.dxy, s.sol);   // constraints: (A dx)_i
+    __syncthreads();
+    double bad[1] = {0.0};
+    for (int p = threadIdx.x; p < q.Nk; p += ADMM_THREADS)
+        if (s.flag[p]) {
+            const double a = s.sol[p] / s.sc[p];
+            if ((s.hi[p] < thr && a > eps * norm_dx) || (s.lo[p] > -thr && a < -eps * norm_dx)) bad[0] = 1.0;
+        }
+    block_reduce<1, true>(bad, s.red);
+    return bad[0] == 0.0;
+}
+
+__global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_vehicle;
+    const QpDev& q = a.q;
+    const AdmmSettings& st = a.st;
+    Smem s;
+    carve(q, smem_raw, s);
+    const int tid = threadIdx.x;
+    // index tables of the triangular solves: global -> shared, once per CTA
+    for (int e = tid; e < q.nnzL; e += ADMM_THREADS) { s.lrow_col[e] = q.lrow_col[e]; s.lcol_row[e] = q.lcol_row[e]; s.lcol_val[e] = q.lcol_val[e]; }
+    for (int p = tid; p <= q.Nk; p += ADMM_THREADS) { s.lrow_ptr[p] = q.lrow_ptr[p]; s.lcol_ptr[p] = q.lcol_ptr[p]; }
+    for (int l = tid; l <= q.nlev; l += ADMM_THREADS) s.lvl_ptr[l] = q.lvl_ptr[l];
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_vehicle = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int v = s_vehicle;
+        __syncthreads();
+        if (v >= a.B) break;
+        const double* rec = a.rec + (size_t)v * q.rec_len;
+
+        // ---- 1. gather the QP values --------------------------------------------------------------------------------
+        for (int e = tid; e < q.nnzA; e += ADMM_THREADS) {
+            const int src = __ldg(q.a_src + e);
+            s.Aval[e] = src >= 0 ? rec[src] : (src == -1 ? 1.0 : -1.0);
+        }
+        for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
+            const int idx = __ldg(q.pos2idx + p);
+            if (__ldg(q.is_con + p)) {
+                double b[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int ty = k == 0 ? __ldg(q.l_type + idx) : __ldg(q.u_type + idx);
+                    const int ix = k == 0 ? __ldg(q.l_idx + idx) : __ldg(q.u_idx + idx);
+                    double val;
+                    if (ty == BND_CONST) val = __ldg(q.ctab + ix);
+                    else if (ty == BND_REC) val = rec[ix];
+                    else if (ty == BND_NEG_REC) val = -rec[ix];
+                    else if (ty == BND_DT_SCALED) val = __ldg(q.ctab + CT_DDELTA_N) * rec[ix];
+                    else val = -__ldg(q.ctab + CT_DDELTA_N) * rec[ix];
+                    b[k] = val;
+                }
+                s.lo[p] = fmax(b[0], -OSQP_INFTY);
+                s.hi[p] = fmin(b[1], OSQP_INFTY);
+                s.flag[p] = 1;
+                s.yq[p] = st.warm_start ? a.ws_y[(size_t)v * q.Nk + p] : 0.0;
+            } else {
+                const int pm = __ldg(q.P_mode + idx), qm = __ldg(q.q_mode + idx);
+                double Pv = 0.0, qv = 0.0;
+                if (pm == PQ_TIMES_DT) Pv = 2.0 * __ldg(q.wtab + __ldg(q.P_w + idx)) * rec[__ldg(q.P_t + idx)];
+                else if (pm == PQ_OVER_DT) Pv = 2.0 * __ldg(q.wtab + __ldg(q.P_w + idx)) / rec[__ldg(q.P_t + idx)];
+                if (qm == PQ_TIMES_DT) qv = __ldg(q.wtab + __ldg(q.q_w + idx)) * rec[__ldg(q.q_t + idx)];
+                else if (qm == PQ_CONST) qv = (__ldg(q.q_hji_t + idx) < q.n_hji) ? __ldg(q.wtab + __ldg(q.q_w + idx)) : 0.0;
+                s.lo[p] = Pv;      // P_jj
+                s.hi[p] = 0.0;
+                s.yq[p] = qv;      // q_j
+                s.flag[p] = 0;
+            }
+            s.sc[p] = 1.0;         // D_j | E_i
+            s.xz[p] = st.warm_start ? a.ws_xz[(size_t)v * q.Nk + p] : 0.0;
+        }
+        double rho = st.warm_start ? a.rho[v] : st.rho;
+        double c = 1.0;
+        __syncthreads();
+
+        // ---- 2. modified Ruiz equilibration (scale_data of OSQP) -------------------------------------------------------
+        for (int it = 0; it < st.scaling; it++) {
+            for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
+                double nrm = s.flag[p] ? 0.0 : fabs(s.lo[p]);
+                const int e1 = __ldg(q.kadj_ptr + p + 1);
+                for (int e = __ldg(q.kadj_ptr + p); e < e1; e++) nrm = fmax(nrm, fabs(s.Aval[__ldg(q.kadj_e + e)]));
+                s.sol[p] = 1.0 / sqrt(limit_scaling(nrm));
+            }
+            __syncthreads();
+            for (int e = tid; e < q.nnzA; e += ADMM_THREADS) s.Aval[e] *= s.sol[__ldg(q.a_rowpos + e)] * s.sol[__ldg(q.a_colpos + e)];
+            double v2[2] = {0.0, 0.0};   // sum |P_jj|, max |q_j|
+            for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
+                const double d = s.sol[p];
+                s.sc[p] *= d;
+                if (!s.flag[p]) {
+                    s.lo[p] *= d * d;
+                    s.yq[p] *= d;
+                    v2[0] += fabs(s.lo[p]);
+                    v2[1] = fmax(v2[1], fabs(s.yq[p]));
+                }
+            }
+            double vs[1] = {v2[0]}, vm[1] = {v2[1]};
+            block_reduce<1, false>(vs, s.red);
+            block_reduce<1, true>(vm, s.red);
+            double c_temp = vs[0] / q.n;
+            const double inf_q = limit_scaling(vm[0]);
+            c_temp = limit_scaling(fmax(c_temp, inf_q));
+            c_temp = 1.0 / c_temp;
+            for (int p = tid; p < q.Nk; p += ADMM_THREADS)
+                if (!s.flag[p]) { s.lo[p] *= c_temp; s.yq[p] *= c_temp; }
+            c *= c_temp;
+            __syncthreads();
+        }
+        const double cinv = 1.0 / c;
+        // bounds scaled by E; constraint classes (set_rho_vec of OSQP)
+        for (int p = tid; p < q.Nk; p += ADMM_THREADS)
+            if (s.flag[p]) {
+                const double E = s.sc[p];
+                const double l = s.lo[p] * E, u = s.hi[p] * E;
+                s.lo[p] = l; s.hi[p] = u;
+                s.flag[p] = (l < -OSQP_INFTY * 1e-4 && u > OSQP_INFTY * 1e-4) ? 3 : ((u - l < 1e-4) ? 2 : 1);
+            }
+        __syncthreads();
+
+        // ---- 3. factor ----------------------------------------------------------------------------------------------------
+        factor(q, s, st.sigma, rho);
+
+        // ---- 4. ADMM iterations ---------------------------------------------------------------------------------------------
+        int iter = 0, status = PGN_QP_UNSOLVED, n_rho_upd = 0;
+        double pri_res = 0.0, dua_res = 0.0;
+        const double alpha = st.alpha;
+        RhoInv rinv = make_rho_inv(rho);
+        for (iter = 1; iter <= st.max_iter; iter++) {
+            const bool check = st.check_termination && (iter % st.check_termination == 0);
+            const bool adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+            const bool need_delta = check || adapt;
+            // rhs
+            for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
+                const uint8_t f = s.flag[p];
+                s.sol[p] = f ? s.xz[p] - rinv_of(f, rinv) * s.yq[p] : st.sigma * s.xz[p] - s.yq[p];
+            }
+            __syncthreads();
+            kkt_solve(q, s);
+            // x, z, y updates
+            for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
+                const uint8_t f = s.flag[p];
+                if (f) {
+                    const double r = rho_of(f, rho), ri = rinv_of(f, rinv);
+                    const double zp = s.xz[p], y = s.yq[p];
+                    const double zt = zp + ri * (s.sol[p] - y);
+                    const double zr = alpha * zt + (1.0 - alpha) * zp;
+                    const double zn = fmin(fmax(zr + ri * y, s.lo[p]), s.hi[p]);
+                    const double dy = r * (zr - zn);
+                    s.xz[p] = zn;
+                    s.yq[p] = y + dy;
+                    if (need_delta) s.dxy[p] = dy;
+                } else {
+                    const double xp = s.xz[p];
+                    const double xn = alpha * s.sol[p] + (1.0 - alpha) * xp;
+                    s.xz[p] = xn;
+                    if (need_delta) s.dxy[p] = xn - xp;
+                }
+            }
+            __syncthreads();
+            if (!need_delta) continue;
+            Resid R = residuals(q, s, cinv);
+            pri_res = R.pri_res; dua_res = R.dua_res;
+            if (check) {
+                const double eps_prim = st.eps_abs + st.eps_rel * R.eps_pri_n;
+                const double eps_dual = st.eps_abs + st.eps_rel * R.eps_dua_n;
+                const bool prim_ok = R.pri_res < eps_prim, dual_ok = R.dua_res < eps_dual;
+                bool pinf = false, dinf = false;
+                if (!prim_ok) pinf = primal_infeasible(q, s, st.eps_prim_inf);
+                if (!dual_ok) dinf = dual_infeasible(q, s, st.eps_dual_inf, c);
+                if (prim_ok && dual_ok) { status = PGN_QP_SOLVED; break; }
+                if (pinf) { status = PGN_QP_PRIMAL_INFEASIBLE; break; }
+                if (dinf) { status = PGN_QP_DUAL_INFEASIBLE; break; }
+            }
+            if (adapt) {
+                // compute_rho_estimate / adapt_rho of OSQP (scaled norms)
+                const double pr = R.s_pri / (R.s_pn + 1e-10), du = R.s_dua / (R.s_dn + 1e-10);
+                double rho_new = rho * sqrt(pr / (du + 1e-10));
+                rho_new = fmin(fmax(rho_new, 1e-6), 1e6);
+                if (rho_new > rho * st.adaptive_rho_tolerance || rho_new < rho / st.adaptive_rho_tolerance) {
+                    rho = rho_new;
+                    rinv = make_rho_inv(rho);
+                    n_rho_upd++;
+                    __syncthreads();
+                    factor(q, s, st.sigma, rho);
+                }
+            }
+        }
+        if (iter > st.max_iter) {
+            iter = st.max_iter;
+            // approximate termination test (10x tolerances) before declaring max_iter_reached
+            Resid R = residuals(q, s, cinv);
+            pri_res = R.pri_res; dua_res = R.dua_res;
+            const double eps_prim = 10 * st.eps_abs + 10 * st.eps_rel * R.eps_pri_n, eps_dual = 10 * st.eps_abs + 10 * st.eps_rel * R.eps_dua_n;
+            status = (R.pri_res < eps_prim && R.dua_res < eps_dual) ? PGN_QP_SOLVED_INACCURATE : PGN_QP_MAX_ITER_REACHED;
+        }
+
+        // ---- 5. store ------------------------------------------------------------------------------------------------------------
+        const bool infeas = (status == PGN_QP_PRIMAL_INFEASIBLE || status == PGN_QP_DUAL_INFEASIBLE);
+        for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
+            const int idx = __ldg(q.pos2idx + p);
+            if (s.flag[p]) {
+                a.sol_y[(size_t)v * q.m + idx] = infeas ? NAN : s.sc[p] * s.yq[p] * cinv;
+                a.ws_y[(size_t)v * q.Nk + p] = infeas ? 0.0 : s.yq[p];
+            } else {
+                a.sol_x[(size_t)v * q.n + idx] = infeas ? NAN : s.sc[p] * s.xz[p];
+                a.ws_y[(size_t)v * q.Nk + p] = 0.0;
+            }
+            a.ws_xz[(size_t)v * q.Nk + p] = infeas ? 0.0 : s.xz[p];
+        }
+        if (tid == 0) {
+            a.rho[v] = rho;
+            a.iters[v] = iter; a.status[v] = status; a.rho_updates[v] = n_rho_upd;
+            a.pri_res[v] = pri_res; a.dua_res[v] = dua_res;
+            a.solved[v] = 1;
+        }
+        __syncthreads();
+    }
+}
+
+int admm_configure(pgn_handle* h) {
+    h->admm_smem_bytes = (int)admm_smem_bytes(h->tab);
+    h->admm_threads = ADMM_THREADS;
+    cudaError_t e = cudaFuncSetAttribute(k_admm, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
+    return (int)e;
+}
+
+void launch_admm(pgn_handle* h) {
+    AdmmArgs a;
+    a.q = h->qd; a.st = h->st; a.B = h->B;
+    a.rec = h->d_rec; a.ws_xz = h->d_ws_xz; a.ws_y = h->d_ws_y; a.rho = h->d_rho;
+    a.sol_x = h->d_sol_x; a.sol_y = h->d_sol_y;
+    a.iters = h->d_iters; a.status = h->d_status; a.rho_updates = h->d_rho_updates; a.pri_res = h->d_pri_res; a.dua_res = h->d_dua_res;
+    a.solved = h->d_solved; a.counter = h->d_counter;
+    cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream);
+    int ctas_per_sm = 1;
+    if (h->admm_smem_bytes * 2 + 2048 <= 227 * 1024) ctas_per_sm = 2;
+    if (h->admm_smem_bytes * 3 + 3072 <= 227 * 1024) ctas_per_sm = 3;
+    int grid = h->num_sms * ctas_per_sm;
+    if (grid > h->B) grid = h->B;
+    k_admm<<<grid, ADMM_THREADS, h->admm_smem_bytes, h->stream>>>(a);
+    h->launches++;
+}
+
+}  // namespace pgn

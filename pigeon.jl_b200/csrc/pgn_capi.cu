@@ -1,0 +1,550 @@
+// pgn_capi.cu — the extern "C" boundary of libpigeon_b200.so (declared in include/pigeon_b200.h).
+// Host arrays in, host arrays out; CUDA errors become return codes; no CPU compute path exists behind these calls.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "pgn_internal.h"
+
+using namespace pgn;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CK(call)                                                                                                              \
+    do {                                                                                                                      \
+        cudaError_t e__ = (call);                                                                                             \
+        if (e__ != cudaSuccess) return set_err(PGN_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define REQUIRE(cond, msg)                                   \
+    do {                                                     \
+        if (!(cond)) return set_err(PGN_EINVAL, "%s", msg);  \
+    } while (0)
+
+namespace {
+
+struct StageTimer {
+    pgn_handle* h; int idx;
+    StageTimer(pgn_handle* h_, int idx_) : h(h_), idx(idx_) { if (h->profiling) cudaEventRecord(h->ev[0], h->stream); }
+    ~StageTimer() {
+        if (h->profiling) {
+            cudaEventRecord(h->ev[1], h->stream);
+            cudaEventSynchronize(h->ev[1]);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+            h->stage_ms[idx] += ms;
+        }
+    }
+};
+
+template <class T>
+int dev_alloc(pgn_handle* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return set_err(PGN_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return PGN_OK;
+}
+template <class T>
+int dev_upload(pgn_handle* h, const std::vector<T>& v, const T** out) {
+    T* p = nullptr;
+    int rc = dev_alloc(h, &p, v.size() + 1);
+    if (rc) return rc;
+    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = p;
+    return PGN_OK;
+}
+
+int ensure_stage(pgn_handle* h, size_t bytes) {
+    if (h->stage_bytes >= bytes) return PGN_OK;
+    double* p = nullptr;
+    int rc = dev_alloc(h, &p, bytes / 8 + 1);
+    if (rc) return rc;
+    h->d_stage = p; h->stage_bytes = bytes;
+    return PGN_OK;
+}
+
+// host [B][k] -> device SoA [k][B]
+int upload_aos(pgn_handle* h, const double* host, double* d_soa, int k) {
+    size_t bytes = (size_t)h->B * k * sizeof(double);
+    int rc = ensure_stage(h, bytes);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
+    launch_transpose_in(h, h->d_stage, d_soa, k);
+    return PGN_OK;
+}
+int download_aos(pgn_handle* h, const double* d_soa, double* host, int k) {
+    size_t bytes = (size_t)h->B * k * sizeof(double);
+    int rc = ensure_stage(h, bytes);
+    if (rc) return rc;
+    launch_transpose_out(h, d_soa, h->d_stage, k);
+    CK(cudaMemcpyAsync(host, h->d_stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+
+void refresh_constants(pgn_handle* h, double* ctab, double* wtab) {
+    const VehParams& P = h->veh;
+    const CtrlParams& C = h->ctl;
+    h->un[0] = P.delta_max;
+    h->un[1] = fmax(-P.Fx_min, P.Fx_max);
+    const bool cpl = h->cfg.kind == PGN_COUPLED;
+    ctab[CT_ZERO] = 0.0; ctab[CT_PINF] = INFINITY; ctab[CT_NINF] = -INFINITY;
+    ctab[CT_VMIN] = C.V_min; ctab[CT_VMAX] = C.V_max; ctab[CT_FXMIN_N] = P.Fx_min / h->un[1];
+    ctab[CT_DDELTA_N] = cpl ? C.ddelta_max / h->un[0] : C.ddelta_max;
+    for (int i = 0; i < W_LEN; i++) wtab[i] = 0.0;
+    wtab[W_Q_DS] = C.Q_ds; wtab[W_Q_DPSI] = C.Q_dpsi; wtab[W_Q_E] = C.Q_e; wtab[W_R_DELTA] = C.R_delta; wtab[W_R_FX] = C.R_Fx;
+    wtab[W_R_DDELTA] = C.R_ddelta; wtab[W_R_DFX] = C.R_dFx; wtab[W_W_BETA] = C.W_beta; wtab[W_W_R] = C.W_r; wtab[W_W_HJI] = C.W_HJI;
+}
+int upload_constants(pgn_handle* h) {
+    double ctab[CT_LEN], wtab[W_LEN];
+    refresh_constants(h, ctab, wtab);
+    CK(cudaMemcpyAsync((void*)h->qd.ctab, ctab, sizeof(ctab), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync((void*)h->qd.wtab, wtab, sizeof(wtab), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->qd.n_hji = (int)h->ctl.N_HJI;
+    return PGN_OK;
+}
+
+void x1_params(double* vp) {
+    VehParams P;
+    P.G = 9.80665;
+    const double mfl = 484, mfr = 455, mrl = 521, mrr = 504;
+    P.m = mfl + mfr + mrl + mrr; P.Izz = 2900; P.L = 2.87;
+    P.a = (mrl + mrr) / P.m * P.L; P.b = (mfl + mfr) / P.m * P.L;
+    P.h = 0.1 * P.b / P.L + 0.1 * P.a / P.L + 0.37;
+    P.mu = 0.92; P.Caf = 150e3; P.Car = 220e3; P.Fx_max = 5600; P.Px_max = 75e3; P.Cd0 = 241.0; P.Cd1 = 25.1; P.Cd2 = 0.0;
+    P.fwd_frac = 0.0; P.rwd_frac = 1 - P.fwd_frac; P.fwb_frac = 0.6; P.rwb_frac = 1 - P.fwb_frac;
+    const double f1 = -P.m * P.G * P.a * P.mu / (P.L * P.rwb_frac + P.mu * P.h), f2 = -P.m * P.G * P.b * P.mu / (P.L * P.fwb_frac - P.mu * P.h);
+    P.Fx_min = f1 > f2 ? f1 : f2;
+    P.delta_max = 18 * M_PI / 180; P.kappa_max = tan(P.delta_max) / P.L; P.inv_fiala_corrected = 0.0;
+    memcpy(vp, &P, sizeof(double) * PGN_VEHICLE_PARAMS_LEN);
+}
+void default_control(int kind, double* c) {
+    const double d10 = 10 * M_PI / 180;
+    double v[16] = {1.0, 15.0, 10.0 / 4 / 100, 10.0 / 4 / 10000, 0.344, 1.0, 1.0, 1.0, 50 / d10, 50.0, 500.0, 3, 0.0, 0.1, 0.0, 0.5};
+    if (kind == PGN_DECOUPLED) { v[6] = 1 / (d10 * d10); v[7] = 1.0; v[12] = 0.0; v[13] = 0.01 / (d10 * d10); }
+    memcpy(c, v, sizeof(v));
+}
+
+int set_hji_internal(pgn_handle* h, const int32_t dims[7], const float* knots, const float* V, const float* gradV) {
+    size_t nn = 1, nk = 0;
+    for (int d = 0; d < 7; d++) { REQUIRE(dims[d] >= 2, "HJI grid needs >= 2 knots per dimension"); nn *= dims[d]; nk += dims[d]; }
+    std::vector<float> recs(nn * 8);
+    for (size_t i = 0; i < nn; i++) {
+        for (int k = 0; k < 7; k++) recs[i * 8 + k] = gradV[i * 7 + k];
+        recs[i * 8 + 7] = V[i];
+    }
+    float *d_k = nullptr, *d_r = nullptr;
+    int rc = dev_alloc(h, &d_k, nk + 8); if (rc) return rc;
+    rc = dev_alloc(h, &d_r, nn * 8 + 8); if (rc) return rc;
+    CK(cudaMemcpy(d_k, knots, nk * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_r, recs.data(), recs.size() * sizeof(float), cudaMemcpyHostToDevice));
+    HjiView& H = h->hji;
+    int off = 0;
+    long long st = 1;
+    for (int d = 0; d < 7; d++) { H.dims[d] = dims[d]; H.kofs[d] = off; off += dims[d]; H.stride[d] = st; st *= dims[d]; }
+    H.knots = d_k; H.V = nullptr; H.gV = d_r; H.valid = 1;
+    return PGN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pgn_last_error(void) { return g_err; }
+
+int pgn_default_config(pgn_config* c, int32_t kind) {
+    REQUIRE(c, "cfg is NULL");
+    memset(c, 0, sizeof(*c));
+    c->kind = kind; c->batch = 1; c->N_short = 10; c->N_long = 20; c->dt_short = 0.01; c->dt_long = 0.2; c->use_correction_step = 1; c->device = -1;
+    c->rho = 0.1; c->sigma = 1e-6; c->alpha = 1.6; c->eps_abs = 1e-3; c->eps_rel = 1e-3; c->eps_prim_inf = 1e-4; c->eps_dual_inf = 1e-4;
+    c->max_iter = 4000; c->scaling = 10; c->check_termination = 25; c->adaptive_rho = 1; c->adaptive_rho_interval = 25; c->adaptive_rho_tolerance = 5.0;
+    c->warm_start = 1; c->rk4_substeps = 10; c->hji_eps = 0.05; c->kkt_ordering = 0;
+    return PGN_OK;
+}
+int pgn_x1_vehicle_params(double* vp) { REQUIRE(vp, "vp is NULL"); x1_params(vp); return PGN_OK; }
+int pgn_default_control_params(int32_t kind, double* cp) { REQUIRE(cp, "cp is NULL"); default_control(kind, cp); return PGN_OK; }
+
+int pgn_create(const pgn_config* cfg, pgn_handle** out) {
+    REQUIRE(cfg && out, "NULL argument");
+    REQUIRE(cfg->kind == PGN_COUPLED || cfg->kind == PGN_DECOUPLED, "kind must be PGN_COUPLED or PGN_DECOUPLED");
+    REQUIRE(cfg->batch >= 1, "batch must be >= 1");
+    REQUIRE(cfg->N_short >= 1 && cfg->N_long >= 0, "N_short >= 1 and N_long >= 0 required");
+    REQUIRE(cfg->rk4_substeps >= 1, "rk4_substeps must be >= 1");
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0) return set_err(PGN_ECUDA, "no CUDA device available (%s); libpigeon_b200 has no CPU path", cudaGetErrorString(e0));
+    int dev = cfg->device;
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    REQUIRE(dev < ndev, "device ordinal out of range");
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return set_err(PGN_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    pgn_handle* h = new (std::nothrow) pgn_handle();
+    if (!h) return set_err(PGN_ENOMEM, "out of host memory");
+    h->cfg = *cfg; h->device = dev; h->B = cfg->batch; h->N = 1 + cfg->N_short + cfg->N_long; h->T = h->N - 1;
+    h->nx = cfg->kind == PGN_COUPLED ? 6 : 4; h->nu = cfg->kind == PGN_COUPLED ? 2 : 1;
+    h->num_sms = prop.multiProcessorCount;
+    h->profiling = 0; h->launches = 0; memset(h->stage_ms, 0, sizeof(h->stage_ms));
+    h->have_traj = false; h->have_assign = false; h->stage_bytes = 0; h->d_stage = nullptr;
+    memset(&h->hji, 0, sizeof(h->hji)); memset(&h->traj, 0, sizeof(h->traj));
+    char err[256];
+    if (!build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err))) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
+    auto bail = [&](int rc) { pgn_destroy(h); return rc; };
+    cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return set_err(PGN_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+    h->stream = h->own_stream;
+    cudaEventCreate(&h->ev[0]); cudaEventCreate(&h->ev[1]);
+    double vp[PGN_VEHICLE_PARAMS_LEN], cp[PGN_CONTROL_PARAMS_LEN];
+    x1_params(vp); default_control(cfg->kind, cp);
+    memcpy(&h->veh, vp, sizeof(vp)); memcpy(&h->ctl, cp, sizeof(cp));
+    h->st.rho = cfg->rho; h->st.sigma = cfg->sigma; h->st.alpha = cfg->alpha; h->st.eps_abs = cfg->eps_abs; h->st.eps_rel = cfg->eps_rel;
+    h->st.eps_prim_inf = cfg->eps_prim_inf; h->st.eps_dual_inf = cfg->eps_dual_inf; h->st.adaptive_rho_tolerance = cfg->adaptive_rho_tolerance;
+    h->st.max_iter = cfg->max_iter; h->st.scaling = cfg->scaling; h->st.check_termination = cfg->check_termination; h->st.adaptive_rho = cfg->adaptive_rho;
+    h->st.adaptive_rho_interval = cfg->adaptive_rho_interval; h->st.warm_start = cfg->warm_start;
+
+    // static tables -> device
+    const QpTables& t = h->tab;
+    QpDev& q = h->qd;
+    memset(&q, 0, sizeof(q));
+    q.kind = t.kind; q.N = t.N; q.T = t.T; q.Ns = t.Ns; q.nx = t.nx; q.nu = t.nu; q.n = t.n; q.m = t.m; q.Nk = t.Nk; q.nnzA = t.nnzA; q.nnzL = t.nnzL; q.nlev = t.nlev;
+    q.rec_len = t.rec.rec_len; q.o_dt = t.rec.o_dt; q.var_u1_delta = t.var_u1_delta; q.var_u1_fx = t.var_u1_fx;
+    int rc;
+#define UP(field) if ((rc = dev_upload(h, t.field, &q.field))) return bail(rc)
+    UP(a_src); UP(a_rowpos); UP(a_colpos); UP(a_lpos); UP(l_type); UP(u_type); UP(l_idx); UP(u_idx); UP(P_mode); UP(q_mode); UP(P_w); UP(q_w); UP(P_t); UP(q_t);
+    UP(q_hji_t); UP(pos_var); UP(pos_con); UP(pos2idx); UP(is_con); UP(lrow_ptr); UP(lrow_col); UP(lcol_ptr); UP(lcol_row); UP(lcol_val); UP(lvl_ptr);
+    UP(kadj_ptr); UP(kadj_e); UP(kadj_nb); UP(ftgt_ptr); UP(fac_ptr); UP(ftgt_id); UP(ftgt_col); UP(fac_a); UP(fac_b); UP(fac_k);
+#undef UP
+    double *ctab = nullptr, *wtab = nullptr;
+    if ((rc = dev_alloc(h, &ctab, CT_LEN + 1))) return bail(rc);
+    if ((rc = dev_alloc(h, &wtab, W_LEN + 1))) return bail(rc);
+    q.ctab = ctab; q.wtab = wtab;
+    if ((rc = upload_constants(h))) return bail(rc);
+
+    const size_t B = h->B, N = h->N, T = h->T;
+#define AL(ptr, count) if ((rc = dev_alloc(h, &h->ptr, (count)))) return bail(rc)
+    AL(d_state, 6 * B); AL(d_control, 3 * B); AL(d_other, 4 * B); AL(d_toff, B); AL(d_solved, B); AL(d_traj_id, B);
+    AL(d_ts, B * N); AL(d_dt, B * T); AL(d_prev_ts, B * N);
+    AL(d_qs, B * N * h->nx); AL(d_us, B * N * 2); AL(d_ps, B * N * 4);
+    AL(d_rec, B * (size_t)t.rec.rec_len);
+    AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
+    AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
+    AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_counter, 4);
+#undef AL
+    CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
+    CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
+    CK(cudaMemset(h->d_sol_x, 0, B * t.n * 8)); CK(cudaMemset(h->d_sol_y, 0, B * t.m * 8));
+    CK(cudaMemset(h->d_iters, 0, B * 4)); CK(cudaMemset(h->d_status, 0, B * 4)); CK(cudaMemset(h->d_rho_updates, 0, B * 4));
+    CK(cudaMemset(h->d_rec, 0, B * (size_t)t.rec.rec_len * 8)); CK(cudaMemset(h->d_controls, 0, 3 * B * 8));
+    {   // other car far away, time_offset = NaN (path mode), ts = 1..N (MPCTimeSteps ctor), rho = setting
+        std::vector<double> tmp(4 * B, 0.0), nanv(B, NAN), rho(B, cfg->rho), ts(B * N);
+        for (size_t v = 0; v < B; v++) for (size_t i = 0; i < N; i++) ts[v * N + i] = (double)(i + 1);
+        std::vector<double> dt(B * T, 1.0);
+        CK(cudaMemcpy(h->d_other, tmp.data(), 4 * B * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_toff, nanv.data(), B * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_rho, rho.data(), B * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_ts, ts.data(), B * N * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_prev_ts, ts.data(), B * N * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_dt, dt.data(), B * T * 8, cudaMemcpyHostToDevice));
+    }
+    // placeholder_HJICache() (HJI_computation.jl:32-37): 2^7 zero grid on +-1000
+    {
+        int32_t dims[7]; float knots[14]; std::vector<float> V(128, 0.f), g(128 * 7, 0.f);
+        for (int d = 0; d < 7; d++) { dims[d] = 2; knots[2 * d] = -1000.f; knots[2 * d + 1] = 1000.f; }
+        if ((rc = set_hji_internal(h, dims, knots, V.data(), g.data()))) return bail(rc);
+    }
+    // straight_trajectory(30., 5.) as the default trajectory (Pigeon.jl:34-35)
+    {
+        const double f[12][2] = {{0, 6}, {0, 30}, {5, 5}, {0, 0}, {0, 0}, {0, 30}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {4, 4}, {-4, -4}};
+        const double* fp[12];
+        for (int k = 0; k < 12; k++) fp[k] = f[k];
+        if ((rc = pgn_set_trajectories(h, 1, 2, fp))) return bail(rc);
+    }
+    int ce = admm_configure(h);
+    if (ce != 0) return bail(set_err(PGN_ECUDA, "ADMM kernel needs %d bytes of shared memory per CTA: %s", h->admm_smem_bytes, cudaGetErrorString((cudaError_t)ce)));
+    CK(cudaDeviceSynchronize());
+    *out = h;
+    return PGN_OK;
+}
+
+int pgn_destroy(pgn_handle* h) {
+    if (!h) return PGN_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaEventDestroy(h->ev[0]); cudaEventDestroy(h->ev[1]);
+    delete h;
+    return PGN_OK;
+}
+
+int pgn_set_stream(pgn_handle* h, void* s) { REQUIRE(h, "NULL handle"); h->stream = s ? (cudaStream_t)s : h->own_stream; return PGN_OK; }
+int pgn_synchronize(pgn_handle* h) { REQUIRE(h, "NULL handle"); CK(cudaStreamSynchronize(h->stream)); return PGN_OK; }
+
+int pgn_set_vehicle_params(pgn_handle* h, const double* vp) {
+    REQUIRE(h && vp, "NULL argument");
+    memcpy(&h->veh, vp, sizeof(double) * PGN_VEHICLE_PARAMS_LEN);
+    return upload_constants(h);
+}
+int pgn_set_control_params(pgn_handle* h, const double* cp) {
+    REQUIRE(h && cp, "NULL argument");
+    memcpy(&h->ctl, cp, sizeof(double) * PGN_CONTROL_PARAMS_LEN);
+    REQUIRE(h->ctl.N_HJI >= 0 && h->ctl.N_HJI <= h->cfg.N_short, "N_HJI must be within [0, N_short]");
+    return upload_constants(h);
+}
+int pgn_set_trajectories(pgn_handle* h, int32_t n_traj, int32_t n_nodes, const double* const fields[12]) {
+    REQUIRE(h && fields, "NULL argument");
+    REQUIRE(n_traj >= 1 && n_nodes >= 2, "need n_traj >= 1 and n_nodes >= 2");
+    const size_t cnt = (size_t)n_traj * n_nodes;
+    double* base = nullptr;
+    int rc = dev_alloc(h, &base, 12 * cnt);
+    if (rc) return rc;
+    for (int k = 0; k < 12; k++) {
+        REQUIRE(fields[k], "NULL trajectory field");
+        CK(cudaMemcpy(base + k * cnt, fields[k], cnt * sizeof(double), cudaMemcpyHostToDevice));
+        h->traj.f[k] = base + k * cnt;
+    }
+    h->traj.n_traj = n_traj; h->traj.n_nodes = n_nodes;
+    h->have_traj = true;
+    CK(cudaMemset(h->d_traj_id, 0, (size_t)h->B * 4));
+    return PGN_OK;
+}
+int pgn_assign_trajectories(pgn_handle* h, const int32_t* traj_id) {
+    REQUIRE(h && traj_id, "NULL argument");
+    for (int v = 0; v < h->B; v++) REQUIRE(traj_id[v] >= 0 && traj_id[v] < h->traj.n_traj, "trajectory id out of range");
+    CK(cudaMemcpy(h->d_traj_id, traj_id, (size_t)h->B * 4, cudaMemcpyHostToDevice));
+    return PGN_OK;
+}
+int pgn_set_hji_cache(pgn_handle* h, const int32_t dims[7], const float* knots, const float* V, const float* gradV) {
+    REQUIRE(h && dims && knots && V && gradV, "NULL argument");
+    return set_hji_internal(h, dims, knots, V, gradV);
+}
+int pgn_set_state(pgn_handle* h, const double* q, const double* u, const double* other, const double* toff) {
+    REQUIRE(h, "NULL handle");
+    int rc;
+    if (q && (rc = upload_aos(h, q, h->d_state, 6))) return rc;
+    if (u && (rc = upload_aos(h, u, h->d_control, 3))) return rc;
+    if (other && (rc = upload_aos(h, other, h->d_other, 4))) return rc;
+    if (toff) CK(cudaMemcpyAsync(h->d_toff, toff, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // host buffers may be reused by the caller
+    return PGN_OK;
+}
+int pgn_reset_solved(pgn_handle* h, const uint8_t* mask) {
+    REQUIRE(h, "NULL handle");
+    if (!mask) { CK(cudaMemsetAsync(h->d_solved, 0, h->B, h->stream)); return PGN_OK; }
+    std::vector<uint8_t> cur(h->B);
+    CK(cudaMemcpy(cur.data(), h->d_solved, h->B, cudaMemcpyDeviceToHost));
+    for (int v = 0; v < h->B; v++) if (mask[v]) cur[v] = 0;
+    CK(cudaMemcpy(h->d_solved, cur.data(), h->B, cudaMemcpyHostToDevice));
+    return PGN_OK;
+}
+int pgn_reset_solver(pgn_handle* h, const uint8_t* mask) {
+    REQUIRE(h, "NULL handle");
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t Nk = h->tab.Nk;
+    if (!mask) {
+        CK(cudaMemset(h->d_ws_xz, 0, (size_t)h->B * Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, (size_t)h->B * Nk * 8));
+        std::vector<double> rho(h->B, h->cfg.rho);
+        CK(cudaMemcpy(h->d_rho, rho.data(), (size_t)h->B * 8, cudaMemcpyHostToDevice));
+        return PGN_OK;
+    }
+    for (int v = 0; v < h->B; v++) if (mask[v]) {
+        CK(cudaMemset(h->d_ws_xz + (size_t)v * Nk, 0, Nk * 8)); CK(cudaMemset(h->d_ws_y + (size_t)v * Nk, 0, Nk * 8));
+        CK(cudaMemcpy(h->d_rho + v, &h->cfg.rho, 8, cudaMemcpyHostToDevice));
+    }
+    return PGN_OK;
+}
+
+// ---- the step API -------------------------------------------------------------------------------------------------------------
+static int step_time_steps_dev(pgn_handle* h, const double* d_t0) { StageTimer T(h, 0); launch_time_steps(h, d_t0); return PGN_OK; }
+static int step_nodes(pgn_handle* h) { StageTimer T(h, 0); launch_nodes(h); return PGN_OK; }
+static int step_update(pgn_handle* h) {
+    { StageTimer T(h, 1); launch_linearize(h); }
+    if (h->cfg.kind == PGN_COUPLED) { StageTimer T(h, 2); launch_hji_constraint(h); }
+    return PGN_OK;
+}
+static int step_solve(pgn_handle* h) { StageTimer T(h, 3); launch_admm(h); return PGN_OK; }
+static int step_controls(pgn_handle* h, double* d_out) { StageTimer T(h, 4); launch_controls(h, d_out); return PGN_OK; }
+
+int pgn_compute_time_steps(pgn_handle* h, const double* t0) {
+    REQUIRE(h && t0, "NULL argument");
+    CK(cudaMemcpyAsync(h->d_t0, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    step_time_steps_dev(h, h->d_t0);
+    CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+int pgn_compute_linearization_nodes(pgn_handle* h) { REQUIRE(h, "NULL handle"); step_nodes(h); CK(cudaGetLastError()); return PGN_OK; }
+int pgn_update_qp(pgn_handle* h) { REQUIRE(h, "NULL handle"); step_update(h); CK(cudaGetLastError()); return PGN_OK; }
+int pgn_solve(pgn_handle* h) { REQUIRE(h, "NULL handle"); step_solve(h); CK(cudaGetLastError()); return PGN_OK; }
+int pgn_get_next_control(pgn_handle* h, double* out) {
+    REQUIRE(h && out, "NULL argument");
+    step_controls(h, h->d_controls);
+    return download_aos(h, h->d_controls, out, 3);
+}
+int pgn_step_device(pgn_handle* h, const double* d_t0, double* d_out) {
+    REQUIRE(h && d_t0, "NULL argument");
+    step_time_steps_dev(h, d_t0);
+    step_nodes(h);
+    step_update(h);
+    step_solve(h);
+    step_controls(h, h->d_controls);
+    if (d_out) CK(cudaMemcpyAsync(d_out, h->d_controls, (size_t)h->B * 3 * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaGetLastError());
+    return PGN_OK;
+}
+int pgn_step(pgn_handle* h, const double* t0, double* out) {
+    REQUIRE(h && t0, "NULL argument");
+    CK(cudaMemcpyAsync(h->d_t0, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = pgn_step_device(h, h->d_t0, nullptr);
+    if (rc) return rc;
+    if (out) return download_aos(h, h->d_controls, out, 3);
+    CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+int pgn_rollout(pgn_handle* h, double dt) {
+    REQUIRE(h, "NULL handle");
+    { StageTimer T(h, 5); launch_rollout(h, dt); }
+    CK(cudaGetLastError());
+    return PGN_OK;
+}
+int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
+    REQUIRE(h && t0 && n_steps >= 0, "bad argument");
+    CK(cudaMemcpyAsync(h->d_t0, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    for (int k = 0; k < n_steps; k++) {
+        int rc = pgn_step_device(h, h->d_t0, nullptr);
+        if (rc) return rc;
+        { StageTimer T(h, 5); launch_rollout(h, dt); }
+        launch_add_scalar(h, h->d_t0, dt, h->B);
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return PGN_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------------------------------------
+int pgn_qp_dims(pgn_handle* h, int32_t* o) {
+    REQUIRE(h && o, "NULL argument");
+    o[0] = h->N; o[1] = h->nx; o[2] = h->nu; o[3] = h->tab.n; o[4] = h->tab.m; o[5] = h->tab.nnzA; o[6] = h->tab.nnzL; o[7] = h->tab.nlev;
+    return PGN_OK;
+}
+int pgn_get_state(pgn_handle* h, double* q, double* u) {
+    REQUIRE(h, "NULL handle");
+    int rc;
+    if (q && (rc = download_aos(h, h->d_state, q, 6))) return rc;
+    if (u && (rc = download_aos(h, h->d_control, u, 3))) return rc;
+    return PGN_OK;
+}
+#define D2H(dst, src, count)                                                                             \
+    do {                                                                                                 \
+        if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(count) * sizeof(*(dst)), cudaMemcpyDeviceToHost, h->stream)); \
+    } while (0)
+int pgn_get_time_steps(pgn_handle* h, double* ts, double* dt, double* prev_ts) {
+    REQUIRE(h, "NULL handle");
+    D2H(ts, h->d_ts, (size_t)h->B * h->N); D2H(dt, h->d_dt, (size_t)h->B * h->T); D2H(prev_ts, h->d_prev_ts, (size_t)h->B * h->N);
+    CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+int pgn_get_nodes(pgn_handle* h, double* qs, double* us, double* ps) {
+    REQUIRE(h, "NULL handle");
+    D2H(qs, h->d_qs, (size_t)h->B * h->N * h->nx); D2H(us, h->d_us, (size_t)h->B * h->N * 2); D2H(ps, h->d_ps, (size_t)h->B * h->N * 4);
+    CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+int pgn_set_nodes(pgn_handle* h, const double* qs, const double* us, const double* ps) {
+    REQUIRE(h, "NULL handle");
+    if (qs) CK(cudaMemcpyAsync(h->d_qs, qs, (size_t)h->B * h->N * h->nx * 8, cudaMemcpyHostToDevice, h->stream));
+    if (us) CK(cudaMemcpyAsync(h->d_us, us, (size_t)h->B * h->N * 2 * 8, cudaMemcpyHostToDevice, h->stream));
+    if (ps) CK(cudaMemcpyAsync(h->d_ps, ps, (size_t)h->B * h->N * 4 * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+int pgn_get_qp_data(pgn_handle* h, double* A, double* B0, double* Bf, double* c, double* H, double* G, double* dmin, double* dmax, double* fxmax,
+                    double* hji) {
+    REQUIRE(h, "NULL handle");
+    const RecLayout& R = h->tab.rec;
+    const size_t B = h->B, T = h->T, nx = h->nx, nu = h->nu;
+    std::vector<double> rec(B * (size_t)R.rec_len);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(rec.data(), h->d_rec, rec.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t v = 0; v < B; v++) {
+        const double* r = rec.data() + v * R.rec_len;
+        for (size_t t = 0; t < T; t++) {
+            const double* p = r + R.piece((int)t);
+            if (A) memcpy(A + (v * T + t) * nx * nx, p + R.oA, nx * nx * 8);
+            if (B0) memcpy(B0 + (v * T + t) * nx * nu, p + R.oB0, nx * nu * 8);
+            if (Bf) memcpy(Bf + (v * T + t) * nx * nu, p + R.oBf, nx * nu * 8);
+            if (c) memcpy(c + (v * T + t) * nx, p + R.oc, nx * 8);
+            if (H) memcpy(H + (v * T + t) * 8, p + R.oH, 64);
+            if (G) memcpy(G + (v * T + t) * 4, p + R.oG, 32);
+            if (dmin) dmin[v * T + t] = p[R.odmin];
+            if (dmax) dmax[v * T + t] = p[R.odmax];
+            if (fxmax) fxmax[v * T + t] = p[R.ofxmax];
+        }
+        if (hji) memcpy(hji + v * 3, r + R.o_hji, 24);
+    }
+    return PGN_OK;
+}
+int pgn_get_solution(pgn_handle* h, double* x, double* y) {
+    REQUIRE(h, "NULL handle");
+    D2H(x, h->d_sol_x, (size_t)h->B * h->tab.n); D2H(y, h->d_sol_y, (size_t)h->B * h->tab.m);
+    CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+int pgn_get_stats(pgn_handle* h, int32_t* iters, int32_t* status, double* pri, double* dua, double* rho, int32_t* rho_updates) {
+    REQUIRE(h, "NULL handle");
+    D2H(iters, h->d_iters, h->B); D2H(status, h->d_status, h->B); D2H(pri, h->d_pri_res, h->B); D2H(dua, h->d_dua_res, h->B); D2H(rho, h->d_rho, h->B);
+    D2H(rho_updates, h->d_rho_updates, h->B);
+    CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+int pgn_hji_lookup_device(pgn_handle* h, int32_t M, const double* d_x, double* d_V, double* d_gV) {
+    REQUIRE(h && d_x && d_V && d_gV && M >= 0, "bad argument");
+    if (M == 0) return PGN_OK;
+    { StageTimer T(h, 2); launch_hji_lookup(h, M, d_x, d_V, d_gV); }
+    CK(cudaGetLastError());
+    return PGN_OK;
+}
+int pgn_hji_lookup(pgn_handle* h, int32_t M, const double* x, double* V, double* gradV) {
+    REQUIRE(h && x && V && gradV && M >= 0, "bad argument");
+    if (M == 0) return PGN_OK;
+    double *dx = nullptr, *dV = nullptr, *dg = nullptr;
+    CK(cudaMalloc(&dx, (size_t)M * 7 * 8)); CK(cudaMalloc(&dV, (size_t)M * 8)); CK(cudaMalloc(&dg, (size_t)M * 7 * 8));
+    std::vector<double> xt((size_t)M * 7), gt((size_t)M * 7);
+    for (int i = 0; i < M; i++) for (int d = 0; d < 7; d++) xt[(size_t)d * M + i] = x[(size_t)i * 7 + d];
+    cudaError_t e = cudaMemcpy(dx, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { launch_hji_lookup(h, M, dx, dV, dg); e = cudaStreamSynchronize(h->stream); }
+    if (e == cudaSuccess) e = cudaMemcpy(V, dV, (size_t)M * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(gt.data(), dg, gt.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dV); cudaFree(dg);
+    if (e != cudaSuccess) return set_err(PGN_ECUDA, "hji lookup failed: %s", cudaGetErrorString(e));
+    for (int i = 0; i < M; i++) for (int d = 0; d < 7; d++) gradV[(size_t)i * 7 + d] = gt[(size_t)d * M + i];
+    return PGN_OK;
+}
+int pgn_device_controls(pgn_handle* h, double** d_out) { REQUIRE(h && d_out, "NULL argument"); *d_out = h->d_controls; return PGN_OK; }
+int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_status) {
+    REQUIRE(h, "NULL handle");
+    if (d_iters) *d_iters = h->d_iters;
+    if (d_status) *d_status = h->d_status;
+    return PGN_OK;
+}
+int pgn_set_profiling(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->profiling = on; return PGN_OK; }
+int pgn_get_stage_ms(pgn_handle* h, double* out, int32_t reset) {
+    REQUIRE(h && out, "NULL argument");
+    for (int i = 0; i < 6; i++) out[i] = h->stage_ms[i];
+    out[6] = (double)h->launches; out[7] = 0;
+    if (reset) { memset(h->stage_ms, 0, sizeof(h->stage_ms)); h->launches = 0; }
+    return PGN_OK;
+}
+
+}  // extern "C"

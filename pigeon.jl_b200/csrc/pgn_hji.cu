@@ -1,0 +1,160 @@
+// pgn_hji.cu — HJI value/gradient lookup and the reachability (safety) constraint of the coupled controller.
+//   HJIRelativeState          reference src/HJI_computation.jl:20-24
+//   cache[x] (7-D multilinear) src/HJI_computation.jl:66-72  (Interpolations.jl Gridded(Linear()), Float32 table, Float64 weights)
+//   optimal_disturbance       src/HJI_computation.jl:90-131
+//   compute_reachability_constraint  src/HJI_computation.jl:160-170, call site src/coupled_lat_long.jl:341-346
+//
+// HBM layout: the reference keeps V (Float32) and gradV (SVector{7,Float32}) as two tables; here every grid node is ONE
+// 32-byte record {gradV[0..6], V} (the 7->8 padding slot carries V), dimension 1 fastest.  A query touches the 2^7 corners of
+// its cell = 128 records = 128 sectors of 32 B = exactly the algorithmic 4096 B, fetched as 256 x LDG.128 with all of a
+// thread's loads for one dim-1 pair issued back to back (64 B contiguous).
+#include "pgn_internal.h"
+
+namespace pgn {
+
+struct HjiCell { int idx[7]; double w[7]; bool inside; };
+
+__device__ __forceinline__ HjiCell hji_locate(const HjiView& H, const double* x) {
+    HjiCell c;
+    c.inside = true;
+#pragma unroll
+    for (int d = 0; d < 7; d++) {
+        const float* k = H.knots + H.kofs[d];
+        const int nk = H.dims[d];
+        const double lo = (double)__ldg(k), hi = (double)__ldg(k + nk - 1);
+        if (!(lo <= x[d] && x[d] <= hi)) c.inside = false;
+        int a = 0, b = nk;
+        while (a < b) { int mid = (a + b) >> 1; if ((double)__ldg(k + mid) <= x[d]) a = mid + 1; else b = mid; }
+        int i = min(max(a, 1), nk - 1);
+        c.idx[d] = i - 1;
+        const double k0 = (double)__ldg(k + i - 1), k1 = (double)__ldg(k + i);
+        c.w[d] = (x[d] - k0) / (k1 - k0);
+    }
+    return c;
+}
+
+// multilinear interpolation of the 8-float node records; out[0..6] = gradV, out[7] = V
+__device__ __forceinline__ void hji_interp(const HjiView& H, const HjiCell& c, double* out) {
+    long long base = 0;
+#pragma unroll
+    for (int d = 0; d < 7; d++) base += (long long)c.idx[d] * H.stride[d];
+    const float4* tab = reinterpret_cast<const float4*>(H.gV);
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.0;
+    // dims 2..7 enumerate 64 corner pairs; the pair along dim 1 is 64 contiguous bytes
+    for (int cnr = 0; cnr < 64; cnr++) {
+        long long off = base;
+        double wgt = 1.0;
+#pragma unroll
+        for (int d = 1; d < 7; d++) {
+            const int bit = (cnr >> (d - 1)) & 1;
+            off += bit ? H.stride[d] : 0;
+            wgt *= bit ? c.w[d] : (1.0 - c.w[d]);
+        }
+        const float4 a0 = __ldg(tab + 2 * off), a1 = __ldg(tab + 2 * off + 1), b0 = __ldg(tab + 2 * off + 2), b1 = __ldg(tab + 2 * off + 3);
+        const double w0 = wgt * (1.0 - c.w[0]), w1 = wgt * c.w[0];
+        acc[0] += w0 * a0.x + w1 * b0.x; acc[1] += w0 * a0.y + w1 * b0.y; acc[2] += w0 * a0.z + w1 * b0.z; acc[3] += w0 * a0.w + w1 * b0.w;
+        acc[4] += w0 * a1.x + w1 * b1.x; acc[5] += w0 * a1.y + w1 * b1.y; acc[6] += w0 * a1.z + w1 * b1.z; acc[7] += w0 * a1.w + w1 * b1.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) out[k] = acc[k];
+}
+
+// stand-alone lookup: x [7][M] field-major, V [M], gradV [7][M]
+__global__ void __launch_bounds__(128) k_hji_lookup(HjiView H, int M, const double* __restrict__ x, double* __restrict__ V, double* __restrict__ gV) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double xq[7];
+#pragma unroll
+    for (int d = 0; d < 7; d++) xq[d] = x[(size_t)d * M + i];
+    HjiCell c = hji_locate(H, xq);
+    double out[8];
+    if (c.inside) hji_interp(H, c, out);
+    else {
+#pragma unroll
+        for (int k = 0; k < 7; k++) out[k] = 0.0;
+        out[7] = INFINITY;
+    }
+    V[i] = out[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) gV[(size_t)k * M + i] = out[k];
+}
+
+// reachability constraint M u + b >= -sigma for every vehicle; writes (M1*un1, M2*un2, b) into the record
+__global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, VehParams P, double eps, double un0, double un1, const double* __restrict__ state,
+                                                        const double* __restrict__ control, const double* __restrict__ other, double* __restrict__ rec,
+                                                        int rec_len, int o_hji) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    const double E = state[0 * B + v], N = state[1 * B + v], psi = state[2 * B + v], Ux = state[3 * B + v], Uy = state[4 * B + v], r = state[5 * B + v];
+    const double oE = other[0 * B + v], oN = other[1 * B + v], opsi = other[2 * B + v], oV = other[3 * B + v];
+    // HJIRelativeState: `cψ, sψ = sincos(-ψ)` binds cψ <- sin(-ψ), sψ <- cos(-ψ) (HJI_computation.jl:21-22)
+    double sn, cs;
+    sincos(-psi, &sn, &cs);
+    const double cpsi = sn, spsi = cs;
+    double x7[7];
+    x7[0] = cpsi * (oE - E) + spsi * (oN - N);
+    x7[1] = -spsi * (oE - E) + cpsi * (oN - N);
+    x7[2] = adiff(opsi, psi);
+    x7[3] = Ux; x7[4] = Uy; x7[5] = oV; x7[6] = r;
+    double M0 = 0, M1 = 0, b = 1.0;
+    double g[8];
+    bool active = false;
+    if (H.valid) {
+        HjiCell c = hji_locate(H, x7);
+        if (c.inside) { hji_interp(H, c, g); active = !(g[7] > eps); }
+    }
+    if (active) {
+        // optimal_disturbance (dMode = :min). Deviation: other-car speed <= 0 gives (0,0) instead of NaN
+        double uH0 = 0, uH1 = 0;
+        const double Vo = x7[5];
+        if (Vo > 0) {
+            const double Ax_max = P.Fx_max / P.m, Pmx_max = P.Px_max / P.m, maxA = 0.9 * P.mu * P.G;
+            const double lam_Ax = g[5], lam_Ay = g[2] / Vo;
+            const double lam_norm = hypot(lam_Ax, lam_Ay);
+            if (!(lam_norm < 1e-3)) {
+                const double desAx = -lam_Ax * maxA / lam_norm, desAy = -lam_Ay * maxA / lam_norm;
+                double maxAx = fmin(Ax_max, Pmx_max / Vo), maxAy = P.kappa_max * Vo * Vo;
+                if (desAx > maxAx) {
+                    if (fabs(desAy) < maxAy) maxAy = fmin(maxAy, sqrt(maxA * maxA - maxAx * maxAx));
+                    uH0 = copysign(maxAy, desAy) / Vo; uH1 = maxAx;
+                } else if (fabs(desAy) > maxAy) {
+                    if (desAx > 0) { maxAx = fmin(sqrt(maxA * maxA - maxAy * maxAy), maxAx); uH0 = copysign(maxAy, desAy) / Vo; uH1 = maxAx; }
+                    else { uH0 = copysign(maxAy, desAy) / Vo; uH1 = -sqrt(maxA * maxA - maxAy * maxAy); }
+                } else { uH0 = desAy / Vo; uH1 = maxAx; }
+            }
+        }
+        // H(uR) = gradV . relative_dynamics(x, uR, uH); M = dH/duR by forward AD over (delta, Fx); b = H - M.uR
+        typedef Dual<2> D;
+        const double d0 = control[0 * B + v], Fx0 = control[1 * B + v] + control[2 * B + v];
+        D q[6] = {D(x7[0]), D(x7[1]), D(x7[2]), D(x7[3]), D(x7[4]), D(x7[6])}, out[6];
+        D du(d0), dF(Fx0);
+        du.d[0] = 1.0; dF.d[1] = 1.0;
+        vehicle_model<MODEL_BICYCLE, D>(P, q, du, dF, D(0.0), D(0.0), out);
+        double s3, c3;
+        sincos(x7[2], &s3, &c3);
+        const double f0 = x7[5] * c3 - x7[3] + x7[1] * x7[6];
+        const double f1 = x7[5] * s3 - x7[4] - x7[0] * x7[6];
+        const double f2 = uH0 - x7[6];
+        const double Hv = g[0] * f0 + g[1] * f1 + g[2] * f2 + g[3] * out[3].v + g[4] * out[4].v + g[5] * uH1 + g[6] * out[5].v;
+        M0 = g[3] * out[3].d[0] + g[4] * out[4].d[0] + g[6] * out[5].d[0];
+        M1 = g[3] * out[3].d[1] + g[4] * out[4].d[1] + g[6] * out[5].d[1];
+        b = Hv - (M0 * d0 + M1 * Fx0);
+    }
+    double* glob = rec + (size_t)v * rec_len + o_hji;
+    glob[0] = M0 * un0; glob[1] = M1 * un1; glob[2] = b;
+}
+
+void launch_hji_constraint(pgn_handle* h) {
+    const int B = h->B;
+    k_hji_constraint<<<(B + 127) / 128, 128, 0, h->stream>>>(h->hji, B, h->veh, h->cfg.hji_eps, h->un[0], h->un[1], h->d_state, h->d_control, h->d_other,
+                                                             h->d_rec, h->tab.rec.rec_len, h->tab.rec.o_hji);
+    h->launches++;
+}
+void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV) {
+    k_hji_lookup<<<(M + 127) / 128, 128, 0, h->stream>>>(h->hji, M, d_x, d_V, d_gV);
+    h->launches++;
+}
+
+}  // namespace pgn

@@ -1,0 +1,119 @@
+// pgn_internal.h — handle layout and device-side table views shared by the translation units of libpigeon_b200.so.
+//
+// HBM layout (B = batch):
+//   state / control / other car / time offset / flags      SoA  [field][B]      (thread-per-vehicle kernels, coalesced)
+//   ts, dt, prev_ts                                         [B][N], [B][T], [B][N]
+//   nodes qs / us / ps                                      [B][N][nx], [B][N][2], [B][N][4]
+//   QP piece record (A,B0,Bf,c,H,G,limits per interval + q_curr,u_curr,hji,dt)   [B][rec_len]   (one CTA gathers one record)
+//   ADMM warm iterates in KKT-position space (x|z and y)    [B][Nk] each, rho [B]
+//   QP solution x [B][n], y [B][m]; stats                   SoA [B]
+//   trajectories                                            [12][n_traj][n_nodes]
+//   HJI grid                                                V f32 [n1..n7] (dim 1 fastest), gradV f32 [8][n1..n7]-interleaved (7 -> 8 padded)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pigeon_b200.h"
+#include "pgn_device.cuh"
+#include "pgn_structure.h"
+
+namespace pgn {
+
+struct TrajView {
+    const double* f[12];   // t,s,V,A,E,N,psi,kappa,theta,phi,edge_L,edge_R  each [n_traj][n_nodes]
+    int n_traj, n_nodes;
+};
+
+struct HjiView {
+    int dims[7];
+    int kofs[7];             // offset of each dimension's knots in `knots`
+    const float* knots;
+    const float* V;          // [n1..n7], dim 1 fastest
+    const float* gV;         // 8 floats per node (7 components + pad), dim 1 fastest over nodes
+    long long stride[7];
+    int valid;
+};
+
+// device views of the static QP tables
+struct QpDev {
+    int kind, N, T, Ns, nx, nu, n, m, Nk, nnzA, nnzL, nlev, rec_len, o_dt;
+    const int32_t* a_src;
+    const uint16_t *a_rowpos, *a_colpos, *a_lpos;
+    const uint8_t *l_type, *u_type;
+    const int32_t *l_idx, *u_idx;
+    const uint8_t *P_mode, *q_mode, *P_w, *q_w;
+    const uint16_t *P_t, *q_t, *q_hji_t;
+    const uint16_t *pos_var, *pos_con, *pos2idx;
+    const uint8_t* is_con;
+    const uint16_t *lrow_ptr, *lrow_col, *lcol_ptr, *lcol_row, *lcol_val, *lvl_ptr;
+    const uint16_t *kadj_ptr, *kadj_e, *kadj_nb;
+    const uint32_t *ftgt_ptr, *fac_ptr;
+    const uint16_t *ftgt_id, *ftgt_col, *fac_a, *fac_b, *fac_k;
+    const double* ctab;      // [CT_LEN]
+    const double* wtab;      // [W_LEN] cost weights
+    int n_hji;               // N_HJI
+    int var_u1_delta, var_u1_fx;
+};
+
+struct AdmmSettings {
+    double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, adaptive_rho_tolerance;
+    int max_iter, scaling, check_termination, adaptive_rho, adaptive_rho_interval, warm_start;
+};
+
+}  // namespace pgn
+
+struct pgn_handle {
+    pgn_config cfg;
+    int device;
+    cudaStream_t stream, own_stream;
+    int B, N, T, nx, nu;
+    pgn::VehParams veh;
+    pgn::CtrlParams ctl;
+    double un[2];
+    pgn::QpTables tab;
+    pgn::QpDev qd;
+    pgn::AdmmSettings st;
+    std::vector<void*> allocs;        // every device allocation (freed in pgn_destroy)
+    // per-vehicle device buffers
+    double *d_state, *d_control, *d_other, *d_toff;      // [6][B], [3][B], [4][B], [B]
+    uint8_t* d_solved;                                   // [B]
+    int32_t* d_traj_id;                                  // [B]
+    double *d_ts, *d_dt, *d_prev_ts;                     // [B][N], [B][T], [B][N]
+    double *d_qs, *d_us, *d_ps;                          // nodes
+    double* d_rec;                                       // [B][rec_len]
+    double *d_ws_xz, *d_ws_y, *d_rho;                    // warm iterates
+    double *d_sol_x, *d_sol_y;                           // [B][n], [B][m]
+    int32_t *d_iters, *d_status, *d_rho_updates;
+    double *d_pri_res, *d_dua_res;
+    double* d_controls;                                  // [3][B]
+    double* d_t0;                                        // [B]
+    int* d_counter;                                      // work-queue ticket for the persistent ADMM kernel
+    double* d_stage;                                     // AoS<->SoA staging
+    size_t stage_bytes;
+    // trajectories / HJI
+    pgn::TrajView traj; bool have_traj, have_assign;
+    pgn::HjiView hji;
+    // profiling
+    int profiling; cudaEvent_t ev[2]; double stage_ms[8]; long long launches;
+    int admm_smem_bytes, admm_threads, num_sms;
+};
+
+namespace pgn {
+// kernels (defined in the .cu files)
+void launch_time_steps(pgn_handle* h, const double* d_t0);
+void launch_nodes(pgn_handle* h);
+void launch_linearize(pgn_handle* h);
+void launch_hji_constraint(pgn_handle* h);
+void launch_admm(pgn_handle* h);
+void launch_controls(pgn_handle* h, double* d_out);
+void launch_rollout(pgn_handle* h, double dt);
+void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV);
+void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]
+void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
+void launch_add_scalar(pgn_handle* h, double* d_v, double a, int n);
+size_t admm_smem_bytes(const QpTables& t);
+int admm_configure(pgn_handle* h);   // sets the max dynamic shared memory attribute; returns cudaError
+}  // namespace pgn

@@ -1,0 +1,362 @@
+// pgn_nodes.cu — time steps, linearisation-node generation, control extraction and plant rollout; one vehicle per thread over
+// SoA HBM arrays.
+//   compute_time_steps!            reference src/model_predictive_control.jl:17-30
+//   compute_linearization_nodes!   src/coupled_lat_long.jl:62-142, src/decoupled_lat_long.jl:52-104
+//   trajectory lookups             src/trajectories.jl:47-94, src/math.jl:4-9
+//   get_next_control               src/coupled_lat_long.jl:370-374, src/decoupled_lat_long.jl:275-278
+//   simulate's plant step          src/model_predictive_control.jl:94-95
+#include "pgn_internal.h"
+
+namespace pgn {
+
+// ---- trajectory lookups -----------------------------------------------------------------------------------------------
+struct TrajNode { double t, s, V, A, E, N, psi, kappa, theta, phi; };
+
+// number of elements < x (Julia searchsortedfirst - 1) / <= x (searchsortedlast) in a sorted array
+__device__ __forceinline__ int count_lt(const double* __restrict__ v, int n, double x) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(v + mid) < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int count_le(const double* __restrict__ v, int n, double x) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(v + mid) <= x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// interp_by_s: gridded linear in s with Line() extrapolation (trajectories.jl:32-35)
+__device__ __forceinline__ void interp_by_s(const TrajView& tv, int base, double sq, TrajNode& o) {
+    const int nn = tv.n_nodes;
+    const double* s = tv.f[1] + base;
+    int i = count_le(s, nn, sq);
+    i = min(max(i, 1), nn - 1);
+    const int k = i - 1;
+    const double s0 = __ldg(s + k), s1 = __ldg(s + k + 1);
+    const double w = (sq - s0) / (s1 - s0);
+#define PGN_L(F) ((1 - w) * __ldg(tv.f[F] + base + k) + w * __ldg(tv.f[F] + base + k + 1))
+    o.E = PGN_L(4); o.N = PGN_L(5); o.psi = PGN_L(6); o.kappa = PGN_L(7); o.theta = PGN_L(8); o.phi = PGN_L(9);
+#undef PGN_L
+}
+// traj(t) (trajectories.jl:47-54)
+__device__ __forceinline__ TrajNode traj_at_time(const TrajView& tv, int base, double tq) {
+    const int nn = tv.n_nodes;
+    const double *t = tv.f[0] + base, *s = tv.f[1] + base, *V = tv.f[2] + base;
+    int i = count_lt(t, nn, tq);
+    i = min(max(i, 1), nn - 1);
+    const int k = i - 1;
+    const double Vk = __ldg(V + k), tk = __ldg(t + k);
+    const double A = (__ldg(V + k + 1) - Vk) / (__ldg(t + k + 1) - tk);
+    const double dt = tq - tk;
+    TrajNode o;
+    o.t = tq; o.s = __ldg(s + k) + Vk * dt + A * dt * dt / 2; o.V = Vk + A * dt; o.A = A;
+    interp_by_s(tv, base, o.s, o);
+    return o;
+}
+// traj[s] (trajectories.jl:55-68)
+__device__ __forceinline__ TrajNode traj_at_s(const TrajView& tv, int base, double sq) {
+    const int nn = tv.n_nodes;
+    const double *t = tv.f[0] + base, *s = tv.f[1] + base, *V = tv.f[2] + base;
+    int i = count_lt(s, nn, sq);
+    i = min(max(i, 1), nn - 1);
+    const int k = i - 1;
+    const double Vk = __ldg(V + k), tk = __ldg(t + k);
+    const double A = (__ldg(V + k + 1) - Vk) / (__ldg(t + k + 1) - tk);
+    const double ds = sq - __ldg(s + k);
+    double dt;
+    if (fabs(A) < 1e-3 || sq > __ldg(s + nn - 1)) dt = ds / Vk;
+    else dt = (sqrt(2 * A * ds + Vk * Vk) - Vk) / A;
+    TrajNode o;
+    o.t = tk + dt; o.s = sq; o.V = Vk + A * dt; o.A = A;
+    interp_by_s(tv, base, sq, o);
+    return o;
+}
+// path_coordinates (trajectories.jl:71-93): closest segment by an O(n_nodes) scan (first minimum wins), then (s, e).
+// Deviation: the sqrt argument is floored at 0 (the reference raises a DomainError on negative round-off).
+__device__ __forceinline__ void path_coordinates(const TrajView& tv, int base, double x, double y, double& s_out, double& e_out) {
+    const int nn = tv.n_nodes;
+    const double *E = tv.f[4] + base, *Nn = tv.f[5] + base;
+    double d2min = INFINITY;
+    int imin = 0;
+    double ax = __ldg(E), ay = __ldg(Nn);
+    for (int i = 0; i < nn - 1; i++) {
+        const double bx = __ldg(E + i + 1), by = __ldg(Nn + i + 1);
+        const double vx = bx - ax, vy = by - ay;
+        double lam = (vx * (x - ax) + vy * (y - ay)) / (vx * vx + vy * vy);
+        lam = lam > 1 ? 1 : (lam < 0 ? 0 : lam);
+        const double px = (1 - lam) * ax + lam * bx, py = (1 - lam) * ay + lam * by;
+        const double d2 = (px - x) * (px - x) + (py - y) * (py - y);
+        if (d2 < d2min) { d2min = d2; imin = i; }
+        ax = bx; ay = by;
+    }
+    const int i = imin;
+    const double ex = __ldg(E + i), ey = __ldg(Nn + i);
+    const double vx = __ldg(E + i + 1) - ex, vy = __ldg(Nn + i + 1) - ey;
+    const double wx = x - ex, wy = y - ey;
+    const double arg = wx * wx + wy * wy - d2min;
+    const double ds = sqrt(arg > 0 ? arg : 0.0);
+    s_out = __ldg(tv.f[1] + base + i) + ds;
+    e_out = sqrt(d2min) * sign_(vx * wy - vy * wx);
+}
+
+// ---- compute_time_steps! ---------------------------------------------------------------------------------------------
+__global__ void k_time_steps(int B, int Ns, int Nl, double dt_short, double dt_long, int corr, const double* __restrict__ t0v,
+                             double* __restrict__ ts, double* __restrict__ dtv, double* __restrict__ prev_ts) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    const int N = 1 + Ns + Nl;
+    double* tsv = ts + (size_t)v * N;
+    double* pv = prev_ts + (size_t)v * N;
+    double* dv = dtv + (size_t)v * (N - 1);
+    for (int i = 0; i < N; i++) pv[i] = tsv[i];
+    const double t0 = t0v[v];
+    double t0_long = t0 + Ns * dt_short;
+    if (corr) t0_long = dt_long * ceil((t0_long + dt_short) / dt_long - 1);
+    for (int i = 0; i <= Ns; i++) tsv[i] = t0 + dt_short * i;
+    for (int i = 1; i <= Nl; i++) tsv[Ns + i] = t0_long + dt_long * i;
+    for (int i = 0; i < N - 1; i++) dv[i] = tsv[i + 1] - tsv[i];
+}
+
+// ---- compute_linearization_nodes! ------------------------------------------------------------------------------------
+struct NodeArgs {
+    int B, N, Ns, kind, n_sol;
+    VehParams P; CtrlParams C; double un0, un1;
+    TrajView tv;
+    const double *state, *control, *toff; const uint8_t* solved; const int32_t* traj_id;
+    const double *ts, *dt, *prev_ts, *sol_x;
+    double *qs, *us, *ps;
+};
+
+__global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.B) return;
+    const int B = a.B, N = a.N, Ns = a.Ns;
+    const VehParams& P = a.P;
+    const CtrlParams& C = a.C;
+    const double E0 = a.state[0 * B + v], N0 = a.state[1 * B + v], psi0 = a.state[2 * B + v];
+    const double Ux0 = a.state[3 * B + v], Uy0 = a.state[4 * B + v], r0 = a.state[5 * B + v];
+    const double d0 = a.control[0 * B + v], Fxf0 = a.control[1 * B + v], Fxr0 = a.control[2 * B + v];
+    const double Fx0 = Fxf0 + Fxr0;
+    const bool path_mode = isnan(a.toff[v]);
+    const int base = a.traj_id[v] * a.tv.n_nodes;
+    const double* ts = a.ts + (size_t)v * N;
+    const double* dt = a.dt + (size_t)v * (N - 1);
+    const int nx = a.kind == PGN_COUPLED ? 6 : 4;
+    double* qs = a.qs + (size_t)v * N * nx;
+    double* us = a.us + (size_t)v * N * 2;
+    double* ps = a.ps + (size_t)v * N * 4;
+
+    double s0, e0;
+    path_coordinates(a.tv, base, E0, N0, s0, e0);
+
+    if (a.kind == PGN_COUPLED) {
+        TrajNode tj = traj_at_s(a.tv, base, s0);
+        double ds = s0 - traj_at_time(a.tv, base, ts[0]).s;
+        const double dpsi = adiff(psi0, tj.psi);
+        qs[0] = ds; qs[1] = Ux0; qs[2] = Uy0; qs[3] = r0; qs[4] = dpsi; qs[5] = e0;
+        us[0] = d0; us[1] = Fx0;
+        ps[0] = tj.V; ps[1] = tj.kappa; ps[2] = 0; ps[3] = 0;
+        if (a.solved[v]) {
+            // warm: previous QP solution interpolated in prev_ts (update_interpolations!, coupled_lat_long.jl:86-102,189-195)
+            const double* pts = a.prev_ts + (size_t)v * N;
+            const double* X = a.sol_x + (size_t)v * a.n_sol;
+            const double tend = pts[N - 1];
+            for (int i = 1; i < N; i++) {
+                const double t = ts[i];
+                const double tq = t < tend ? t : tend;
+                int k = 0;
+                { int lo = 0, hi = N; while (lo < hi) { int mid = (lo + hi) >> 1; if (pts[mid] <= tq) lo = mid + 1; else hi = mid; } k = lo; }
+                k = min(max(k, 1), N - 1) - 1;
+                const double w = (tq - pts[k]) / (pts[k + 1] - pts[k]);
+                double q0 = 0;
+                for (int c = 0; c < 6; c++) {
+                    const double qv = (1 - w) * X[6 * k + c] + w * X[6 * (k + 1) + c];
+                    qs[6 * i + c] = qv;
+                    if (c == 0) q0 = qv;
+                }
+                us[2 * i + 0] = ((1 - w) * X[6 * N + 2 * k + 0] + w * X[6 * N + 2 * (k + 1) + 0]) * a.un0;
+                us[2 * i + 1] = ((1 - w) * X[6 * N + 2 * k + 1] + w * X[6 * N + 2 * (k + 1) + 1]) * a.un1;
+                const double s = traj_at_time(a.tv, base, t).s + q0;
+                tj = traj_at_s(a.tv, base, s);
+                ps[4 * i + 0] = tj.V; ps[4 * i + 1] = tj.kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
+            }
+        } else {
+            // cold: forward rollout of (V, s) with steady-state cornering estimates (coupled_lat_long.jl:103-141)
+            double s = s0, sp, cp;
+            sincos(dpsi, &sp, &cp);
+            double V = Ux0 * cp - Uy0 * sp;
+            const double beta0 = atan2(Uy0, Ux0);
+            double Fyf0, Fyr0;
+            {
+                double sd, cd;
+                sincos(d0, &sd, &cd);
+                lateral_tire_forces<double>(P, atan2(Uy0 + P.a * r0, Ux0) - d0, atan2(Uy0 - P.b * r0, Ux0), Fxf0, Fxr0, sd, cd, Fyf0, Fyr0);
+            }
+            for (int i = 0; i < N; i++) {
+                const double tau = (i == N - 1) ? dt[i - 1] : dt[i];
+                tj = traj_at_s(a.tv, base, s);
+                ds = s - traj_at_time(a.tv, base, ts[i]).s;
+                double A_des = tj.A + C.k_V * (tj.V - V) / tau + (path_mode ? 0.0 : -C.k_s * ds / tau / tau);
+                A_des = fmin(fmax(A_des, (C.V_min - V) / tau), (C.V_max - V) / tau);
+                double A;
+                if (i == 0) {
+                    double q6[6] = {E0, N0, psi0, Ux0, Uy0, r0}, qd[6];
+                    vehicle_model<MODEL_BICYCLE, double>(P, q6, d0, Fx0, 0.0, 0.0, qd);
+                    A = (qd[3] - r0 * Uy0) * cp - (qd[4] + r0 * Ux0) * sp;
+                } else {
+                    SteadyState est;
+                    if (i <= Ns) {
+                        est = steady_state_estimates(P, V, A_des, tj.kappa, 1, r0, beta0, d0, Fyf0);
+                        qs[6 * i + 0] = ds; qs[6 * i + 1] = Ux0; qs[6 * i + 2] = Uy0; qs[6 * i + 3] = r0; qs[6 * i + 4] = adiff(psi0, tj.psi); qs[6 * i + 5] = e0;
+                    } else {
+                        est = steady_state_estimates(P, V, A_des, tj.kappa, 4, V * tj.kappa, 0.0, 0.0, 0.0);
+                        qs[6 * i + 0] = ds; qs[6 * i + 1] = est.Ux; qs[6 * i + 2] = est.Uy; qs[6 * i + 3] = est.r; qs[6 * i + 4] = -est.beta; qs[6 * i + 5] = 0;
+                    }
+                    us[2 * i + 0] = est.delta; us[2 * i + 1] = est.Fxf + est.Fxr;
+                    ps[4 * i + 0] = tj.V; ps[4 * i + 1] = tj.kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
+                    A = est.A;
+                }
+                if (i == N - 1) break;
+                V = V + A * tau;
+                s = s + V * tau + A * tau * tau / 2;
+            }
+        }
+    } else {
+        // decoupled: always the steady-state rollout (decoupled_lat_long.jl:65-103)
+        double s = s0;
+        double V = hypot(Ux0, Uy0);
+        const double beta0 = atan2(Uy0, Ux0);
+        double Fyf0, Fyr0;
+        {
+            double sd, cd;
+            sincos(d0, &sd, &cd);
+            lateral_tire_forces<double>(P, atan2(Uy0 + P.a * r0, Ux0) - d0, atan2(Uy0 - P.b * r0, Ux0), Fxf0, Fxr0, sd, cd, Fyf0, Fyr0);
+        }
+        double sb0, cb0;
+        sincos(beta0, &sb0, &cb0);
+        for (int i = 0; i < N; i++) {
+            const double tau = (i == N - 1) ? dt[i - 1] : dt[i];
+            TrajNode tj = traj_at_s(a.tv, base, s);
+            const double kappa = tj.kappa;
+            double A_des = tj.A + C.k_V * (tj.V - V) / tau + (path_mode ? 0.0 : C.k_s * (traj_at_time(a.tv, base, ts[i]).s - s) / tau / tau);
+            A_des = fmin(fmax(A_des, (C.V_min - V) / tau), (C.V_max - V) / tau);
+            double A;
+            if (i == 0) {
+                qs[0] = Uy0; qs[1] = r0; qs[2] = adiff(psi0, tj.psi); qs[3] = e0;
+                us[0] = d0; us[1] = Fx0;
+                ps[0] = Ux0; ps[1] = kappa; ps[2] = 0; ps[3] = 0;
+                double q6[6] = {E0, N0, psi0, Ux0, Uy0, r0}, qd[6];
+                vehicle_model<MODEL_BICYCLE, double>(P, q6, d0, Fx0, 0.0, 0.0, qd);
+                A = (qd[3] - r0 * Uy0) * cb0 + (qd[4] + r0 * Ux0) * sb0;
+            } else if (i <= Ns) {
+                SteadyState est = steady_state_estimates(P, V, A_des, kappa, 1, r0, beta0, d0, Fyf0);
+                qs[4 * i + 0] = Uy0; qs[4 * i + 1] = r0; qs[4 * i + 2] = adiff(psi0, tj.psi); qs[4 * i + 3] = e0;
+                us[2 * i + 0] = est.delta; us[2 * i + 1] = est.Fxf + est.Fxr;
+                ps[4 * i + 0] = est.Ux; ps[4 * i + 1] = kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
+                A = est.A;
+            } else {
+                SteadyState est = steady_state_estimates(P, V, A_des, kappa, 4, V * kappa, 0.0, 0.0, 0.0);
+                qs[4 * i + 0] = est.Uy; qs[4 * i + 1] = est.r; qs[4 * i + 2] = -est.beta; qs[4 * i + 3] = 0;
+                us[2 * i + 0] = est.delta; us[2 * i + 1] = est.Fxf + est.Fxr;
+                ps[4 * i + 0] = est.Ux; ps[4 * i + 1] = kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
+                A = est.A;
+            }
+            if (i == N - 1) break;
+            V = V + A * tau;
+            s = s + V * tau + A * tau * tau / 2;
+        }
+    }
+}
+
+// ---- get_next_control ------------------------------------------------------------------------------------------------
+__global__ void k_controls(int B, int kind, int n_sol, int iv_delta, int iv_fx, double un0, double un1, VehParams P,
+                           const double* __restrict__ sol_x, const double* __restrict__ us, int N, double* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    double d, Fx;
+    if (kind == PGN_COUPLED) { d = sol_x[(size_t)v * n_sol + iv_delta] * un0; Fx = sol_x[(size_t)v * n_sol + iv_fx] * un1; }
+    else { d = sol_x[(size_t)v * n_sol + iv_delta]; Fx = us[(size_t)v * N * 2 + 2 * 1 + 1]; }
+    double Fxf, Fxr;
+    if (Fx > 0) { Fxf = Fx * P.fwd_frac; Fxr = Fx * P.rwd_frac; } else { Fxf = Fx * P.fwb_frac; Fxr = Fx * P.rwb_frac; }
+    out[0 * B + v] = d; out[1 * B + v] = Fxf; out[2 * B + v] = Fxr;
+}
+
+// ---- plant rollout: state <- propagate(BicycleModel, state, StepControl(dt, (delta, Fxf+Fxr))); control <- new control --
+__global__ void __launch_bounds__(128) k_rollout(int B, VehParams P, double dt, int nsub, double* __restrict__ state, double* __restrict__ control,
+                                                 const double* __restrict__ new_control) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    double x[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] = state[i * B + v];
+    double u[4] = {control[0 * B + v], control[1 * B + v] + control[2 * B + v], 0.0, 0.0};
+    flow_rk4<MODEL_BICYCLE, 6, double>(P, x, dt, u, u, nsub);
+#pragma unroll
+    for (int i = 0; i < 6; i++) state[i * B + v] = x[i];
+    if (new_control) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) control[i * B + v] = new_control[i * B + v];
+    }
+}
+
+// ---- layout helpers --------------------------------------------------------------------------------------------------
+__global__ void k_transpose_in(int B, int k, const double* __restrict__ aos, double* __restrict__ soa) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * k) return;
+    const int v = idx / k, f = idx - v * k;
+    soa[(size_t)f * B + v] = aos[idx];
+}
+__global__ void k_transpose_out(int B, int k, const double* __restrict__ soa, double* __restrict__ aos) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * k) return;
+    const int v = idx / k, f = idx - v * k;
+    aos[idx] = soa[(size_t)f * B + v];
+}
+__global__ void k_add_scalar(int n, double a, double* __restrict__ v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += a;
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------------------
+void launch_time_steps(pgn_handle* h, const double* d_t0) {
+    const int B = h->B;
+    k_time_steps<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.N_short, h->cfg.N_long, h->cfg.dt_short, h->cfg.dt_long, h->cfg.use_correction_step,
+                                                         d_t0, h->d_ts, h->d_dt, h->d_prev_ts);
+    h->launches++;
+}
+void launch_nodes(pgn_handle* h) {
+    NodeArgs a;
+    a.B = h->B; a.N = h->N; a.Ns = h->cfg.N_short; a.kind = h->cfg.kind; a.n_sol = h->tab.n;
+    a.P = h->veh; a.C = h->ctl; a.un0 = h->un[0]; a.un1 = h->un[1];
+    a.tv = h->traj;
+    a.state = h->d_state; a.control = h->d_control; a.toff = h->d_toff; a.solved = h->d_solved; a.traj_id = h->d_traj_id;
+    a.ts = h->d_ts; a.dt = h->d_dt; a.prev_ts = h->d_prev_ts; a.sol_x = h->d_sol_x;
+    a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps;
+    k_nodes<<<(h->B + 127) / 128, 128, 0, h->stream>>>(a);
+    h->launches++;
+}
+void launch_controls(pgn_handle* h, double* d_out) {
+    const int B = h->B;
+    k_controls<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.kind, h->tab.n, h->tab.var_u1_delta, h->tab.var_u1_fx, h->un[0], h->un[1], h->veh,
+                                                       h->d_sol_x, h->d_us, h->N, d_out);
+    h->launches++;
+}
+void launch_rollout(pgn_handle* h, double dt) {
+    const int B = h->B;
+    k_rollout<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->veh, dt, h->cfg.rk4_substeps, h->d_state, h->d_control, h->d_controls);
+    h->launches++;
+}
+void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k) {
+    const int n = h->B * k;
+    k_transpose_in<<<(n + 255) / 256, 256, 0, h->stream>>>(h->B, k, d_aos, d_soa);
+    h->launches++;
+}
+void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k) {
+    const int n = h->B * k;
+    k_transpose_out<<<(n + 255) / 256, 256, 0, h->stream>>>(h->B, k, d_soa, d_aos);
+    h->launches++;
+}
+void launch_add_scalar(pgn_handle* h, double* d_v, double a, int n) {
+    k_add_scalar<<<(n + 255) / 256, 256, 0, h->stream>>>(n, a, d_v);
+    h->launches++;
+}
+
+}  // namespace pgn
