@@ -1,0 +1,292 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances: QP data (Jacobians, discretisation, envelope) 1e-9 absolute on O(1) quantities; controls 1e-4
+relative to the actuator range at the reference's eps_abs = eps_rel = 1e-3 with IDENTICAL iteration counts and statuses;
+HJI value/gradient 1e-6 (BASELINE.json north_star)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import oracle_py as o  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+FAR = np.array([1e4, 1e4, 0.0, 5.0])
+U_RANGE = np.array([0.3141592653589793, 16793.73299576057, 16793.73299576057])
+
+
+@pytest.fixture(scope="module")
+def p():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import pigeon.jl_b200 as pkg
+    pkg.load()
+    return pkg
+
+
+def oracles_for(kind, trajs, tid, state, control, other, hji=None, vp=None, **kw):
+    cache, ms = {}, []
+    for i in range(len(tid)):
+        j = int(tid[i])
+        if j not in cache:
+            cache[j] = o.Trajectory(**{k: trajs[k][j] for k in o.TRAJ_FIELDS})
+        m = o.Mpc(kind, vp=vp, **kw)
+        m.set_trajectory(cache[j])
+        if hji is not None:
+            m.set_hji(hji)
+        m.set_state(state[i], control[i], other4=other[i])
+        ms.append(m)
+    return ms
+
+
+def compare_step(p, g, ms, tk, kind, check_solution=True):
+    g.compute_time_steps(tk); g.compute_linearization_nodes(); g.update_QP(); g.solve()
+    ug = g.get_next_control()
+    for i, m in enumerate(ms):
+        m.compute_time_steps(tk[i]); m.compute_linearization_nodes(); m.update_qp(); m.solve()
+    uo = np.array([m.get_next_control() for m in ms])
+    ts_g, dt_g, pts_g = g.time_steps()
+    assert np.allclose(ts_g, np.array([m.time_steps()[0] for m in ms]), rtol=0, atol=1e-12)
+    assert np.allclose(dt_g, np.array([m.time_steps()[1] for m in ms]), rtol=0, atol=1e-12)
+    qs_g, us_g, ps_g = g.nodes()
+    no = [m.nodes() for m in ms]
+    assert np.allclose(qs_g, np.array([x[0] for x in no]), rtol=1e-9, atol=1e-9)
+    assert np.allclose(us_g, np.array([x[1] for x in no]), rtol=1e-9, atol=1e-6)       # Fx in newtons
+    assert np.allclose(ps_g, np.array([x[2] for x in no]), rtol=1e-9, atol=1e-9)
+    d = g.qp_data()
+    po = [m.qp_pieces() for m in ms]
+    un = g.u_normalization if kind == 0 else np.array([1.0, 1.0])
+    for key, scale in (("A", 1.0), ("c", 1.0), ("H", 1.0), ("dmin", 1.0), ("dmax", 1.0), ("fxmax", 1.0)):
+        ref = np.array([x[key] for x in po])
+        assert np.allclose(d[key], ref, rtol=1e-8, atol=1e-8), key
+    for key in ("B0", "Bf"):
+        ref = np.array([x[key] for x in po]) * un[None, None, None, :g.nu]
+        assert np.allclose(d[key], ref, rtol=1e-8, atol=1e-8), key
+    Gref = np.array([x["G"] for x in po])
+    assert np.allclose(d["G"], Gref, rtol=1e-7, atol=1e-7)
+    st = g.stats()
+    it_o = np.array([m.stats()["iter"] for m in ms]); st_o = np.array([m.stats()["status"] for m in ms])
+    assert np.array_equal(st["iters"], it_o), (st["iters"], it_o)
+    assert np.array_equal(st["status"], st_o)
+    assert np.allclose(st["rho"], np.array([m.stats()["rho"] for m in ms]), rtol=1e-6)
+    if check_solution:
+        xg, yg = g.solution()
+        xo = np.array([m.solution()[0] for m in ms])
+        assert np.allclose(xg, xo, rtol=1e-5, atol=1e-5)
+    # the headline tolerance: steering and longitudinal force within 1e-4 relative (to the actuator range)
+    assert np.max(np.abs(ug - uo) / U_RANGE) < 1e-4
+    return ug, uo
+
+
+@pytest.mark.parametrize("kind,Ns,Nl", [(0, 10, 20), (1, 10, 20), (0, 5, 10)])
+def test_closed_loop_parity_with_oracle(p, kind, Ns, Nl):
+    B, steps = 48, 5
+    trajs = p.synthetic.synthetic_trajectories(n_traj=6, n_nodes=400)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    ctor = p.BatchedCoupledTrajectoryTrackingMPC if kind == 0 else p.BatchedDecoupledTrajectoryTrackingMPC
+    g = ctor(p.X1(), trajs, B, N_short=Ns, N_long=Nl, trajectory_index=tid)
+    ms0 = o.Mpc(kind, N_short=Ns, N_long=Nl)
+    assert (g.n, g.m, g.nnzA) == (ms0.n, ms0.m, ms0.nnzA)
+    g.set_state(state, control, other)
+    ms = oracles_for(kind, trajs, tid, state, control, other, N_short=Ns, N_long=Nl)
+    for k in range(steps):
+        ug, uo = compare_step(p, g, ms, t0 + 0.01 * k, kind)
+        g.rollout(0.01)
+        for i, m in enumerate(ms):      # oracle closed loop with its own control
+            q, u = m.get_state()
+            xn = o.flow(o.MODEL_BICYCLE, m.vp, q, 0.01, [u[0], u[1] + u[2], 0, 0, 0, 0])
+            m.set_state(xn, uo[i], other4=other[i])
+        qg, ucur = g.get_state()
+        assert np.allclose(qg, np.array([m.get_state()[0] for m in ms]), rtol=1e-9, atol=1e-8)
+    g.close()
+
+
+def test_fixture_trajectory_single_vehicle_config1(p):
+    """configs[0]: single X1 vehicle, coupled MPC, reference fixture test/path/skidpadoval.world, closed loop."""
+    w = np.load(os.path.join(ROOT, "tests", "golden", "world_skidpadoval.npz"))
+    tr = p.TrajectoryTube.from_path(w)
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), tr, 1)
+    k0 = 200
+    q0 = np.array([[w["posE_m"][k0], w["posN_m"][k0], w["psi_rad"][k0], 6.0, 0.0, 0.0]])
+    g.set_state(q0, np.zeros((1, 3)), FAR[None])
+    m = o.Mpc(o.MPC_COUPLED)
+    m.set_trajectory(o.Trajectory(**{k: getattr(tr, k) for k in o.TRAJ_FIELDS}))
+    m.set_state(q0[0], [0, 0, 0], other4=FAR)
+    t0 = tr.t[k0]
+    for k in range(60):
+        ug = g.step(t0 + 0.01 * k)
+        g.rollout(0.01)
+        m.simulate_step(t0 + 0.01 * k)
+        qo, uo = m.get_state()
+        assert g.stats()["iters"][0] == m.stats()["iter"]
+        assert np.max(np.abs(ug[0] - uo) / U_RANGE) < 1e-4
+    qg, _ = g.get_state()
+    assert np.allclose(qg[0], qo, rtol=1e-8, atol=1e-7)
+    g.close()
+
+
+def test_simulate_on_device_matches_stepwise(p):
+    B = 32
+    trajs = p.synthetic.synthetic_trajectories(n_traj=4, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    a = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    b = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    a.set_state(state, control, other); b.set_state(state, control, other)
+    a.simulate_device(t0, 0.01, 6)
+    for k in range(6):
+        b.step(t0 + 0.01 * k); b.rollout(0.01)
+    qa, ua = a.get_state(); qb, ub = b.get_state()
+    assert np.array_equal(qa, qb) and np.array_equal(ua, ub)      # bitwise: same kernels, same order
+    qs, us = p.simulate(b, state, control, 0.01, t0=t0, n_steps=3)
+    assert qs.shape == (3, B, 6) and np.array_equal(qs[0], state)
+    a.close(); b.close()
+
+
+def test_decoupled_uses_feedforward_force(p):
+    # decoupled_lat_long.jl:275-278: delta from the QP, Fx from the node generator (us[2].Fx)
+    B = 8
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    g = p.BatchedDecoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g.set_state(state, control, np.tile(FAR, (B, 1)))
+    u = g.step(t0)
+    _, us, _ = g.nodes()
+    assert np.allclose(u[:, 1] + u[:, 2], us[:, 1, 1], rtol=1e-14)
+    x, _ = g.solution()
+    assert np.allclose(u[:, 0], x[:, 4 * 31 + 1], rtol=1e-14)
+    g.close()
+
+
+def test_settings_variants_keep_iteration_parity(p):
+    B = 16
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    for kw in (dict(adaptive_rho_interval=50), dict(adaptive_rho_interval=100), dict(adaptive_rho=0), dict(kkt_ordering=1), dict(eps_abs=1e-5, eps_rel=1e-5)):
+        g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid, **kw)
+        g.set_state(state, control, other)
+        okw = {k: v for k, v in kw.items() if k != "kkt_ordering"}
+        ms = oracles_for(0, trajs, tid, state, control, other, settings=o.osqp_settings_default(**okw))
+        for k in range(2):
+            compare_step(p, g, ms, t0 + 0.01 * k, 0, check_solution=(k == 0))
+            for i, m in enumerate(ms):
+                m.set_state(state[i], control[i], other4=other[i])
+        g.close()
+
+
+def test_inv_fiala_corrected_flag(p):
+    B = 8
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    veh = p.X1(); veh["inv_fiala_corrected"] = 1.0
+    vp = o.x1(); vp[22] = 1.0
+    g = p.BatchedDecoupledTrajectoryTrackingMPC(veh, trajs, B, trajectory_index=tid)
+    g.set_state(state, control, other)
+    ms = oracles_for(1, trajs, tid, state, control, other, vp=vp)
+    compare_step(p, g, ms, t0, 1)
+    g.close()
+
+
+def test_hji_lookup_parity_and_edges(p):
+    dims = (7, 6, 5, 5, 4, 5, 4)
+    knots, V, gV = p.synthetic.analytic_hji_grid(dims)
+    cache_o = o.HjiCache(knots, V, gV)
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), p.straight_trajectory(30.0, 5.0), 4)
+    g.set_HJI_cache(p.HJICache(knots, V, gV))
+    rng = np.random.default_rng(0)
+    lo = np.array([k[0] for k in knots], float); hi = np.array([k[-1] for k in knots], float)
+    x = lo + (hi - lo) * rng.random((4096, 7))
+    x[:7] = np.where(np.eye(7, dtype=bool), hi, x[:7]); x[7:14] = np.where(np.eye(7, dtype=bool), lo, x[7:14])      # on the faces
+    x[14:21] = np.where(np.eye(7, dtype=bool), hi + 1e-9, x[14:21])                                                 # just outside
+    x[21] = [float(k[2]) for k in knots]                                                                            # exactly on a node
+    Vg, gg = g.hji_lookup(x)
+    Vo, go = cache_o.lookup(x)
+    fin = np.isfinite(Vo)
+    assert np.array_equal(np.isfinite(Vg), fin) and np.all(Vg[~fin] == np.inf) and (~fin).sum() == 7
+    assert np.max(np.abs(Vg[fin] - Vo[fin])) < 1e-6 and np.max(np.abs(gg - go)) < 1e-6       # north_star tolerance
+    assert np.max(np.abs(Vg[fin] - Vo[fin])) < 1e-12                                          # what is actually achieved
+    assert Vg[21] == np.float64(V[2, 2, 2, 2, 2, 2, 2])
+    assert np.all(g.hji_lookup(np.zeros((0, 7)))[0].shape == (0,))
+    g.close()
+
+
+def test_hji_constraint_parity_active_and_inactive(p):
+    knots, V, gV = p.synthetic.analytic_hji_grid((13, 13, 7, 7, 5, 7, 5))
+    cache_o = o.HjiCache(knots, V, gV)
+    B = 256
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    rng = np.random.default_rng(1)
+    other = np.zeros((B, 4))
+    # other car placed a few metres around the ego vehicle: ~half inside the unsafe set, 10% far outside the grid, one with V=0
+    rad = rng.uniform(0.5, 9.0, B); ang = rng.uniform(-np.pi, np.pi, B)
+    other[:, 0] = state[:, 0] + rad * np.cos(ang); other[:, 1] = state[:, 1] + rad * np.sin(ang)
+    other[:, 2] = state[:, 2] + rng.normal(0, 0.5, B); other[:, 3] = rng.uniform(1.5, 12, B)
+    other[::10, 0] += 500.0
+    other[3, 3] = 0.0
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g.set_HJI_cache(p.HJICache(knots, V, gV))
+    g.set_state(state, control, other)
+    ms = oracles_for(0, trajs, tid, state, control, other, hji=cache_o)
+    ug, uo = compare_step(p, g, ms, t0, 0)
+    hg = g.qp_data()["hji"]
+    ho = np.array([m.qp_pieces()["hji"] for m in ms]) * np.array([g.u_normalization[0], g.u_normalization[1], 1.0])
+    active = ~((ho[:, 0] == 0) & (ho[:, 1] == 0) & (ho[:, 2] == 1.0))
+    assert 40 < active.sum() < B - 40
+    assert np.allclose(hg, ho, rtol=1e-9, atol=1e-9)
+    assert np.all(np.isfinite(hg))
+    g.close()
+
+
+def test_reset_solved_and_reset_solver(p):
+    B = 8
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g.set_state(state, control, other)
+    u1 = g.step(t0); it1 = g.stats()["iters"].copy()
+    g.reset_solved(); g.reset_solver()
+    u2 = g.step(t0); it2 = g.stats()["iters"].copy()
+    assert np.array_equal(u1, u2) and np.array_equal(it1, it2)          # a full reset reproduces the cold step bit for bit
+    mask = np.zeros(B, np.uint8); mask[:4] = 1
+    g.reset_solved(mask)
+    g.compute_time_steps(t0 + 0.01); g.compute_linearization_nodes()
+    qs, _, _ = g.nodes()
+    assert np.allclose(qs[:4, 1, 1], state[:4, 3])                     # cold short nodes freeze Ux (coupled_lat_long.jl:123)
+    assert not np.allclose(qs[4:, 1, 1], state[4:, 3])                 # warm nodes interpolate the previous solution
+    g.close()
+
+
+def test_error_paths(p):
+    with pytest.raises(p.PigeonError):
+        p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), p.straight_trajectory(30.0, 5.0), 0)
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), p.straight_trajectory(30.0, 5.0), 2)
+    with pytest.raises(p.PigeonError):
+        g.assign_trajectories([0, 5])
+    with pytest.raises(p.PigeonError):
+        g.set_control_params(p.CoupledControlParams(N_HJI=99))
+    g.close()
+
+
+def test_smoke_scenario_known_answers(p):
+    """Pigeon.jl:34-57 dry run: straight 30 m at 5 m/s, state (0,0,0,5,0,0), zero control, placeholder HJI cache."""
+    for kind in (0, 1):
+        ctor = p.BatchedCoupledTrajectoryTrackingMPC if kind == 0 else p.BatchedDecoupledTrajectoryTrackingMPC
+        kw = dict(N_short=5, N_long=10) if kind == 0 else {}
+        g = ctor(p.X1(), p.straight_trajectory(30.0, 5.0), 1, **kw)
+        g.set_state([[0, 0, 0, 5, 0, 0]], [[0, 0, 0]], FAR[None])
+        u = g.step(0.0)
+        assert g.stats()["status"][0] == 1
+        assert abs(u[0, 0]) < 1e-6 and u[0, 1] == 0 and u[0, 2] > 0
+        if kind == 1:
+            assert u[0, 2] == pytest.approx(366.5, rel=0.05)        # drag equilibrium Cd0 + Cd1*Ux
+        g.close()

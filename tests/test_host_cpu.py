@@ -1,0 +1,164 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/pigeon_b200.h declares (no compute calls
+without a GPU), the static QP analysis is correct (emulated factor/solve against a dense solve), the Python mirror of the
+reference API, the synthetic workload generators and the world_size-2 sharding/gather plumbing (gloo)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_py as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def p():
+    sys.path.insert(0, ROOT)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pgn_build", os.path.join(ROOT, "pigeon.jl_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build()
+    import pigeon.jl_b200 as pkg
+    return pkg
+
+
+def test_library_exports_every_declared_symbol(p):
+    hdr = open(os.path.join(ROOT, "include", "pigeon_b200.h")).read()
+    declared = re.findall(r"PGN_API\s+(?:const char\*|int)\s+(pgn_\w+)\s*\(", hdr)
+    assert len(declared) >= 35
+    assert sorted(declared) == sorted(p.SYMBOLS)
+    lib = p.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    nm = subprocess.run(["nm", "-D", "--defined-only", p.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (pgn_\w+)", nm))
+    assert set(declared) <= exported
+    assert not any(s.startswith("orc_") for s in re.findall(r" T (\w+)", nm))      # the oracle is not linked into the product
+
+
+def test_no_cpu_fallback_without_gpu(p):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(p.PigeonError, match="no CUDA device|CUDA"):
+        p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), p.straight_trajectory(30.0, 5.0), 4)
+
+
+def test_product_does_not_reference_the_oracle():
+    for dp, _, files in os.walk(os.path.join(ROOT, "pigeon.jl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle_py" not in src and "liboracle" not in src and '#include "../../oracle' not in src, f
+
+
+@pytest.mark.parametrize("args", ["0 10 20 0", "0 10 20 1", "0 5 10 0", "1 10 20 0", "1 10 20 1", "0 1 0 0", "1 3 2 0"])
+def test_static_qp_tables_factor_and_solve(args, tmp_path):
+    exe = str(tmp_path / "structure_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "structure_check.cpp"),
+                           os.path.join(ROOT, "pigeon.jl_b200", "csrc", "pgn_structure.cpp")])
+    r = subprocess.run([exe] + args.split(), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    kv = dict(x.split("=") for x in r.stdout.split())
+    kind, Ns, Nl = (int(a) for a in args.split()[:3])
+    m = o.Mpc(kind, N_short=Ns, N_long=Nl)
+    assert (int(kv["n"]), int(kv["m"]), int(kv["nnzA"])) == (m.n, m.m, m.nnzA)      # same canonical QP as the oracle
+
+
+def test_nested_dissection_cuts_solve_depth(tmp_path):
+    exe = str(tmp_path / "structure_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "structure_check.cpp"),
+                           os.path.join(ROOT, "pigeon.jl_b200", "csrc", "pgn_structure.cpp")])
+    nd = dict(x.split("=") for x in subprocess.run([exe, "0", "10", "20", "0"], capture_output=True, text=True).stdout.split())
+    md = dict(x.split("=") for x in subprocess.run([exe, "0", "10", "20", "1"], capture_output=True, text=True).stdout.split())
+    assert int(nd["nlev"]) * 3 < int(md["nlev"])
+    assert int(nd["nnzL"]) < 1.6 * int(md["nnzL"])
+
+
+def test_python_mirror_parameters_match_oracle(p):
+    x1 = p.X1()
+    vp = o.x1()
+    assert [x1[k] for k in o.VP_NAMES] == list(vp)
+    assert list(p.CoupledControlParams().values()) == list(o.control_params_default(o.MPC_COUPLED))
+    assert list(p.DecoupledControlParams().values()) == list(o.control_params_default(o.MPC_DECOUPLED))
+    assert p.CoupledControlParams(Q_e=3.0)["Q_e"] == 3.0
+    with pytest.raises(TypeError):
+        p.CoupledControlParams(nope=1)
+
+
+def test_trajectory_tube_from_path_matches_oracle(p):
+    w = np.load(os.path.join(ROOT, "tests", "golden", "world_vail.npz"))
+    tr = p.TrajectoryTube.from_path(w)
+    assert np.array_equal(tr.t, o.invcumtrapz(w["UxDes_mps"], w["s_m"]))
+    assert len(tr) == 1000 and np.all(tr.phi == 0)
+    st = p.straight_trajectory(30.0, 5.0)
+    assert list(st.t) == [0.0, 6.0] and list(st.N) == [0.0, 30.0] and list(st.edge_L) == [4.0, 4.0]
+    with pytest.raises(ValueError):
+        p.TrajectoryTube([0, 1], [0, 1, 2], [1, 1], [0, 0], [0, 0], [0, 1], [0, 0], [0, 0])
+
+
+def test_synthetic_workload_is_deterministic_and_feasible(p):
+    a = p.synthetic.synthetic_trajectories(n_traj=4, n_nodes=200)
+    b = p.synthetic.synthetic_trajectories(n_traj=4, n_nodes=200)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    assert np.all(np.diff(a["t"], axis=1) > 0) and np.all(np.abs(a["kappa"]) <= 0.07 + 1e-12)
+    assert np.all(a["V"] >= 4 - 1e-9) and np.all(a["V"] <= 12 + 1e-9)
+    assert np.all(a["V"] ** 2 * np.abs(a["kappa"]) <= 0.5 * 0.92 * 9.80665 + 1e-9)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(a, 16)
+    # the sampled states are near their trajectory: oracle path_coordinates gives |e| ~ 0.3 m
+    for i in range(16):
+        tr = o.Trajectory(**{k: a[k][tid[i]] for k in o.TRAJ_FIELDS})
+        s, e, _ = tr.path_coordinates(state[i, 0], state[i, 1])
+        assert abs(e) < 1.5
+    knots, V, g = p.synthetic.analytic_hji_grid((3, 3, 3, 3, 3, 3, 3))
+    assert V.shape == (3,) * 7 and g.shape == (7,) + (3,) * 7 and V.dtype == np.float32
+
+
+def test_shard_range_partitions_exactly(p):
+    from pigeon.jl_b200 import sharding
+    for total in (1, 7, 8, 1024, 65536, 1000003):
+        for world in (1, 2, 3, 8):
+            r = [sharding.shard_range(total, world, k) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, total, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import pigeon.jl_b200  # noqa: F401
+    from pigeon.jl_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = np.arange(total * 3, dtype=np.float64).reshape(total, 3)
+    iters = (np.arange(total) % 7).astype(np.int32)
+    lo, hi = sharding.shard_range(total, world, rank)
+    g = sharding.gather_batch(full[lo:hi], total, dist).numpy()
+    gi = sharding.gather_batch(iters[lo:hi], total, dist).numpy()
+    q.put((rank, bool(np.array_equal(g, full)), bool(np.array_equal(gi, iters))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [10, 11])
+def test_gather_world_size_2_gloo(total):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + total
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] for r in res)
