@@ -135,7 +135,8 @@ def run_gpu(args):
     B, K, W = args.batch, args.steps, args.warmup
     trajs, tid, state, control, t0, other = make_workload(B, seed_shift=1000 * rank)
     mpc = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid, device=local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: the library launches on it, the events are recorded on it
+    torch.cuda.set_stream(stream)
     mpc.set_stream(stream.cuda_stream)
     dt = 0.01
 
@@ -195,6 +196,7 @@ def run_gpu(args):
         dev_step(False)
     nprof = min(K, 5)
     stage = mpc.stage_ms(reset=True)
+    cyc = mpc.admm_cycles(reset=True)
     mpc.set_profiling(0)
     admm_ms = stage["admm"] / nprof
     mean_iters = float(st["iters"].mean())
@@ -278,6 +280,7 @@ def run_gpu(args):
                 "admm": {"mean_iters": mean_iters, "p50_iters": float(np.median(st["iters"])), "p99_iters": float(np.percentile(st["iters"], 99)), "max_iters": int(st["iters"].max()),
                          "pct_not_solved": float((st["status"] != 1).mean() * 100)},
                 "stage_ms_per_step": {k: stage[k] / nprof for k in ("nodes", "linearize", "hji", "admm", "controls", "rollout")},
+                "admm_phase_share": {k: v / max(1.0, sum(cyc.values())) for k, v in cyc.items()},
                 "p50_latency_ms_per_batched_step": ms_max / K, "gather": gathered}
         print(json.dumps(line), flush=True)
     mpc.close()

@@ -141,6 +141,9 @@ PGN_API int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_statu
  * [0] time steps + nodes, [1] linearisation + envelope, [2] HJI, [3] ADMM, [4] controls, [5] rollout, [6] launches counted */
 PGN_API int pgn_set_profiling(pgn_handle* h, int32_t on);
 PGN_API int pgn_get_stage_ms(pgn_handle* h, double* out /*[8]*/, int32_t reset);
+/* SM cycles spent by the ADMM CTAs per phase while profiling is on (summed over CTAs):
+ * [0] gather, [1] Ruiz scaling, [2] LDL' factorisation, [3] triangular solves, [4] x/z/y update, [5] residuals/termination/rho, [6] store, [7] ticket */
+PGN_API int pgn_get_admm_cycles(pgn_handle* h, double* out /*[8]*/, int32_t reset);
 
 #ifdef __cplusplus
 }

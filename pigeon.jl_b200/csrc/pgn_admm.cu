@@ -34,6 +34,7 @@ struct AdmmArgs {
     double *pri_res, *dua_res;
     uint8_t* solved;
     int* counter;
+    unsigned long long* cycles;   // optional per-phase cycle counters (profiling builds of the host call): gather, ruiz, factor, solve, update, check, store
 };
 
 struct Smem {
@@ -275,6 +276,15 @@ __device__ bool dual_infeasible(const QpDev& q, const Smem& s, double eps, doubl
     return bad[0] == 0.0;
 }
 
+#define PHASE(idx)                                                                  \
+    do {                                                                            \
+        if (a.cycles && threadIdx.x == 0) {                                         \
+            const long long now__ = clock64();                                      \
+            atomicAdd(a.cycles + (idx), (unsigned long long)(now__ - t_phase));     \
+            t_phase = now__;                                                        \
+        }                                                                           \
+    } while (0)
+
 __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_vehicle;
@@ -289,6 +299,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
     for (int l = tid; l <= q.nlev; l += ADMM_THREADS) s.lvl_ptr[l] = q.lvl_ptr[l];
     __syncthreads();
 
+    long long t_phase = clock64();
     for (;;) {
         if (tid == 0) s_vehicle = atomicAdd(a.counter, 1);
         __syncthreads();
@@ -296,6 +307,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         __syncthreads();
         if (v >= a.B) break;
         const double* rec = a.rec + (size_t)v * q.rec_len;
+        PHASE(7);
 
         // ---- 1. gather the QP values --------------------------------------------------------------------------------
         for (int e = tid; e < q.nnzA; e += ADMM_THREADS) {
@@ -340,6 +352,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         double rho = st.warm_start ? a.rho[v] : st.rho;
         double c = 1.0;
         __syncthreads();
+        PHASE(0);
 
         // ---- 2. modified Ruiz equilibration (scale_data of OSQP) -------------------------------------------------------
         for (int it = 0; it < st.scaling; it++) {
@@ -385,8 +398,10 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
             }
         __syncthreads();
 
+        PHASE(1);
         // ---- 3. factor ----------------------------------------------------------------------------------------------------
         factor(q, s, st.sigma, rho);
+        PHASE(2);
 
         // ---- 4. ADMM iterations ---------------------------------------------------------------------------------------------
         int iter = 0, status = PGN_QP_UNSOLVED, n_rho_upd = 0;
@@ -404,6 +419,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
             }
             __syncthreads();
             kkt_solve(q, s);
+            PHASE(3);
             // x, z, y updates
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
                 const uint8_t f = s.flag[p];
@@ -425,6 +441,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                 }
             }
             __syncthreads();
+            PHASE(4);
             if (!need_delta) continue;
             Resid R = residuals(q, s, cinv);
             pri_res = R.pri_res; dua_res = R.dua_res;
@@ -449,9 +466,12 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                     rinv = make_rho_inv(rho);
                     n_rho_upd++;
                     __syncthreads();
+                    PHASE(5);
                     factor(q, s, st.sigma, rho);
+                    PHASE(2);
                 }
             }
+            PHASE(5);
         }
         if (iter > st.max_iter) {
             iter = st.max_iter;
@@ -462,6 +482,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
             status = (R.pri_res < eps_prim && R.dua_res < eps_dual) ? PGN_QP_SOLVED_INACCURATE : PGN_QP_MAX_ITER_REACHED;
         }
 
+        PHASE(5);
         // ---- 5. store ------------------------------------------------------------------------------------------------------------
         const bool infeas = (status == PGN_QP_PRIMAL_INFEASIBLE || status == PGN_QP_DUAL_INFEASIBLE);
         for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
@@ -482,6 +503,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
             a.solved[v] = 1;
         }
         __syncthreads();
+        PHASE(6);
     }
 }
 
@@ -499,6 +521,7 @@ void launch_admm(pgn_handle* h) {
     a.sol_x = h->d_sol_x; a.sol_y = h->d_sol_y;
     a.iters = h->d_iters; a.status = h->d_status; a.rho_updates = h->d_rho_updates; a.pri_res = h->d_pri_res; a.dua_res = h->d_dua_res;
     a.solved = h->d_solved; a.counter = h->d_counter;
+    a.cycles = h->profiling ? h->d_cycles : nullptr;
     cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream);
     int ctas_per_sm = 1;
     if (h->admm_smem_bytes * 2 + 2048 <= 227 * 1024) ctas_per_sm = 2;

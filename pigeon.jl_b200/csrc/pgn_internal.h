@@ -91,6 +91,7 @@ struct pgn_handle {
     double* d_controls;                                  // [3][B]
     double* d_t0;                                        // [B]
     int* d_counter;                                      // work-queue ticket for the persistent ADMM kernel
+    unsigned long long* d_cycles;                        // [8] per-phase cycle counters of the ADMM kernel (profiling only)
     double* d_stage;                                     // AoS<->SoA staging
     size_t stage_bytes;
     // trajectories / HJI

@@ -319,6 +319,12 @@ class BatchedTrajectoryTrackingMPC:
         return dict(nodes=out[0], linearize=out[1], hji=out[2], admm=out[3], controls=out[4], rollout=out[5], launches=int(out[6]))
 
 
+    def admm_cycles(self, reset=True):
+        out = np.zeros(8)
+        check(self._lib.pgn_get_admm_cycles(self._h, dptr(out), int(reset)))
+        return dict(zip(["gather", "ruiz", "factor", "solve", "update", "check", "store", "ticket"], out))
+
+
 def BatchedCoupledTrajectoryTrackingMPC(vehicle, trajectories, batch, control_params=None, **kw):
     return BatchedTrajectoryTrackingMPC(PGN_COUPLED, vehicle, trajectories, batch, control_params=control_params, **kw)
 

