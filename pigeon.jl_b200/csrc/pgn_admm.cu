@@ -38,17 +38,18 @@ struct AdmmArgs {
 };
 
 struct Smem {
-    double *Lval, *Dinv, *Aval, *xz, *sol, *yq, *lo, *hi, *sc, *dxy, *red;
-    uint16_t *lrow_col, *lcol_row, *lcol_val, *lrow_ptr, *lcol_ptr, *lvl_ptr;
-    uint8_t* flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
+    double *Lval, *Dinv, *Aval, *xz, *sol, *dxy, *yq, *lo, *hi, *sc, *Tinv, *red;   // sol and dxy are adjacent: together they hold the dense tail copy
+    uint16_t *lrow_col, *lcol_row, *lcol_val, *lrow_ptr, *lcol_ptr, *lvl_ptr, *lrow_split;
+    uint8_t *flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
+    uint8_t *gf, *gb;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t admm_smem_bytes(const QpTables& t) {
-    size_t d = (size_t)t.nnzL + t.Nk + t.nnzA + 7 * (size_t)t.Nk + 16 * NW + 8;
-    size_t u16 = 3 * (size_t)t.nnzL + 2 * (size_t)(t.Nk + 1) + (t.nlev + 1) + 8;
-    return d * 8 + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + 64;
+    size_t d = (size_t)t.nnzL + t.Nk + t.nnzA + 7 * (size_t)t.Nk + (size_t)t.tail_dim * (t.tail_dim - 1) / 2 + 16 * NW + 8;
+    size_t u16 = 3 * (size_t)t.nnzL + 2 * (size_t)(t.Nk + 1) + (t.nlev + 1) + t.tail_dim + 8;
+    return d * 8 + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + align_up(2 * (size_t)t.nlev, 8) + 64;
 }
 
 __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem& s) {
@@ -58,11 +59,12 @@ __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem&
     s.Aval = d; d += q.nnzA;
     s.xz = d; d += q.Nk;
     s.sol = d; d += q.Nk;
+    s.dxy = d; d += q.Nk;
     s.yq = d; d += q.Nk;
     s.lo = d; d += q.Nk;
     s.hi = d; d += q.Nk;
     s.sc = d; d += q.Nk;
-    s.dxy = d; d += q.Nk;
+    s.Tinv = d; d += q.tail_dim * (q.tail_dim - 1) / 2;
     s.red = d; d += 16 * NW + 8;
     uint16_t* u = reinterpret_cast<uint16_t*>(d);
     s.lrow_col = u; u += q.nnzL;
@@ -71,8 +73,11 @@ __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem&
     s.lrow_ptr = u; u += q.Nk + 1;
     s.lcol_ptr = u; u += q.Nk + 1;
     s.lvl_ptr = u; u += q.nlev + 1;
+    s.lrow_split = u; u += q.tail_dim;
     size_t off = align_up((size_t)(reinterpret_cast<unsigned char*>(u) - base), 8);
     s.flag = base + off;
+    s.gf = s.flag + align_up((size_t)q.Nk, 8);
+    s.gb = s.gf + q.nlev;
 }
 
 // block-wide max / sum of NV values per thread; every thread returns with the results in v[]
@@ -114,7 +119,14 @@ struct RhoInv { double in, eq, loose; };
 __device__ __forceinline__ RhoInv make_rho_inv(double rho) { RhoInv r; r.in = 1.0 / rho; r.eq = 1.0 / (1e3 * rho); r.loose = 1.0 / 1e-6; return r; }
 __device__ __forceinline__ double rinv_of(uint8_t flag, const RhoInv& r) { return flag == 2 ? r.eq : (flag == 3 ? r.loose : r.in); }
 
-// numeric LDL' of K = [P + sigma I, A'; A, -1/rho] (position space) with the static gather program
+// sum over the g (power of two) adjacent lanes of a group; every lane of the warp must call
+__device__ __forceinline__ double group_sum(double v, int g) {
+    for (int o = g >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// numeric LDL' of K = [P + sigma I, A'; A, -1/rho] (position space) with the static gather program.  Each target (an entry of L or a
+// pivot) is reduced by g = lvl_gfac[level] adjacent lanes that read consecutive (coalesced) pairs of the program.
 __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) {
     const int tid = threadIdx.x;
     const RhoInv ri = make_rho_inv(rho);
@@ -127,19 +139,28 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) 
     double* D = s.sol;
     for (int l = 0; l < q.nlev; l++) {
         const uint32_t t0 = __ldg(q.ftgt_ptr + l), t1 = __ldg(q.ftgt_ptr + l + 1);
-        for (uint32_t t = t0 + tid; t < t1; t += ADMM_THREADS) {
-            const int id = __ldg(q.ftgt_id + t);
-            const uint32_t x0 = __ldg(q.fac_ptr + t), x1 = __ldg(q.fac_ptr + t + 1);
-            if (id >= q.nnzL) {
-                const int j = id - q.nnzL;
-                double acc = D[j];
-                for (uint32_t x = x0; x < x1; x++) { const double v = s.Lval[__ldg(q.fac_a + x)]; acc -= v * v * D[__ldg(q.fac_k + x)]; }
-                D[j] = acc;
-                s.Dinv[j] = 1.0 / acc;
-            } else {
-                double acc = s.Lval[id];
-                for (uint32_t x = x0; x < x1; x++) acc -= s.Lval[__ldg(q.fac_a + x)] * s.Lval[__ldg(q.fac_b + x)] * D[__ldg(q.fac_k + x)];
-                s.Lval[id] = acc;
+        const int g = __ldg(q.lvl_gfac + l);
+        const int sh = 31 - __clz(g);
+        const uint32_t slots = (((t1 - t0) << sh) + 31u) & ~31u;
+        for (uint32_t i = tid; i < slots; i += ADMM_THREADS) {
+            const uint32_t t = t0 + (i >> sh);
+            const int sub = i & (g - 1);
+            const bool live = t < t1;
+            double acc = 0.0;
+            int id = 0;
+            if (live) {
+                id = __ldg(q.ftgt_id + t);
+                const uint32_t x1 = __ldg(q.fac_ptr + t + 1);
+                if (id >= q.nnzL) {
+                    for (uint32_t x = __ldg(q.fac_ptr + t) + sub; x < x1; x += g) { const double v = s.Lval[__ldg(q.fac_a + x)]; acc += v * v * D[__ldg(q.fac_k + x)]; }
+                } else {
+                    for (uint32_t x = __ldg(q.fac_ptr + t) + sub; x < x1; x += g) acc += s.Lval[__ldg(q.fac_a + x)] * s.Lval[__ldg(q.fac_b + x)] * D[__ldg(q.fac_k + x)];
+                }
+            }
+            acc = group_sum(acc, g);
+            if (live && sub == 0) {
+                if (id >= q.nnzL) { const int j = id - q.nnzL; const double d = D[j] - acc; D[j] = d; s.Dinv[j] = 1.0 / d; }
+                else s.Lval[id] -= acc;
             }
         }
         __syncthreads();
@@ -149,28 +170,134 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) 
         }
         __syncthreads();
     }
-}
-
-// sol <- K^-1 sol   (level-scheduled forward, diagonal, backward substitution)
-__device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
-    const int tid = threadIdx.x;
-    for (int l = 1; l < q.nlev; l++) {
-        const int r0 = s.lvl_ptr[l], r1 = s.lvl_ptr[l + 1];
-        for (int r = r0 + tid; r < r1; r += ADMM_THREADS) {
-            double acc = s.sol[r];
-            const int e1 = s.lrow_ptr[r + 1];
-            for (int e = s.lrow_ptr[r]; e < e1; e++) acc -= s.Lval[e] * s.sol[s.lrow_col[e]];
-            s.sol[r] = acc;
+    // dense tail: packed strictly-lower copy Ld of L[tail, tail] (aliasing sol|dxy, free now) and its explicit inverse Tinv,
+    // one column per group of 4 lanes by forward substitution:  z_j = 1,  z_i = -(L_ij + sum_{j<k<i} L_ik z_k)
+    const int Dm = q.tail_dim;
+    if (Dm > 0) {
+        double* Ld = s.sol;
+        const int npk = Dm * (Dm - 1) / 2;
+        for (int e = tid; e < npk; e += ADMM_THREADS) Ld[e] = 0.0;
+        __syncthreads();
+        for (int e = tid; e < q.n_tl; e += ADMM_THREADS) Ld[__ldg(q.tl_dst + e)] = s.Lval[__ldg(q.tl_src + e)];
+        __syncthreads();
+        const int slots = ((Dm * 4) + 31) & ~31;
+        for (int i = tid; i < slots; i += ADMM_THREADS) {
+            const int j = i >> 2, sub = i & 3;
+            for (int r = 1; r < Dm; r++) {          // uniform trip count: the shuffles below need every lane of the warp
+                const bool act = j < Dm && r > j;
+                double acc = 0.0;
+                const int rb = r * (r - 1) / 2;
+                if (act)
+                    for (int k = j + 1 + sub; k < r; k += 4) acc += Ld[rb + k] * s.Tinv[k * (k - 1) / 2 + j];
+                acc = group_sum(acc, 4);
+                if (act && sub == 0) s.Tinv[rb + j] = -(Ld[rb + j] + acc);
+                __syncwarp();
+            }
         }
         __syncthreads();
     }
-    for (int l = q.nlev - 1; l >= 0; l--) {
-        const int r0 = s.lvl_ptr[l], r1 = s.lvl_ptr[l + 1];
-        for (int r = r0 + tid; r < r1; r += ADMM_THREADS) {
-            double acc = s.sol[r] * s.Dinv[r];
-            const int e1 = s.lcol_ptr[r + 1];
-            for (int e = s.lcol_ptr[r]; e < e1; e++) acc -= s.Lval[s.lcol_val[e]] * s.sol[s.lcol_row[e]];
-            s.sol[r] = acc;
+}
+
+// sol <- K^-1 sol.  Level-scheduled forward substitution over the sparse levels (rows split over lane groups, shuffle-reduced), the
+// dense tail as two mat-vec levels with the explicit inverse, then the mirror image backwards.
+__device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
+    const int tid = threadIdx.x;
+    const int Lt = q.tail_level, ts = q.tail_start, Dm = q.tail_dim;
+    for (int l = 1; l < Lt; l++) {
+        const int r0 = s.lvl_ptr[l], w = s.lvl_ptr[l + 1] - r0;
+        const int g = s.gf[l], sh = 31 - __clz(g);
+        const int slots = ((w << sh) + 31) & ~31;
+        for (int i = tid; i < slots; i += ADMM_THREADS) {
+            const int r = r0 + (i >> sh), sub = i & (g - 1);
+            const bool live = (i >> sh) < w;
+            double acc = 0.0;
+            if (live) {
+                const int e1 = s.lrow_ptr[r + 1];
+                int e = s.lrow_ptr[r] + sub;
+                for (; e + g < e1; e += 2 * g) {
+                    const int c0 = s.lrow_col[e], c1 = s.lrow_col[e + g];
+                    const double l0 = s.Lval[e], l1 = s.Lval[e + g];
+                    acc += l0 * s.sol[c0] + l1 * s.sol[c1];
+                }
+                if (e < e1) acc += s.Lval[e] * s.sol[s.lrow_col[e]];
+            }
+            acc = group_sum(acc, g);
+            if (live && sub == 0) s.sol[r] -= acc;
+        }
+        __syncthreads();
+    }
+    if (Dm > 0) {
+        // tail, stage 1: t = b_tail - L[tail, early] y_early  -> dxy[tail]
+        {
+            const int g = q.tail_g1, sh = 31 - __clz(g);
+            const int slots = ((Dm << sh) + 31) & ~31;
+            for (int i = tid; i < slots; i += ADMM_THREADS) {
+                const int rr = i >> sh, sub = i & (g - 1);
+                const bool live = rr < Dm;
+                double acc = 0.0;
+                if (live) {
+                    const int r = ts + rr;
+                    const int e1 = s.lrow_split[rr];
+                    for (int e = s.lrow_ptr[r] + sub; e < e1; e += g) acc += s.Lval[e] * s.sol[s.lrow_col[e]];
+                }
+                acc = group_sum(acc, g);
+                if (live && sub == 0) s.dxy[ts + rr] = s.sol[ts + rr] - acc;
+            }
+        }
+        __syncthreads();
+        // stage 2 + diagonal: w = Dinv .* (Tinv t)  -> sol[tail]
+        {
+            const int slots = ((Dm * 4) + 31) & ~31;
+            for (int i = tid; i < slots; i += ADMM_THREADS) {
+                const int rr = i >> 2, sub = i & 3;
+                const bool live = rr < Dm;
+                double acc = 0.0;
+                if (live) {
+                    const int rb = rr * (rr - 1) / 2;
+                    for (int k = sub; k < rr; k += 4) acc += s.Tinv[rb + k] * s.dxy[ts + k];
+                }
+                acc = group_sum(acc, 4);
+                if (live && sub == 0) s.sol[ts + rr] = (s.dxy[ts + rr] + acc) * s.Dinv[ts + rr];
+            }
+        }
+        __syncthreads();
+        // backward through the tail: x = Tinv' w  -> dxy[tail], then copied into sol[tail]
+        {
+            const int slots = ((Dm * 4) + 31) & ~31;
+            for (int i = tid; i < slots; i += ADMM_THREADS) {
+                const int rr = i >> 2, sub = i & 3;
+                const bool live = rr < Dm;
+                double acc = 0.0;
+                if (live)
+                    for (int k = rr + 1 + sub; k < Dm; k += 4) acc += s.Tinv[k * (k - 1) / 2 + rr] * s.sol[ts + k];
+                acc = group_sum(acc, 4);
+                if (live && sub == 0) s.dxy[ts + rr] = s.sol[ts + rr] + acc;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < Dm; i += ADMM_THREADS) s.sol[ts + i] = s.dxy[ts + i];
+        __syncthreads();
+    }
+    for (int l = Lt - 1; l >= 0; l--) {
+        const int r0 = s.lvl_ptr[l], w = s.lvl_ptr[l + 1] - r0;
+        const int g = s.gb[l], sh = 31 - __clz(g);
+        const int slots = ((w << sh) + 31) & ~31;
+        for (int i = tid; i < slots; i += ADMM_THREADS) {
+            const int r = r0 + (i >> sh), sub = i & (g - 1);
+            const bool live = (i >> sh) < w;
+            double acc = 0.0;
+            if (live) {
+                const int e1 = s.lcol_ptr[r + 1];
+                int e = s.lcol_ptr[r] + sub;
+                for (; e + g < e1; e += 2 * g) {
+                    const int v0 = s.lcol_val[e], v1 = s.lcol_val[e + g];
+                    const int c0 = s.lcol_row[e], c1 = s.lcol_row[e + g];
+                    acc += s.Lval[v0] * s.sol[c0] + s.Lval[v1] * s.sol[c1];
+                }
+                if (e < e1) acc += s.Lval[s.lcol_val[e]] * s.sol[s.lcol_row[e]];
+            }
+            acc = group_sum(acc, g);
+            if (live && sub == 0) s.sol[r] = s.sol[r] * s.Dinv[r] - acc;
         }
         __syncthreads();
     }
@@ -297,6 +424,8 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
     for (int e = tid; e < q.nnzL; e += ADMM_THREADS) { s.lrow_col[e] = q.lrow_col[e]; s.lcol_row[e] = q.lcol_row[e]; s.lcol_val[e] = q.lcol_val[e]; }
     for (int p = tid; p <= q.Nk; p += ADMM_THREADS) { s.lrow_ptr[p] = q.lrow_ptr[p]; s.lcol_ptr[p] = q.lcol_ptr[p]; }
     for (int l = tid; l <= q.nlev; l += ADMM_THREADS) s.lvl_ptr[l] = q.lvl_ptr[l];
+    for (int l = tid; l < q.nlev; l += ADMM_THREADS) { s.gf[l] = q.lvl_gf[l]; s.gb[l] = q.lvl_gb[l]; }
+    for (int i = tid; i < q.tail_dim; i += ADMM_THREADS) s.lrow_split[i] = q.lrow_split[q.tail_start + i];
     __syncthreads();
 
     long long t_phase = clock64();

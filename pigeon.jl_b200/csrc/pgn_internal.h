@@ -52,6 +52,9 @@ struct QpDev {
     const uint16_t *kadj_ptr, *kadj_e, *kadj_nb;
     const uint32_t *ftgt_ptr, *fac_ptr;
     const uint16_t *ftgt_id, *ftgt_col, *fac_a, *fac_b, *fac_k;
+    const uint8_t *lvl_gf, *lvl_gb, *lvl_gfac;
+    const uint16_t *lrow_split, *tl_src, *tl_dst;
+    int tail_level, tail_start, tail_dim, tail_g1, n_tl;
     const double* ctab;      // [CT_LEN]
     const double* wtab;      // [W_LEN] cost weights
     int n_hji;               // N_HJI

@@ -273,6 +273,45 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         Q.kadj_e[Q.kadj_ptr[p] + x] = (uint16_t)kadj[p][x].first;
         Q.kadj_nb[Q.kadj_ptr[p] + x] = (uint16_t)kadj[p][x].second;
     }
+    // dense tail: trailing levels of width <= 4 (the top separators of the nested dissection), at most 64 positions and small enough
+    // for its packed dense copy to fit the 2*Nk-double scratch region of the kernel
+    {
+        int Lt = nlev;
+        while (Lt > 1) {
+            int w = Q.lvl_ptr[Lt] - Q.lvl_ptr[Lt - 1];
+            int D = Nk - Q.lvl_ptr[Lt - 1];
+            if (w > 4 || D > 64 || D * (D - 1) / 2 > 2 * Nk - 8) break;
+            Lt--;
+        }
+        if (nlev - Lt < 4) Lt = nlev;      // not worth it
+        Q.tail_level = Lt; Q.tail_start = Q.lvl_ptr[Lt]; Q.tail_dim = Nk - Q.tail_start;
+        Q.lrow_split.resize(Nk);
+        for (int i = 0; i < Nk; i++) {
+            int e = Q.lrow_ptr[i + 1];
+            if (i >= Q.tail_start) { e = Q.lrow_ptr[i]; while (e < Q.lrow_ptr[i + 1] && Q.lrow_col[e] < Q.tail_start) e++; }
+            Q.lrow_split[i] = (uint16_t)e;
+            for (int x = e; x < Q.lrow_ptr[i + 1]; x++) {
+                int ii = i - Q.tail_start, jj = Q.lrow_col[x] - Q.tail_start;
+                Q.tl_src.push_back((uint16_t)x); Q.tl_dst.push_back((uint16_t)(ii * (ii - 1) / 2 + jj));
+            }
+        }
+    }
+    // lanes per row: enough to bring the per-lane chain down to ~3 entries, without exceeding ~2 passes of the CTA
+    auto lanes_for = [](int maxlen, int width) {
+        int g = 1;
+        while (g < 32 && (maxlen + g - 1) / g > 3) g *= 2;
+        while (g > 1 && width * g > 512) g /= 2;
+        return (uint8_t)g;
+    };
+    Q.lvl_gf.assign(nlev, 1); Q.lvl_gb.assign(nlev, 1); Q.lvl_gfac.assign(nlev, 1);
+    for (int l = 0; l < nlev; l++) {
+        int w = Q.lvl_ptr[l + 1] - Q.lvl_ptr[l], mr = 0, mc = 0;
+        for (int r = Q.lvl_ptr[l]; r < Q.lvl_ptr[l + 1]; r++) {
+            mr = std::max(mr, (int)(Q.lrow_ptr[r + 1] - Q.lrow_ptr[r]));
+            mc = std::max(mc, (int)(Q.lcol_ptr[r + 1] - Q.lcol_ptr[r]));
+        }
+        Q.lvl_gf[l] = lanes_for(mr, w); Q.lvl_gb[l] = lanes_for(mc, w);
+    }
     // numeric factorisation program
     Q.ftgt_ptr.assign(nlev + 1, 0);
     Q.fac_ptr.push_back(0);
@@ -305,6 +344,14 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
             Q.fac_ptr.push_back((uint32_t)Q.fac_a.size());
         }
         Q.ftgt_ptr[l + 1] = (uint32_t)Q.ftgt_id.size();
+        {
+            int mp = 0;
+            for (auto& t : tg) mp = std::max(mp, (int)t.pairs.size());
+            int g = 1;
+            while (g < 32 && (mp + g - 1) / g > 4) g *= 2;
+            while (g > 1 && (int)tg.size() * g > 1024) g /= 2;
+            Q.lvl_gfac[l] = (uint8_t)g;
+        }
     }
     return true;
 }

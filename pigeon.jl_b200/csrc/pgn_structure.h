@@ -63,6 +63,13 @@ struct QpTables {
     std::vector<uint16_t> ftgt_id, ftgt_col;            // target: L value index (< nnzL) or nnzL + column for a diagonal; its column
     std::vector<uint32_t> fac_ptr;                      // per target -> range of pairs
     std::vector<uint16_t> fac_a, fac_b, fac_k;          // pair: L value indices (row i col k), (row j col k) and the column k
+    // lanes cooperating on one row / column / factor target, per level (powers of two)
+    std::vector<uint8_t> lvl_gf, lvl_gb, lvl_gfac;
+    // dense tail: the last `tail_dim` positions (levels >= tail_level) form a (nearly dense) unit lower triangular block whose explicit
+    // inverse is rebuilt after every numeric factorisation; it replaces tail_dim narrow levels by two dense mat-vec levels
+    int tail_level, tail_start, tail_dim;
+    std::vector<uint16_t> lrow_split;                   // per row: first entry whose column lies in the tail (== row end outside the tail)
+    std::vector<uint16_t> tl_src, tl_dst;               // sparse L entry -> packed strictly-lower dense index i*(i-1)/2 + j
     // where the solution components consumed by the host-side API live
     int var_u1_delta, var_u1_fx;                        // variable indices of u[:,2] (node 2)
 };

@@ -39,12 +39,25 @@ int main(int argc, char** argv) {
         }
         for (uint32_t t = Q.ftgt_ptr[l]; t < Q.ftgt_ptr[l + 1]; t++) { int id = Q.ftgt_id[t]; if (id < Q.nnzL) L[id] *= Dinv[Q.ftgt_col[t]]; }
     }
-    // solve K x = b with the level schedule
-    std::vector<double> b(Nk), x(Nk);
+    // dense tail: packed copy of L[tail, tail] and its explicit inverse (column-wise forward substitution), as in the kernel
+    const int ts = Q.tail_start, Dm = Q.tail_dim, Lt = Q.tail_level;
+    std::vector<double> Ld(Dm * (Dm - 1) / 2 + 1, 0.0), Ti(Dm * (Dm - 1) / 2 + 1, 0.0);
+    for (size_t e = 0; e < Q.tl_src.size(); e++) Ld[Q.tl_dst[e]] = L[Q.tl_src[e]];
+    for (int j = 0; j < Dm; j++) for (int r = j + 1; r < Dm; r++) {
+        double acc = 0; int rb = r * (r - 1) / 2;
+        for (int k = j + 1; k < r; k++) acc += Ld[rb + k] * Ti[k * (k - 1) / 2 + j];
+        Ti[rb + j] = -(Ld[rb + j] + acc);
+    }
+    // solve K x = b: sparse levels < tail_level, dense tail with the inverse, mirror image backwards
+    std::vector<double> b(Nk), x(Nk), t(Nk);
     for (auto& v : b) v = U(rng);
     x = b;
-    for (int l = 1; l < Q.nlev; l++) for (int r = Q.lvl_ptr[l]; r < Q.lvl_ptr[l + 1]; r++) { double s = x[r]; for (int e = Q.lrow_ptr[r]; e < Q.lrow_ptr[r + 1]; e++) s -= L[e] * x[Q.lrow_col[e]]; x[r] = s; }
-    for (int l = Q.nlev - 1; l >= 0; l--) for (int r = Q.lvl_ptr[l]; r < Q.lvl_ptr[l + 1]; r++) { double s = x[r] * Dinv[r]; for (int e = Q.lcol_ptr[r]; e < Q.lcol_ptr[r + 1]; e++) s -= L[Q.lcol_val[e]] * x[Q.lcol_row[e]]; x[r] = s; }
+    for (int l = 1; l < Lt; l++) for (int r = Q.lvl_ptr[l]; r < Q.lvl_ptr[l + 1]; r++) { double s = x[r]; for (int e = Q.lrow_ptr[r]; e < Q.lrow_ptr[r + 1]; e++) s -= L[e] * x[Q.lrow_col[e]]; x[r] = s; }
+    for (int rr = 0; rr < Dm; rr++) { int r = ts + rr; double s = x[r]; for (int e = Q.lrow_ptr[r]; e < Q.lrow_split[r]; e++) s -= L[e] * x[Q.lrow_col[e]]; t[r] = s; }
+    for (int rr = 0; rr < Dm; rr++) { double s = t[ts + rr]; for (int k = 0; k < rr; k++) s += Ti[rr * (rr - 1) / 2 + k] * t[ts + k]; x[ts + rr] = s * Dinv[ts + rr]; }
+    for (int rr = 0; rr < Dm; rr++) { double s = x[ts + rr]; for (int k = rr + 1; k < Dm; k++) s += Ti[k * (k - 1) / 2 + rr] * x[ts + k]; t[ts + rr] = s; }
+    for (int rr = 0; rr < Dm; rr++) x[ts + rr] = t[ts + rr];
+    for (int l = Lt - 1; l >= 0; l--) for (int r = Q.lvl_ptr[l]; r < Q.lvl_ptr[l + 1]; r++) { double s = x[r] * Dinv[r]; for (int e = Q.lcol_ptr[r]; e < Q.lcol_ptr[r + 1]; e++) s -= L[Q.lcol_val[e]] * x[Q.lcol_row[e]]; x[r] = s; }
     // residual ||K x - b||_inf and the kadj product against the dense one
     double res = 0, kadj_err = 0;
     for (int r = 0; r < Nk; r++) {
@@ -56,7 +69,7 @@ int main(int argc, char** argv) {
         kadj_err = std::fmax(kadj_err, std::fabs(t - off));
     }
     int wmax = 0; for (int l = 0; l < Q.nlev; l++) wmax = std::max(wmax, (int)(Q.lvl_ptr[l + 1] - Q.lvl_ptr[l]));
-    printf("kind=%d N=%d n=%d m=%d Nk=%d nnzA=%d nnzL=%d nlev=%d maxwidth=%d pairs=%zu rec_len=%d res=%.3e kadj_err=%.3e\n", kind, Q.N, n, m, Nk, Q.nnzA,
-           Q.nnzL, Q.nlev, wmax, npairs, Q.rec.rec_len, res, kadj_err);
+    printf("kind=%d N=%d n=%d m=%d Nk=%d nnzA=%d nnzL=%d nlev=%d maxwidth=%d pairs=%zu rec_len=%d tail_level=%d tail_dim=%d res=%.3e kadj_err=%.3e\n", kind, Q.N, n, m, Nk, Q.nnzA,
+           Q.nnzL, Q.nlev, wmax, npairs, Q.rec.rec_len, Q.tail_level, Q.tail_dim, res, kadj_err);
     return (res < 1e-8 && kadj_err < 1e-10) ? 0 : 2;
 }
