@@ -44,31 +44,40 @@ def oracles_for(kind, trajs, tid, state, control, other, hji=None, vp=None, **kw
     return ms
 
 
-def compare_step(p, g, ms, tk, kind, check_solution=True):
-    g.compute_time_steps(tk); g.compute_linearization_nodes(); g.update_QP(); g.solve()
-    ug = g.get_next_control()
+def compare_step(p, g, ms, tk, kind, check_solution=True, sync_nodes=True):
+    """One MPC step on both sides.  Stage by stage: time steps, nodes, QP data, ADMM solution/statistics, control.
+    With sync_nodes the oracle linearises about the GPU's nodes (which were just checked against its own), so that the
+    QP-data and solution comparisons are made on bit-identical inputs instead of inheriting the ~1e-9 solution difference of
+    the previous step through the warm-start interpolation."""
+    g.compute_time_steps(tk); g.compute_linearization_nodes()
     for i, m in enumerate(ms):
-        m.compute_time_steps(tk[i]); m.compute_linearization_nodes(); m.update_qp(); m.solve()
-    uo = np.array([m.get_next_control() for m in ms])
+        m.compute_time_steps(tk[i]); m.compute_linearization_nodes()
     ts_g, dt_g, pts_g = g.time_steps()
     assert np.allclose(ts_g, np.array([m.time_steps()[0] for m in ms]), rtol=0, atol=1e-12)
     assert np.allclose(dt_g, np.array([m.time_steps()[1] for m in ms]), rtol=0, atol=1e-12)
     qs_g, us_g, ps_g = g.nodes()
     no = [m.nodes() for m in ms]
-    assert np.allclose(qs_g, np.array([x[0] for x in no]), rtol=1e-9, atol=1e-9)
-    assert np.allclose(us_g, np.array([x[1] for x in no]), rtol=1e-7, atol=1e-4)       # Fx in newtons; warm nodes inherit the 1e-9 solution agreement x 1.7e4 N
-    assert np.allclose(ps_g, np.array([x[2] for x in no]), rtol=1e-9, atol=1e-9)
+    assert np.allclose(qs_g, np.array([x[0] for x in no]), rtol=1e-7, atol=1e-7)
+    assert np.allclose(us_g, np.array([x[1] for x in no]), rtol=1e-7, atol=1e-3)       # Fx in newtons (range 1.7e4)
+    assert np.allclose(ps_g, np.array([x[2] for x in no]), rtol=1e-7, atol=1e-7)
+    if sync_nodes:
+        for i, m in enumerate(ms):
+            m.set_nodes(qs_g[i], us_g[i], ps_g[i])
+    g.update_QP(); g.solve()
+    ug = g.get_next_control()
+    for m in ms:
+        m.update_qp(); m.solve()
+    uo = np.array([m.get_next_control() for m in ms])
     d = g.qp_data()
     po = [m.qp_pieces() for m in ms]
     un = g.u_normalization if kind == 0 else np.array([1.0, 1.0])
-    for key, scale in (("A", 1.0), ("c", 1.0), ("H", 1.0), ("dmin", 1.0), ("dmax", 1.0), ("fxmax", 1.0)):
+    tol = dict(rtol=1e-9, atol=1e-9) if sync_nodes else dict(rtol=1e-5, atol=1e-5)
+    for key in ("A", "c", "H", "G", "dmin", "dmax", "fxmax"):
         ref = np.array([x[key] for x in po])
-        assert np.allclose(d[key], ref, rtol=1e-8, atol=1e-8), key
+        assert np.allclose(d[key], ref, **tol), key
     for key in ("B0", "Bf"):
         ref = np.array([x[key] for x in po]) * un[None, None, None, :g.nu]
-        assert np.allclose(d[key], ref, rtol=1e-8, atol=1e-8), key
-    Gref = np.array([x["G"] for x in po])
-    assert np.allclose(d["G"], Gref, rtol=1e-7, atol=1e-7)
+        assert np.allclose(d[key], ref, **tol), key
     st = g.stats()
     it_o = np.array([m.stats()["iter"] for m in ms]); st_o = np.array([m.stats()["status"] for m in ms])
     assert np.array_equal(st["iters"], it_o), (st["iters"], it_o)
@@ -77,7 +86,7 @@ def compare_step(p, g, ms, tk, kind, check_solution=True):
     if check_solution:
         xg, yg = g.solution()
         xo = np.array([m.solution()[0] for m in ms])
-        assert np.allclose(xg, xo, rtol=1e-5, atol=1e-5)
+        assert np.allclose(xg, xo, rtol=1e-6, atol=1e-6)
     # the headline tolerance: steering and longitudinal force within 1e-4 relative (to the actuator range)
     assert np.max(np.abs(ug - uo) / U_RANGE) < 1e-4
     return ug, uo
@@ -104,6 +113,32 @@ def test_closed_loop_parity_with_oracle(p, kind, Ns, Nl):
             m.set_state(xn, uo[i], other4=other[i])
         qg, ucur = g.get_state()
         assert np.allclose(qg, np.array([m.get_state()[0] for m in ms]), rtol=1e-9, atol=1e-8)
+        assert np.max(np.abs(ucur - uo) / U_RANGE) < 1e-4
+    g.close()
+
+
+def test_free_running_closed_loops_stay_within_tolerance(p):
+    """No re-synchronisation at all: GPU and oracle closed loops run independently for 25 steps."""
+    B = 24
+    trajs = p.synthetic.synthetic_trajectories(n_traj=4, n_nodes=400)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g.set_state(state, control, other)
+    ms = oracles_for(0, trajs, tid, state, control, other)
+    same_iters = 0
+    for k in range(25):
+        ug = g.step(t0 + 0.01 * k)
+        g.rollout(0.01)
+        it = g.stats()["iters"]
+        for i, m in enumerate(ms):
+            m.simulate_step(t0[i] + 0.01 * k)
+            same_iters += int(it[i] == m.stats()["iter"])
+        uo = np.array([m.get_state()[1] for m in ms])
+        assert np.max(np.abs(ug - uo) / U_RANGE) < 1e-4, k
+    qg, _ = g.get_state()
+    assert np.allclose(qg, np.array([m.get_state()[0] for m in ms]), rtol=1e-7, atol=1e-6)
+    assert same_iters >= 25 * B - 2          # iteration counts agree (a borderline termination test may flip once in a while)
     g.close()
 
 
