@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpigeon_b200.so")
+LIB_PATH = os.environ.get("PGN_LIB_PATH", os.path.join(HERE, "libpigeon_b200.so"))    # override: A/B builds of the same C ABI
 
 PGN_COUPLED, PGN_DECOUPLED = 0, 1
 STATUS_NAMES = {1: "solved", 2: "solved_inaccurate", 3: "primal_infeasible_inaccurate", 4: "dual_infeasible_inaccurate", -2: "max_iter_reached",

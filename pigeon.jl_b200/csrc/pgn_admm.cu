@@ -18,7 +18,9 @@
 
 namespace pgn {
 
+#ifndef ADMM_THREADS
 #define ADMM_THREADS 256
+#endif
 #define NW (ADMM_THREADS / 32)
 
 static const double OSQP_INFTY = 1e20;
@@ -39,17 +41,19 @@ struct AdmmArgs {
 
 struct Smem {
     double *Lval, *Dinv, *Aval, *xz, *sol, *dxy, *yq, *lo, *hi, *sc, *Tinv, *red;   // sol and dxy are adjacent: together they hold the dense tail copy
-    uint16_t *lrow_col, *lcol_row, *lcol_val, *lrow_ptr, *lcol_ptr, *lvl_ptr, *lrow_split;
+    uint32_t *frow, *brow, *bent;   // per row: first entry | length << 16 (forward CSR / backward CSC); per CSC entry: value index | row << 16
+    uint2* lvd;                     // per level: {first row | width << 16, log2(lanes fwd) | log2(lanes bwd) << 8}
+    uint16_t *lrow_col, *lrow_split;
     uint8_t *flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
-    uint8_t *gf, *gb;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t admm_smem_bytes(const QpTables& t) {
     size_t d = (size_t)t.nnzL + t.Nk + t.nnzA + 7 * (size_t)t.Nk + (size_t)t.tail_dim * (t.tail_dim - 1) / 2 + 16 * NW + 8;
-    size_t u16 = 3 * (size_t)t.nnzL + 2 * (size_t)(t.Nk + 1) + (t.nlev + 1) + t.tail_dim + 8;
-    return d * 8 + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + align_up(2 * (size_t)t.nlev, 8) + 64;
+    size_t u32 = 2 * (size_t)t.Nk + (size_t)t.nnzL + 2 * (size_t)t.nlev + 8;
+    size_t u16 = (size_t)t.nnzL + t.tail_dim + 8;
+    return d * 8 + align_up(u32 * 4, 8) + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + 64;
 }
 
 __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem& s) {
@@ -66,18 +70,16 @@ __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem&
     s.sc = d; d += q.Nk;
     s.Tinv = d; d += q.tail_dim * (q.tail_dim - 1) / 2;
     s.red = d; d += 16 * NW + 8;
-    uint16_t* u = reinterpret_cast<uint16_t*>(d);
+    s.lvd = reinterpret_cast<uint2*>(d);
+    uint32_t* w = reinterpret_cast<uint32_t*>(s.lvd + q.nlev);
+    s.frow = w; w += q.Nk;
+    s.brow = w; w += q.Nk;
+    s.bent = w; w += q.nnzL;
+    uint16_t* u = reinterpret_cast<uint16_t*>(w);
     s.lrow_col = u; u += q.nnzL;
-    s.lcol_row = u; u += q.nnzL;
-    s.lcol_val = u; u += q.nnzL;
-    s.lrow_ptr = u; u += q.Nk + 1;
-    s.lcol_ptr = u; u += q.Nk + 1;
-    s.lvl_ptr = u; u += q.nlev + 1;
     s.lrow_split = u; u += q.tail_dim;
     size_t off = align_up((size_t)(reinterpret_cast<unsigned char*>(u) - base), 8);
     s.flag = base + off;
-    s.gf = s.flag + align_up((size_t)q.Nk, 8);
-    s.gb = s.gf + q.nlev;
 }
 
 // block-wide max / sum of NV values per thread; every thread returns with the results in v[]
@@ -121,7 +123,14 @@ __device__ __forceinline__ double rinv_of(uint8_t flag, const RhoInv& r) { retur
 
 // sum over the g (power of two) adjacent lanes of a group; every lane of the warp must call
 __device__ __forceinline__ double group_sum(double v, int g) {
-    for (int o = g >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    switch (g) {      // warp-uniform; falls through the remaining butterfly steps
+        case 32: v += __shfl_xor_sync(0xffffffffu, v, 16);
+        case 16: v += __shfl_xor_sync(0xffffffffu, v, 8);
+        case 8: v += __shfl_xor_sync(0xffffffffu, v, 4);
+        case 4: v += __shfl_xor_sync(0xffffffffu, v, 2);
+        case 2: v += __shfl_xor_sync(0xffffffffu, v, 1);
+        default: break;
+    }
     return v;
 }
 
@@ -204,25 +213,27 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
     const int tid = threadIdx.x;
     const int Lt = q.tail_level, ts = q.tail_start, Dm = q.tail_dim;
     for (int l = 1; l < Lt; l++) {
-        const int r0 = s.lvl_ptr[l], w = s.lvl_ptr[l + 1] - r0;
-        const int g = s.gf[l], sh = 31 - __clz(g);
+        const uint2 ld = s.lvd[l];
+        const int r0 = ld.x & 0xffff, w = ld.x >> 16, sh = ld.y & 0xff, g = 1 << sh;
         const int slots = ((w << sh) + 31) & ~31;
         for (int i = tid; i < slots; i += ADMM_THREADS) {
-            const int r = r0 + (i >> sh), sub = i & (g - 1);
-            const bool live = (i >> sh) < w;
-            double acc = 0.0;
+            const int row = i >> sh, sub = i & (g - 1);
+            const bool live = row < w;
+            double acc = 0.0, acc2 = 0.0;
             if (live) {
-                const int e1 = s.lrow_ptr[r + 1];
-                int e = s.lrow_ptr[r] + sub;
+                const uint32_t rd = s.frow[r0 + row];
+                int e = (rd & 0xffff) + sub;
+                const int e1 = (rd & 0xffff) + (rd >> 16);
                 for (; e + g < e1; e += 2 * g) {
                     const int c0 = s.lrow_col[e], c1 = s.lrow_col[e + g];
                     const double l0 = s.Lval[e], l1 = s.Lval[e + g];
-                    acc += l0 * s.sol[c0] + l1 * s.sol[c1];
+                    acc += l0 * s.sol[c0];
+                    acc2 += l1 * s.sol[c1];
                 }
                 if (e < e1) acc += s.Lval[e] * s.sol[s.lrow_col[e]];
             }
-            acc = group_sum(acc, g);
-            if (live && sub == 0) s.sol[r] -= acc;
+            acc = group_sum(acc + acc2, g);
+            if (live && sub == 0) s.sol[r0 + row] -= acc;
         }
         __syncthreads();
     }
@@ -234,13 +245,18 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
             for (int i = tid; i < slots; i += ADMM_THREADS) {
                 const int rr = i >> sh, sub = i & (g - 1);
                 const bool live = rr < Dm;
-                double acc = 0.0;
+                double acc = 0.0, acc2 = 0.0;
                 if (live) {
-                    const int r = ts + rr;
                     const int e1 = s.lrow_split[rr];
-                    for (int e = s.lrow_ptr[r] + sub; e < e1; e += g) acc += s.Lval[e] * s.sol[s.lrow_col[e]];
+                    int e = (s.frow[ts + rr] & 0xffff) + sub;
+                    for (; e + g < e1; e += 2 * g) {
+                        const int c0 = s.lrow_col[e], c1 = s.lrow_col[e + g];
+                        acc += s.Lval[e] * s.sol[c0];
+                        acc2 += s.Lval[e + g] * s.sol[c1];
+                    }
+                    if (e < e1) acc += s.Lval[e] * s.sol[s.lrow_col[e]];
                 }
-                acc = group_sum(acc, g);
+                acc = group_sum(acc + acc2, g);
                 if (live && sub == 0) s.dxy[ts + rr] = s.sol[ts + rr] - acc;
             }
         }
@@ -251,53 +267,65 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
             for (int i = tid; i < slots; i += ADMM_THREADS) {
                 const int rr = i >> 2, sub = i & 3;
                 const bool live = rr < Dm;
-                double acc = 0.0;
+                double acc = 0.0, acc2 = 0.0;
                 if (live) {
-                    const int rb = rr * (rr - 1) / 2;
-                    for (int k = sub; k < rr; k += 4) acc += s.Tinv[rb + k] * s.dxy[ts + k];
+                    const double* trow = s.Tinv + rr * (rr - 1) / 2;
+                    const double* tv = s.dxy + ts;
+                    int k = sub;
+                    for (; k + 4 < rr; k += 8) { acc += trow[k] * tv[k]; acc2 += trow[k + 4] * tv[k + 4]; }
+                    if (k < rr) acc += trow[k] * tv[k];
                 }
-                acc = group_sum(acc, 4);
+                acc = group_sum(acc + acc2, 4);
                 if (live && sub == 0) s.sol[ts + rr] = (s.dxy[ts + rr] + acc) * s.Dinv[ts + rr];
             }
         }
         __syncthreads();
-        // backward through the tail: x = Tinv' w  -> dxy[tail], then copied into sol[tail]
+        // backward through the tail: x = Tinv' w, computed into registers, then written back over w
         {
             const int slots = ((Dm * 4) + 31) & ~31;
-            for (int i = tid; i < slots; i += ADMM_THREADS) {
-                const int rr = i >> 2, sub = i & 3;
-                const bool live = rr < Dm;
-                double acc = 0.0;
-                if (live)
-                    for (int k = rr + 1 + sub; k < Dm; k += 4) acc += s.Tinv[k * (k - 1) / 2 + rr] * s.sol[ts + k];
-                acc = group_sum(acc, 4);
-                if (live && sub == 0) s.dxy[ts + rr] = s.sol[ts + rr] + acc;
+            double xr = 0.0;
+            const int i = tid;
+            const int rr = i >> 2, sub = i & 3;
+            const bool live = rr < Dm;
+            if (i < slots) {
+                double acc = 0.0, acc2 = 0.0;
+                if (live) {
+                    int k = rr + 1 + sub;
+                    for (; k + 4 < Dm; k += 8) {
+                        acc += s.Tinv[k * (k - 1) / 2 + rr] * s.sol[ts + k];
+                        acc2 += s.Tinv[(k + 4) * (k + 3) / 2 + rr] * s.sol[ts + k + 4];
+                    }
+                    if (k < Dm) acc += s.Tinv[k * (k - 1) / 2 + rr] * s.sol[ts + k];
+                }
+                acc = group_sum(acc + acc2, 4);
+                if (live) xr = s.sol[ts + rr] + acc;
             }
+            __syncthreads();
+            if (i < slots && live && sub == 0) s.sol[ts + rr] = xr;
         }
-        __syncthreads();
-        for (int i = tid; i < Dm; i += ADMM_THREADS) s.sol[ts + i] = s.dxy[ts + i];
         __syncthreads();
     }
     for (int l = Lt - 1; l >= 0; l--) {
-        const int r0 = s.lvl_ptr[l], w = s.lvl_ptr[l + 1] - r0;
-        const int g = s.gb[l], sh = 31 - __clz(g);
+        const uint2 ld = s.lvd[l];
+        const int r0 = ld.x & 0xffff, w = ld.x >> 16, sh = (ld.y >> 8) & 0xff, g = 1 << sh;
         const int slots = ((w << sh) + 31) & ~31;
         for (int i = tid; i < slots; i += ADMM_THREADS) {
-            const int r = r0 + (i >> sh), sub = i & (g - 1);
-            const bool live = (i >> sh) < w;
-            double acc = 0.0;
+            const int row = i >> sh, sub = i & (g - 1);
+            const bool live = row < w;
+            double acc = 0.0, acc2 = 0.0;
             if (live) {
-                const int e1 = s.lcol_ptr[r + 1];
-                int e = s.lcol_ptr[r] + sub;
+                const uint32_t rd = s.brow[r0 + row];
+                int e = (rd & 0xffff) + sub;
+                const int e1 = (rd & 0xffff) + (rd >> 16);
                 for (; e + g < e1; e += 2 * g) {
-                    const int v0 = s.lcol_val[e], v1 = s.lcol_val[e + g];
-                    const int c0 = s.lcol_row[e], c1 = s.lcol_row[e + g];
-                    acc += s.Lval[v0] * s.sol[c0] + s.Lval[v1] * s.sol[c1];
+                    const uint32_t b0 = s.bent[e], b1 = s.bent[e + g];
+                    acc += s.Lval[b0 & 0xffff] * s.sol[b0 >> 16];
+                    acc2 += s.Lval[b1 & 0xffff] * s.sol[b1 >> 16];
                 }
-                if (e < e1) acc += s.Lval[s.lcol_val[e]] * s.sol[s.lcol_row[e]];
+                if (e < e1) { const uint32_t b0 = s.bent[e]; acc += s.Lval[b0 & 0xffff] * s.sol[b0 >> 16]; }
             }
-            acc = group_sum(acc, g);
-            if (live && sub == 0) s.sol[r] = s.sol[r] * s.Dinv[r] - acc;
+            acc = group_sum(acc + acc2, g);
+            if (live && sub == 0) s.sol[r0 + row] = s.sol[r0 + row] * s.Dinv[r0 + row] - acc;
         }
         __syncthreads();
     }
@@ -420,14 +448,21 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
     Smem s;
     carve(q, smem_raw, s);
     const int tid = threadIdx.x;
-    // index tables of the triangular solves: global -> shared, once per CTA
-    for (int e = tid; e < q.nnzL; e += ADMM_THREADS) { s.lrow_col[e] = q.lrow_col[e]; s.lcol_row[e] = q.lcol_row[e]; s.lcol_val[e] = q.lcol_val[e]; }
-    for (int p = tid; p <= q.Nk; p += ADMM_THREADS) { s.lrow_ptr[p] = q.lrow_ptr[p]; s.lcol_ptr[p] = q.lcol_ptr[p]; }
-    for (int l = tid; l <= q.nlev; l += ADMM_THREADS) s.lvl_ptr[l] = q.lvl_ptr[l];
-    for (int l = tid; l < q.nlev; l += ADMM_THREADS) { s.gf[l] = q.lvl_gf[l]; s.gb[l] = q.lvl_gb[l]; }
+    // index tables of the triangular solves: global -> shared (packed), once per CTA
+    for (int e = tid; e < q.nnzL; e += ADMM_THREADS) {
+        s.lrow_col[e] = q.lrow_col[e];
+        s.bent[e] = (uint32_t)q.lcol_val[e] | ((uint32_t)q.lcol_row[e] << 16);
+    }
+    for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
+        s.frow[p] = (uint32_t)q.lrow_ptr[p] | ((uint32_t)(q.lrow_ptr[p + 1] - q.lrow_ptr[p]) << 16);
+        s.brow[p] = (uint32_t)q.lcol_ptr[p] | ((uint32_t)(q.lcol_ptr[p + 1] - q.lcol_ptr[p]) << 16);
+    }
+    for (int l = tid; l < q.nlev; l += ADMM_THREADS) {
+        const uint32_t r0 = q.lvl_ptr[l], w = q.lvl_ptr[l + 1] - q.lvl_ptr[l];
+        s.lvd[l] = make_uint2(r0 | (w << 16), (uint32_t)(31 - __clz((int)q.lvl_gf[l])) | ((uint32_t)(31 - __clz((int)q.lvl_gb[l])) << 8));
+    }
     for (int i = tid; i < q.tail_dim; i += ADMM_THREADS) s.lrow_split[i] = q.lrow_split[q.tail_start + i];
     __syncthreads();
-
     long long t_phase = clock64();
     for (;;) {
         if (tid == 0) s_vehicle = atomicAdd(a.counter, 1);

@@ -251,7 +251,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_counter, 4); AL(d_cycles, 8);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_cycles, 8);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
@@ -432,12 +432,12 @@ int pgn_rollout(pgn_handle* h, double dt) {
 }
 int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
     REQUIRE(h && t0 && n_steps >= 0, "bad argument");
-    CK(cudaMemcpyAsync(h->d_t0, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_t0_base, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
     for (int k = 0; k < n_steps; k++) {
+        launch_time_axpy(h, h->d_t0_base, (double)k, dt, h->d_t0, h->B);
         int rc = pgn_step_device(h, h->d_t0, nullptr);
         if (rc) return rc;
         { StageTimer T(h, 5); launch_rollout(h, dt); }
-        launch_add_scalar(h, h->d_t0, dt, h->B);
     }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());

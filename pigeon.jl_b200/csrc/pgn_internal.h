@@ -92,7 +92,7 @@ struct pgn_handle {
     int32_t *d_iters, *d_status, *d_rho_updates;
     double *d_pri_res, *d_dua_res;
     double* d_controls;                                  // [3][B]
-    double* d_t0;                                        // [B]
+    double *d_t0, *d_t0_base;                            // [B]
     int* d_counter;                                      // work-queue ticket for the persistent ADMM kernel
     unsigned long long* d_cycles;                        // [8] per-phase cycle counters of the ADMM kernel (profiling only)
     double* d_stage;                                     // AoS<->SoA staging
@@ -117,7 +117,7 @@ void launch_rollout(pgn_handle* h, double dt);
 void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV);
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
-void launch_add_scalar(pgn_handle* h, double* d_v, double a, int n);
+void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n);
 size_t admm_smem_bytes(const QpTables& t);
 int admm_configure(pgn_handle* h);   // sets the max dynamic shared memory attribute; returns cudaError
 }  // namespace pgn

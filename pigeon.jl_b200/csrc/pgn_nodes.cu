@@ -310,9 +310,10 @@ __global__ void k_transpose_out(int B, int k, const double* __restrict__ soa, do
     const int v = idx / k, f = idx - v * k;
     aos[idx] = soa[(size_t)f * B + v];
 }
-__global__ void k_add_scalar(int n, double a, double* __restrict__ v) {
+// t[i] = base[i] + k * dt  (the reference iterates a range `0:dt:T`, i.e. t_k = k*dt, not an accumulated sum)
+__global__ void k_time_axpy(int n, const double* __restrict__ base, double k, double dt, double* __restrict__ v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] += a;
+    if (i < n) v[i] = base[i] + k * dt;
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------------------
@@ -354,8 +355,8 @@ void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int
     k_transpose_out<<<(n + 255) / 256, 256, 0, h->stream>>>(h->B, k, d_soa, d_aos);
     h->launches++;
 }
-void launch_add_scalar(pgn_handle* h, double* d_v, double a, int n) {
-    k_add_scalar<<<(n + 255) / 256, 256, 0, h->stream>>>(n, a, d_v);
+void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n) {
+    k_time_axpy<<<(n + 255) / 256, 256, 0, h->stream>>>(n, d_base, k, dt, d_v);
     h->launches++;
 }
 
