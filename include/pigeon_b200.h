@@ -143,7 +143,7 @@ PGN_API int pgn_set_profiling(pgn_handle* h, int32_t on);
 PGN_API int pgn_get_stage_ms(pgn_handle* h, double* out /*[8]*/, int32_t reset);
 /* SM cycles spent by the ADMM CTAs per phase while profiling is on (summed over CTAs):
  * [0] gather, [1] Ruiz scaling, [2] LDL' factorisation, [3] triangular solves, [4] x/z/y update, [5] residuals/termination/rho, [6] store, [7] ticket */
-PGN_API int pgn_get_admm_cycles(pgn_handle* h, double* out /*[8]*/, int32_t reset);
+PGN_API int pgn_get_admm_cycles(pgn_handle* h, double* out /*[512]: [0..7] phases, [16+l] forward level l, [116..118] dense tail, [144+l] backward level l (CTA 0 only)*/, int32_t reset);
 
 #ifdef __cplusplus
 }

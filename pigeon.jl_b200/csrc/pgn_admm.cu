@@ -209,8 +209,17 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) 
 
 // sol <- K^-1 sol.  Level-scheduled forward substitution over the sparse levels (rows split over lane groups, shuffle-reduced), the
 // dense tail as two mat-vec levels with the explicit inverse, then the mirror image backwards.
-__device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
+#define LVL_T(idx)                                                                         \
+    do {                                                                                   \
+        if (lvl_cyc && threadIdx.x == 0 && blockIdx.x == 0) {                              \
+            const long long now__ = clock64();                                             \
+            lvl_cyc[(idx)] += (unsigned long long)(now__ - t_lvl);                         \
+            t_lvl = now__;                                                                 \
+        }                                                                                  \
+    } while (0)
+__device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigned long long* lvl_cyc) {
     const int tid = threadIdx.x;
+    long long t_lvl = clock64();
     const int Lt = q.tail_level, ts = q.tail_start, Dm = q.tail_dim;
     for (int l = 1; l < Lt; l++) {
         const uint2 ld = s.lvd[l];
@@ -236,6 +245,7 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
             if (live && sub == 0) s.sol[r0 + row] -= acc;
         }
         __syncthreads();
+        LVL_T(l);
     }
     if (Dm > 0) {
         // tail, stage 1: t = b_tail - L[tail, early] y_early  -> dxy[tail]
@@ -261,6 +271,7 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
             }
         }
         __syncthreads();
+        LVL_T(100);
         // stage 2 + diagonal: w = Dinv .* (Tinv t)  -> sol[tail]
         {
             const int slots = ((Dm * 4) + 31) & ~31;
@@ -280,6 +291,7 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
             }
         }
         __syncthreads();
+        LVL_T(101);
         // backward through the tail: x = Tinv' w, computed into registers, then written back over w
         {
             const int slots = ((Dm * 4) + 31) & ~31;
@@ -304,6 +316,7 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
             if (i < slots && live && sub == 0) s.sol[ts + rr] = xr;
         }
         __syncthreads();
+        LVL_T(102);
     }
     for (int l = Lt - 1; l >= 0; l--) {
         const uint2 ld = s.lvd[l];
@@ -328,6 +341,7 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s) {
             if (live && sub == 0) s.sol[r0 + row] = s.sol[r0 + row] * s.Dinv[r0 + row] - acc;
         }
         __syncthreads();
+        LVL_T(128 + l);
     }
 }
 
@@ -582,7 +596,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                 s.sol[p] = f ? s.xz[p] - rinv_of(f, rinv) * s.yq[p] : st.sigma * s.xz[p] - s.yq[p];
             }
             __syncthreads();
-            kkt_solve(q, s);
+            kkt_solve(q, s, a.cycles ? a.cycles + 16 : nullptr);
             PHASE(3);
             // x, z, y updates
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {

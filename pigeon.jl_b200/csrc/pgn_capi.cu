@@ -251,12 +251,12 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_cycles, 8);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_cycles, 512);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
     CK(cudaMemset(h->d_sol_x, 0, B * t.n * 8)); CK(cudaMemset(h->d_sol_y, 0, B * t.m * 8));
-    CK(cudaMemset(h->d_cycles, 0, 64));
+    CK(cudaMemset(h->d_cycles, 0, 4096));
     CK(cudaMemset(h->d_iters, 0, B * 4)); CK(cudaMemset(h->d_status, 0, B * 4)); CK(cudaMemset(h->d_rho_updates, 0, B * 4));
     CK(cudaMemset(h->d_rec, 0, B * (size_t)t.rec.rec_len * 8)); CK(cudaMemset(h->d_controls, 0, 3 * B * 8));
     {   // other car far away, time_offset = NaN (path mode), ts = 1..N (MPCTimeSteps ctor), rho = setting
@@ -553,11 +553,11 @@ int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_status) {
 int pgn_set_profiling(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->profiling = on; return PGN_OK; }
 int pgn_get_admm_cycles(pgn_handle* h, double* out, int32_t reset) {
     REQUIRE(h && out, "NULL argument");
-    unsigned long long c[8];
+    unsigned long long c[512];
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(c, h->d_cycles, 64, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 8; i++) out[i] = (double)c[i];
-    if (reset) CK(cudaMemset(h->d_cycles, 0, 64));
+    CK(cudaMemcpy(c, h->d_cycles, 4096, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 512; i++) out[i] = (double)c[i];
+    if (reset) CK(cudaMemset(h->d_cycles, 0, 4096));
     return PGN_OK;
 }
 int pgn_get_stage_ms(pgn_handle* h, double* out, int32_t reset) {

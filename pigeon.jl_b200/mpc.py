@@ -320,9 +320,10 @@ class BatchedTrajectoryTrackingMPC:
 
 
     def admm_cycles(self, reset=True):
-        out = np.zeros(8)
+        out = np.zeros(512)
         check(self._lib.pgn_get_admm_cycles(self._h, dptr(out), int(reset)))
-        return dict(zip(["gather", "ruiz", "factor", "solve", "update", "check", "store", "ticket"], out))
+        self.level_cycles = out[16:].copy()
+        return dict(zip(["gather", "ruiz", "factor", "solve", "update", "check", "store", "ticket"], out[:8]))
 
 
 def BatchedCoupledTrajectoryTrackingMPC(vehicle, trajectories, batch, control_params=None, **kw):
