@@ -42,7 +42,7 @@ struct AdmmArgs {
 struct Smem {
     double *Lval, *Dinv, *Aval, *xz, *sol, *dxy, *yq, *lo, *hi, *sc, *Tinv, *red;   // sol and dxy are adjacent: together they hold the dense tail copy
     uint32_t *frow, *brow, *bent;   // per row: first entry | length << 16 (forward CSR / backward CSC); per CSC entry: value index | row << 16
-    uint2* lvd;                     // per level: {first row | width << 16, log2(lanes fwd) | log2(lanes bwd) << 8}
+    uint2 *stf, *stb;               // step programs of the forward / backward sparse solves
     uint16_t *lrow_col, *lrow_split;
     uint8_t *flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
 };
@@ -51,7 +51,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 size_t admm_smem_bytes(const QpTables& t) {
     size_t d = (size_t)t.nnzL + t.Nk + t.nnzA + 7 * (size_t)t.Nk + (size_t)t.tail_dim * (t.tail_dim - 1) / 2 + 16 * NW + 8;
-    size_t u32 = 2 * (size_t)t.Nk + (size_t)t.nnzL + 2 * (size_t)t.nlev + 8;
+    size_t u32 = 2 * (size_t)t.Nk + (size_t)t.nnzL + t.step_f.size() + t.step_b.size() + 8;
     size_t u16 = (size_t)t.nnzL + t.tail_dim + 8;
     return d * 8 + align_up(u32 * 4, 8) + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + 64;
 }
@@ -70,8 +70,9 @@ __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem&
     s.sc = d; d += q.Nk;
     s.Tinv = d; d += q.tail_dim * (q.tail_dim - 1) / 2;
     s.red = d; d += 16 * NW + 8;
-    s.lvd = reinterpret_cast<uint2*>(d);
-    uint32_t* w = reinterpret_cast<uint32_t*>(s.lvd + q.nlev);
+    s.stf = reinterpret_cast<uint2*>(d);
+    s.stb = s.stf + q.n_step_f;
+    uint32_t* w = reinterpret_cast<uint32_t*>(s.stb + q.n_step_b);
     s.frow = w; w += q.Nk;
     s.brow = w; w += q.Nk;
     s.bent = w; w += q.nnzL;
@@ -209,6 +210,57 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) 
 
 // sol <- K^-1 sol.  Level-scheduled forward substitution over the sparse levels (rows split over lane groups, shuffle-reduced), the
 // dense tail as two mat-vec levels with the explicit inverse, then the mirror image backwards.
+// One lane's share of one step: up to 4 (L value, iterate index) pairs of one row, fetched ahead of the barrier because they
+// do not depend on the iterate.
+enum { JOB_LIVE = 1, JOB_LEAD = 2, JOB_LAST = 4 };
+struct SolveJob {
+    double l[4];
+    double dinv;
+    int c[4];
+    int r, n, sh, flags;
+};
+template <bool FWD>
+__device__ __forceinline__ SolveJob fetch_job(const Smem& s, const uint2* steps, int st, int nsteps, int tid) {
+    SolveJob j;
+    j.flags = 0; j.n = 0; j.sh = 0; j.r = 0; j.dinv = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { j.l[k] = 0.0; j.c[k] = 0; }
+    if (st >= nsteps) return j;
+    const uint2 d = steps[st];
+    const int sh = d.y & 0xff;
+    j.sh = sh;
+    j.flags = (d.y & 0x100) ? JOB_LAST : 0;
+    const int row = tid >> sh, sub = tid & ((1 << sh) - 1);
+    if (row < (int)(d.x >> 16)) {
+        const int r = (d.x & 0xffff) + row;
+        const uint32_t rd = FWD ? s.frow[r] : s.brow[r];
+        const int base = rd & 0xffff, len = rd >> 16;
+        j.r = r;
+        j.flags |= JOB_LIVE | (sub == 0 ? JOB_LEAD : 0);
+        if (!FWD) j.dinv = s.Dinv[r];
+        int n = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int idx = sub + (k << sh);
+            if (idx < len) {
+                if (FWD) { j.c[k] = s.lrow_col[base + idx]; j.l[k] = s.Lval[base + idx]; }
+                else { const uint32_t b = s.bent[base + idx]; j.c[k] = b >> 16; j.l[k] = s.Lval[b & 0xffff]; }
+                n = k + 1;
+            }
+        }
+        j.n = n;
+    }
+    return j;
+}
+__device__ __forceinline__ double group_sum_sh(double v, int sh) {     // sh is warp-uniform
+    if (sh > 4) v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (sh > 3) v += __shfl_xor_sync(0xffffffffu, v, 8);
+    if (sh > 2) v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (sh > 1) v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (sh > 0) v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
 #define LVL_T(idx)                                                                         \
     do {                                                                                   \
         if (lvl_cyc && threadIdx.x == 0 && blockIdx.x == 0) {                              \
@@ -220,33 +272,27 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) 
 __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigned long long* lvl_cyc) {
     const int tid = threadIdx.x;
     long long t_lvl = clock64();
-    const int Lt = q.tail_level, ts = q.tail_start, Dm = q.tail_dim;
-    for (int l = 1; l < Lt; l++) {
-        const uint2 ld = s.lvd[l];
-        const int r0 = ld.x & 0xffff, w = ld.x >> 16, sh = ld.y & 0xff, g = 1 << sh;
-        const int slots = ((w << sh) + 31) & ~31;
-        for (int i = tid; i < slots; i += ADMM_THREADS) {
-            const int row = i >> sh, sub = i & (g - 1);
-            const bool live = row < w;
-            double acc = 0.0, acc2 = 0.0;
-            if (live) {
-                const uint32_t rd = s.frow[r0 + row];
-                int e = (rd & 0xffff) + sub;
-                const int e1 = (rd & 0xffff) + (rd >> 16);
-                for (; e + g < e1; e += 2 * g) {
-                    const int c0 = s.lrow_col[e], c1 = s.lrow_col[e + g];
-                    const double l0 = s.Lval[e], l1 = s.Lval[e + g];
-                    acc += l0 * s.sol[c0];
-                    acc2 += l1 * s.sol[c1];
-                }
-                if (e < e1) acc += s.Lval[e] * s.sol[s.lrow_col[e]];
+    const int ts = q.tail_start, Dm = q.tail_dim;
+    {   // forward over the sparse levels: software-pipelined step program
+        SolveJob j = fetch_job<true>(s, s.stf, 0, q.n_step_f, tid);
+        for (int st = 0; st < q.n_step_f; st++) {
+            const SolveJob jn = fetch_job<true>(s, s.stf, st + 1, q.n_step_f, tid);
+            double acc = 0.0;
+            if (j.flags & JOB_LIVE) {
+                double a1 = 0.0;
+                if (j.n > 0) acc = j.l[0] * s.sol[j.c[0]];
+                if (j.n > 1) a1 = j.l[1] * s.sol[j.c[1]];
+                if (j.n > 2) acc += j.l[2] * s.sol[j.c[2]];
+                if (j.n > 3) a1 += j.l[3] * s.sol[j.c[3]];
+                acc += a1;
             }
-            acc = group_sum(acc + acc2, g);
-            if (live && sub == 0) s.sol[r0 + row] -= acc;
+            acc = group_sum_sh(acc, j.sh);
+            if ((j.flags & (JOB_LIVE | JOB_LEAD)) == (JOB_LIVE | JOB_LEAD)) s.sol[j.r] -= acc;
+            if (j.flags & JOB_LAST) __syncthreads();
+            j = jn;
         }
-        __syncthreads();
-        LVL_T(l);
     }
+    LVL_T(1);
     if (Dm > 0) {
         // tail, stage 1: t = b_tail - L[tail, early] y_early  -> dxy[tail]
         {
@@ -318,31 +364,26 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigne
         __syncthreads();
         LVL_T(102);
     }
-    for (int l = Lt - 1; l >= 0; l--) {
-        const uint2 ld = s.lvd[l];
-        const int r0 = ld.x & 0xffff, w = ld.x >> 16, sh = (ld.y >> 8) & 0xff, g = 1 << sh;
-        const int slots = ((w << sh) + 31) & ~31;
-        for (int i = tid; i < slots; i += ADMM_THREADS) {
-            const int row = i >> sh, sub = i & (g - 1);
-            const bool live = row < w;
-            double acc = 0.0, acc2 = 0.0;
-            if (live) {
-                const uint32_t rd = s.brow[r0 + row];
-                int e = (rd & 0xffff) + sub;
-                const int e1 = (rd & 0xffff) + (rd >> 16);
-                for (; e + g < e1; e += 2 * g) {
-                    const uint32_t b0 = s.bent[e], b1 = s.bent[e + g];
-                    acc += s.Lval[b0 & 0xffff] * s.sol[b0 >> 16];
-                    acc2 += s.Lval[b1 & 0xffff] * s.sol[b1 >> 16];
-                }
-                if (e < e1) { const uint32_t b0 = s.bent[e]; acc += s.Lval[b0 & 0xffff] * s.sol[b0 >> 16]; }
+    {   // backward over the sparse levels (tail_level-1 .. 0)
+        SolveJob j = fetch_job<false>(s, s.stb, 0, q.n_step_b, tid);
+        for (int st = 0; st < q.n_step_b; st++) {
+            const SolveJob jn = fetch_job<false>(s, s.stb, st + 1, q.n_step_b, tid);
+            double acc = 0.0;
+            if (j.flags & JOB_LIVE) {
+                double a1 = 0.0;
+                if (j.n > 0) acc = j.l[0] * s.sol[j.c[0]];
+                if (j.n > 1) a1 = j.l[1] * s.sol[j.c[1]];
+                if (j.n > 2) acc += j.l[2] * s.sol[j.c[2]];
+                if (j.n > 3) a1 += j.l[3] * s.sol[j.c[3]];
+                acc += a1;
             }
-            acc = group_sum(acc + acc2, g);
-            if (live && sub == 0) s.sol[r0 + row] = s.sol[r0 + row] * s.Dinv[r0 + row] - acc;
+            acc = group_sum_sh(acc, j.sh);
+            if ((j.flags & (JOB_LIVE | JOB_LEAD)) == (JOB_LIVE | JOB_LEAD)) s.sol[j.r] = s.sol[j.r] * j.dinv - acc;
+            if (j.flags & JOB_LAST) __syncthreads();
+            j = jn;
         }
-        __syncthreads();
-        LVL_T(128 + l);
     }
+    LVL_T(2);
 }
 
 // out[p] = sum over the off-diagonal KKT entries of row p:  constraints get (A x)_i, variables get (A' y)_j
@@ -471,10 +512,8 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         s.frow[p] = (uint32_t)q.lrow_ptr[p] | ((uint32_t)(q.lrow_ptr[p + 1] - q.lrow_ptr[p]) << 16);
         s.brow[p] = (uint32_t)q.lcol_ptr[p] | ((uint32_t)(q.lcol_ptr[p + 1] - q.lcol_ptr[p]) << 16);
     }
-    for (int l = tid; l < q.nlev; l += ADMM_THREADS) {
-        const uint32_t r0 = q.lvl_ptr[l], w = q.lvl_ptr[l + 1] - q.lvl_ptr[l];
-        s.lvd[l] = make_uint2(r0 | (w << 16), (uint32_t)(31 - __clz((int)q.lvl_gf[l])) | ((uint32_t)(31 - __clz((int)q.lvl_gb[l])) << 8));
-    }
+    for (int i = tid; i < q.n_step_f; i += ADMM_THREADS) s.stf[i] = make_uint2(q.step_f[2 * i], q.step_f[2 * i + 1]);
+    for (int i = tid; i < q.n_step_b; i += ADMM_THREADS) s.stb[i] = make_uint2(q.step_b[2 * i], q.step_b[2 * i + 1]);
     for (int i = tid; i < q.tail_dim; i += ADMM_THREADS) s.lrow_split[i] = q.lrow_split[q.tail_start + i];
     __syncthreads();
     long long t_phase = clock64();

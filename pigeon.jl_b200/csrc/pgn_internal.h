@@ -55,6 +55,8 @@ struct QpDev {
     const uint8_t *lvl_gf, *lvl_gb, *lvl_gfac;
     const uint16_t *lrow_split, *tl_src, *tl_dst;
     int tail_level, tail_start, tail_dim, tail_g1, n_tl;
+    const uint32_t *step_f, *step_b;
+    int n_step_f, n_step_b;
     const double* ctab;      // [CT_LEN]
     const double* wtab;      // [W_LEN] cost weights
     int n_hji;               // N_HJI

@@ -312,6 +312,31 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         }
         Q.lvl_gf[l] = lanes_for(mr, w); Q.lvl_gb[l] = lanes_for(mc, w);
     }
+    // step programs (256 threads per CTA): lanes per row so that every lane owns <= 4 entries
+    {
+        const int T = 256;
+        bool too_long = false;
+        auto emit = [&](std::vector<uint32_t>& out, int l, bool fwd) {
+            int r0 = Q.lvl_ptr[l], w = Q.lvl_ptr[l + 1] - r0, mx = 0;
+            for (int r = r0; r < r0 + w; r++)
+                mx = std::max(mx, fwd ? (int)(Q.lrow_ptr[r + 1] - Q.lrow_ptr[r]) : (int)(Q.lcol_ptr[r + 1] - Q.lcol_ptr[r]));
+            int sh = 0;
+            while (sh < 5 && ((mx + (1 << sh) - 1) >> sh) > 4) sh++;
+            if (((mx + (1 << sh) - 1) >> sh) > 4) too_long = true;
+            // prefer fewer entries per lane when the level still fits one pass
+            while (sh < 5 && ((mx + (1 << sh) - 1) >> sh) > 2 && (w << (sh + 1)) <= T) sh++;
+            int rows_per_pass = T >> sh;
+            for (int a = 0; a < w; a += rows_per_pass) {
+                int rows = std::min(rows_per_pass, w - a);
+                bool last = a + rows >= w;
+                out.push_back((uint32_t)(r0 + a) | ((uint32_t)rows << 16));
+                out.push_back((uint32_t)sh | ((uint32_t)last << 8));
+            }
+        };
+        for (int l = 1; l < Q.tail_level; l++) emit(Q.step_f, l, true);
+        for (int l = Q.tail_level - 1; l >= 0; l--) emit(Q.step_b, l, false);
+        if (too_long) return fail("a sparse-level row of L has more than 128 entries (unsupported by the solve step program)");
+    }
     // numeric factorisation program
     Q.ftgt_ptr.assign(nlev + 1, 0);
     Q.fac_ptr.push_back(0);

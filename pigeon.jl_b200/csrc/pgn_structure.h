@@ -65,6 +65,10 @@ struct QpTables {
     std::vector<uint16_t> fac_a, fac_b, fac_k;          // pair: L value indices (row i col k), (row j col k) and the column k
     // lanes cooperating on one row / column / factor target, per level (powers of two)
     std::vector<uint8_t> lvl_gf, lvl_gb, lvl_gfac;
+    // flattened step programs of the triangular solves over the sparse levels (forward: levels 1..tail_level-1, backward:
+    // tail_level-1..0).  One step = one pass of the CTA: rows [r0, r0+rows) handled by 2^sh lanes each, <= 4 entries per lane;
+    // x = r0 | rows << 16, y = sh | last_step_of_level << 8
+    std::vector<uint32_t> step_f, step_b;
     // dense tail: the last `tail_dim` positions (levels >= tail_level) form a (nearly dense) unit lower triangular block whose explicit
     // inverse is rebuilt after every numeric factorisation; it replaces tail_dim narrow levels by two dense mat-vec levels
     int tail_level, tail_start, tail_dim;
