@@ -41,9 +41,9 @@ struct AdmmArgs {
 
 struct Smem {
     double *Lval, *Dinv, *Aval, *xz, *sol, *dxy, *yq, *lo, *hi, *sc, *Tinv, *red;   // sol and dxy are adjacent: together they hold the dense tail copy
-    uint32_t *frow, *brow, *bent;   // per row: first entry | length << 16 (forward CSR / backward CSC); per CSC entry: value index | row << 16
+    uint32_t *seg, *bent;           // [4][Nk] per row segment descriptors (first entry | count << 16) in STEP_SEG_* order; per CSC entry: value index | row << 16
     uint2 *stf, *stb;               // step programs of the forward / backward sparse solves
-    uint16_t *lrow_col, *lrow_split;
+    uint16_t *lrow_col;
     uint8_t *flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
 };
 
@@ -51,8 +51,8 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 size_t admm_smem_bytes(const QpTables& t) {
     size_t d = (size_t)t.nnzL + t.Nk + t.nnzA + 7 * (size_t)t.Nk + (size_t)t.tail_dim * (t.tail_dim - 1) / 2 + 16 * NW + 8;
-    size_t u32 = 2 * (size_t)t.Nk + (size_t)t.nnzL + t.step_f.size() + t.step_b.size() + 8;
-    size_t u16 = (size_t)t.nnzL + t.tail_dim + 8;
+    size_t u32 = 4 * (size_t)t.Nk + (size_t)t.nnzL + t.step_f.size() + t.step_b.size() + 8;
+    size_t u16 = (size_t)t.nnzL + 8;
     return d * 8 + align_up(u32 * 4, 8) + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + 64;
 }
 
@@ -73,12 +73,10 @@ __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem&
     s.stf = reinterpret_cast<uint2*>(d);
     s.stb = s.stf + q.n_step_f;
     uint32_t* w = reinterpret_cast<uint32_t*>(s.stb + q.n_step_b);
-    s.frow = w; w += q.Nk;
-    s.brow = w; w += q.Nk;
+    s.seg = w; w += 4 * q.Nk;
     s.bent = w; w += q.nnzL;
     uint16_t* u = reinterpret_cast<uint16_t*>(w);
     s.lrow_col = u; u += q.nnzL;
-    s.lrow_split = u; u += q.tail_dim;
     size_t off = align_up((size_t)(reinterpret_cast<unsigned char*>(u) - base), 8);
     s.flag = base + off;
 }
@@ -180,6 +178,30 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) 
         }
         __syncthreads();
     }
+    // level ranges: replace the unit lower block L[range, range] by its explicit inverse, in place, level by level:
+    //   M_ij = -(S_ij + sum_{j<k<i} S_ik M_kj)     (targets of one level are computed into registers before any is written)
+    for (int l = 0; l < q.n_inv_levels; l++) {
+        const uint32_t t0 = __ldg(q.itgt_ptr + l), t1 = __ldg(q.itgt_ptr + l + 1);
+        double v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {           // <= 4 * ADMM_THREADS targets per level (checked on the host)
+            const uint32_t t = t0 + tid + k * ADMM_THREADS;
+            v[k] = 0.0;
+            if (t < t1) {
+                double acc = s.Lval[__ldg(q.itgt_id + t)];
+                const uint32_t x1 = __ldg(q.inv_ptr + t + 1);
+                for (uint32_t x = __ldg(q.inv_ptr + t); x < x1; x++) acc += s.Lval[__ldg(q.inv_a + x)] * s.Lval[__ldg(q.inv_b + x)];
+                v[k] = -acc;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t t = t0 + tid + k * ADMM_THREADS;
+            if (t < t1) s.Lval[__ldg(q.itgt_id + t)] = v[k];
+        }
+        __syncthreads();
+    }
     // dense tail: packed strictly-lower copy Ld of L[tail, tail] (aliasing sol|dxy, free now) and its explicit inverse Tinv,
     // one column per group of 4 lanes by forward substitution:  z_j = 1,  z_i = -(L_ij + sum_{j<k<i} L_ik z_k)
     const int Dm = q.tail_dim;
@@ -210,48 +232,6 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) 
 
 // sol <- K^-1 sol.  Level-scheduled forward substitution over the sparse levels (rows split over lane groups, shuffle-reduced), the
 // dense tail as two mat-vec levels with the explicit inverse, then the mirror image backwards.
-// One lane's share of one step: up to 4 (L value, iterate index) pairs of one row, fetched ahead of the barrier because they
-// do not depend on the iterate.
-enum { JOB_LIVE = 1, JOB_LEAD = 2, JOB_LAST = 4 };
-struct SolveJob {
-    double l[4];
-    double dinv;
-    int c[4];
-    int r, n, sh, flags;
-};
-template <bool FWD>
-__device__ __forceinline__ SolveJob fetch_job(const Smem& s, const uint2* steps, int st, int nsteps, int tid) {
-    SolveJob j;
-    j.flags = 0; j.n = 0; j.sh = 0; j.r = 0; j.dinv = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { j.l[k] = 0.0; j.c[k] = 0; }
-    if (st >= nsteps) return j;
-    const uint2 d = steps[st];
-    const int sh = d.y & 0xff;
-    j.sh = sh;
-    j.flags = (d.y & 0x100) ? JOB_LAST : 0;
-    const int row = tid >> sh, sub = tid & ((1 << sh) - 1);
-    if (row < (int)(d.x >> 16)) {
-        const int r = (d.x & 0xffff) + row;
-        const uint32_t rd = FWD ? s.frow[r] : s.brow[r];
-        const int base = rd & 0xffff, len = rd >> 16;
-        j.r = r;
-        j.flags |= JOB_LIVE | (sub == 0 ? JOB_LEAD : 0);
-        if (!FWD) j.dinv = s.Dinv[r];
-        int n = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int idx = sub + (k << sh);
-            if (idx < len) {
-                if (FWD) { j.c[k] = s.lrow_col[base + idx]; j.l[k] = s.Lval[base + idx]; }
-                else { const uint32_t b = s.bent[base + idx]; j.c[k] = b >> 16; j.l[k] = s.Lval[b & 0xffff]; }
-                n = k + 1;
-            }
-        }
-        j.n = n;
-    }
-    return j;
-}
 __device__ __forceinline__ double group_sum_sh(double v, int sh) {     // sh is warp-uniform
     if (sh > 4) v += __shfl_xor_sync(0xffffffffu, v, 16);
     if (sh > 3) v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -259,6 +239,54 @@ __device__ __forceinline__ double group_sum_sh(double v, int sh) {     // sh is 
     if (sh > 1) v += __shfl_xor_sync(0xffffffffu, v, 2);
     if (sh > 0) v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
+}
+
+// Executes a step program.  One step: rows [r0, r0+rows), 2^sh lanes per row, <= 4 entries per lane of one segment of the row:
+//     out[r] = in[r] (* 1/D_r) -/+ sum_e L_e * in[c_e]          in, out in {sol, tmp}
+__device__ __forceinline__ void run_steps(const Smem& s, const uint2* __restrict__ steps, int nsteps, int Nk) {
+    const int tid = threadIdx.x;
+    for (int st = 0; st < nsteps; st++) {
+        const uint2 d = steps[st];
+        const int sh = d.y & 0xff, fl = d.y >> 8;
+        const int row = tid >> sh, sub = tid & ((1 << sh) - 1);
+        const bool live = row < (int)(d.x >> 16);
+        const double* in = (fl & STEP_SRC_TMP) ? s.dxy : s.sol;
+        const int r = (d.x & 0xffff) + row;
+        double acc = 0.0, acc2 = 0.0;
+        if (live) {
+            const int sg = (fl & STEP_SEG_MASK) >> 1;
+            const uint32_t rd = s.seg[sg * Nk + r];
+            const int base = rd & 0xffff, len = rd >> 16;
+            if (sg < 2) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int idx = sub + (k << sh);
+                    if (idx < len) {
+                        const double t = s.Lval[base + idx] * in[s.lrow_col[base + idx]];
+                        if (k & 1) acc2 += t; else acc += t;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int idx = sub + (k << sh);
+                    if (idx < len) {
+                        const uint32_t b = s.bent[base + idx];
+                        const double t = s.Lval[b & 0xffff] * in[b >> 16];
+                        if (k & 1) acc2 += t; else acc += t;
+                    }
+                }
+            }
+        }
+        acc = group_sum_sh(acc + acc2, sh);
+        if (live && sub == 0) {
+            double x = in[r];
+            if (fl & STEP_SCALE) x *= s.Dinv[r];
+            double* out = (fl & STEP_DST_TMP) ? s.dxy : s.sol;
+            out[r] = (fl & STEP_ADD) ? x + acc : x - acc;
+        }
+        if (fl & STEP_LAST) __syncthreads();
+    }
 }
 
 #define LVL_T(idx)                                                                         \
@@ -269,56 +297,16 @@ __device__ __forceinline__ double group_sum_sh(double v, int sh) {     // sh is 
             t_lvl = now__;                                                                 \
         }                                                                                  \
     } while (0)
+// sol <- K^-1 sol:  forward over the level ranges (two steps each: external part, then the in-range explicit inverse), the dense
+// tail (its external part is the last forward step), the diagonal, and the mirror image backwards down to level 0.
 __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigned long long* lvl_cyc) {
     const int tid = threadIdx.x;
     long long t_lvl = clock64();
     const int ts = q.tail_start, Dm = q.tail_dim;
-    {   // forward over the sparse levels: software-pipelined step program
-        SolveJob j = fetch_job<true>(s, s.stf, 0, q.n_step_f, tid);
-        for (int st = 0; st < q.n_step_f; st++) {
-            const SolveJob jn = fetch_job<true>(s, s.stf, st + 1, q.n_step_f, tid);
-            double acc = 0.0;
-            if (j.flags & JOB_LIVE) {
-                double a1 = 0.0;
-                if (j.n > 0) acc = j.l[0] * s.sol[j.c[0]];
-                if (j.n > 1) a1 = j.l[1] * s.sol[j.c[1]];
-                if (j.n > 2) acc += j.l[2] * s.sol[j.c[2]];
-                if (j.n > 3) a1 += j.l[3] * s.sol[j.c[3]];
-                acc += a1;
-            }
-            acc = group_sum_sh(acc, j.sh);
-            if ((j.flags & (JOB_LIVE | JOB_LEAD)) == (JOB_LIVE | JOB_LEAD)) s.sol[j.r] -= acc;
-            if (j.flags & JOB_LAST) __syncthreads();
-            j = jn;
-        }
-    }
+    run_steps(s, s.stf, q.n_step_f, q.Nk);
     LVL_T(1);
     if (Dm > 0) {
-        // tail, stage 1: t = b_tail - L[tail, early] y_early  -> dxy[tail]
-        {
-            const int g = q.tail_g1, sh = 31 - __clz(g);
-            const int slots = ((Dm << sh) + 31) & ~31;
-            for (int i = tid; i < slots; i += ADMM_THREADS) {
-                const int rr = i >> sh, sub = i & (g - 1);
-                const bool live = rr < Dm;
-                double acc = 0.0, acc2 = 0.0;
-                if (live) {
-                    const int e1 = s.lrow_split[rr];
-                    int e = (s.frow[ts + rr] & 0xffff) + sub;
-                    for (; e + g < e1; e += 2 * g) {
-                        const int c0 = s.lrow_col[e], c1 = s.lrow_col[e + g];
-                        acc += s.Lval[e] * s.sol[c0];
-                        acc2 += s.Lval[e + g] * s.sol[c1];
-                    }
-                    if (e < e1) acc += s.Lval[e] * s.sol[s.lrow_col[e]];
-                }
-                acc = group_sum(acc + acc2, g);
-                if (live && sub == 0) s.dxy[ts + rr] = s.sol[ts + rr] - acc;
-            }
-        }
-        __syncthreads();
-        LVL_T(100);
-        // stage 2 + diagonal: w = Dinv .* (Tinv t)  -> sol[tail]
+        // tail stage 2 + diagonal: w = Dinv .* (Tinv t)   (t in tmp[tail]) -> sol[tail]
         {
             const int slots = ((Dm * 4) + 31) & ~31;
             for (int i = tid; i < slots; i += ADMM_THREADS) {
@@ -364,25 +352,7 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigne
         __syncthreads();
         LVL_T(102);
     }
-    {   // backward over the sparse levels (tail_level-1 .. 0)
-        SolveJob j = fetch_job<false>(s, s.stb, 0, q.n_step_b, tid);
-        for (int st = 0; st < q.n_step_b; st++) {
-            const SolveJob jn = fetch_job<false>(s, s.stb, st + 1, q.n_step_b, tid);
-            double acc = 0.0;
-            if (j.flags & JOB_LIVE) {
-                double a1 = 0.0;
-                if (j.n > 0) acc = j.l[0] * s.sol[j.c[0]];
-                if (j.n > 1) a1 = j.l[1] * s.sol[j.c[1]];
-                if (j.n > 2) acc += j.l[2] * s.sol[j.c[2]];
-                if (j.n > 3) a1 += j.l[3] * s.sol[j.c[3]];
-                acc += a1;
-            }
-            acc = group_sum_sh(acc, j.sh);
-            if ((j.flags & (JOB_LIVE | JOB_LEAD)) == (JOB_LIVE | JOB_LEAD)) s.sol[j.r] = s.sol[j.r] * j.dinv - acc;
-            if (j.flags & JOB_LAST) __syncthreads();
-            j = jn;
-        }
-    }
+    run_steps(s, s.stb, q.n_step_b, q.Nk);
     LVL_T(2);
 }
 
@@ -509,12 +479,10 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         s.bent[e] = (uint32_t)q.lcol_val[e] | ((uint32_t)q.lcol_row[e] << 16);
     }
     for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
-        s.frow[p] = (uint32_t)q.lrow_ptr[p] | ((uint32_t)(q.lrow_ptr[p + 1] - q.lrow_ptr[p]) << 16);
-        s.brow[p] = (uint32_t)q.lcol_ptr[p] | ((uint32_t)(q.lcol_ptr[p + 1] - q.lcol_ptr[p]) << 16);
+        s.seg[p] = q.fwd_ext[p]; s.seg[q.Nk + p] = q.fwd_in[p]; s.seg[2 * q.Nk + p] = q.bwd_in[p]; s.seg[3 * q.Nk + p] = q.bwd_ext[p];
     }
     for (int i = tid; i < q.n_step_f; i += ADMM_THREADS) s.stf[i] = make_uint2(q.step_f[2 * i], q.step_f[2 * i + 1]);
     for (int i = tid; i < q.n_step_b; i += ADMM_THREADS) s.stb[i] = make_uint2(q.step_b[2 * i], q.step_b[2 * i + 1]);
-    for (int i = tid; i < q.tail_dim; i += ADMM_THREADS) s.lrow_split[i] = q.lrow_split[q.tail_start + i];
     __syncthreads();
     long long t_phase = clock64();
     for (;;) {

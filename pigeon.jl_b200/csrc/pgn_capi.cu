@@ -225,17 +225,12 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     UP(a_src); UP(a_rowpos); UP(a_colpos); UP(a_lpos); UP(l_type); UP(u_type); UP(l_idx); UP(u_idx); UP(P_mode); UP(q_mode); UP(P_w); UP(q_w); UP(P_t); UP(q_t);
     UP(q_hji_t); UP(pos_var); UP(pos_con); UP(pos2idx); UP(is_con); UP(lrow_ptr); UP(lrow_col); UP(lcol_ptr); UP(lcol_row); UP(lcol_val); UP(lvl_ptr);
     UP(kadj_ptr); UP(kadj_e); UP(kadj_nb); UP(ftgt_ptr); UP(fac_ptr); UP(ftgt_id); UP(ftgt_col); UP(fac_a); UP(fac_b); UP(fac_k);
-    UP(lvl_gf); UP(lvl_gb); UP(lvl_gfac); UP(lrow_split); UP(tl_src); UP(tl_dst); UP(step_f); UP(step_b);
+    UP(lvl_gf); UP(lvl_gb); UP(lvl_gfac); UP(tl_src); UP(tl_dst); UP(step_f); UP(step_b);
+    UP(fwd_ext); UP(fwd_in); UP(bwd_in); UP(bwd_ext); UP(itgt_ptr); UP(inv_ptr); UP(itgt_id); UP(inv_a); UP(inv_b);
+    q.n_inv_levels = (int)t.itgt_ptr.size() - 1;
     q.n_step_f = (int)t.step_f.size() / 2; q.n_step_b = (int)t.step_b.size() / 2;
     q.tail_level = t.tail_level; q.tail_start = t.tail_start; q.tail_dim = t.tail_dim; q.n_tl = (int)t.tl_src.size();
-    {
-        int mx = 0;
-        for (int r = t.tail_start; r < t.Nk; r++) mx = std::max(mx, (int)t.lrow_split[r] - (int)t.lrow_ptr[r]);
-        int g = 1;
-        while (g < 32 && (mx + g - 1) / g > 6) g *= 2;
-        while (g > 1 && t.tail_dim * g > 512) g /= 2;
-        q.tail_g1 = g;
-    }
+    q.tail_g1 = 1;
 #undef UP
     double *ctab = nullptr, *wtab = nullptr;
     if ((rc = dev_alloc(h, &ctab, CT_LEN + 1))) return bail(rc);

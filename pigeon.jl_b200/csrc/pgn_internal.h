@@ -53,7 +53,10 @@ struct QpDev {
     const uint32_t *ftgt_ptr, *fac_ptr;
     const uint16_t *ftgt_id, *ftgt_col, *fac_a, *fac_b, *fac_k;
     const uint8_t *lvl_gf, *lvl_gb, *lvl_gfac;
-    const uint16_t *lrow_split, *tl_src, *tl_dst;
+    const uint16_t *tl_src, *tl_dst;
+    const uint32_t *fwd_ext, *fwd_in, *bwd_in, *bwd_ext, *itgt_ptr, *inv_ptr;
+    const uint16_t *itgt_id, *inv_a, *inv_b;
+    int n_inv_levels;
     int tail_level, tail_start, tail_dim, tail_g1, n_tl;
     const uint32_t *step_f, *step_b;
     int n_step_f, n_step_b;

@@ -222,13 +222,66 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     for (int j = 0; j < n; j++) { Q.pos_var[j] = (uint16_t)pos2[j]; Q.pos2idx[pos2[j]] = (uint16_t)j; }
     for (int i = 0; i < m; i++) { Q.pos_con[i] = (uint16_t)pos2[n + i]; Q.is_con[pos2[n + i]] = 1; Q.pos2idx[pos2[n + i]] = (uint16_t)i; }
 
+    // dense tail: trailing levels of width <= 4 (the top separators of the nested dissection), at most 64 positions and small enough
+    // for its packed dense copy to fit the 2*Nk-double scratch region of the kernel
+    {
+        int Lt = nlev;
+        while (Lt > 1) {
+            int w = Q.lvl_ptr[Lt] - Q.lvl_ptr[Lt - 1];
+            int D = Nk - Q.lvl_ptr[Lt - 1];
+            if (w > 4 || D > 64 || D * (D - 1) / 2 > 2 * Nk - 8) break;
+            Lt--;
+        }
+        if (nlev - Lt < 4) Lt = nlev;      // not worth it
+        Q.tail_level = Lt; Q.tail_start = Q.lvl_ptr[Lt]; Q.tail_dim = Nk - Q.tail_start;
+    }
+    std::vector<std::vector<int>> rows(Nk);
+    for (int k = 0; k < Nk; k++) for (int i : cs[k]) rows[i].push_back(k);   // ascending k by construction
+    // level ranges of the sparse part [1, tail_level): the unit lower block L[range, range] is replaced, after every numeric
+    // factorisation, by its explicit inverse (same pattern once padded with the transitive closure), so a whole range costs two
+    // parallel steps in the triangular solves instead of one step per level.  Ranges grow greedily while the closure adds
+    // little fill.
+    {
+        auto closure = [&](int la, int lb, std::vector<std::set<int>>& M, long& snz, long& cnz, int& maxin) {
+            const int pa = Q.lvl_ptr[la], pb = Q.lvl_ptr[lb];
+            M.assign(pb - pa, {});
+            snz = cnz = 0; maxin = 0;
+            for (int r = pa; r < pb; r++) {
+                for (int c : rows[r]) if (c >= pa) { snz++; M[r - pa].insert(c); for (int k : M[c - pa]) M[r - pa].insert(k); }
+                cnz += (long)M[r - pa].size();
+                maxin = std::max(maxin, (int)M[r - pa].size());
+            }
+        };
+        int la = 1;
+        Q.range_lvl.clear();
+        while (la < Q.tail_level) {
+            int lb = la + 1;
+            std::vector<std::set<int>> M, M2;
+            long snz, cnz; int mi;
+            closure(la, lb, M, snz, cnz, mi);
+            while (lb < Q.tail_level) {
+                long s2, c2; int mi2;
+                closure(la, lb + 1, M2, s2, c2, mi2);
+                if (c2 <= s2 + s2 / 4 + 32 && mi2 <= 96) { lb++; M.swap(M2); snz = s2; cnz = c2; mi = mi2; }
+                else break;
+            }
+            const int pa = Q.lvl_ptr[la];
+            for (size_t x = 0; x < M.size(); x++) {            // pad the pattern of L with the closure
+                std::set<int> merged(rows[pa + x].begin(), rows[pa + x].end());
+                merged.insert(M[x].begin(), M[x].end());
+                rows[pa + x].assign(merged.begin(), merged.end());
+            }
+            Q.range_lvl.push_back(la); Q.range_lvl.push_back(lb);
+            la = lb;
+        }
+        for (auto& c : cs) c.clear();
+        for (int i = 0; i < Nk; i++) for (int k : rows[i]) cs[k].push_back(i);       // ascending i
+    }
     // L by rows (CSR) and by columns (CSC)
     size_t nnzL = 0;
     for (auto& c : cs) nnzL += c.size();
     if (nnzL + Nk >= 65535) return fail("nnz(L) exceeds the 16-bit index range of the device tables");
     Q.nnzL = (int)nnzL;
-    std::vector<std::vector<int>> rows(Nk);
-    for (int k = 0; k < Nk; k++) for (int i : cs[k]) rows[i].push_back(k);   // ascending k by construction
     Q.lrow_ptr.assign(Nk + 1, 0);
     for (int i = 0; i < Nk; i++) Q.lrow_ptr[i + 1] = (uint16_t)(Q.lrow_ptr[i] + rows[i].size());
     Q.lrow_col.resize(nnzL);
@@ -273,70 +326,101 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         Q.kadj_e[Q.kadj_ptr[p] + x] = (uint16_t)kadj[p][x].first;
         Q.kadj_nb[Q.kadj_ptr[p] + x] = (uint16_t)kadj[p][x].second;
     }
-    // dense tail: trailing levels of width <= 4 (the top separators of the nested dissection), at most 64 positions and small enough
-    // for its packed dense copy to fit the 2*Nk-double scratch region of the kernel
-    {
-        int Lt = nlev;
-        while (Lt > 1) {
-            int w = Q.lvl_ptr[Lt] - Q.lvl_ptr[Lt - 1];
-            int D = Nk - Q.lvl_ptr[Lt - 1];
-            if (w > 4 || D > 64 || D * (D - 1) / 2 > 2 * Nk - 8) break;
-            Lt--;
-        }
-        if (nlev - Lt < 4) Lt = nlev;      // not worth it
-        Q.tail_level = Lt; Q.tail_start = Q.lvl_ptr[Lt]; Q.tail_dim = Nk - Q.tail_start;
-        Q.lrow_split.resize(Nk);
-        for (int i = 0; i < Nk; i++) {
-            int e = Q.lrow_ptr[i + 1];
-            if (i >= Q.tail_start) { e = Q.lrow_ptr[i]; while (e < Q.lrow_ptr[i + 1] && Q.lrow_col[e] < Q.tail_start) e++; }
-            Q.lrow_split[i] = (uint16_t)e;
-            for (int x = e; x < Q.lrow_ptr[i + 1]; x++) {
+    // dense tail tables: sparse entries of L[tail, tail] -> packed strictly-lower dense index
+    for (int i = Q.tail_start; i < Nk; i++)
+        for (int x = Q.lrow_ptr[i]; x < Q.lrow_ptr[i + 1]; x++)
+            if (Q.lrow_col[x] >= Q.tail_start) {
                 int ii = i - Q.tail_start, jj = Q.lrow_col[x] - Q.tail_start;
                 Q.tl_src.push_back((uint16_t)x); Q.tl_dst.push_back((uint16_t)(ii * (ii - 1) / 2 + jj));
             }
+    // row descriptors (first entry | count << 16) of the four segments used by the range steps:
+    //   forward : CSR row r  = [entries left of the range (external) | entries inside the range]
+    //   backward: CSC column r = [entries inside the range | entries below the range (external)]
+    std::vector<int> range_of(Nk, -1), range_pa, range_pb;
+    {
+        const int nr = (int)Q.range_lvl.size() / 2;
+        for (int k = 0; k < nr; k++) {
+            range_pa.push_back(Q.lvl_ptr[Q.range_lvl[2 * k]]); range_pb.push_back(Q.lvl_ptr[Q.range_lvl[2 * k + 1]]);
+            for (int p = range_pa[k]; p < range_pb[k]; p++) range_of[p] = k;
+        }
+        // level 0 and the tail behave as ranges whose in-range part is handled elsewhere (none / dense)
+        Q.fwd_ext.assign(Nk, 0); Q.fwd_in.assign(Nk, 0); Q.bwd_in.assign(Nk, 0); Q.bwd_ext.assign(Nk, 0);
+        for (int r = 0; r < Nk; r++) {
+            int pa, pb;
+            if (range_of[r] >= 0) { pa = range_pa[range_of[r]]; pb = range_pb[range_of[r]]; }
+            else if (r >= Q.tail_start) { pa = Q.tail_start; pb = Nk; }
+            else { pa = 0; pb = Q.lvl_ptr[1]; }
+            int e0 = Q.lrow_ptr[r], e1 = Q.lrow_ptr[r + 1], sp = e0;
+            while (sp < e1 && Q.lrow_col[sp] < pa) sp++;
+            Q.fwd_ext[r] = (uint32_t)e0 | ((uint32_t)(sp - e0) << 16);
+            Q.fwd_in[r] = (uint32_t)sp | ((uint32_t)(e1 - sp) << 16);
+            int c0 = Q.lcol_ptr[r], c1 = Q.lcol_ptr[r + 1], cp = c0;
+            while (cp < c1 && Q.lcol_row[cp] < pb) cp++;
+            Q.bwd_in[r] = (uint32_t)c0 | ((uint32_t)(cp - c0) << 16);
+            Q.bwd_ext[r] = (uint32_t)cp | ((uint32_t)(c1 - cp) << 16);
+            if ((sp - e0) > 255 || (e1 - sp) > 255 || (cp - c0) > 255 || (c1 - cp) > 255) return fail("row segment longer than 255 entries");
         }
     }
-    // lanes per row: enough to bring the per-lane chain down to ~3 entries, without exceeding ~2 passes of the CTA
-    auto lanes_for = [](int maxlen, int width) {
-        int g = 1;
-        while (g < 32 && (maxlen + g - 1) / g > 3) g *= 2;
-        while (g > 1 && width * g > 512) g /= 2;
-        return (uint8_t)g;
-    };
-    Q.lvl_gf.assign(nlev, 1); Q.lvl_gb.assign(nlev, 1); Q.lvl_gfac.assign(nlev, 1);
-    for (int l = 0; l < nlev; l++) {
-        int w = Q.lvl_ptr[l + 1] - Q.lvl_ptr[l], mr = 0, mc = 0;
-        for (int r = Q.lvl_ptr[l]; r < Q.lvl_ptr[l + 1]; r++) {
-            mr = std::max(mr, (int)(Q.lrow_ptr[r + 1] - Q.lrow_ptr[r]));
-            mc = std::max(mc, (int)(Q.lcol_ptr[r + 1] - Q.lcol_ptr[r]));
-        }
-        Q.lvl_gf[l] = lanes_for(mr, w); Q.lvl_gb[l] = lanes_for(mc, w);
-    }
-    // step programs (256 threads per CTA): lanes per row so that every lane owns <= 4 entries
+    // step programs of the sparse part (256 lanes): a step = rows [r0, r0+rows) x 2^sh lanes, <= 4 entries per lane;
+    // word 0 = r0 | rows << 16, word 1 = sh | flags << 8
     {
         const int T = 256;
         bool too_long = false;
-        auto emit = [&](std::vector<uint32_t>& out, int l, bool fwd) {
-            int r0 = Q.lvl_ptr[l], w = Q.lvl_ptr[l + 1] - r0, mx = 0;
-            for (int r = r0; r < r0 + w; r++)
-                mx = std::max(mx, fwd ? (int)(Q.lrow_ptr[r + 1] - Q.lrow_ptr[r]) : (int)(Q.lcol_ptr[r + 1] - Q.lcol_ptr[r]));
+        auto emit = [&](std::vector<uint32_t>& out, int pa, int pb, const std::vector<uint32_t>& desc, uint32_t flags) {
+            int w = pb - pa, mx = 0;
+            for (int r = pa; r < pb; r++) mx = std::max(mx, (int)(desc[r] >> 16));
             int sh = 0;
             while (sh < 5 && ((mx + (1 << sh) - 1) >> sh) > 4) sh++;
             if (((mx + (1 << sh) - 1) >> sh) > 4) too_long = true;
-            // prefer fewer entries per lane when the level still fits one pass
             while (sh < 5 && ((mx + (1 << sh) - 1) >> sh) > 2 && (w << (sh + 1)) <= T) sh++;
             int rows_per_pass = T >> sh;
             for (int a = 0; a < w; a += rows_per_pass) {
-                int rows = std::min(rows_per_pass, w - a);
-                bool last = a + rows >= w;
-                out.push_back((uint32_t)(r0 + a) | ((uint32_t)rows << 16));
-                out.push_back((uint32_t)sh | ((uint32_t)last << 8));
+                int nrows = std::min(rows_per_pass, w - a);
+                bool last = a + nrows >= w;
+                out.push_back((uint32_t)(pa + a) | ((uint32_t)nrows << 16));
+                out.push_back((uint32_t)sh | ((flags | (last ? (uint32_t)STEP_LAST : 0u)) << 8));
             }
         };
-        for (int l = 1; l < Q.tail_level; l++) emit(Q.step_f, l, true);
-        for (int l = Q.tail_level - 1; l >= 0; l--) emit(Q.step_b, l, false);
-        if (too_long) return fail("a sparse-level row of L has more than 128 entries (unsupported by the solve step program)");
+        const int nr = (int)range_pa.size();
+        for (int k = 0; k < nr; k++) {
+            emit(Q.step_f, range_pa[k], range_pb[k], Q.fwd_ext, STEP_SEG_FWD_EXT | STEP_DST_TMP);                       // t = b - L_ext y      (sol -> tmp)
+            emit(Q.step_f, range_pa[k], range_pb[k], Q.fwd_in, STEP_SEG_FWD_IN | STEP_SRC_TMP | STEP_ADD);              // y = t + Minv t       (tmp -> sol)
+        }
+        if (Q.tail_dim > 0) emit(Q.step_f, Q.tail_start, Nk, Q.fwd_ext, STEP_SEG_FWD_EXT | STEP_DST_TMP);               // tail stage 1          (sol -> tmp)
+        for (int k = nr - 1; k >= 0; k--) {
+            emit(Q.step_b, range_pa[k], range_pb[k], Q.bwd_ext, STEP_SEG_BWD_EXT | STEP_DST_TMP | STEP_SCALE);          // u = w/D - L_ext' x    (sol -> tmp)
+            emit(Q.step_b, range_pa[k], range_pb[k], Q.bwd_in, STEP_SEG_BWD_IN | STEP_SRC_TMP | STEP_ADD);              // x = u + Minv' u       (tmp -> sol)
+        }
+        emit(Q.step_b, 0, Q.lvl_ptr[1], Q.bwd_ext, STEP_SEG_BWD_EXT | STEP_SCALE);                                       // level 0: x = w/D - L' x  (sol -> sol)
+        if (too_long) return fail("a row segment of L has more than 128 entries (unsupported by the solve step program)");
     }
+    // inverse program: for every range, level by level, each in-range entry (i,j) becomes  M_ij = -(S_ij + sum_{j<k<i} S_ik M_kj)
+    {
+        Q.inv_ptr.push_back(0);
+        Q.itgt_ptr.push_back(0);
+        const int nr = (int)range_pa.size();
+        for (int k = 0; k < nr; k++) {
+            const int pa = range_pa[k];
+            for (int l = Q.range_lvl[2 * k] + 1; l < Q.range_lvl[2 * k + 1]; l++) {      // the first level of a range has no in-range entries
+                for (int i = Q.lvl_ptr[l]; i < Q.lvl_ptr[l + 1]; i++) {
+                    const int e0 = (int)(Q.fwd_in[i] & 0xffff), cnt = (int)(Q.fwd_in[i] >> 16);
+                    for (int x = e0; x < e0 + cnt; x++) {
+                        const int j = Q.lrow_col[x];
+                        Q.itgt_id.push_back((uint16_t)x);
+                        for (int y = x + 1; y < e0 + cnt; y++) {           // k = column of entry y, j < k < i
+                            const int kk = Q.lrow_col[y];
+                            const int mkj = lidx(kk, j);
+                            if (mkj >= 0 && j >= pa) { Q.inv_a.push_back((uint16_t)y); Q.inv_b.push_back((uint16_t)mkj); }
+                        }
+                        Q.inv_ptr.push_back((uint32_t)Q.inv_a.size());
+                    }
+                }
+                if (Q.itgt_id.size() - Q.itgt_ptr.back() > 1024) return fail("range inverse: more than 1024 targets in one level");
+                Q.itgt_ptr.push_back((uint32_t)Q.itgt_id.size());
+            }
+        }
+    }
+    Q.lvl_gf.assign(nlev, 1); Q.lvl_gb.assign(nlev, 1); Q.lvl_gfac.assign(nlev, 1);
     // numeric factorisation program
     Q.ftgt_ptr.assign(nlev + 1, 0);
     Q.fac_ptr.push_back(0);

@@ -34,6 +34,9 @@ enum { CT_ZERO = 0, CT_PINF, CT_NINF, CT_VMIN, CT_VMAX, CT_FXMIN_N, CT_DDELTA_N,
 enum { BND_CONST = 0, BND_REC = 1, BND_NEG_REC = 2, BND_DT_SCALED = 3, BND_NEG_DT_SCALED = 4 };
 // modes of the cost tables
 enum { PQ_ZERO = 0, PQ_TIMES_DT = 1, PQ_OVER_DT = 2, PQ_CONST = 3 };
+// step flags (word 1 >> 8)
+enum { STEP_LAST = 1, STEP_SEG_FWD_EXT = 0 << 1, STEP_SEG_FWD_IN = 1 << 1, STEP_SEG_BWD_IN = 2 << 1, STEP_SEG_BWD_EXT = 3 << 1, STEP_SEG_MASK = 3 << 1,
+       STEP_SRC_TMP = 1 << 3, STEP_DST_TMP = 1 << 4, STEP_ADD = 1 << 5, STEP_SCALE = 1 << 6 };
 // weight ids (resolved against the control parameters at run time so that pgn_set_control_params needs no re-analysis)
 enum { W_NONE = 0, W_Q_DS, W_Q_DPSI, W_Q_E, W_R_DELTA, W_R_FX, W_R_DDELTA, W_R_DFX, W_W_BETA, W_W_R, W_W_HJI, W_LEN };
 
@@ -65,14 +68,19 @@ struct QpTables {
     std::vector<uint16_t> fac_a, fac_b, fac_k;          // pair: L value indices (row i col k), (row j col k) and the column k
     // lanes cooperating on one row / column / factor target, per level (powers of two)
     std::vector<uint8_t> lvl_gf, lvl_gb, lvl_gfac;
-    // flattened step programs of the triangular solves over the sparse levels (forward: levels 1..tail_level-1, backward:
-    // tail_level-1..0).  One step = one pass of the CTA: rows [r0, r0+rows) handled by 2^sh lanes each, <= 4 entries per lane;
-    // x = r0 | rows << 16, y = sh | last_step_of_level << 8
+    // level ranges [la, lb) of the sparse part whose in-range block of L is replaced by its explicit inverse after factorisation
+    std::vector<int> range_lvl;
+    // per-row segment descriptors (first entry | count << 16): forward CSR row = [external | in-range], backward CSC column = [in-range | external]
+    std::vector<uint32_t> fwd_ext, fwd_in, bwd_in, bwd_ext;
+    // flattened step programs of the triangular solves.  One step = one pass of the CTA: rows [r0, r0+rows) handled by 2^sh lanes
+    // each, <= 4 entries per lane; word 0 = r0 | rows << 16, word 1 = sh | STEP_* flags << 8
     std::vector<uint32_t> step_f, step_b;
+    // in-place inversion program of the range blocks: targets (L value indices) per in-range level, pairs (S_ik, M_kj) per target
+    std::vector<uint32_t> itgt_ptr, inv_ptr;
+    std::vector<uint16_t> itgt_id, inv_a, inv_b;
     // dense tail: the last `tail_dim` positions (levels >= tail_level) form a (nearly dense) unit lower triangular block whose explicit
     // inverse is rebuilt after every numeric factorisation; it replaces tail_dim narrow levels by two dense mat-vec levels
     int tail_level, tail_start, tail_dim;
-    std::vector<uint16_t> lrow_split;                   // per row: first entry whose column lies in the tail (== row end outside the tail)
     std::vector<uint16_t> tl_src, tl_dst;               // sparse L entry -> packed strictly-lower dense index i*(i-1)/2 + j
     // where the solution components consumed by the host-side API live
     int var_u1_delta, var_u1_fx;                        // variable indices of u[:,2] (node 2)
