@@ -18,9 +18,6 @@
 
 namespace pgn {
 
-#ifndef ADMM_THREADS
-#define ADMM_THREADS 256
-#endif
 #define NW (ADMM_THREADS / 32)
 
 static const double OSQP_INFTY = 1e20;

@@ -364,7 +364,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     // step programs of the sparse part (256 lanes): a step = rows [r0, r0+rows) x 2^sh lanes, <= 4 entries per lane;
     // word 0 = r0 | rows << 16, word 1 = sh | flags << 8
     {
-        const int T = 256;
+        const int T = ADMM_THREADS;
         bool too_long = false;
         auto emit = [&](std::vector<uint32_t>& out, int pa, int pb, const std::vector<uint32_t>& desc, uint32_t flags) {
             int w = pb - pa, mx = 0;
@@ -415,7 +415,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
                         Q.inv_ptr.push_back((uint32_t)Q.inv_a.size());
                     }
                 }
-                if (Q.itgt_id.size() - Q.itgt_ptr.back() > 1024) return fail("range inverse: more than 1024 targets in one level");
+                if (Q.itgt_id.size() - Q.itgt_ptr.back() > 4 * ADMM_THREADS) return fail("range inverse: too many targets in one level");
                 Q.itgt_ptr.push_back((uint32_t)Q.itgt_id.size());
             }
         }

@@ -15,6 +15,11 @@
 #define PGN_HOSTDEV
 #endif
 
+// threads per ADMM CTA: the step programs of the triangular solves are laid out for exactly this many lanes
+#ifndef ADMM_THREADS
+#define ADMM_THREADS 256
+#endif
+
 namespace pgn {
 
 // layout of the per-vehicle "QP piece record" written by the linearisation / HJI kernels and gathered by the ADMM kernel
