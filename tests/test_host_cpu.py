@@ -63,7 +63,7 @@ def test_static_qp_tables_factor_and_solve(args, tmp_path):
                            os.path.join(ROOT, "pigeon.jl_b200", "csrc", "pgn_structure.cpp")])
     r = subprocess.run([exe] + args.split(), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    kv = dict(x.split("=") for x in r.stdout.split())
+    kv = dict(x.split("=") for x in r.stdout.splitlines()[0].split())
     kind, Ns, Nl = (int(a) for a in args.split()[:3])
     m = o.Mpc(kind, N_short=Ns, N_long=Nl)
     assert (int(kv["n"]), int(kv["m"]), int(kv["nnzA"])) == (m.n, m.m, m.nnzA)      # same canonical QP as the oracle
@@ -73,8 +73,8 @@ def test_nested_dissection_cuts_solve_depth(tmp_path):
     exe = str(tmp_path / "structure_check")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "structure_check.cpp"),
                            os.path.join(ROOT, "pigeon.jl_b200", "csrc", "pgn_structure.cpp")])
-    nd = dict(x.split("=") for x in subprocess.run([exe, "0", "10", "20", "0"], capture_output=True, text=True).stdout.split())
-    md = dict(x.split("=") for x in subprocess.run([exe, "0", "10", "20", "1"], capture_output=True, text=True).stdout.split())
+    nd = dict(x.split("=") for x in subprocess.run([exe, "0", "10", "20", "0"], capture_output=True, text=True).stdout.splitlines()[0].split())
+    md = dict(x.split("=") for x in subprocess.run([exe, "0", "10", "20", "1"], capture_output=True, text=True).stdout.splitlines()[0].split())
     assert int(nd["nlev"]) * 3 < int(md["nlev"])
     assert int(nd["nnzL"]) < 1.6 * int(md["nnzL"])
 
