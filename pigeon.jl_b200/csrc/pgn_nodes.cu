@@ -313,7 +313,7 @@ __global__ void k_transpose_out(int B, int k, const double* __restrict__ soa, do
 // t[i] = base[i] + k * dt  (the reference iterates a range `0:dt:T`, i.e. t_k = k*dt, not an accumulated sum)
 __global__ void k_time_axpy(int n, const double* __restrict__ base, double k, double dt, double* __restrict__ v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = base[i] + k * dt;
+    if (i < n) v[i] = __dadd_rn(base[i], __dmul_rn(k, dt));   // no FMA contraction: bitwise the host's t0 + k*dt
 }
 
 // ---- launchers -------------------------------------------------------------------------------------------------------
