@@ -17,7 +17,7 @@
 
 // threads per ADMM CTA: the step programs of the triangular solves are laid out for exactly this many lanes
 #ifndef ADMM_THREADS
-#define ADMM_THREADS 256
+#define ADMM_THREADS 1024
 #endif
 
 namespace pgn {
