@@ -119,7 +119,7 @@ PGN_API int pgn_simulate(pgn_handle* h, const double* t0 /*[B]*/, double dt, int
 PGN_API int pgn_rollout(pgn_handle* h, double dt);
 
 /* --- outputs / introspection (used by the parity tests) ----------------------------------------------------------- */
-PGN_API int pgn_qp_dims(pgn_handle* h, int32_t* out /*[8] = N, nx, nu, n, m, nnz(A), nnz(L), n_levels*/);
+PGN_API int pgn_qp_dims(pgn_handle* h, int32_t* out /*[16] = N, nx, nu, n, m, nnz(A), nnz(L), n_levels, L slots, solve phases, factor entries, inverse entries, tail dim, backward entries, ADMM smem bytes, ADMM threads*/);
 PGN_API int pgn_get_state(pgn_handle* h, double* q /*[B][6]*/, double* u /*[B][3]*/);
 PGN_API int pgn_get_time_steps(pgn_handle* h, double* ts /*[B][N]*/, double* dt /*[B][N-1]*/, double* prev_ts /*[B][N]*/);
 PGN_API int pgn_get_nodes(pgn_handle* h, double* qs /*[B][N][nx]*/, double* us /*[B][N][2]*/, double* ps /*[B][N][4]*/);
@@ -143,7 +143,7 @@ PGN_API int pgn_set_profiling(pgn_handle* h, int32_t on);
 PGN_API int pgn_get_stage_ms(pgn_handle* h, double* out /*[8]*/, int32_t reset);
 /* SM cycles spent by the ADMM CTAs per phase while profiling is on (summed over CTAs):
  * [0] gather, [1] Ruiz scaling, [2] LDL' factorisation, [3] triangular solves, [4] x/z/y update, [5] residuals/termination/rho, [6] store, [7] ticket */
-PGN_API int pgn_get_admm_cycles(pgn_handle* h, double* out /*[512]: [0..7] phases, [16+l] forward level l, [116..118] dense tail, [144+l] backward level l (CTA 0 only)*/, int32_t reset);
+PGN_API int pgn_get_admm_cycles(pgn_handle* h, double* out /*[512]: [0..7] phases (all CTAs); CTA 0 only: [16+p] solve phase p, [116..117] dense tail, [126..128] factor init / range inverses / tail, [136+l] factor level l*/, int32_t reset);
 
 #ifdef __cplusplus
 }

@@ -120,7 +120,7 @@ function BatchedTrajectoryTrackingMPC(kind::Int32, vehicle::Dict{Symbol,Float64}
     cfg.use_correction_step = use_correction_step ? 1 : 0; cfg.device = device
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:pgn_create, libpigeon), Cint, (Ref{PgnConfig}, Ref{Ptr{Cvoid}}), cfg, h))
-    d = zeros(Int32, 8)
+    d = zeros(Int32, 16)
     check(ccall((:pgn_qp_dims, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Int32}), h[], d))
     mpc = BatchedTrajectoryTrackingMPC(h[], kind, B, d[1], d[2], d[3], d[4], d[5], vehicle, control_params, trajectories, nothing)
     finalizer(m -> (m.handle != C_NULL && ccall((:pgn_destroy, libpigeon), Cint, (Ptr{Cvoid},), m.handle); m.handle = C_NULL), mpc)

@@ -19,6 +19,7 @@
 namespace pgn {
 
 #define NW (ADMM_THREADS / 32)
+#define ADMM_NCYC 256
 
 static const double OSQP_INFTY = 1e20;
 
@@ -33,78 +34,101 @@ struct AdmmArgs {
     double *pri_res, *dua_res;
     uint8_t* solved;
     int* counter;
+    const int32_t* order;          // ticket -> vehicle (longest previous solve first)
     unsigned long long* cycles;   // optional per-phase cycle counters (profiling builds of the host call): gather, ruiz, factor, solve, update, check, store
 };
 
 struct Smem {
     double *Lval, *Dinv, *Aval, *xz, *sol, *dxy, *yq, *lo, *hi, *sc, *Tinv, *red;   // sol and dxy are adjacent: together they hold the dense tail copy
-    uint32_t *seg, *bent;           // [4][Nk] per row segment descriptors (first entry | count << 16) in STEP_SEG_* order; per CSC entry: value index | row << 16
-    uint2 *stf, *stb;               // step programs of the forward / backward sparse solves
-    uint16_t *lrow_col;
-    uint8_t *flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
+    const uint2 *sol_task, *fac_task, *inv_task;      // packed warp-task descriptors
+    const uint32_t *bent, *fac_lvl, *inv_lvl;
+    const uint16_t *fidx, *orow, *ph_ptr;
+    uint8_t* flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
+    // aliases inside the Lval region, valid between the gather and the first factorisation of a QP (Ruiz equilibration)
+    uint16_t *kptr, *ke;
+    uint32_t* arc;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline int vec_len(int Nk) { return (Nk + 2) & ~1; }                 // Nk values + the always-zero element Nk
+__host__ __device__ inline size_t lval_region_doubles(int nslots, int Nk, int nnzA) {
+    const size_t alias = align_up((size_t)(Nk + 1) * 2 + (size_t)nnzA * 4, 4) + (size_t)nnzA * 4;      // kptr, ke (u16) + arc (u32)
+    const size_t a = (alias + 7) / 8;
+    return a > (size_t)nslots ? a : (size_t)nslots;
+}
 
 size_t admm_smem_bytes(const QpTables& t) {
-    size_t d = (size_t)t.nnzL + t.Nk + t.nnzA + 7 * (size_t)t.Nk + (size_t)t.tail_dim * (t.tail_dim - 1) / 2 + 16 * NW + 8;
-    size_t u32 = 4 * (size_t)t.Nk + (size_t)t.nnzL + t.step_f.size() + t.step_b.size() + 8;
-    size_t u16 = (size_t)t.nnzL + 8;
-    return d * 8 + align_up(u32 * 4, 8) + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + 64;
+    const size_t V = vec_len(t.Nk);
+    size_t d = lval_region_doubles(t.nslots, t.Nk, t.nnzA) + V + align_up(t.nnzA, 2) + 7 * V + (size_t)t.tail_dim * (t.tail_dim - 1) / 2 + 16 * NW + 8;
+    size_t u64 = (t.sol_task.size() + t.fac_task.size() + t.inv_task.size()) / 4;
+    size_t u32 = t.bent.size() + t.fac_lvl_ptr.size() + t.inv_lvl_ptr.size() + 4;
+    size_t u16 = (size_t)t.nslots + t.sol_orow.size() + t.sol_ph_ptr.size() + 8;
+    return d * 8 + u64 * 8 + align_up(u32 * 4, 8) + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + 64;
 }
 
-__device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem& s) {
+__device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem& s, uint2*& w_task, uint32_t*& w_u32, uint16_t*& w_u16) {
+    const int V = vec_len(q.Nk);
     double* d = reinterpret_cast<double*>(base);
-    s.Lval = d; d += q.nnzL;
-    s.Dinv = d; d += q.Nk;
-    s.Aval = d; d += q.nnzA;
-    s.xz = d; d += q.Nk;
-    s.sol = d; d += q.Nk;
-    s.dxy = d; d += q.Nk;
-    s.yq = d; d += q.Nk;
-    s.lo = d; d += q.Nk;
-    s.hi = d; d += q.Nk;
-    s.sc = d; d += q.Nk;
+    s.Lval = d; d += lval_region_doubles(q.nslots, q.Nk, q.nnzA);
+    s.Dinv = d; d += V;
+    s.Aval = d; d += (q.nnzA + 1) & ~1;
+    s.xz = d; d += V;
+    s.sol = d; d += V;
+    s.dxy = d; d += V;
+    s.yq = d; d += V;
+    s.lo = d; d += V;
+    s.hi = d; d += V;
+    s.sc = d; d += V;
     s.Tinv = d; d += q.tail_dim * (q.tail_dim - 1) / 2;
     s.red = d; d += 16 * NW + 8;
-    s.stf = reinterpret_cast<uint2*>(d);
-    s.stb = s.stf + q.n_step_f;
-    uint32_t* w = reinterpret_cast<uint32_t*>(s.stb + q.n_step_b);
-    s.seg = w; w += 4 * q.Nk;
-    s.bent = w; w += q.nnzL;
-    uint16_t* u = reinterpret_cast<uint16_t*>(w);
-    s.lrow_col = u; u += q.nnzL;
-    size_t off = align_up((size_t)(reinterpret_cast<unsigned char*>(u) - base), 8);
+    w_task = reinterpret_cast<uint2*>(d);
+    s.sol_task = w_task; s.fac_task = s.sol_task + q.n_sol_task; s.inv_task = s.fac_task + q.n_fac_task;
+    w_u32 = reinterpret_cast<uint32_t*>(w_task + q.n_sol_task + q.n_fac_task + q.n_inv_task);
+    s.bent = w_u32; s.fac_lvl = s.bent + q.n_bent; s.inv_lvl = s.fac_lvl + q.nlev + 1;
+    size_t off = align_up((size_t)(reinterpret_cast<const unsigned char*>(s.inv_lvl + q.n_inv_levels + 1) - base), 8);
+    w_u16 = reinterpret_cast<uint16_t*>(base + off);
+    s.fidx = w_u16; s.orow = s.fidx + q.nslots; s.ph_ptr = s.orow + q.n_orow;
+    off = align_up((size_t)(reinterpret_cast<const unsigned char*>(s.ph_ptr + q.n_fwd_ph + q.n_bwd_ph + 1) - base), 8);
     s.flag = base + off;
+    s.kptr = reinterpret_cast<uint16_t*>(s.Lval);
+    s.ke = s.kptr + q.Nk + 1;
+    s.arc = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(s.Lval) + align_up((size_t)(q.Nk + 1) * 2 + (size_t)q.nnzA * 4, 4));
 }
 
+// warp-level butterfly over all 32 lanes
+template <bool IS_MAX>
+__device__ __forceinline__ double warp_all(double a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double b = __shfl_xor_sync(0xffffffffu, a, o);
+        a = IS_MAX ? fmax(a, b) : a + b;
+    }
+    return a;
+}
 // block-wide max / sum of NV values per thread; every thread returns with the results in v[]
 template <int NV, bool IS_MAX>
 __device__ __forceinline__ void block_reduce(double* v, double* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-        double a = v[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double b = __shfl_xor_sync(0xffffffffu, a, o);
-            a = IS_MAX ? fmax(a, b) : a + b;
-        }
-        v[k] = a;
-    }
+    for (int k = 0; k < NV; k++) v[k] = warp_all<IS_MAX>(v[k]);
     __syncthreads();   // red[] free
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < NV; k++) red[w * NV + k] = v[k];
+        for (int k = 0; k < NV; k++) red[k * NW + w] = v[k];
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-        double a = red[k];
-#pragma unroll
-        for (int ww = 1; ww < NW; ww++) a = IS_MAX ? fmax(a, red[ww * NV + k]) : a + red[ww * NV + k];
-        v[k] = a;
-    }
+    for (int k = 0; k < NV; k++) v[k] = warp_all<IS_MAX>(lane < NW ? red[k * NW + lane] : (IS_MAX ? -1e300 : 0.0));
+}
+// block-wide (sum, max) pair in one pass
+__device__ __forceinline__ void block_reduce_sum_max(double& sum, double& mx, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    sum = warp_all<false>(sum); mx = warp_all<true>(mx);
+    __syncthreads();
+    if (lane == 0) { red[w] = sum; red[NW + w] = mx; }
+    __syncthreads();
+    sum = warp_all<false>(lane < NW ? red[lane] : 0.0);
+    mx = warp_all<true>(lane < NW ? red[NW + lane] : -1e300);
 }
 
 __device__ __forceinline__ double limit_scaling(double a) {
@@ -129,85 +153,114 @@ __device__ __forceinline__ double group_sum(double v, int g) {
     }
     return v;
 }
+__device__ __forceinline__ double group_sum_sh(double v, int sh) {     // sh is warp-uniform
+    if (sh > 4) v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (sh > 3) v += __shfl_xor_sync(0xffffffffu, v, 8);
+    if (sh > 2) v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (sh > 1) v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (sh > 0) v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
 
-// numeric LDL' of K = [P + sigma I, A'; A, -1/rho] (position space) with the static gather program.  Each target (an entry of L or a
-// pivot) is reduced by g = lvl_gfac[level] adjacent lanes that read consecutive (coalesced) pairs of the program.
-__device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) {
-    const int tid = threadIdx.x;
+// One warp task of a gather program (factorisation / range inverse): returns, in the lanes with sub == 0, the sum over the row's
+// entries of W[a] * W[b] / d_k.  Entries stream from global memory (static, coalesced: slot k of lane l is at ebase + 32 k + l); loads are
+// issued in batches of four so that their latencies overlap.
+#define GATHER_TERM(e) (s.Lval[(e) & 0xffff] * s.Lval[((e) >> 16) & 0xffff] * s.Dinv[(e) >> 32])
+__device__ __forceinline__ double gather_task(const Smem& s, const uint2 d, const unsigned long long* __restrict__ ents, int lane) {
+    const int K = d.y & 0xff, sh = (d.y >> 16) & 0xff;
+    const unsigned long long* e = ents + ((size_t)(d.x & 0xffff) << 5) + lane;
+    double acc0 = 0.0, acc1 = 0.0;
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+        const unsigned long long e0 = __ldg(e + k * 32), e1 = __ldg(e + k * 32 + 32), e2 = __ldg(e + k * 32 + 64), e3 = __ldg(e + k * 32 + 96);
+        const double t0 = GATHER_TERM(e0), t1 = GATHER_TERM(e1), t2 = GATHER_TERM(e2), t3 = GATHER_TERM(e3);
+        acc0 += t0; acc1 += t1; acc0 += t2; acc1 += t3;
+    }
+    const int r = K - k;
+    if (r > 0) {
+        const unsigned long long e0 = __ldg(e + k * 32), e1 = __ldg(e + (r > 1 ? k + 1 : k) * 32), e2 = __ldg(e + (r > 2 ? k + 2 : k) * 32);
+        const double t0 = GATHER_TERM(e0), t1 = GATHER_TERM(e1), t2 = GATHER_TERM(e2);
+        acc0 += t0;
+        if (r > 1) acc1 += t1;
+        if (r > 2) acc0 += t2;
+    }
+    return group_sum_sh(acc0 + acc1, sh);
+}
+
+// numeric LDL' of K = [P + sigma I, A'; A, -1/rho] (position space) in the unscaled form W = L D with the static gather programs:
+//   d_j = K_jj - sum_k W_jk^2 / d_k,     W_ij = K_ij - sum_k W_ik W_jk / d_k        (one pass and one barrier per level)
+// then the explicit inverses of the level ranges (in place) and of the dense tail.
+#define FAC_T(idx)                                                                         \
+    do {                                                                                   \
+        if (lvl_cyc && threadIdx.x == 0 && blockIdx.x == 0) {                              \
+            const long long now__ = clock64();                                             \
+            lvl_cyc[(idx)] += (unsigned int)(now__ - t_lvl);                               \
+            t_lvl = now__;                                                                 \
+        }                                                                                  \
+    } while (0)
+__device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, unsigned int* lvl_cyc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long t_lvl = clock64();
     const RhoInv ri = make_rho_inv(rho);
-    for (int e = tid; e < q.nnzL; e += ADMM_THREADS) s.Lval[e] = 0.0;
-    // D workspace lives in s.sol during the factorisation
-    for (int p = tid; p < q.Nk; p += ADMM_THREADS) s.sol[p] = s.flag[p] ? -rinv_of(s.flag[p], ri) : s.lo[p] + sigma;
+    for (int e = tid; e < q.nslots; e += ADMM_THREADS) s.Lval[e] = 0.0;
+    // Dinv[p] holds K_pp until the pivot of p is formed
+    for (int p = tid; p < q.Nk; p += ADMM_THREADS) s.Dinv[p] = s.flag[p] ? -rinv_of(s.flag[p], ri) : s.lo[p] + sigma;
     __syncthreads();
-    for (int e = tid; e < q.nnzA; e += ADMM_THREADS) s.Lval[__ldg(q.a_lpos + e)] = s.Aval[e];
+    for (int e = tid; e < q.nnzA; e += ADMM_THREADS) s.Lval[__ldg(q.a_slot + e)] = s.Aval[e];
     __syncthreads();
-    double* D = s.sol;
+    FAC_T(110);
     for (int l = 0; l < q.nlev; l++) {
-        const uint32_t t0 = __ldg(q.ftgt_ptr + l), t1 = __ldg(q.ftgt_ptr + l + 1);
-        const int g = __ldg(q.lvl_gfac + l);
-        const int sh = 31 - __clz(g);
-        const uint32_t slots = (((t1 - t0) << sh) + 31u) & ~31u;
-        for (uint32_t i = tid; i < slots; i += ADMM_THREADS) {
-            const uint32_t t = t0 + (i >> sh);
-            const int sub = i & (g - 1);
-            const bool live = t < t1;
-            double acc = 0.0;
-            int id = 0;
-            if (live) {
-                id = __ldg(q.ftgt_id + t);
-                const uint32_t x1 = __ldg(q.fac_ptr + t + 1);
-                if (id >= q.nnzL) {
-                    for (uint32_t x = __ldg(q.fac_ptr + t) + sub; x < x1; x += g) { const double v = s.Lval[__ldg(q.fac_a + x)]; acc += v * v * D[__ldg(q.fac_k + x)]; }
-                } else {
-                    for (uint32_t x = __ldg(q.fac_ptr + t) + sub; x < x1; x += g) acc += s.Lval[__ldg(q.fac_a + x)] * s.Lval[__ldg(q.fac_b + x)] * D[__ldg(q.fac_k + x)];
-                }
-            }
-            acc = group_sum(acc, g);
-            if (live && sub == 0) {
-                if (id >= q.nnzL) { const int j = id - q.nnzL; const double d = D[j] - acc; D[j] = d; s.Dinv[j] = 1.0 / d; }
+        const int t1 = s.fac_lvl[l + 1];
+        for (int t = s.fac_lvl[l] + warp; t < t1; t += NW) {
+            const uint2 d = s.fac_task[t];
+            const double acc = gather_task(s, d, q.fac_ent, lane);
+            const int sh = (d.y >> 16) & 0xff, rr = lane >> sh;
+            if ((lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff)) {
+                const int id = __ldg(q.fac_tgt + (d.x >> 16) + rr) & 0xffff;
+                if (id >= q.nslots) { const int j = id - q.nslots; s.Dinv[j] = 1.0 / (s.Dinv[j] - acc); }
                 else s.Lval[id] -= acc;
             }
         }
         __syncthreads();
-        for (uint32_t t = t0 + tid; t < t1; t += ADMM_THREADS) {
-            const int id = __ldg(q.ftgt_id + t);
-            if (id < q.nnzL) s.Lval[id] *= s.Dinv[__ldg(q.ftgt_col + t)];
-        }
-        __syncthreads();
+        FAC_T(120 + (l < 100 ? l : 99));
     }
-    // level ranges: replace the unit lower block L[range, range] by its explicit inverse, in place, level by level:
-    //   M_ij = -(S_ij + sum_{j<k<i} S_ik M_kj)     (targets of one level are computed into registers before any is written)
+    // level ranges: replace the in-range block of W by the explicit inverse M of the unit lower block L[range, range], level by level:
+    //   M_ij = -(W_ij / d_j + sum_{j<k<i} W_ik / d_k M_kj)     (targets of one level are computed into registers before any is written)
     for (int l = 0; l < q.n_inv_levels; l++) {
-        const uint32_t t0 = __ldg(q.itgt_ptr + l), t1 = __ldg(q.itgt_ptr + l + 1);
-        double v[4];
+        const int t0 = s.inv_lvl[l] + warp, t1 = s.inv_lvl[l + 1];
+        double v[INV_MAX_TASKS_PER_WARP];
+        int id[INV_MAX_TASKS_PER_WARP];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {           // <= 4 * ADMM_THREADS targets per level (checked on the host)
-            const uint32_t t = t0 + tid + k * ADMM_THREADS;
-            v[k] = 0.0;
+        for (int k = 0; k < INV_MAX_TASKS_PER_WARP; k++) {
+            const int t = t0 + k * NW;
+            id[k] = -1;
             if (t < t1) {
-                double acc = s.Lval[__ldg(q.itgt_id + t)];
-                const uint32_t x1 = __ldg(q.inv_ptr + t + 1);
-                for (uint32_t x = __ldg(q.inv_ptr + t); x < x1; x++) acc += s.Lval[__ldg(q.inv_a + x)] * s.Lval[__ldg(q.inv_b + x)];
-                v[k] = -acc;
+                const uint2 d = s.inv_task[t];
+                const double acc = gather_task(s, d, q.inv_ent, lane);
+                const int sh = (d.y >> 16) & 0xff, rr = lane >> sh;
+                if ((lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff)) {
+                    const uint32_t tg = __ldg(q.inv_tgt + (d.x >> 16) + rr);
+                    id[k] = tg & 0xffff;
+                    v[k] = -(s.Lval[id[k]] * s.Dinv[tg >> 16] + acc);
+                }
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t t = t0 + tid + k * ADMM_THREADS;
-            if (t < t1) s.Lval[__ldg(q.itgt_id + t)] = v[k];
-        }
+        for (int k = 0; k < INV_MAX_TASKS_PER_WARP; k++)
+            if (id[k] >= 0) s.Lval[id[k]] = v[k];
         __syncthreads();
     }
-    // dense tail: packed strictly-lower copy Ld of L[tail, tail] (aliasing sol|dxy, free now) and its explicit inverse Tinv,
-    // one column per group of 4 lanes by forward substitution:  z_j = 1,  z_i = -(L_ij + sum_{j<k<i} L_ik z_k)
+    FAC_T(111);
+    // dense tail: packed strictly-lower copy Ld of the unit lower L[tail, tail] = W / d_col (aliasing sol|dxy, free now) and its explicit
+    // inverse Tinv, one column per group of 4 lanes by forward substitution:  z_j = 1,  z_i = -(L_ij + sum_{j<k<i} L_ik z_k)
     const int Dm = q.tail_dim;
     if (Dm > 0) {
         double* Ld = s.sol;
         const int npk = Dm * (Dm - 1) / 2;
         for (int e = tid; e < npk; e += ADMM_THREADS) Ld[e] = 0.0;
         __syncthreads();
-        for (int e = tid; e < q.n_tl; e += ADMM_THREADS) Ld[__ldg(q.tl_dst + e)] = s.Lval[__ldg(q.tl_src + e)];
+        for (int e = tid; e < q.n_tl; e += ADMM_THREADS) Ld[__ldg(q.tl_dst + e)] = s.Lval[__ldg(q.tl_src + e)] * s.Dinv[__ldg(q.tl_col + e)];
         __syncthreads();
         const int slots = ((Dm * 4) + 31) & ~31;
         for (int i = tid; i < slots; i += ADMM_THREADS) {
@@ -225,85 +278,95 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho) 
         }
         __syncthreads();
     }
+    if (tid == 0) { s.sol[q.Nk] = 0.0; s.dxy[q.Nk] = 0.0; }      // the always-zero element read by the padding entries
+    __syncthreads();
+    FAC_T(112);
 }
 
-// sol <- K^-1 sol.  Level-scheduled forward substitution over the sparse levels (rows split over lane groups, shuffle-reduced), the
-// dense tail as two mat-vec levels with the explicit inverse, then the mirror image backwards.
-__device__ __forceinline__ double group_sum_sh(double v, int sh) {     // sh is warp-uniform
-    if (sh > 4) v += __shfl_xor_sync(0xffffffffu, v, 16);
-    if (sh > 3) v += __shfl_xor_sync(0xffffffffu, v, 8);
-    if (sh > 2) v += __shfl_xor_sync(0xffffffffu, v, 4);
-    if (sh > 1) v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (sh > 0) v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v;
-}
-
-// Executes a step program.  One step: rows [r0, r0+rows), 2^sh lanes per row, <= 4 entries per lane of one segment of the row:
-//     out[r] = in[r] (* 1/D_r) -/+ sum_e L_e * in[c_e]          in, out in {sol, tmp}
-__device__ __forceinline__ void run_steps(const Smem& s, const uint2* __restrict__ steps, int nsteps, int Nk) {
-    const int tid = threadIdx.x;
-    for (int st = 0; st < nsteps; st++) {
-        const uint2 d = steps[st];
-        const int sh = d.y & 0xff, fl = d.y >> 8;
-        const int row = tid >> sh, sub = tid & ((1 << sh) - 1);
-        const bool live = row < (int)(d.x >> 16);
-        const double* in = (fl & STEP_SRC_TMP) ? s.dxy : s.sol;
-        const int r = (d.x & 0xffff) + row;
-        double acc = 0.0, acc2 = 0.0;
-        if (live) {
-            const int sg = (fl & STEP_SEG_MASK) >> 1;
-            const uint32_t rd = s.seg[sg * Nk + r];
-            const int base = rd & 0xffff, len = rd >> 16;
-            if (sg < 2) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int idx = sub + (k << sh);
-                    if (idx < len) {
-                        const double t = s.Lval[base + idx] * in[s.lrow_col[base + idx]];
-                        if (k & 1) acc2 += t; else acc += t;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int idx = sub + (k << sh);
-                    if (idx < len) {
-                        const uint32_t b = s.bent[base + idx];
-                        const double t = s.Lval[b & 0xffff] * in[b >> 16];
-                        if (k & 1) acc2 += t; else acc += t;
-                    }
-                }
+// One phase of a triangular solve: every warp runs its tasks,  out[r] = f(in[r], sum_e W_e * in[c_e])  (flags in pgn_structure.h).
+// Forward phases read the L values in slot order (conflict-free); backward phases gather them through (slot, source) pairs.
+template <bool BWD>
+__device__ __forceinline__ void run_phase(const Smem& s, int ph) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t1 = s.ph_ptr[ph + 1];
+    for (int t = s.ph_ptr[ph] + warp; t < t1; t += NW) {
+        const uint2 d = s.sol_task[t];
+        const int K = d.y & 0xff, sh = (d.y >> 16) & 0xff, fl = d.y >> 24;
+        const double* in = (fl & TASK_SRC_TMP) ? s.dxy : s.sol;
+        const int e = ((d.x & 0xffff) << 5) + lane;
+        double acc0 = 0.0, acc1 = 0.0;
+        int k = 0;
+        // loads are issued in batches of four (indices, values, gathered operands) so that their latencies overlap
+        if (!BWD) {
+            const double* lv = s.Lval + e;
+            const uint16_t* ix = s.fidx + e;
+            for (; k + 4 <= K; k += 4) {
+                const int i0 = ix[k * 32], i1 = ix[k * 32 + 32], i2 = ix[k * 32 + 64], i3 = ix[k * 32 + 96];
+                const double l0 = lv[k * 32], l1 = lv[k * 32 + 32], l2 = lv[k * 32 + 64], l3 = lv[k * 32 + 96];
+                const double x0 = in[i0], x1 = in[i1], x2 = in[i2], x3 = in[i3];
+                acc0 += l0 * x0; acc1 += l1 * x1; acc0 += l2 * x2; acc1 += l3 * x3;
+            }
+            const int r = K - k;
+            if (r > 0) {
+                const int k1 = r > 1 ? k + 1 : k, k2 = r > 2 ? k + 2 : k;
+                const int i0 = ix[k * 32], i1 = ix[k1 * 32], i2 = ix[k2 * 32];
+                const double l0 = lv[k * 32], l1 = lv[k1 * 32], l2 = lv[k2 * 32];
+                const double x0 = in[i0], x1 = in[i1], x2 = in[i2];
+                acc0 += l0 * x0;
+                if (r > 1) acc1 += l1 * x1;
+                if (r > 2) acc0 += l2 * x2;
+            }
+        } else {
+            const uint32_t* be = s.bent + e;
+            for (; k + 4 <= K; k += 4) {
+                const uint32_t b0 = be[k * 32], b1 = be[k * 32 + 32], b2 = be[k * 32 + 64], b3 = be[k * 32 + 96];
+                const double l0 = s.Lval[b0 & 0xffff], l1 = s.Lval[b1 & 0xffff], l2 = s.Lval[b2 & 0xffff], l3 = s.Lval[b3 & 0xffff];
+                const double x0 = in[b0 >> 16], x1 = in[b1 >> 16], x2 = in[b2 >> 16], x3 = in[b3 >> 16];
+                acc0 += l0 * x0; acc1 += l1 * x1; acc0 += l2 * x2; acc1 += l3 * x3;
+            }
+            const int r = K - k;
+            if (r > 0) {
+                const uint32_t b0 = be[k * 32], b1 = be[(r > 1 ? k + 1 : k) * 32], b2 = be[(r > 2 ? k + 2 : k) * 32];
+                const double l0 = s.Lval[b0 & 0xffff], l1 = s.Lval[b1 & 0xffff], l2 = s.Lval[b2 & 0xffff];
+                const double x0 = in[b0 >> 16], x1 = in[b1 >> 16], x2 = in[b2 >> 16];
+                acc0 += l0 * x0;
+                if (r > 1) acc1 += l1 * x1;
+                if (r > 2) acc0 += l2 * x2;
             }
         }
-        acc = group_sum_sh(acc + acc2, sh);
-        if (live && sub == 0) {
+        double acc = group_sum_sh(acc0 + acc1, sh);
+        const int rr = lane >> sh;
+        if ((lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff)) {
+            const int r = s.orow[(d.x >> 16) + rr];
             double x = in[r];
-            if (fl & STEP_SCALE) x *= s.Dinv[r];
-            double* out = (fl & STEP_DST_TMP) ? s.dxy : s.sol;
-            out[r] = (fl & STEP_ADD) ? x + acc : x - acc;
+            if (fl & TASK_SCALE_ACC) acc *= s.Dinv[r];
+            x = (fl & TASK_ADD) ? x + acc : x - acc;
+            if (fl & TASK_SCALE_OUT) x *= s.Dinv[r];
+            double* out = (fl & TASK_DST_TMP) ? s.dxy : s.sol;
+            out[r] = x;
         }
-        if (fl & STEP_LAST) __syncthreads();
     }
+    __syncthreads();
 }
 
 #define LVL_T(idx)                                                                         \
     do {                                                                                   \
         if (lvl_cyc && threadIdx.x == 0 && blockIdx.x == 0) {                              \
             const long long now__ = clock64();                                             \
-            lvl_cyc[(idx)] += (unsigned long long)(now__ - t_lvl);                         \
+            lvl_cyc[(idx)] += (unsigned int)(now__ - t_lvl);                               \
             t_lvl = now__;                                                                 \
         }                                                                                  \
     } while (0)
-// sol <- K^-1 sol:  forward over the level ranges (two steps each: external part, then the in-range explicit inverse), the dense
-// tail (its external part is the last forward step), the diagonal, and the mirror image backwards down to level 0.
-__device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigned long long* lvl_cyc) {
+// sol <- K^-1 sol (level-0 rows of the right-hand side already divided by their pivots):  forward over the level ranges (two phases each:
+// external part, then the in-range explicit inverse), the dense tail (its external part is the last forward phase), and the mirror
+// image backwards down to level 0.
+__device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigned int* lvl_cyc) {
     const int tid = threadIdx.x;
     long long t_lvl = clock64();
     const int ts = q.tail_start, Dm = q.tail_dim;
-    run_steps(s, s.stf, q.n_step_f, q.Nk);
-    LVL_T(1);
+    for (int ph = 0; ph < q.n_fwd_ph; ph++) { run_phase<false>(s, ph); LVL_T(ph); }
     if (Dm > 0) {
-        // tail stage 2 + diagonal: w = Dinv .* (Tinv t)   (t in tmp[tail]) -> sol[tail]
+        // tail stage 2 + diagonal: w = Dinv .* (t + Tinv t)   (t in tmp[tail]) -> sol[tail]
         {
             const int slots = ((Dm * 4) + 31) & ~31;
             for (int i = tid; i < slots; i += ADMM_THREADS) {
@@ -322,7 +385,7 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigne
             }
         }
         __syncthreads();
-        LVL_T(101);
+        LVL_T(100);
         // backward through the tail: x = Tinv' w, computed into registers, then written back over w
         {
             const int slots = ((Dm * 4) + 31) & ~31;
@@ -347,10 +410,9 @@ __device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigne
             if (i < slots && live && sub == 0) s.sol[ts + rr] = xr;
         }
         __syncthreads();
-        LVL_T(102);
+        LVL_T(101);
     }
-    run_steps(s, s.stb, q.n_step_b, q.Nk);
-    LVL_T(2);
+    for (int ph = q.n_fwd_ph; ph < q.n_fwd_ph + q.n_bwd_ph; ph++) { run_phase<true>(s, ph); LVL_T(ph); }
 }
 
 // out[p] = sum over the off-diagonal KKT entries of row p:  constraints get (A x)_i, variables get (A' y)_j
@@ -457,7 +519,7 @@ __device__ bool dual_infeasible(const QpDev& q, const Smem& s, double eps, doubl
     do {                                                                            \
         if (a.cycles && threadIdx.x == 0) {                                         \
             const long long now__ = clock64();                                      \
-            atomicAdd(a.cycles + (idx), (unsigned long long)(now__ - t_phase));     \
+            s_cyc[(idx)] += (unsigned int)(now__ - t_phase);                        \
             t_phase = now__;                                                        \
         }                                                                           \
     } while (0)
@@ -465,29 +527,34 @@ __device__ bool dual_infeasible(const QpDev& q, const Smem& s, double eps, doubl
 __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_vehicle;
+    __shared__ unsigned int s_cyc[ADMM_NCYC];      // profiling only: cycle counters kept on chip, flushed once when the CTA retires
     const QpDev& q = a.q;
     const AdmmSettings& st = a.st;
     Smem s;
-    carve(q, smem_raw, s);
     const int tid = threadIdx.x;
-    // index tables of the triangular solves: global -> shared (packed), once per CTA
-    for (int e = tid; e < q.nnzL; e += ADMM_THREADS) {
-        s.lrow_col[e] = q.lrow_col[e];
-        s.bent[e] = (uint32_t)q.lcol_val[e] | ((uint32_t)q.lcol_row[e] << 16);
+    {   // static tables of the warp programs: global -> shared, once per CTA
+        uint2* w_task; uint32_t* w_u32; uint16_t* w_u16;
+        carve(q, smem_raw, s, w_task, w_u32, w_u16);
+        for (int i = tid; i < q.n_sol_task; i += ADMM_THREADS) w_task[i] = q.sol_task[i];
+        for (int i = tid; i < q.n_fac_task; i += ADMM_THREADS) w_task[q.n_sol_task + i] = q.fac_task[i];
+        for (int i = tid; i < q.n_inv_task; i += ADMM_THREADS) w_task[q.n_sol_task + q.n_fac_task + i] = q.inv_task[i];
+        for (int i = tid; i < q.n_bent; i += ADMM_THREADS) w_u32[i] = q.bent[i];
+        for (int i = tid; i <= q.nlev; i += ADMM_THREADS) w_u32[q.n_bent + i] = q.fac_lvl_ptr[i];
+        for (int i = tid; i <= q.n_inv_levels; i += ADMM_THREADS) w_u32[q.n_bent + q.nlev + 1 + i] = q.inv_lvl_ptr[i];
+        for (int i = tid; i < q.nslots; i += ADMM_THREADS) w_u16[i] = q.fidx[i];
+        for (int i = tid; i < q.n_orow; i += ADMM_THREADS) w_u16[q.nslots + i] = q.sol_orow[i];
+        for (int i = tid; i <= q.n_fwd_ph + q.n_bwd_ph; i += ADMM_THREADS) w_u16[q.nslots + q.n_orow + i] = q.sol_ph_ptr[i];
     }
-    for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
-        s.seg[p] = q.fwd_ext[p]; s.seg[q.Nk + p] = q.fwd_in[p]; s.seg[2 * q.Nk + p] = q.bwd_in[p]; s.seg[3 * q.Nk + p] = q.bwd_ext[p];
-    }
-    for (int i = tid; i < q.n_step_f; i += ADMM_THREADS) s.stf[i] = make_uint2(q.step_f[2 * i], q.step_f[2 * i + 1]);
-    for (int i = tid; i < q.n_step_b; i += ADMM_THREADS) s.stb[i] = make_uint2(q.step_b[2 * i], q.step_b[2 * i + 1]);
+    for (int i = threadIdx.x; i < ADMM_NCYC; i += ADMM_THREADS) s_cyc[i] = 0;
     __syncthreads();
     long long t_phase = clock64();
     for (;;) {
         if (tid == 0) s_vehicle = atomicAdd(a.counter, 1);
         __syncthreads();
-        const int v = s_vehicle;
+        const int ticket = s_vehicle;
         __syncthreads();
-        if (v >= a.B) break;
+        if (ticket >= a.B) break;
+        const int v = a.order[ticket];
         const double* rec = a.rec + (size_t)v * q.rec_len;
         PHASE(7);
 
@@ -495,7 +562,10 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         for (int e = tid; e < q.nnzA; e += ADMM_THREADS) {
             const int src = __ldg(q.a_src + e);
             s.Aval[e] = src >= 0 ? rec[src] : (src == -1 ? 1.0 : -1.0);
+            s.arc[e] = __ldg(q.a_rc + e);
         }
+        for (int e = tid; e < 2 * q.nnzA; e += ADMM_THREADS) s.ke[e] = __ldg(q.kadj_e + e);
+        for (int p = tid; p <= q.Nk; p += ADMM_THREADS) s.kptr[p] = __ldg(q.kadj_ptr + p);
         for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
             const int idx = __ldg(q.pos2idx + p);
             if (__ldg(q.is_con + p)) {
@@ -540,28 +610,26 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         for (int it = 0; it < st.scaling; it++) {
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
                 double nrm = s.flag[p] ? 0.0 : fabs(s.lo[p]);
-                const int e1 = __ldg(q.kadj_ptr + p + 1);
-                for (int e = __ldg(q.kadj_ptr + p); e < e1; e++) nrm = fmax(nrm, fabs(s.Aval[__ldg(q.kadj_e + e)]));
+                const int e1 = s.kptr[p + 1];
+                for (int e = s.kptr[p]; e < e1; e++) nrm = fmax(nrm, fabs(s.Aval[s.ke[e]]));
                 s.sol[p] = 1.0 / sqrt(limit_scaling(nrm));
             }
             __syncthreads();
-            for (int e = tid; e < q.nnzA; e += ADMM_THREADS) s.Aval[e] *= s.sol[__ldg(q.a_rowpos + e)] * s.sol[__ldg(q.a_colpos + e)];
-            double v2[2] = {0.0, 0.0};   // sum |P_jj|, max |q_j|
+            for (int e = tid; e < q.nnzA; e += ADMM_THREADS) { const uint32_t rc = s.arc[e]; s.Aval[e] *= s.sol[rc & 0xffff] * s.sol[rc >> 16]; }
+            double sumP = 0.0, maxq = 0.0;   // sum |P_jj|, max |q_j|
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
                 const double d = s.sol[p];
                 s.sc[p] *= d;
                 if (!s.flag[p]) {
                     s.lo[p] *= d * d;
                     s.yq[p] *= d;
-                    v2[0] += fabs(s.lo[p]);
-                    v2[1] = fmax(v2[1], fabs(s.yq[p]));
+                    sumP += fabs(s.lo[p]);
+                    maxq = fmax(maxq, fabs(s.yq[p]));
                 }
             }
-            double vs[1] = {v2[0]}, vm[1] = {v2[1]};
-            block_reduce<1, false>(vs, s.red);
-            block_reduce<1, true>(vm, s.red);
-            double c_temp = vs[0] / q.n;
-            const double inf_q = limit_scaling(vm[0]);
+            block_reduce_sum_max(sumP, maxq, s.red);
+            double c_temp = sumP / q.n;
+            const double inf_q = limit_scaling(maxq);
             c_temp = limit_scaling(fmax(c_temp, inf_q));
             c_temp = 1.0 / c_temp;
             for (int p = tid; p < q.Nk; p += ADMM_THREADS)
@@ -582,7 +650,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
 
         PHASE(1);
         // ---- 3. factor ----------------------------------------------------------------------------------------------------
-        factor(q, s, st.sigma, rho);
+        factor(q, s, st.sigma, rho, a.cycles ? s_cyc + 16 : nullptr);
         PHASE(2);
 
         // ---- 4. ADMM iterations ---------------------------------------------------------------------------------------------
@@ -597,10 +665,11 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
             // rhs
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
                 const uint8_t f = s.flag[p];
-                s.sol[p] = f ? s.xz[p] - rinv_of(f, rinv) * s.yq[p] : st.sigma * s.xz[p] - s.yq[p];
+                const double b = f ? s.xz[p] - rinv_of(f, rinv) * s.yq[p] : st.sigma * s.xz[p] - s.yq[p];
+                s.sol[p] = p < q.lvl0_end ? b * s.Dinv[p] : b;      // level 0 of the forward solve: y^ = b / d
             }
             __syncthreads();
-            kkt_solve(q, s, a.cycles ? a.cycles + 16 : nullptr);
+            kkt_solve(q, s, a.cycles ? s_cyc + 16 : nullptr);
             PHASE(3);
             // x, z, y updates
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
@@ -649,7 +718,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                     n_rho_upd++;
                     __syncthreads();
                     PHASE(5);
-                    factor(q, s, st.sigma, rho);
+                    factor(q, s, st.sigma, rho, a.cycles ? s_cyc + 16 : nullptr);
                     PHASE(2);
                 }
             }
@@ -687,6 +756,27 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         __syncthreads();
         PHASE(6);
     }
+    if (a.cycles) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ADMM_NCYC; i += ADMM_THREADS)
+            if (s_cyc[i]) atomicAdd(a.cycles + i, (unsigned long long)s_cyc[i]);
+    }
+}
+
+// Ticket order of the persistent CTAs: vehicles whose previous solve took the most iterations go first (longest-processing-time-first),
+// so that a slow QP starts at the beginning of the launch instead of becoming its tail.  Counting sort on iters / 25 in one CTA.
+__global__ void __launch_bounds__(1024) k_admm_order(const int32_t* __restrict__ iters, int32_t* __restrict__ order, int B) {
+    __shared__ int hist[257];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int v = threadIdx.x; v < B; v += blockDim.x) atomicAdd(&hist[255 - min(iters[v] / 25, 255)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < 256; i++) { const int c = hist[i]; hist[i] = acc; acc += c; }
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < B; v += blockDim.x) order[atomicAdd(&hist[255 - min(iters[v] / 25, 255)], 1)] = v;
 }
 
 int admm_configure(pgn_handle* h) {
@@ -703,8 +793,11 @@ void launch_admm(pgn_handle* h) {
     a.sol_x = h->d_sol_x; a.sol_y = h->d_sol_y;
     a.iters = h->d_iters; a.status = h->d_status; a.rho_updates = h->d_rho_updates; a.pri_res = h->d_pri_res; a.dua_res = h->d_dua_res;
     a.solved = h->d_solved; a.counter = h->d_counter;
-    a.cycles = h->profiling ? h->d_cycles : nullptr;
+    a.cycles = h->profiling >= 2 ? h->d_cycles : nullptr;      // 1: stage timers only, 2: + in-kernel cycle counters
     cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream);
+    k_admm_order<<<1, 1024, 0, h->stream>>>(h->d_iters, h->d_order, h->B);
+    h->launches++;
+    a.order = h->d_order;
     int ctas_per_sm = 1;
     if (h->admm_smem_bytes * 2 + 2048 <= 227 * 1024) ctas_per_sm = 2;
     if (h->admm_smem_bytes * 3 + 3072 <= 227 * 1024) ctas_per_sm = 3;

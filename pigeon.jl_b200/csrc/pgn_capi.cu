@@ -220,17 +220,37 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     memset(&q, 0, sizeof(q));
     q.kind = t.kind; q.N = t.N; q.T = t.T; q.Ns = t.Ns; q.nx = t.nx; q.nu = t.nu; q.n = t.n; q.m = t.m; q.Nk = t.Nk; q.nnzA = t.nnzA; q.nnzL = t.nnzL; q.nlev = t.nlev;
     q.rec_len = t.rec.rec_len; q.o_dt = t.rec.o_dt; q.var_u1_delta = t.var_u1_delta; q.var_u1_fx = t.var_u1_fx;
-    int rc;
+    int rc, rc_;
 #define UP(field) if ((rc = dev_upload(h, t.field, &q.field))) return bail(rc)
-    UP(a_src); UP(a_rowpos); UP(a_colpos); UP(a_lpos); UP(l_type); UP(u_type); UP(l_idx); UP(u_idx); UP(P_mode); UP(q_mode); UP(P_w); UP(q_w); UP(P_t); UP(q_t);
-    UP(q_hji_t); UP(pos_var); UP(pos_con); UP(pos2idx); UP(is_con); UP(lrow_ptr); UP(lrow_col); UP(lcol_ptr); UP(lcol_row); UP(lcol_val); UP(lvl_ptr);
-    UP(kadj_ptr); UP(kadj_e); UP(kadj_nb); UP(ftgt_ptr); UP(fac_ptr); UP(ftgt_id); UP(ftgt_col); UP(fac_a); UP(fac_b); UP(fac_k);
-    UP(lvl_gf); UP(lvl_gb); UP(lvl_gfac); UP(tl_src); UP(tl_dst); UP(step_f); UP(step_b);
-    UP(fwd_ext); UP(fwd_in); UP(bwd_in); UP(bwd_ext); UP(itgt_ptr); UP(inv_ptr); UP(itgt_id); UP(inv_a); UP(inv_b);
-    q.n_inv_levels = (int)t.itgt_ptr.size() - 1;
-    q.n_step_f = (int)t.step_f.size() / 2; q.n_step_b = (int)t.step_b.size() / 2;
+    UP(a_src); UP(a_slot); UP(l_type); UP(u_type); UP(l_idx); UP(u_idx); UP(P_mode); UP(q_mode); UP(P_w); UP(q_w); UP(P_t); UP(q_t);
+    UP(q_hji_t); UP(pos_var); UP(pos_con); UP(pos2idx); UP(is_con); UP(kadj_ptr); UP(kadj_e); UP(kadj_nb);
+    UP(sol_ph_ptr); UP(sol_orow); UP(fidx); UP(bent); UP(fac_lvl_ptr); UP(fac_tgt); UP(inv_lvl_ptr); UP(inv_tgt); UP(tl_src); UP(tl_dst); UP(tl_col);
+    {
+        std::vector<uint32_t> rc(t.nnzA);
+        for (int e = 0; e < t.nnzA; e++) rc[e] = (uint32_t)t.a_rowpos[e] | ((uint32_t)t.a_colpos[e] << 16);
+        if ((rc_ = dev_upload(h, rc, &q.a_rc))) return bail(rc_);
+        auto pack = [](const std::vector<uint32_t>& w) {      // 4-word host tasks -> packed 8-byte device descriptors
+            std::vector<uint2> o(w.size() / 4);
+            for (size_t i = 0; i < o.size(); i++) {
+                const uint32_t ebase = w[4 * i], rbase = w[4 * i + 1] & 0xffff, nrows = (w[4 * i + 1] >> 16) & 0xff, sh = w[4 * i + 1] >> 24, K = w[4 * i + 2] & 0xffff, fl = w[4 * i + 2] >> 16;
+                o[i] = make_uint2((ebase >> 5) | (rbase << 16), K | (nrows << 8) | (sh << 16) | (fl << 24));
+            }
+            return o;
+        };
+        for (size_t i = 0; i < t.fac_task.size() / 4; i++) if ((t.fac_task[4 * i] >> 5) > 0xffff || (t.fac_task[4 * i + 1] & 0xffff) != (t.fac_task[4 * i + 1] & 0xffff)) return bail(set_err(PGN_EINVAL, "factor program too large"));
+        if (t.fac_tgt.size() > 0xffff || t.inv_tgt.size() > 0xffff || t.fac_ent.size() / 32 > 0xffff || t.inv_ent.size() / 32 > 0xffff)
+            return bail(set_err(PGN_EINVAL, "QP too large for the packed task descriptors"));
+        if ((rc_ = dev_upload(h, pack(t.sol_task), &q.sol_task))) return bail(rc_);
+        if ((rc_ = dev_upload(h, pack(t.fac_task), &q.fac_task))) return bail(rc_);
+        if ((rc_ = dev_upload(h, pack(t.inv_task), &q.inv_task))) return bail(rc_);
+        std::vector<unsigned long long> fe(t.fac_ent.begin(), t.fac_ent.end()), ie(t.inv_ent.begin(), t.inv_ent.end());
+        if ((rc_ = dev_upload(h, fe, &q.fac_ent))) return bail(rc_);
+        if ((rc_ = dev_upload(h, ie, &q.inv_ent))) return bail(rc_);
+    }
+    q.nslots = t.nslots; q.zslot = t.zslot; q.lvl0_end = t.lvl0_end; q.n_fwd_ph = t.n_fwd_ph; q.n_bwd_ph = t.n_bwd_ph;
+    q.n_sol_task = (int)t.sol_task.size() / 4; q.n_fac_task = (int)t.fac_task.size() / 4; q.n_inv_task = (int)t.inv_task.size() / 4;
+    q.n_bent = (int)t.bent.size(); q.n_orow = (int)t.sol_orow.size(); q.n_inv_levels = (int)t.inv_lvl_ptr.size() - 1;
     q.tail_level = t.tail_level; q.tail_start = t.tail_start; q.tail_dim = t.tail_dim; q.n_tl = (int)t.tl_src.size();
-    q.tail_g1 = 1;
 #undef UP
     double *ctab = nullptr, *wtab = nullptr;
     if ((rc = dev_alloc(h, &ctab, CT_LEN + 1))) return bail(rc);
@@ -247,7 +267,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_cycles, 512);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_cycles, 512);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
@@ -444,6 +464,8 @@ int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
 int pgn_qp_dims(pgn_handle* h, int32_t* o) {
     REQUIRE(h && o, "NULL argument");
     o[0] = h->N; o[1] = h->nx; o[2] = h->nu; o[3] = h->tab.n; o[4] = h->tab.m; o[5] = h->tab.nnzA; o[6] = h->tab.nnzL; o[7] = h->tab.nlev;
+    o[8] = h->tab.nslots; o[9] = h->tab.n_fwd_ph + h->tab.n_bwd_ph; o[10] = (int)h->tab.fac_ent.size(); o[11] = (int)h->tab.inv_ent.size(); o[12] = h->tab.tail_dim;
+    o[13] = (int)h->tab.bent.size(); o[14] = h->admm_smem_bytes; o[15] = h->admm_threads;
     return PGN_OK;
 }
 int pgn_get_state(pgn_handle* h, double* q, double* u) {

@@ -48,18 +48,18 @@ struct QpDev {
     const uint16_t *P_t, *q_t, *q_hji_t;
     const uint16_t *pos_var, *pos_con, *pos2idx;
     const uint8_t* is_con;
-    const uint16_t *lrow_ptr, *lrow_col, *lcol_ptr, *lcol_row, *lcol_val, *lvl_ptr;
     const uint16_t *kadj_ptr, *kadj_e, *kadj_nb;
-    const uint32_t *ftgt_ptr, *fac_ptr;
-    const uint16_t *ftgt_id, *ftgt_col, *fac_a, *fac_b, *fac_k;
-    const uint8_t *lvl_gf, *lvl_gb, *lvl_gfac;
-    const uint16_t *tl_src, *tl_dst;
-    const uint32_t *fwd_ext, *fwd_in, *bwd_in, *bwd_ext, *itgt_ptr, *inv_ptr;
-    const uint16_t *itgt_id, *inv_a, *inv_b;
-    int n_inv_levels;
-    int tail_level, tail_start, tail_dim, tail_g1, n_tl;
-    const uint32_t *step_f, *step_b;
-    int n_step_f, n_step_b;
+    const uint32_t* a_rc;                       // per A entry: row position | column position << 16
+    const uint16_t* a_slot;                     // per A entry: L slot
+    // warp programs (pgn_structure.h): packed task descriptors {ebase/32 | rbase << 16, K | nrows << 8 | sh << 16 | flags << 24}
+    const uint2 *sol_task, *fac_task, *inv_task;
+    const uint16_t *sol_ph_ptr, *sol_orow, *fidx;
+    const uint32_t* bent;
+    const uint32_t *fac_lvl_ptr, *fac_tgt, *inv_lvl_ptr, *inv_tgt;
+    const unsigned long long *fac_ent, *inv_ent;
+    int nslots, zslot, lvl0_end, n_fwd_ph, n_bwd_ph, n_sol_task, n_fac_task, n_inv_task, n_bent, n_orow, n_inv_levels;
+    int tail_level, tail_start, tail_dim, n_tl;
+    const uint16_t *tl_src, *tl_dst, *tl_col;
     const double* ctab;      // [CT_LEN]
     const double* wtab;      // [W_LEN] cost weights
     int n_hji;               // N_HJI
@@ -98,6 +98,7 @@ struct pgn_handle {
     double *d_pri_res, *d_dua_res;
     double* d_controls;                                  // [3][B]
     double *d_t0, *d_t0_base;                            // [B]
+    int32_t* d_order;                                    // ticket -> vehicle order of the ADMM launch
     int* d_counter;                                      // work-queue ticket for the persistent ADMM kernel
     unsigned long long* d_cycles;                        // [8] per-phase cycle counters of the ADMM kernel (profiling only)
     double* d_stage;                                     // AoS<->SoA staging

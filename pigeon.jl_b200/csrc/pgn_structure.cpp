@@ -63,6 +63,50 @@ std::vector<int> constrained_min_degree(int Nk, const std::vector<std::vector<in
     return perm;
 }
 
+// ---- warp-task scheduling ------------------------------------------------------------------------------------------------------
+struct SchedTask { int sh, K; std::vector<int> rows; };   // rows: indices into the phase's row list
+
+// Packs rows (by decreasing length) into warp tasks: 32 >> sh rows per task, 2^sh lanes per row, K = ceil(maxlen / 2^sh) slots per lane.
+std::vector<SchedTask> schedule_rows(const std::vector<int>& len, int kmax) {
+    std::vector<int> ord(len.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return len[a] > len[b]; });
+    std::vector<SchedTask> out;
+    size_t i = 0;
+    while (i < ord.size()) {
+        const int L = len[ord[i]];
+        int sh = 0;
+        while (sh < 5 && ((L + (1 << sh) - 1) >> sh) > kmax) sh++;
+        SchedTask t; t.sh = sh; t.K = (L + (1 << sh) - 1) >> sh;
+        const int nr = 32 >> sh;
+        for (int k = 0; k < nr && i < ord.size(); k++, i++) t.rows.push_back(ord[i]);
+        out.push_back(std::move(t));
+    }
+    return out;
+}
+// Picks the slots-per-lane cap that minimises a simple cost model of the phase on `nw` warps (task t runs on warp t % nw):
+// the longest warp's latency chain against the issue slots of the whole CTA.
+std::vector<SchedTask> schedule_phase(const std::vector<int>& len, int nw) {
+    static const int ladder[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 64, 255};
+    std::vector<SchedTask> best;
+    double best_cost = 1e300;
+    for (int kmax : ladder) {
+        std::vector<SchedTask> t = schedule_rows(len, kmax);
+        bool ok = true;
+        std::vector<double> lat(nw, 0.0);
+        double issue = 0.0;
+        for (size_t i = 0; i < t.size(); i++) {
+            if (t[i].K > 255) ok = false;
+            lat[i % nw] += 120.0 + 22.0 * t[i].K + 30.0 * t[i].sh;      // measured: ~90 cycles per batch of 4 entries, ~30 per shuffle stage
+            issue += 40.0 + 6.0 * t[i].K + 8.0 * t[i].sh;
+        }
+        if (!ok) continue;
+        const double cost = std::max(*std::max_element(lat.begin(), lat.end()), issue / 2.0);
+        if (cost < best_cost) { best_cost = cost; best = std::move(t); }
+    }
+    return best;
+}
+
 void nd_classes(int lo, int hi, int depth, int leaf, std::vector<int>& sep_depth) {
     if (hi - lo + 1 <= leaf) return;
     int mid = (lo + hi) / 2;
@@ -326,142 +370,168 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         Q.kadj_e[Q.kadj_ptr[p] + x] = (uint16_t)kadj[p][x].first;
         Q.kadj_nb[Q.kadj_ptr[p] + x] = (uint16_t)kadj[p][x].second;
     }
-    // dense tail tables: sparse entries of L[tail, tail] -> packed strictly-lower dense index
+
+    // ---- warp programs -----------------------------------------------------------------------------------------------------------
+    const int NWARP = ADMM_THREADS / 32;
+    std::vector<int> range_pa, range_pb;
+    for (size_t k = 0; k + 1 < Q.range_lvl.size(); k += 2) { range_pa.push_back(Q.lvl_ptr[Q.range_lvl[k]]); range_pb.push_back(Q.lvl_ptr[Q.range_lvl[k + 1]]); }
+    const int nr = (int)range_pa.size();
+    Q.lvl0_end = Q.lvl_ptr[1];
+    std::vector<int> slot(nnzL, -1);          // CSR entry -> L slot
+    // -- forward solve: L slots are allocated in the order the forward phases consume them
+    Q.sol_ph_ptr.assign(1, 0);
+    int nslots = 0;
+    auto add_task_words = [&](std::vector<uint32_t>& tasks, int ebase, int rbase, const SchedTask& t, int flags) {
+        tasks.push_back((uint32_t)ebase);
+        tasks.push_back((uint32_t)rbase | ((uint32_t)t.rows.size() << 16) | ((uint32_t)t.sh << 24));
+        tasks.push_back((uint32_t)t.K | ((uint32_t)flags << 16));
+        tasks.push_back(0u);
+    };
+    auto fwd_phase = [&](int pa, int pb, int c_lo, int c_hi, int flags) {      // rows [pa, pb), CSR entries with c_lo <= col < c_hi
+        std::vector<std::vector<int>> ents(pb - pa);
+        std::vector<int> len(pb - pa);
+        for (int r = pa; r < pb; r++) {
+            for (int x = Q.lrow_ptr[r]; x < Q.lrow_ptr[r + 1]; x++) if (Q.lrow_col[x] >= c_lo && Q.lrow_col[x] < c_hi) ents[r - pa].push_back(x);
+            len[r - pa] = (int)ents[r - pa].size();
+        }
+        for (const SchedTask& t : schedule_phase(len, NWARP)) {
+            const int g = 1 << t.sh, ebase = nslots, rbase = (int)Q.sol_orow.size();
+            Q.fidx.resize(ebase + 32 * t.K, (uint16_t)Nk);
+            for (size_t rr = 0; rr < t.rows.size(); rr++) {
+                Q.sol_orow.push_back((uint16_t)(pa + t.rows[rr]));
+                const auto& E = ents[t.rows[rr]];
+                for (size_t x = 0; x < E.size(); x++) {
+                    const int lane = (int)(rr << t.sh) + (int)(x % g), k = (int)(x / g), sl = ebase + k * 32 + lane;
+                    slot[E[x]] = sl;
+                    Q.fidx[sl] = Q.lrow_col[E[x]];
+                }
+            }
+            nslots += 32 * t.K;
+            add_task_words(Q.sol_task, ebase, rbase, t, flags);
+        }
+        Q.sol_ph_ptr.push_back((uint16_t)(Q.sol_task.size() / 4));
+    };
+    for (int k = 0; k < nr; k++) {
+        fwd_phase(range_pa[k], range_pb[k], 0, range_pa[k], TASK_DST_TMP);                                         // t = b - W_ext y^           (sol -> tmp)
+        fwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD | TASK_SCALE_OUT);   // y^ = (t + M t) / d         (tmp -> sol)
+    }
+    if (Q.tail_dim > 0) fwd_phase(Q.tail_start, Nk, 0, Q.tail_start, TASK_DST_TMP);                               // tail stage 1               (sol -> tmp)
+    Q.n_fwd_ph = (int)Q.sol_ph_ptr.size() - 1;
+    for (int e = 0; e < (int)nnzL; e++) if (slot[e] < 0) slot[e] = nslots++;     // entries inside the dense tail block: no solve phase reads them
+    Q.zslot = nslots++;
+    nslots = (nslots + 31) & ~31;
+    Q.nslots = nslots;
+    Q.fidx.resize(nslots, (uint16_t)Nk);
+    if (nslots + Nk >= 65535) return fail("L slots exceed the 16-bit index range of the device tables");
+    // -- backward solve: (L slot, source) pairs in program order
+    auto bwd_phase = [&](int pa, int pb, int r_lo, int r_hi, int flags) {      // columns [pa, pb), CSC entries with r_lo <= row < r_hi
+        std::vector<std::vector<int>> ents(pb - pa);
+        std::vector<int> len(pb - pa);
+        for (int c = pa; c < pb; c++) {
+            for (int x = Q.lcol_ptr[c]; x < Q.lcol_ptr[c + 1]; x++) if (Q.lcol_row[x] >= r_lo && Q.lcol_row[x] < r_hi) ents[c - pa].push_back(x);
+            len[c - pa] = (int)ents[c - pa].size();
+        }
+        for (const SchedTask& t : schedule_phase(len, NWARP)) {
+            const int g = 1 << t.sh, ebase = (int)Q.bent.size(), rbase = (int)Q.sol_orow.size();
+            Q.bent.resize(ebase + 32 * t.K, (uint32_t)Q.zslot | ((uint32_t)Nk << 16));
+            for (size_t rr = 0; rr < t.rows.size(); rr++) {
+                Q.sol_orow.push_back((uint16_t)(pa + t.rows[rr]));
+                const auto& E = ents[t.rows[rr]];
+                for (size_t x = 0; x < E.size(); x++) {
+                    const int lane = (int)(rr << t.sh) + (int)(x % g), k = (int)(x / g);
+                    Q.bent[ebase + k * 32 + lane] = (uint32_t)slot[Q.lcol_val[E[x]]] | ((uint32_t)Q.lcol_row[E[x]] << 16);
+                }
+            }
+            add_task_words(Q.sol_task, ebase, rbase, t, flags);
+        }
+        Q.sol_ph_ptr.push_back((uint16_t)(Q.sol_task.size() / 4));
+    };
+    for (int k = nr - 1; k >= 0; k--) {
+        bwd_phase(range_pa[k], range_pb[k], range_pb[k], Nk, TASK_DST_TMP | TASK_SCALE_ACC);                       // v = y^ - (W_below' x) / d  (sol -> tmp)
+        bwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD);                    // x = v + M' v               (tmp -> sol)
+    }
+    bwd_phase(0, Q.lvl_ptr[1], 0, Nk, TASK_SCALE_ACC);                                                             // level 0: x = y^ - (W' x) / d   (sol -> sol)
+    Q.n_bwd_ph = (int)Q.sol_ph_ptr.size() - 1 - Q.n_fwd_ph;
+
+    Q.a_slot.resize(Q.nnzA);
+    for (int e = 0; e < Q.nnzA; e++) Q.a_slot[e] = (uint16_t)slot[Q.a_lpos[e]];
+    // dense tail tables: entries of L[tail, tail] -> packed strictly-lower dense index
     for (int i = Q.tail_start; i < Nk; i++)
         for (int x = Q.lrow_ptr[i]; x < Q.lrow_ptr[i + 1]; x++)
             if (Q.lrow_col[x] >= Q.tail_start) {
                 int ii = i - Q.tail_start, jj = Q.lrow_col[x] - Q.tail_start;
-                Q.tl_src.push_back((uint16_t)x); Q.tl_dst.push_back((uint16_t)(ii * (ii - 1) / 2 + jj));
+                Q.tl_src.push_back((uint16_t)slot[x]); Q.tl_dst.push_back((uint16_t)(ii * (ii - 1) / 2 + jj)); Q.tl_col.push_back(Q.lrow_col[x]);
             }
-    // row descriptors (first entry | count << 16) of the four segments used by the range steps:
-    //   forward : CSR row r  = [entries left of the range (external) | entries inside the range]
-    //   backward: CSC column r = [entries inside the range | entries below the range (external)]
-    std::vector<int> range_of(Nk, -1), range_pa, range_pb;
-    {
-        const int nr = (int)Q.range_lvl.size() / 2;
-        for (int k = 0; k < nr; k++) {
-            range_pa.push_back(Q.lvl_ptr[Q.range_lvl[2 * k]]); range_pb.push_back(Q.lvl_ptr[Q.range_lvl[2 * k + 1]]);
-            for (int p = range_pa[k]; p < range_pb[k]; p++) range_of[p] = k;
-        }
-        // level 0 and the tail behave as ranges whose in-range part is handled elsewhere (none / dense)
-        Q.fwd_ext.assign(Nk, 0); Q.fwd_in.assign(Nk, 0); Q.bwd_in.assign(Nk, 0); Q.bwd_ext.assign(Nk, 0);
-        for (int r = 0; r < Nk; r++) {
-            int pa, pb;
-            if (range_of[r] >= 0) { pa = range_pa[range_of[r]]; pb = range_pb[range_of[r]]; }
-            else if (r >= Q.tail_start) { pa = Q.tail_start; pb = Nk; }
-            else { pa = 0; pb = Q.lvl_ptr[1]; }
-            int e0 = Q.lrow_ptr[r], e1 = Q.lrow_ptr[r + 1], sp = e0;
-            while (sp < e1 && Q.lrow_col[sp] < pa) sp++;
-            Q.fwd_ext[r] = (uint32_t)e0 | ((uint32_t)(sp - e0) << 16);
-            Q.fwd_in[r] = (uint32_t)sp | ((uint32_t)(e1 - sp) << 16);
-            int c0 = Q.lcol_ptr[r], c1 = Q.lcol_ptr[r + 1], cp = c0;
-            while (cp < c1 && Q.lcol_row[cp] < pb) cp++;
-            Q.bwd_in[r] = (uint32_t)c0 | ((uint32_t)(cp - c0) << 16);
-            Q.bwd_ext[r] = (uint32_t)cp | ((uint32_t)(c1 - cp) << 16);
-            if ((sp - e0) > 255 || (e1 - sp) > 255 || (cp - c0) > 255 || (c1 - cp) > 255) return fail("row segment longer than 255 entries");
-        }
-    }
-    // step programs of the sparse part (256 lanes): a step = rows [r0, r0+rows) x 2^sh lanes, <= 4 entries per lane;
-    // word 0 = r0 | rows << 16, word 1 = sh | flags << 8
-    {
-        const int T = ADMM_THREADS;
-        bool too_long = false;
-        auto emit = [&](std::vector<uint32_t>& out, int pa, int pb, const std::vector<uint32_t>& desc, uint32_t flags) {
-            int w = pb - pa, mx = 0;
-            for (int r = pa; r < pb; r++) mx = std::max(mx, (int)(desc[r] >> 16));
-            int sh = 0;
-            while (sh < 5 && ((mx + (1 << sh) - 1) >> sh) > 4) sh++;
-            if (((mx + (1 << sh) - 1) >> sh) > 4) too_long = true;
-            while (sh < 5 && ((mx + (1 << sh) - 1) >> sh) > 2 && (w << (sh + 1)) <= T) sh++;
-            int rows_per_pass = T >> sh;
-            for (int a = 0; a < w; a += rows_per_pass) {
-                int nrows = std::min(rows_per_pass, w - a);
-                bool last = a + nrows >= w;
-                out.push_back((uint32_t)(pa + a) | ((uint32_t)nrows << 16));
-                out.push_back((uint32_t)sh | ((flags | (last ? (uint32_t)STEP_LAST : 0u)) << 8));
+
+    // generic emitter for the gather programs (factorisation, range inverses): targets with (a, b, k) entry lists
+    struct Tgt { uint32_t tgt; std::vector<uint64_t> ents; };
+    auto emit_level = [&](const std::vector<Tgt>& tg, std::vector<uint32_t>& tasks, std::vector<uint32_t>& lvl_ptr, std::vector<uint32_t>& tgts, std::vector<uint64_t>& ents) {
+        std::vector<int> len(tg.size());
+        for (size_t i = 0; i < tg.size(); i++) len[i] = (int)tg[i].ents.size();
+        const uint64_t padent = (uint64_t)Q.zslot | ((uint64_t)Q.zslot << 16);
+        for (const SchedTask& t : schedule_phase(len, NWARP)) {
+            const int g = 1 << t.sh, ebase = (int)ents.size(), rbase = (int)tgts.size();
+            ents.resize(ebase + 32 * t.K, padent);
+            for (size_t rr = 0; rr < t.rows.size(); rr++) {
+                const Tgt& T = tg[t.rows[rr]];
+                tgts.push_back(T.tgt);
+                for (size_t x = 0; x < T.ents.size(); x++) ents[ebase + (x / g) * 32 + (rr << t.sh) + (x % g)] = T.ents[x];
             }
-        };
-        const int nr = (int)range_pa.size();
-        for (int k = 0; k < nr; k++) {
-            emit(Q.step_f, range_pa[k], range_pb[k], Q.fwd_ext, STEP_SEG_FWD_EXT | STEP_DST_TMP);                       // t = b - L_ext y      (sol -> tmp)
-            emit(Q.step_f, range_pa[k], range_pb[k], Q.fwd_in, STEP_SEG_FWD_IN | STEP_SRC_TMP | STEP_ADD);              // y = t + Minv t       (tmp -> sol)
+            add_task_words(tasks, ebase, rbase, t, 0);
         }
-        if (Q.tail_dim > 0) emit(Q.step_f, Q.tail_start, Nk, Q.fwd_ext, STEP_SEG_FWD_EXT | STEP_DST_TMP);               // tail stage 1          (sol -> tmp)
-        for (int k = nr - 1; k >= 0; k--) {
-            emit(Q.step_b, range_pa[k], range_pb[k], Q.bwd_ext, STEP_SEG_BWD_EXT | STEP_DST_TMP | STEP_SCALE);          // u = w/D - L_ext' x    (sol -> tmp)
-            emit(Q.step_b, range_pa[k], range_pb[k], Q.bwd_in, STEP_SEG_BWD_IN | STEP_SRC_TMP | STEP_ADD);              // x = u + Minv' u       (tmp -> sol)
-        }
-        emit(Q.step_b, 0, Q.lvl_ptr[1], Q.bwd_ext, STEP_SEG_BWD_EXT | STEP_SCALE);                                       // level 0: x = w/D - L' x  (sol -> sol)
-        if (too_long) return fail("a row segment of L has more than 128 entries (unsupported by the solve step program)");
-    }
-    // inverse program: for every range, level by level, each in-range entry (i,j) becomes  M_ij = -(S_ij + sum_{j<k<i} S_ik M_kj)
-    {
-        Q.inv_ptr.push_back(0);
-        Q.itgt_ptr.push_back(0);
-        const int nr = (int)range_pa.size();
-        for (int k = 0; k < nr; k++) {
-            const int pa = range_pa[k];
-            for (int l = Q.range_lvl[2 * k] + 1; l < Q.range_lvl[2 * k + 1]; l++) {      // the first level of a range has no in-range entries
-                for (int i = Q.lvl_ptr[l]; i < Q.lvl_ptr[l + 1]; i++) {
-                    const int e0 = (int)(Q.fwd_in[i] & 0xffff), cnt = (int)(Q.fwd_in[i] >> 16);
-                    for (int x = e0; x < e0 + cnt; x++) {
-                        const int j = Q.lrow_col[x];
-                        Q.itgt_id.push_back((uint16_t)x);
-                        for (int y = x + 1; y < e0 + cnt; y++) {           // k = column of entry y, j < k < i
-                            const int kk = Q.lrow_col[y];
-                            const int mkj = lidx(kk, j);
-                            if (mkj >= 0 && j >= pa) { Q.inv_a.push_back((uint16_t)y); Q.inv_b.push_back((uint16_t)mkj); }
-                        }
-                        Q.inv_ptr.push_back((uint32_t)Q.inv_a.size());
-                    }
-                }
-                if (Q.itgt_id.size() - Q.itgt_ptr.back() > 4 * ADMM_THREADS) return fail("range inverse: too many targets in one level");
-                Q.itgt_ptr.push_back((uint32_t)Q.itgt_id.size());
-            }
-        }
-    }
-    Q.lvl_gf.assign(nlev, 1); Q.lvl_gb.assign(nlev, 1); Q.lvl_gfac.assign(nlev, 1);
-    // numeric factorisation program
-    Q.ftgt_ptr.assign(nlev + 1, 0);
-    Q.fac_ptr.push_back(0);
+        lvl_ptr.push_back((uint32_t)(tasks.size() / 4));
+    };
+    auto ent3 = [](int a, int b, int k) { return (uint64_t)a | ((uint64_t)b << 16) | ((uint64_t)k << 32); };
+    // numeric factorisation program (left-looking gathers, level scheduled), unscaled form W = L D
+    Q.fac_lvl_ptr.assign(1, 0);
     for (int l = 0; l < nlev; l++) {
-        struct Tgt { int id, col; std::vector<std::pair<int, int>> pairs; std::vector<int> ks; };
         std::vector<Tgt> tg;
         for (int j = Q.lvl_ptr[l]; j < Q.lvl_ptr[l + 1]; j++) {
-            Tgt d; d.id = Q.nnzL + j; d.col = j;
-            for (int kk : rows[j]) { int a = lidx(j, kk); d.pairs.push_back({a, a}); d.ks.push_back(kk); }
+            Tgt d; d.tgt = (uint32_t)(nslots + j) | ((uint32_t)j << 16);
+            for (int kk : rows[j]) { int a = slot[lidx(j, kk)]; d.ents.push_back(ent3(a, a, kk)); }
             tg.push_back(std::move(d));
             for (int i : cs[j]) {
-                Tgt o; o.id = lidx(i, j); o.col = j;
+                Tgt o; o.tgt = (uint32_t)slot[lidx(i, j)] | ((uint32_t)j << 16);
                 const auto &ri = rows[i], &rj = rows[j];
                 size_t x = 0, y = 0;
                 while (x < ri.size() && y < rj.size()) {
                     if (ri[x] >= j) break;
-                    if (ri[x] == rj[y]) { o.pairs.push_back({Q.lrow_ptr[i] + (int)x, Q.lrow_ptr[j] + (int)y}); o.ks.push_back(ri[x]); x++; y++; }
+                    if (ri[x] == rj[y]) { o.ents.push_back(ent3(slot[Q.lrow_ptr[i] + (int)x], slot[Q.lrow_ptr[j] + (int)y], ri[x])); x++; y++; }
                     else if (ri[x] < rj[y]) x++;
                     else y++;
                 }
-                tg.push_back(std::move(o));
+                if (!o.ents.empty()) tg.push_back(std::move(o));      // W_ij = K_ij needs no work
             }
         }
-        std::stable_sort(tg.begin(), tg.end(), [](const Tgt& a, const Tgt& c) { return a.pairs.size() > c.pairs.size(); });
-        for (auto& t : tg) {
-            Q.ftgt_id.push_back((uint16_t)t.id); Q.ftgt_col.push_back((uint16_t)t.col);
-            for (size_t x = 0; x < t.pairs.size(); x++) {
-                Q.fac_a.push_back((uint16_t)t.pairs[x].first); Q.fac_b.push_back((uint16_t)t.pairs[x].second); Q.fac_k.push_back((uint16_t)t.ks[x]);
+        emit_level(tg, Q.fac_task, Q.fac_lvl_ptr, Q.fac_tgt, Q.fac_ent);
+    }
+    // inverse program: for every range, level by level, each in-range entry (i,j) becomes  M_ij = -(W_ij/d_j + sum_{j<k<i} W_ik/d_k M_kj)
+    Q.inv_lvl_ptr.assign(1, 0);
+    Q.inv_max_tasks_per_warp = 0;
+    for (int k = 0; k < nr; k++) {
+        const int pa = range_pa[k];
+        for (int l = Q.range_lvl[2 * k] + 1; l < Q.range_lvl[2 * k + 1]; l++) {      // the first level of a range has no in-range entries
+            std::vector<Tgt> tg;
+            for (int i = Q.lvl_ptr[l]; i < Q.lvl_ptr[l + 1]; i++) {
+                for (int x = Q.lrow_ptr[i]; x < Q.lrow_ptr[i + 1]; x++) {
+                    const int j = Q.lrow_col[x];
+                    if (j < pa) continue;
+                    Tgt t; t.tgt = (uint32_t)slot[x] | ((uint32_t)j << 16);
+                    for (int y = x + 1; y < Q.lrow_ptr[i + 1]; y++) {           // kk = column of entry y, j < kk < i
+                        const int kk = Q.lrow_col[y];
+                        const int mkj = lidx(kk, j);
+                        if (mkj >= 0) t.ents.push_back(ent3(slot[y], slot[mkj], kk));
+                    }
+                    tg.push_back(std::move(t));
+                }
             }
-            Q.fac_ptr.push_back((uint32_t)Q.fac_a.size());
-        }
-        Q.ftgt_ptr[l + 1] = (uint32_t)Q.ftgt_id.size();
-        {
-            int mp = 0;
-            for (auto& t : tg) mp = std::max(mp, (int)t.pairs.size());
-            int g = 1;
-            while (g < 32 && (mp + g - 1) / g > 4) g *= 2;
-            while (g > 1 && (int)tg.size() * g > 1024) g /= 2;
-            Q.lvl_gfac[l] = (uint8_t)g;
+            const size_t before = Q.inv_task.size() / 4;
+            emit_level(tg, Q.inv_task, Q.inv_lvl_ptr, Q.inv_tgt, Q.inv_ent);
+            const int ntask = (int)(Q.inv_task.size() / 4 - before);
+            Q.inv_max_tasks_per_warp = std::max(Q.inv_max_tasks_per_warp, (ntask + NWARP - 1) / NWARP);
         }
     }
+    if (Q.inv_max_tasks_per_warp > INV_MAX_TASKS_PER_WARP) return fail("range inverse: too many targets in one level");
     return true;
 }
 

@@ -17,8 +17,11 @@
 
 // threads per ADMM CTA: the step programs of the triangular solves are laid out for exactly this many lanes
 #ifndef ADMM_THREADS
-#define ADMM_THREADS 1024
+#define ADMM_THREADS 512
 #endif
+
+// in-place range inverse: a warp keeps the results of at most this many tasks of one level in registers before writing them back
+#define INV_MAX_TASKS_PER_WARP 4
 
 namespace pgn {
 
@@ -39,9 +42,12 @@ enum { CT_ZERO = 0, CT_PINF, CT_NINF, CT_VMIN, CT_VMAX, CT_FXMIN_N, CT_DDELTA_N,
 enum { BND_CONST = 0, BND_REC = 1, BND_NEG_REC = 2, BND_DT_SCALED = 3, BND_NEG_DT_SCALED = 4 };
 // modes of the cost tables
 enum { PQ_ZERO = 0, PQ_TIMES_DT = 1, PQ_OVER_DT = 2, PQ_CONST = 3 };
-// step flags (word 1 >> 8)
-enum { STEP_LAST = 1, STEP_SEG_FWD_EXT = 0 << 1, STEP_SEG_FWD_IN = 1 << 1, STEP_SEG_BWD_IN = 2 << 1, STEP_SEG_BWD_EXT = 3 << 1, STEP_SEG_MASK = 3 << 1,
-       STEP_SRC_TMP = 1 << 3, STEP_DST_TMP = 1 << 4, STEP_ADD = 1 << 5, STEP_SCALE = 1 << 6 };
+// flags of a solve task (see WTask): out[r] = f(in[r], acc) with acc = sum of the task's products
+//   default            out = in - acc
+//   TASK_ADD           out = in + acc
+//   TASK_SCALE_OUT     out = Dinv[r] * (in +- acc)
+//   TASK_SCALE_ACC     out = in +- Dinv[r] * acc
+enum { TASK_SRC_TMP = 1 << 0, TASK_DST_TMP = 1 << 1, TASK_ADD = 1 << 2, TASK_SCALE_OUT = 1 << 3, TASK_SCALE_ACC = 1 << 4 };
 // weight ids (resolved against the control parameters at run time so that pgn_set_control_params needs no re-analysis)
 enum { W_NONE = 0, W_Q_DS, W_Q_DPSI, W_Q_E, W_R_DELTA, W_R_FX, W_R_DDELTA, W_R_DFX, W_W_BETA, W_W_R, W_W_HJI, W_LEN };
 
@@ -66,27 +72,40 @@ struct QpTables {
     std::vector<uint16_t> a_rowpos, a_colpos, a_lpos;
     // off-diagonal KKT adjacency in position space: for position p, entries (A value index, neighbour position)
     std::vector<uint16_t> kadj_ptr, kadj_e, kadj_nb;
-    // numeric factorisation program (left-looking gathers, level scheduled)
-    std::vector<uint32_t> ftgt_ptr;                     // per level -> range of targets
-    std::vector<uint16_t> ftgt_id, ftgt_col;            // target: L value index (< nnzL) or nnzL + column for a diagonal; its column
-    std::vector<uint32_t> fac_ptr;                      // per target -> range of pairs
-    std::vector<uint16_t> fac_a, fac_b, fac_k;          // pair: L value indices (row i col k), (row j col k) and the column k
-    // lanes cooperating on one row / column / factor target, per level (powers of two)
-    std::vector<uint8_t> lvl_gf, lvl_gb, lvl_gfac;
     // level ranges [la, lb) of the sparse part whose in-range block of L is replaced by its explicit inverse after factorisation
     std::vector<int> range_lvl;
-    // per-row segment descriptors (first entry | count << 16): forward CSR row = [external | in-range], backward CSC column = [in-range | external]
-    std::vector<uint32_t> fwd_ext, fwd_in, bwd_in, bwd_ext;
-    // flattened step programs of the triangular solves.  One step = one pass of the CTA: rows [r0, r0+rows) handled by 2^sh lanes
-    // each, <= 4 entries per lane; word 0 = r0 | rows << 16, word 1 = sh | STEP_* flags << 8
-    std::vector<uint32_t> step_f, step_b;
-    // in-place inversion program of the range blocks: targets (L value indices) per in-range level, pairs (S_ik, M_kj) per target
-    std::vector<uint32_t> itgt_ptr, inv_ptr;
-    std::vector<uint16_t> itgt_id, inv_a, inv_b;
+    // ---- warp programs -----------------------------------------------------------------------------------------------------------
+    // Every data-parallel phase of the factorisation and of the triangular solves is a list of warp tasks.  One task = one warp:
+    // 32 >> sh rows (targets), 2^sh adjacent lanes per row, K entry slots per lane; the entries of a task are stored slot-major
+    // (index ebase + k * 32 + lane) so that every access to a program array is one coalesced / conflict-free warp access.
+    //   word 0: ebase          word 1: rbase | nrows << 16 | sh << 24          word 2: K | flags << 16          word 3: spare
+    // Padding entries multiply the always-zero L slot `zslot` with the always-zero vector element Nk.
+    //
+    // The factor is kept in the unscaled form W = L D (W_ij = L_ij d_j): W_ij = K_ij - sum_k W_ik W_jk / d_k needs no column scaling
+    // phase, and the solves absorb 1/d (flags above).  L values live in the order the FORWARD solve consumes them (`nslots` slots).
+    int nslots, zslot;
+    std::vector<uint32_t> sol_task;                    // solve tasks, 4 words each: forward phases then backward phases
+    std::vector<uint16_t> sol_ph_ptr;                  // phase -> first task; n_fwd_ph forward phases, then n_bwd_ph backward phases
+    int n_fwd_ph, n_bwd_ph;
+    std::vector<uint16_t> sol_orow;                    // output position per (task, row)
+    std::vector<uint16_t> fidx;                        // forward: source position per L slot (size nslots)
+    std::vector<uint32_t> bent;                        // backward entries in program order: L slot | source position << 16
+    int lvl0_end;                                      // positions [0, lvl0_end) are level 0: y^_r = b_r / d_r is folded into the rhs
+    // numeric factorisation: per level a list of tasks; target (id | col << 16): id < nslots an L slot, id >= nslots the pivot of
+    // position id - nslots; entry: a | b << 16 | k << 32  (product W[a] * W[b] / d_k)
+    std::vector<uint32_t> fac_task, fac_lvl_ptr, fac_tgt;
+    std::vector<uint64_t> fac_ent;
+    // in-place inversion of the range blocks (unit lower M = L_RR^-1), level by level: target (slot | col << 16),
+    //   M_ij = -(W_ij / d_j + sum_{j<k<i} W_ik / d_k * M_kj),   entry a | b << 16 | k << 32  (W[a] * M[b] / d_k)
+    std::vector<uint32_t> inv_task, inv_lvl_ptr, inv_tgt;
+    std::vector<uint64_t> inv_ent;
+    int inv_max_tasks_per_warp;
+    // A entries -> L slot
+    std::vector<uint16_t> a_slot;
     // dense tail: the last `tail_dim` positions (levels >= tail_level) form a (nearly dense) unit lower triangular block whose explicit
     // inverse is rebuilt after every numeric factorisation; it replaces tail_dim narrow levels by two dense mat-vec levels
     int tail_level, tail_start, tail_dim;
-    std::vector<uint16_t> tl_src, tl_dst;               // sparse L entry -> packed strictly-lower dense index i*(i-1)/2 + j
+    std::vector<uint16_t> tl_src, tl_dst, tl_col;       // L slot -> packed strictly-lower dense index i*(i-1)/2 + j; column position (for 1/d)
     // where the solution components consumed by the host-side API live
     int var_u1_delta, var_u1_fx;                        // variable indices of u[:,2] (node 2)
 };

@@ -121,9 +121,11 @@ class BatchedTrajectoryTrackingMPC:
         self._h = C.c_void_p()
         check(lib.pgn_create(C.byref(cfg), C.byref(self._h)))
         self.B = int(batch)
-        d = np.zeros(8, dtype=np.int32)
+        d = np.zeros(16, dtype=np.int32)
         check(lib.pgn_qp_dims(self._h, dptr(d)))
-        self.N, self.nx, self.nu, self.n, self.m, self.nnzA, self.nnzL, self.n_levels = (int(x) for x in d)
+        self.N, self.nx, self.nu, self.n, self.m, self.nnzA, self.nnzL, self.n_levels = (int(x) for x in d[:8])
+        self.qp_program = dict(l_slots=int(d[8]), solve_phases=int(d[9]), factor_entries=int(d[10]), inverse_entries=int(d[11]), tail_dim=int(d[12]),
+                               backward_entries=int(d[13]), admm_smem_bytes=int(d[14]), admm_threads=int(d[15]))
         self.T = self.N - 1
         self.vehicle = dict(vehicle)
         self.control_params = dict(control_params) if control_params is not None else _control_params(kind, {})

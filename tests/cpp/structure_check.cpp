@@ -26,60 +26,96 @@ int main(int argc, char** argv) {
     for (int j = 0; j < n; j++) K[(size_t)Q.pos_var[j] * Nk + Q.pos_var[j]] = Pd[j];
     for (int i = 0; i < m; i++) K[(size_t)Q.pos_con[i] * Nk + Q.pos_con[i]] = -rhoinv[i];
     for (int e = 0; e < Q.nnzA; e++) { int r = Q.a_rowpos[e], c = Q.a_colpos[e]; K[(size_t)r * Nk + c] = Aval[e]; K[(size_t)c * Nk + r] = Aval[e]; }
-    // emulate the kernel factorisation
-    std::vector<double> L(Q.nnzL, 0.0), D(Nk), Dinv(Nk);
-    for (int e = 0; e < Q.nnzA; e++) L[Q.a_lpos[e]] = Aval[e];
-    for (int p = 0; p < Nk; p++) D[p] = Q.is_con[p] ? -rhoinv[Q.pos2idx[p]] : Pd[Q.pos2idx[p]];
-    size_t npairs = Q.fac_a.size();
-    for (int l = 0; l < Q.nlev; l++) {
-        for (uint32_t t = Q.ftgt_ptr[l]; t < Q.ftgt_ptr[l + 1]; t++) {
-            int id = Q.ftgt_id[t];
-            if (id >= Q.nnzL) { int j = id - Q.nnzL; double s = D[j]; for (uint32_t x = Q.fac_ptr[t]; x < Q.fac_ptr[t + 1]; x++) { double v = L[Q.fac_a[x]]; s -= v * v * D[Q.fac_k[x]]; } D[j] = s; Dinv[j] = 1.0 / s; }
-            else { double s = L[id]; for (uint32_t x = Q.fac_ptr[t]; x < Q.fac_ptr[t + 1]; x++) s -= L[Q.fac_a[x]] * L[Q.fac_b[x]] * D[Q.fac_k[x]]; L[id] = s; }
+    // emulate the kernel factorisation (unscaled form W = L D, one gather pass per level, no scaling pass)
+    const int NS = Q.nslots;
+    std::vector<double> L(NS, 0.0), Dinv(Nk);
+    for (int e = 0; e < Q.nnzA; e++) L[Q.a_slot[e]] = Aval[e];
+    for (int p = 0; p < Nk; p++) Dinv[p] = Q.is_con[p] ? -rhoinv[Q.pos2idx[p]] : Pd[Q.pos2idx[p]];      // holds K_pp until the pivot is formed
+    size_t npairs = 0;
+    // a task list executed the way the warps do: every lane accumulates its K slots, the lanes of a row are summed, lane 0 of the row applies the result
+    auto run_gather = [&](const std::vector<uint32_t>& tasks, uint32_t t0, uint32_t t1, const std::vector<uint32_t>& tgts, const std::vector<uint64_t>& ents,
+                          std::vector<std::pair<uint32_t, double>>& results) {
+        for (uint32_t t = t0; t < t1; t++) {
+            const uint32_t ebase = tasks[4 * t], w1 = tasks[4 * t + 1], w2 = tasks[4 * t + 2];
+            const int rbase = w1 & 0xffff, nrows = (w1 >> 16) & 0xff, sh = w1 >> 24, K = w2 & 0xffff, g = 1 << sh;
+            if (nrows > (32 >> sh)) { printf("FAIL task rows\n"); exit(3); }
+            for (int rr = 0; rr < nrows; rr++) {
+                double acc = 0;
+                for (int sub = 0; sub < g; sub++)
+                    for (int k = 0; k < K; k++) {
+                        const uint64_t e = ents[ebase + k * 32 + (rr << sh) + sub];
+                        const int a = e & 0xffff, bb = (e >> 16) & 0xffff, kk = (int)(e >> 32);
+                        acc += L[a] * L[bb] * Dinv[kk];
+                        if (a != Q.zslot) npairs++;
+                    }
+                results.push_back({tgts[rbase + rr], acc});
+            }
+            for (int lane = nrows << sh; lane < 32; lane++) for (int k = 0; k < K; k++) { const uint64_t e = ents[ebase + k * 32 + lane]; if ((int)(e & 0xffff) != Q.zslot) { printf("FAIL pad\n"); exit(3); } }
         }
-        for (uint32_t t = Q.ftgt_ptr[l]; t < Q.ftgt_ptr[l + 1]; t++) { int id = Q.ftgt_id[t]; if (id < Q.nnzL) L[id] *= Dinv[Q.ftgt_col[t]]; }
+    };
+    for (int l = 0; l < Q.nlev; l++) {
+        std::vector<std::pair<uint32_t, double>> res;
+        run_gather(Q.fac_task, Q.fac_lvl_ptr[l], Q.fac_lvl_ptr[l + 1], Q.fac_tgt, Q.fac_ent, res);
+        for (auto& r : res) {
+            const int id = r.first & 0xffff;
+            if (id >= NS) { const int j = id - NS; Dinv[j] = 1.0 / (Dinv[j] - r.second); }
+            else L[id] -= r.second;
+        }
     }
     // range inverses in place (two-phase per level, as in the kernel)
-    for (size_t l = 0; l + 1 < Q.itgt_ptr.size(); l++) {
-        std::vector<double> v;
-        for (uint32_t t = Q.itgt_ptr[l]; t < Q.itgt_ptr[l + 1]; t++) { double acc = L[Q.itgt_id[t]]; for (uint32_t x = Q.inv_ptr[t]; x < Q.inv_ptr[t + 1]; x++) acc += L[Q.inv_a[x]] * L[Q.inv_b[x]]; v.push_back(-acc); }
-        for (uint32_t t = Q.itgt_ptr[l]; t < Q.itgt_ptr[l + 1]; t++) L[Q.itgt_id[t]] = v[t - Q.itgt_ptr[l]];
+    for (size_t l = 0; l + 1 < Q.inv_lvl_ptr.size(); l++) {
+        std::vector<std::pair<uint32_t, double>> res;
+        run_gather(Q.inv_task, Q.inv_lvl_ptr[l], Q.inv_lvl_ptr[l + 1], Q.inv_tgt, Q.inv_ent, res);
+        for (auto& r : res) { const int id = r.first & 0xffff, col = r.first >> 16; r.second = -(L[id] * Dinv[col] + r.second); }
+        for (auto& r : res) L[r.first & 0xffff] = r.second;
     }
-    // dense tail: packed copy of L[tail, tail] and its explicit inverse (column-wise forward substitution), as in the kernel
+    // dense tail: packed copy of the unit lower L[tail, tail] = W / d_col and its explicit inverse (column-wise forward substitution), as in the kernel
     const int ts = Q.tail_start, Dm = Q.tail_dim;
     std::vector<double> Ld(Dm * (Dm - 1) / 2 + 1, 0.0), Ti(Dm * (Dm - 1) / 2 + 1, 0.0);
-    for (size_t e = 0; e < Q.tl_src.size(); e++) Ld[Q.tl_dst[e]] = L[Q.tl_src[e]];
+    for (size_t e = 0; e < Q.tl_src.size(); e++) Ld[Q.tl_dst[e]] = L[Q.tl_src[e]] * Dinv[Q.tl_col[e]];
     for (int j = 0; j < Dm; j++) for (int r = j + 1; r < Dm; r++) {
         double acc = 0; int rb = r * (r - 1) / 2;
         for (int k = j + 1; k < r; k++) acc += Ld[rb + k] * Ti[k * (k - 1) / 2 + j];
         Ti[rb + j] = -(Ld[rb + j] + acc);
     }
-    // solve K x = b with the step programs
-    std::vector<double> b(Nk), x(Nk), tmp(Nk, 0.0);
+    if (L[Q.zslot] != 0.0) { printf("FAIL zslot written\n"); return 3; }
+    // solve K x = b with the solve programs
+    std::vector<double> b(Nk), x(Nk + 1, 0.0), tmp(Nk + 1, 0.0);
     for (auto& v : b) v = U(rng);
-    x = b;
-    const std::vector<uint32_t>* segs[4] = {&Q.fwd_ext, &Q.fwd_in, &Q.bwd_in, &Q.bwd_ext};
-    auto run = [&](const std::vector<uint32_t>& st) {
-        for (size_t i = 0; i < st.size(); i += 2) {
-            int r0 = st[i] & 0xffff, nrows = st[i] >> 16, fl = st[i + 1] >> 8, sg = (fl & STEP_SEG_MASK) >> 1;
-            std::vector<double>& in = (fl & STEP_SRC_TMP) ? tmp : x;
-            std::vector<double>& out = (fl & STEP_DST_TMP) ? tmp : x;
-            std::vector<double> res(nrows);
+    for (int p = 0; p < Nk; p++) x[p] = p < Q.lvl0_end ? b[p] * Dinv[p] : b[p];        // level 0 folded into the right-hand side
+    std::vector<char> written(Nk, 0);
+    auto run_phase = [&](int ph, bool bwd) {
+        std::vector<std::pair<int, double>> outs;
+        int dst_tmp = 0;
+        for (int t = Q.sol_ph_ptr[ph]; t < Q.sol_ph_ptr[ph + 1]; t++) {
+            const uint32_t ebase = Q.sol_task[4 * t], w1 = Q.sol_task[4 * t + 1], w2 = Q.sol_task[4 * t + 2];
+            const int rbase = w1 & 0xffff, nrows = (w1 >> 16) & 0xff, sh = w1 >> 24, K = w2 & 0xffff, fl = w2 >> 16, g = 1 << sh;
+            const std::vector<double>& in = (fl & TASK_SRC_TMP) ? tmp : x;
+            dst_tmp = fl & TASK_DST_TMP;
             for (int rr = 0; rr < nrows; rr++) {
-                int r = r0 + rr; uint32_t rd = (*segs[sg])[r]; int base = rd & 0xffff, len = rd >> 16; double acc = 0;
-                for (int e = base; e < base + len; e++) acc += (sg < 2) ? L[e] * in[Q.lrow_col[e]] : L[Q.lcol_val[e]] * in[Q.lcol_row[e]];
-                double xv = in[r]; if (fl & STEP_SCALE) xv *= Dinv[r];
-                res[rr] = (fl & STEP_ADD) ? xv + acc : xv - acc;
+                double acc = 0;
+                for (int sub = 0; sub < g; sub++)
+                    for (int k = 0; k < K; k++) {
+                        const int e = ebase + k * 32 + (rr << sh) + sub;
+                        if (bwd) acc += L[Q.bent[e] & 0xffff] * in[Q.bent[e] >> 16];
+                        else acc += L[e] * in[Q.fidx[e]];
+                    }
+                const int r = Q.sol_orow[rbase + rr];
+                if (fl & TASK_SCALE_ACC) acc *= Dinv[r];
+                double v = (fl & TASK_ADD) ? in[r] + acc : in[r] - acc;
+                if (fl & TASK_SCALE_OUT) v *= Dinv[r];
+                outs.push_back({r, v});
             }
-            for (int rr = 0; rr < nrows; rr++) out[r0 + rr] = res[rr];
         }
+        for (auto& o : outs) { (dst_tmp ? tmp : x)[o.first] = o.second; if (!dst_tmp) written[o.first]++; }
     };
-    run(Q.step_f);
+    for (int ph = 0; ph < Q.n_fwd_ph; ph++) run_phase(ph, false);
     std::vector<double> t2(Nk);
     for (int rr = 0; rr < Dm; rr++) { double s = tmp[ts + rr]; for (int k = 0; k < rr; k++) s += Ti[rr * (rr - 1) / 2 + k] * tmp[ts + k]; x[ts + rr] = s * Dinv[ts + rr]; }
     for (int rr = 0; rr < Dm; rr++) { double s = x[ts + rr]; for (int k = rr + 1; k < Dm; k++) s += Ti[k * (k - 1) / 2 + rr] * x[ts + k]; t2[ts + rr] = s; }
     for (int rr = 0; rr < Dm; rr++) x[ts + rr] = t2[ts + rr];
-    run(Q.step_b);
+    for (int ph = Q.n_fwd_ph; ph < Q.n_fwd_ph + Q.n_bwd_ph; ph++) run_phase(ph, true);
+    if (x[Nk] != 0.0 || tmp[Nk] != 0.0) { printf("FAIL zero element written\n"); return 3; }
     // residual ||K x - b||_inf and the kadj product against the dense one
     double res = 0, kadj_err = 0;
     for (int r = 0; r < Nk; r++) {
@@ -94,6 +130,19 @@ int main(int argc, char** argv) {
     printf("kind=%d N=%d n=%d m=%d Nk=%d nnzA=%d nnzL=%d nlev=%d maxwidth=%d pairs=%zu rec_len=%d tail_level=%d tail_dim=%d res=%.3e kadj_err=%.3e\n", kind, Q.N, n, m, Nk, Q.nnzA,
            Q.nnzL, Q.nlev, wmax, npairs, Q.rec.rec_len, Q.tail_level, Q.tail_dim, res, kadj_err);
     printf("  ranges:"); for (size_t k = 0; k + 1 < Q.range_lvl.size(); k += 2) printf(" [%d,%d)", Q.range_lvl[k], Q.range_lvl[k + 1]);
-    { size_t mt = 0; for (size_t l = 0; l + 1 < Q.itgt_ptr.size(); l++) mt = std::max(mt, (size_t)(Q.itgt_ptr[l + 1] - Q.itgt_ptr[l])); printf("  steps fwd %zu bwd %zu  inverse levels %zu max targets/level %zu inv pairs %zu\n", Q.step_f.size() / 2, Q.step_b.size() / 2, Q.itgt_ptr.size() - 1, mt, Q.inv_a.size()); }
+    printf("  nslots %d  solve phases fwd %d bwd %d tasks %zu bent %zu  factor tasks %zu ents %zu  inverse levels %zu tasks %zu ents %zu max tasks/warp %d\n", Q.nslots, Q.n_fwd_ph, Q.n_bwd_ph,
+           Q.sol_task.size() / 4, Q.bent.size(), Q.fac_task.size() / 4, Q.fac_ent.size(), Q.inv_lvl_ptr.size() - 1, Q.inv_task.size() / 4, Q.inv_ent.size(), Q.inv_max_tasks_per_warp);
+    if (argc > 5) {   // verbose: per-phase task shapes
+        for (int ph = 0; ph < Q.n_fwd_ph + Q.n_bwd_ph; ph++) {
+            printf("  phase %2d (%s):", ph, ph < Q.n_fwd_ph ? "fwd" : "bwd");
+            for (int t = Q.sol_ph_ptr[ph]; t < Q.sol_ph_ptr[ph + 1]; t++) printf(" %ux%d/K%u", (Q.sol_task[4 * t + 1] >> 16) & 0xff, 1 << (Q.sol_task[4 * t + 1] >> 24), Q.sol_task[4 * t + 2] & 0xffff);
+            printf("\n");
+        }
+        for (int l = 0; l < Q.nlev; l++) {
+            printf("  factor level %2d:", l);
+            for (uint32_t t = Q.fac_lvl_ptr[l]; t < Q.fac_lvl_ptr[l + 1]; t++) printf(" %ux%d/K%u", (Q.fac_task[4 * t + 1] >> 16) & 0xff, 1 << (Q.fac_task[4 * t + 1] >> 24), Q.fac_task[4 * t + 2] & 0xffff);
+            printf("\n");
+        }
+    }
     return (res < 1e-8 && kadj_err < 1e-10) ? 0 : 2;
 }
