@@ -20,6 +20,7 @@ namespace pgn {
 
 #define NW (ADMM_THREADS / 32)
 #define ADMM_NCYC 256
+#define SWEEP_EPT ((64 * 65 / 2 + ADMM_THREADS - 1) / ADMM_THREADS)      // elements of the packed dense tail per thread
 
 static const double OSQP_INFTY = 1e20;
 
@@ -35,14 +36,15 @@ struct AdmmArgs {
     uint8_t* solved;
     int* counter;
     const int32_t* order;          // ticket -> vehicle (longest previous solve first)
+    uint16_t ph_ptr[ADMM_MAX_PHASES + 1];   // first task of every solve phase (forward phases, then backward phases): uniform constant-bank reads
     unsigned long long* cycles;   // optional per-phase cycle counters (profiling builds of the host call): gather, ruiz, factor, solve, update, check, store
 };
 
 struct Smem {
-    double *Lval, *Dinv, *Aval, *xz, *sol, *dxy, *yq, *lo, *hi, *sc, *Tinv, *red;   // sol and dxy are adjacent: together they hold the dense tail copy
+    double *Lval, *S, *Dinv, *Aval, *xz, *sol, *dxy, *yq, *lo, *hi, *sc, *red;   // S: packed lower dense tail block, directly behind the L slots
     const uint2 *sol_task, *fac_task, *inv_task;      // packed warp-task descriptors
     const uint32_t *bent, *fac_lvl, *inv_lvl;
-    const uint16_t *fidx, *orow, *ph_ptr;
+    const uint16_t *fidx, *orow;
     uint8_t* flag;   // 0 variable, 1 inequality, 2 equality, 3 loose
     // aliases inside the Lval region, valid between the gather and the first factorisation of a QP (Ruiz equilibration)
     uint16_t *kptr, *ke;
@@ -51,25 +53,25 @@ struct Smem {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline int vec_len(int Nk) { return (Nk + 2) & ~1; }                 // Nk values + the always-zero element Nk
-__host__ __device__ inline size_t lval_region_doubles(int nslots, int Nk, int nnzA) {
+__host__ __device__ inline size_t lval_region_doubles(int nslots, int tail_dim, int Nk, int nnzA) {
     const size_t alias = align_up((size_t)(Nk + 1) * 2 + (size_t)nnzA * 4, 4) + (size_t)nnzA * 4;      // kptr, ke (u16) + arc (u32)
-    const size_t a = (alias + 7) / 8;
-    return a > (size_t)nslots ? a : (size_t)nslots;
+    const size_t a = (alias + 7) / 8, l = (size_t)nslots + (size_t)tail_dim * (tail_dim + 1) / 2;
+    return a > l ? a : l;
 }
 
 size_t admm_smem_bytes(const QpTables& t) {
     const size_t V = vec_len(t.Nk);
-    size_t d = lval_region_doubles(t.nslots, t.Nk, t.nnzA) + V + align_up(t.nnzA, 2) + 7 * V + (size_t)t.tail_dim * (t.tail_dim - 1) / 2 + 16 * NW + 8;
+    size_t d = lval_region_doubles(t.nslots, t.tail_dim, t.Nk, t.nnzA) + V + align_up(t.nnzA, 2) + 7 * V + 16 * NW + 8;
     size_t u64 = (t.sol_task.size() + t.fac_task.size() + t.inv_task.size()) / 4;
     size_t u32 = t.bent.size() + t.fac_lvl_ptr.size() + t.inv_lvl_ptr.size() + 4;
-    size_t u16 = (size_t)t.nslots + t.sol_orow.size() + t.sol_ph_ptr.size() + 8;
+    size_t u16 = (size_t)t.nslots + t.sol_orow.size() + 8;
     return d * 8 + u64 * 8 + align_up(u32 * 4, 8) + align_up(u16 * 2, 8) + align_up((size_t)t.Nk, 8) + 64;
 }
 
 __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem& s, uint2*& w_task, uint32_t*& w_u32, uint16_t*& w_u16) {
     const int V = vec_len(q.Nk);
     double* d = reinterpret_cast<double*>(base);
-    s.Lval = d; d += lval_region_doubles(q.nslots, q.Nk, q.nnzA);
+    s.Lval = d; s.S = d + q.nslots; d += lval_region_doubles(q.nslots, q.tail_dim, q.Nk, q.nnzA);
     s.Dinv = d; d += V;
     s.Aval = d; d += (q.nnzA + 1) & ~1;
     s.xz = d; d += V;
@@ -79,16 +81,15 @@ __device__ __forceinline__ void carve(const QpDev& q, unsigned char* base, Smem&
     s.lo = d; d += V;
     s.hi = d; d += V;
     s.sc = d; d += V;
-    s.Tinv = d; d += q.tail_dim * (q.tail_dim - 1) / 2;
     s.red = d; d += 16 * NW + 8;
     w_task = reinterpret_cast<uint2*>(d);
     s.sol_task = w_task; s.fac_task = s.sol_task + q.n_sol_task; s.inv_task = s.fac_task + q.n_fac_task;
     w_u32 = reinterpret_cast<uint32_t*>(w_task + q.n_sol_task + q.n_fac_task + q.n_inv_task);
-    s.bent = w_u32; s.fac_lvl = s.bent + q.n_bent; s.inv_lvl = s.fac_lvl + q.nlev + 1;
+    s.bent = w_u32; s.fac_lvl = s.bent + q.n_bent; s.inv_lvl = s.fac_lvl + q.n_fac_lvl + 1;
     size_t off = align_up((size_t)(reinterpret_cast<const unsigned char*>(s.inv_lvl + q.n_inv_levels + 1) - base), 8);
     w_u16 = reinterpret_cast<uint16_t*>(base + off);
-    s.fidx = w_u16; s.orow = s.fidx + q.nslots; s.ph_ptr = s.orow + q.n_orow;
-    off = align_up((size_t)(reinterpret_cast<const unsigned char*>(s.ph_ptr + q.n_fwd_ph + q.n_bwd_ph + 1) - base), 8);
+    s.fidx = w_u16; s.orow = s.fidx + q.nslots;
+    off = align_up((size_t)(reinterpret_cast<const unsigned char*>(s.orow + q.n_orow) - base), 8);
     s.flag = base + off;
     s.kptr = reinterpret_cast<uint16_t*>(s.Lval);
     s.ke = s.kptr + q.Nk + 1;
@@ -202,23 +203,30 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long t_lvl = clock64();
     const RhoInv ri = make_rho_inv(rho);
-    for (int e = tid; e < q.nslots; e += ADMM_THREADS) s.Lval[e] = 0.0;
-    // Dinv[p] holds K_pp until the pivot of p is formed
-    for (int p = tid; p < q.Nk; p += ADMM_THREADS) s.Dinv[p] = s.flag[p] ? -rinv_of(s.flag[p], ri) : s.lo[p] + sigma;
+    const int ts = q.tail_start, Dm = q.tail_dim, npk = Dm * (Dm + 1) / 2;
+    for (int e = tid; e < q.nslots + npk; e += ADMM_THREADS) s.Lval[e] = 0.0;
     __syncthreads();
+    // Dinv[p] holds K_pp until the pivot of p is formed; tail positions put K_pp on the diagonal of the dense block
+    for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
+        const double kpp = s.flag[p] ? -rinv_of(s.flag[p], ri) : s.lo[p] + sigma;
+        if (p >= ts && Dm > 0) { const int i = p - ts; s.S[i * (i + 1) / 2 + i] = kpp; }
+        else s.Dinv[p] = kpp;
+    }
     for (int e = tid; e < q.nnzA; e += ADMM_THREADS) s.Lval[__ldg(q.a_slot + e)] = s.Aval[e];
     __syncthreads();
     FAC_T(110);
-    for (int l = 0; l < q.nlev; l++) {
+    for (int l = 0; l < q.n_fac_lvl; l++) {
         const int t1 = s.fac_lvl[l + 1];
         for (int t = s.fac_lvl[l] + warp; t < t1; t += NW) {
             const uint2 d = s.fac_task[t];
-            const double acc = gather_task(s, d, q.fac_ent, lane);
             const int sh = (d.y >> 16) & 0xff, rr = lane >> sh;
-            if ((lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff)) {
-                const int id = __ldg(q.fac_tgt + (d.x >> 16) + rr) & 0xffff;
-                if (id >= q.nslots) { const int j = id - q.nslots; s.Dinv[j] = 1.0 / (s.Dinv[j] - acc); }
-                else s.Lval[id] -= acc;
+            const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
+            uint32_t tg = 0;
+            if (writer) tg = __ldg(q.fac_tgt + (d.x >> 16) + rr);          // issued before the gather: its latency overlaps the entry stream
+            const double acc = gather_task(s, d, q.fac_ent, lane);
+            if (writer) {
+                if (tg & FAC_TGT_PIVOT) { const int j = tg & 0x7fffffff; s.Dinv[j] = 1.0 / (s.Dinv[j] - acc); }
+                else s.Lval[tg] -= acc;
             }
         }
         __syncthreads();
@@ -236,10 +244,12 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
             id[k] = -1;
             if (t < t1) {
                 const uint2 d = s.inv_task[t];
-                const double acc = gather_task(s, d, q.inv_ent, lane);
                 const int sh = (d.y >> 16) & 0xff, rr = lane >> sh;
-                if ((lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff)) {
-                    const uint32_t tg = __ldg(q.inv_tgt + (d.x >> 16) + rr);
+                const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
+                uint32_t tg = 0;
+                if (writer) tg = __ldg(q.inv_tgt + (d.x >> 16) + rr);
+                const double acc = gather_task(s, d, q.inv_ent, lane);
+                if (writer) {
                     id[k] = tg & 0xffff;
                     v[k] = -(s.Lval[id[k]] * s.Dinv[tg >> 16] + acc);
                 }
@@ -252,51 +262,72 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
         __syncthreads();
     }
     FAC_T(111);
-    // dense tail: packed strictly-lower copy Ld of the unit lower L[tail, tail] = W / d_col (aliasing sol|dxy, free now) and its explicit
-    // inverse Tinv, one column per group of 4 lanes by forward substitution:  z_j = 1,  z_i = -(L_ij + sum_{j<k<i} L_ik z_k)
-    const int Dm = q.tail_dim;
+    // dense tail: symmetric sweep of the packed lower Schur complement S over all pivots, in place:  S <- -S^-1.
+    // Pivot p: S_ik -= S_ip S_kp / d,  S_ip <- S_ip / d,  S_pp <- -1 / d.  The pivot column (and 1/d) of step p+1 is staged into a small
+    // buffer by the threads that produce it during step p, so one barrier per pivot suffices.
     if (Dm > 0) {
-        double* Ld = s.sol;
-        const int npk = Dm * (Dm - 1) / 2;
-        for (int e = tid; e < npk; e += ADMM_THREADS) Ld[e] = 0.0;
-        __syncthreads();
-        for (int e = tid; e < q.n_tl; e += ADMM_THREADS) Ld[__ldg(q.tl_dst + e)] = s.Lval[__ldg(q.tl_src + e)] * s.Dinv[__ldg(q.tl_col + e)];
-        __syncthreads();
-        const int slots = ((Dm * 4) + 31) & ~31;
-        for (int i = tid; i < slots; i += ADMM_THREADS) {
-            const int j = i >> 2, sub = i & 3;
-            for (int r = 1; r < Dm; r++) {          // uniform trip count: the shuffles below need every lane of the warp
-                const bool act = j < Dm && r > j;
-                double acc = 0.0;
-                const int rb = r * (r - 1) / 2;
-                if (act)
-                    for (int k = j + 1 + sub; k < r; k += 4) acc += Ld[rb + k] * s.Tinv[k * (k - 1) / 2 + j];
-                acc = group_sum(acc, 4);
-                if (act && sub == 0) s.Tinv[rb + j] = -(Ld[rb + j] + acc);
-                __syncwarp();
-            }
+        double* col = s.red;                 // [2][64] columns + [2] reciprocal pivots
+        double* dinvb = s.red + 128;
+        int ei[SWEEP_EPT], ek[SWEEP_EPT];
+#pragma unroll
+        for (int x = 0; x < SWEEP_EPT; x++) {
+            const int e = tid + x * ADMM_THREADS;
+            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while ((i + 1) * (i + 2) / 2 <= e) i++;
+            while (i * (i + 1) / 2 > e) i--;
+            ei[x] = e < npk ? i : -1; ek[x] = e - i * (i + 1) / 2;
         }
+        if (tid < Dm) col[tid] = s.S[tid * (tid + 1) / 2];
+        if (tid == 0) dinvb[0] = 1.0 / s.S[0];
         __syncthreads();
+        for (int p = 0; p < Dm; p++) {
+            const double* cc = col + (p & 1) * 64;
+            double* cn = col + ((p + 1) & 1) * 64;
+            const double dinv = dinvb[p & 1];
+#pragma unroll
+            for (int x = 0; x < SWEEP_EPT; x++) {
+                const int i = ei[x], k = ek[x];
+                if (i >= 0) {
+                    const int e = tid + x * ADMM_THREADS;
+                    const double ci = cc[i], ck = cc[k];
+                    double v;
+                    if (i == p) v = (k == p) ? -dinv : ck * dinv;
+                    else if (k == p) v = ci * dinv;
+                    else v = s.S[e] - ci * ck * dinv;
+                    s.S[e] = v;
+                    if (k == p + 1) { cn[i] = v; if (i == p + 1) dinvb[(p + 1) & 1] = 1.0 / v; }
+                    else if (i == p + 1) cn[k] = v;
+                }
+            }
+            __syncthreads();
+        }
     }
-    if (tid == 0) { s.sol[q.Nk] = 0.0; s.dxy[q.Nk] = 0.0; }      // the always-zero element read by the padding entries
-    __syncthreads();
     FAC_T(112);
 }
 
-// One phase of a triangular solve: every warp runs its tasks,  out[r] = f(in[r], sum_e W_e * in[c_e])  (flags in pgn_structure.h).
-// Forward phases read the L values in slot order (conflict-free); backward phases gather them through (slot, source) pairs.
-template <bool BWD>
-__device__ __forceinline__ void run_phase(const Smem& s, int ph) {
+// One phase of a triangular solve: warp w runs tasks t0 + w, t0 + w + NW, ... < t1,   out[r] = f(in[r], sum_e W_e * in[c_e])  with the
+// phase's flags FL known at compile time (pgn_structure.h).  Forward phases read the L values in slot order (conflict-free); backward
+// phases gather them through (slot, source) pairs.  Loads are issued in batches of four so that their latencies overlap.
+template <int FL, bool BWD>
+__device__ __forceinline__ void run_phase(const Smem& s, int t0, int t1) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t1 = s.ph_ptr[ph + 1];
-    for (int t = s.ph_ptr[ph] + warp; t < t1; t += NW) {
+    const double* __restrict__ in = (FL & TASK_SRC_TMP) ? s.dxy : s.sol;
+    double* __restrict__ out = (FL & TASK_DST_TMP) ? s.dxy : s.sol;
+    for (int t = t0 + warp; t < t1; t += NW) {
         const uint2 d = s.sol_task[t];
-        const int K = d.y & 0xff, sh = (d.y >> 16) & 0xff, fl = d.y >> 24;
-        const double* in = (fl & TASK_SRC_TMP) ? s.dxy : s.sol;
+        const int K = d.y & 0xff, sh = (d.y >> 16) & 0xff;
+        const int rr = lane >> sh;
+        const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
+        int r = 0;
+        double x = 0.0, di = 0.0;
+        if (writer) {                      // issued ahead of the gather
+            r = s.orow[(d.x >> 16) + rr];
+            x = in[r];
+            if (FL & (TASK_SCALE_ACC | TASK_SCALE_OUT)) di = s.Dinv[r];
+        }
         const int e = ((d.x & 0xffff) << 5) + lane;
         double acc0 = 0.0, acc1 = 0.0;
         int k = 0;
-        // loads are issued in batches of four (indices, values, gathered operands) so that their latencies overlap
         if (!BWD) {
             const double* lv = s.Lval + e;
             const uint16_t* ix = s.fidx + e;
@@ -306,15 +337,15 @@ __device__ __forceinline__ void run_phase(const Smem& s, int ph) {
                 const double x0 = in[i0], x1 = in[i1], x2 = in[i2], x3 = in[i3];
                 acc0 += l0 * x0; acc1 += l1 * x1; acc0 += l2 * x2; acc1 += l3 * x3;
             }
-            const int r = K - k;
-            if (r > 0) {
-                const int k1 = r > 1 ? k + 1 : k, k2 = r > 2 ? k + 2 : k;
+            const int rem = K - k;
+            if (rem > 0) {
+                const int k1 = rem > 1 ? k + 1 : k, k2 = rem > 2 ? k + 2 : k;
                 const int i0 = ix[k * 32], i1 = ix[k1 * 32], i2 = ix[k2 * 32];
                 const double l0 = lv[k * 32], l1 = lv[k1 * 32], l2 = lv[k2 * 32];
                 const double x0 = in[i0], x1 = in[i1], x2 = in[i2];
                 acc0 += l0 * x0;
-                if (r > 1) acc1 += l1 * x1;
-                if (r > 2) acc0 += l2 * x2;
+                if (rem > 1) acc1 += l1 * x1;
+                if (rem > 2) acc0 += l2 * x2;
             }
         } else {
             const uint32_t* be = s.bent + e;
@@ -324,25 +355,22 @@ __device__ __forceinline__ void run_phase(const Smem& s, int ph) {
                 const double x0 = in[b0 >> 16], x1 = in[b1 >> 16], x2 = in[b2 >> 16], x3 = in[b3 >> 16];
                 acc0 += l0 * x0; acc1 += l1 * x1; acc0 += l2 * x2; acc1 += l3 * x3;
             }
-            const int r = K - k;
-            if (r > 0) {
-                const uint32_t b0 = be[k * 32], b1 = be[(r > 1 ? k + 1 : k) * 32], b2 = be[(r > 2 ? k + 2 : k) * 32];
+            const int rem = K - k;
+            if (rem > 0) {
+                const uint32_t b0 = be[k * 32], b1 = be[(rem > 1 ? k + 1 : k) * 32], b2 = be[(rem > 2 ? k + 2 : k) * 32];
                 const double l0 = s.Lval[b0 & 0xffff], l1 = s.Lval[b1 & 0xffff], l2 = s.Lval[b2 & 0xffff];
                 const double x0 = in[b0 >> 16], x1 = in[b1 >> 16], x2 = in[b2 >> 16];
                 acc0 += l0 * x0;
-                if (r > 1) acc1 += l1 * x1;
-                if (r > 2) acc0 += l2 * x2;
+                if (rem > 1) acc1 += l1 * x1;
+                if (rem > 2) acc0 += l2 * x2;
             }
         }
-        double acc = group_sum_sh(acc0 + acc1, sh);
-        const int rr = lane >> sh;
-        if ((lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff)) {
-            const int r = s.orow[(d.x >> 16) + rr];
-            double x = in[r];
-            if (fl & TASK_SCALE_ACC) acc *= s.Dinv[r];
-            x = (fl & TASK_ADD) ? x + acc : x - acc;
-            if (fl & TASK_SCALE_OUT) x *= s.Dinv[r];
-            double* out = (fl & TASK_DST_TMP) ? s.dxy : s.sol;
+        double acc = acc0 + acc1;
+        if (sh) acc = group_sum_sh(acc, sh);
+        if (writer) {
+            if (FL & TASK_SCALE_ACC) acc *= di;
+            x = (FL & TASK_ADD) ? x + acc : x - acc;
+            if (FL & TASK_SCALE_OUT) x *= di;
             out[r] = x;
         }
     }
@@ -357,62 +385,43 @@ __device__ __forceinline__ void run_phase(const Smem& s, int ph) {
             t_lvl = now__;                                                                 \
         }                                                                                  \
     } while (0)
-// sol <- K^-1 sol (level-0 rows of the right-hand side already divided by their pivots):  forward over the level ranges (two phases each:
-// external part, then the in-range explicit inverse), the dense tail (its external part is the last forward phase), and the mirror
-// image backwards down to level 0.
-__device__ __forceinline__ void kkt_solve(const QpDev& q, const Smem& s, unsigned int* lvl_cyc) {
+// sol <- K^-1 rhs (rhs in sol, except the first range whose rhs is in the scratch vector):  forward over the level ranges (first range:
+// in-range explicit inverse only; others: external part, then in-range inverse), the dense tail (external part as the last forward
+// phase, then one symmetric mat-vec with -S^-1), and the mirror image backwards.
+__device__ __forceinline__ void kkt_solve(const AdmmArgs& a, const Smem& s, unsigned int* lvl_cyc) {
+    const QpDev& q = a.q;
     const int tid = threadIdx.x;
     long long t_lvl = clock64();
+    for (int ph = 0; ph < q.n_fwd_ph; ph++) {
+        if (ph & 1) run_phase<TASK_DST_TMP, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1]);                                   // t = b - W_ext y^
+        else run_phase<TASK_SRC_TMP | TASK_ADD | TASK_SCALE_OUT, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1]);              // y^ = (t + M t) / d
+        LVL_T(ph);
+    }
     const int ts = q.tail_start, Dm = q.tail_dim;
-    for (int ph = 0; ph < q.n_fwd_ph; ph++) { run_phase<false>(s, ph); LVL_T(ph); }
     if (Dm > 0) {
-        // tail stage 2 + diagonal: w = Dinv .* (t + Tinv t)   (t in tmp[tail]) -> sol[tail]
-        {
-            const int slots = ((Dm * 4) + 31) & ~31;
-            for (int i = tid; i < slots; i += ADMM_THREADS) {
-                const int rr = i >> 2, sub = i & 3;
-                const bool live = rr < Dm;
-                double acc = 0.0, acc2 = 0.0;
-                if (live) {
-                    const double* trow = s.Tinv + rr * (rr - 1) / 2;
-                    const double* tv = s.dxy + ts;
-                    int k = sub;
-                    for (; k + 4 < rr; k += 8) { acc += trow[k] * tv[k]; acc2 += trow[k + 4] * tv[k + 4]; }
-                    if (k < rr) acc += trow[k] * tv[k];
-                }
-                acc = group_sum(acc + acc2, 4);
-                if (live && sub == 0) s.sol[ts + rr] = (s.dxy[ts + rr] + acc) * s.Dinv[ts + rr];
+        // x_T = S^-1 t_T with the packed lower -S^-1: 8 lanes per row
+        for (int i8 = tid; i8 < ((Dm * 8 + 31) & ~31); i8 += ADMM_THREADS) {
+            const int i = i8 >> 3, sub = i8 & 7;
+            double acc = 0.0;
+            if (i < Dm) {
+                const double* tv = s.dxy + ts;
+                const double* row = s.S + i * (i + 1) / 2;
+                int k = sub;
+                for (; k <= i; k += 8) acc += row[k] * tv[k];
+                for (; k < Dm; k += 8) acc += s.S[k * (k + 1) / 2 + i] * tv[k];
             }
+            acc = group_sum(acc, 8);
+            if (i < Dm && sub == 0) s.sol[ts + i] = -acc;
         }
         __syncthreads();
         LVL_T(100);
-        // backward through the tail: x = Tinv' w, computed into registers, then written back over w
-        {
-            const int slots = ((Dm * 4) + 31) & ~31;
-            double xr = 0.0;
-            const int i = tid;
-            const int rr = i >> 2, sub = i & 3;
-            const bool live = rr < Dm;
-            if (i < slots) {
-                double acc = 0.0, acc2 = 0.0;
-                if (live) {
-                    int k = rr + 1 + sub;
-                    for (; k + 4 < Dm; k += 8) {
-                        acc += s.Tinv[k * (k - 1) / 2 + rr] * s.sol[ts + k];
-                        acc2 += s.Tinv[(k + 4) * (k + 3) / 2 + rr] * s.sol[ts + k + 4];
-                    }
-                    if (k < Dm) acc += s.Tinv[k * (k - 1) / 2 + rr] * s.sol[ts + k];
-                }
-                acc = group_sum(acc + acc2, 4);
-                if (live) xr = s.sol[ts + rr] + acc;
-            }
-            __syncthreads();
-            if (i < slots && live && sub == 0) s.sol[ts + rr] = xr;
-        }
-        __syncthreads();
-        LVL_T(101);
     }
-    for (int ph = q.n_fwd_ph; ph < q.n_fwd_ph + q.n_bwd_ph; ph++) { run_phase<true>(s, ph); LVL_T(ph); }
+    for (int ph = 0; ph < q.n_bwd_ph; ph++) {
+        const int pp = q.n_fwd_ph + ph;
+        if (ph & 1) run_phase<TASK_SRC_TMP | TASK_ADD, true>(s, a.ph_ptr[pp], a.ph_ptr[pp + 1]);                         // x = v + M' v
+        else run_phase<TASK_DST_TMP | TASK_SCALE_ACC, true>(s, a.ph_ptr[pp], a.ph_ptr[pp + 1]);                          // v = y^ - (W_below' x) / d
+        LVL_T(pp);
+    }
 }
 
 // out[p] = sum over the off-diagonal KKT entries of row p:  constraints get (A x)_i, variables get (A' y)_j
@@ -539,11 +548,11 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         for (int i = tid; i < q.n_fac_task; i += ADMM_THREADS) w_task[q.n_sol_task + i] = q.fac_task[i];
         for (int i = tid; i < q.n_inv_task; i += ADMM_THREADS) w_task[q.n_sol_task + q.n_fac_task + i] = q.inv_task[i];
         for (int i = tid; i < q.n_bent; i += ADMM_THREADS) w_u32[i] = q.bent[i];
-        for (int i = tid; i <= q.nlev; i += ADMM_THREADS) w_u32[q.n_bent + i] = q.fac_lvl_ptr[i];
-        for (int i = tid; i <= q.n_inv_levels; i += ADMM_THREADS) w_u32[q.n_bent + q.nlev + 1 + i] = q.inv_lvl_ptr[i];
+        for (int i = tid; i <= q.n_fac_lvl; i += ADMM_THREADS) w_u32[q.n_bent + i] = q.fac_lvl_ptr[i];
+        for (int i = tid; i <= q.n_inv_levels; i += ADMM_THREADS) w_u32[q.n_bent + q.n_fac_lvl + 1 + i] = q.inv_lvl_ptr[i];
         for (int i = tid; i < q.nslots; i += ADMM_THREADS) w_u16[i] = q.fidx[i];
         for (int i = tid; i < q.n_orow; i += ADMM_THREADS) w_u16[q.nslots + i] = q.sol_orow[i];
-        for (int i = tid; i <= q.n_fwd_ph + q.n_bwd_ph; i += ADMM_THREADS) w_u16[q.nslots + q.n_orow + i] = q.sol_ph_ptr[i];
+        if (tid == 0) { s.sol[q.Nk] = 0.0; s.dxy[q.Nk] = 0.0; }      // the always-zero element read by the padding entries
     }
     for (int i = threadIdx.x; i < ADMM_NCYC; i += ADMM_THREADS) s_cyc[i] = 0;
     __syncthreads();
@@ -658,20 +667,21 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         double pri_res = 0.0, dua_res = 0.0;
         const double alpha = st.alpha;
         RhoInv rinv = make_rho_inv(rho);
+        // right-hand side of the KKT system; the first range reads it from the scratch vector
+#define ADMM_RHS(p, f)                                                                                              \
+        do {                                                                                                        \
+            const double b__ = (f) ? s.xz[p] - rinv_of((f), rinv) * s.yq[p] : st.sigma * s.xz[p] - s.yq[p];         \
+            if ((p) < q.rhs_tmp_end) s.dxy[p] = b__; else s.sol[p] = b__;                                           \
+        } while (0)
+        for (int p = tid; p < q.Nk; p += ADMM_THREADS) { const uint8_t f = s.flag[p]; ADMM_RHS(p, f); }
+        __syncthreads();
         for (iter = 1; iter <= st.max_iter; iter++) {
             const bool check = st.check_termination && (iter % st.check_termination == 0);
             const bool adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
             const bool need_delta = check || adapt;
-            // rhs
-            for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
-                const uint8_t f = s.flag[p];
-                const double b = f ? s.xz[p] - rinv_of(f, rinv) * s.yq[p] : st.sigma * s.xz[p] - s.yq[p];
-                s.sol[p] = p < q.lvl0_end ? b * s.Dinv[p] : b;      // level 0 of the forward solve: y^ = b / d
-            }
-            __syncthreads();
-            kkt_solve(q, s, a.cycles ? s_cyc + 16 : nullptr);
+            kkt_solve(a, s, a.cycles ? s_cyc + 16 : nullptr);
             PHASE(3);
-            // x, z, y updates
+            // x, z, y updates; on iterations without a residual check the next right-hand side is formed in the same pass
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
                 const uint8_t f = s.flag[p];
                 if (f) {
@@ -690,6 +700,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                     s.xz[p] = xn;
                     if (need_delta) s.dxy[p] = xn - xp;
                 }
+                if (!need_delta) ADMM_RHS(p, f);
             }
             __syncthreads();
             PHASE(4);
@@ -722,6 +733,9 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                     PHASE(2);
                 }
             }
+            __syncthreads();       // the checks used sol / the scratch vector as work space
+            for (int p = tid; p < q.Nk; p += ADMM_THREADS) { const uint8_t f = s.flag[p]; ADMM_RHS(p, f); }
+            __syncthreads();
             PHASE(5);
         }
         if (iter > st.max_iter) {
@@ -798,6 +812,7 @@ void launch_admm(pgn_handle* h) {
     k_admm_order<<<1, 1024, 0, h->stream>>>(h->d_iters, h->d_order, h->B);
     h->launches++;
     a.order = h->d_order;
+    for (size_t i = 0; i < h->tab.sol_ph_ptr.size() && i <= ADMM_MAX_PHASES; i++) a.ph_ptr[i] = h->tab.sol_ph_ptr[i];
     int ctas_per_sm = 1;
     if (h->admm_smem_bytes * 2 + 2048 <= 227 * 1024) ctas_per_sm = 2;
     if (h->admm_smem_bytes * 3 + 3072 <= 227 * 1024) ctas_per_sm = 3;

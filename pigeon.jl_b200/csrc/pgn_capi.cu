@@ -224,7 +224,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
 #define UP(field) if ((rc = dev_upload(h, t.field, &q.field))) return bail(rc)
     UP(a_src); UP(a_slot); UP(l_type); UP(u_type); UP(l_idx); UP(u_idx); UP(P_mode); UP(q_mode); UP(P_w); UP(q_w); UP(P_t); UP(q_t);
     UP(q_hji_t); UP(pos_var); UP(pos_con); UP(pos2idx); UP(is_con); UP(kadj_ptr); UP(kadj_e); UP(kadj_nb);
-    UP(sol_ph_ptr); UP(sol_orow); UP(fidx); UP(bent); UP(fac_lvl_ptr); UP(fac_tgt); UP(inv_lvl_ptr); UP(inv_tgt); UP(tl_src); UP(tl_dst); UP(tl_col);
+    UP(sol_orow); UP(fidx); UP(bent); UP(fac_lvl_ptr); UP(fac_tgt); UP(inv_lvl_ptr); UP(inv_tgt);
     {
         std::vector<uint32_t> rc(t.nnzA);
         for (int e = 0; e < t.nnzA; e++) rc[e] = (uint32_t)t.a_rowpos[e] | ((uint32_t)t.a_colpos[e] << 16);
@@ -247,10 +247,11 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
         if ((rc_ = dev_upload(h, fe, &q.fac_ent))) return bail(rc_);
         if ((rc_ = dev_upload(h, ie, &q.inv_ent))) return bail(rc_);
     }
-    q.nslots = t.nslots; q.zslot = t.zslot; q.lvl0_end = t.lvl0_end; q.n_fwd_ph = t.n_fwd_ph; q.n_bwd_ph = t.n_bwd_ph;
+    q.nslots = t.nslots; q.zslot = t.zslot; q.rhs_tmp_end = t.rhs_tmp_end; q.n_fwd_ph = t.n_fwd_ph; q.n_bwd_ph = t.n_bwd_ph;
     q.n_sol_task = (int)t.sol_task.size() / 4; q.n_fac_task = (int)t.fac_task.size() / 4; q.n_inv_task = (int)t.inv_task.size() / 4;
-    q.n_bent = (int)t.bent.size(); q.n_orow = (int)t.sol_orow.size(); q.n_inv_levels = (int)t.inv_lvl_ptr.size() - 1;
-    q.tail_level = t.tail_level; q.tail_start = t.tail_start; q.tail_dim = t.tail_dim; q.n_tl = (int)t.tl_src.size();
+    q.n_bent = (int)t.bent.size(); q.n_orow = (int)t.sol_orow.size(); q.n_fac_lvl = (int)t.fac_lvl_ptr.size() - 1; q.n_inv_levels = (int)t.inv_lvl_ptr.size() - 1;
+    q.tail_level = t.tail_level; q.tail_start = t.tail_start; q.tail_dim = t.tail_dim;
+    if (t.n_fwd_ph + t.n_bwd_ph > ADMM_MAX_PHASES) return bail(set_err(PGN_EINVAL, "too many solve phases for this KKT ordering"));
 #undef UP
     double *ctab = nullptr, *wtab = nullptr;
     if ((rc = dev_alloc(h, &ctab, CT_LEN + 1))) return bail(rc);

@@ -53,13 +53,12 @@ struct QpDev {
     const uint16_t* a_slot;                     // per A entry: L slot
     // warp programs (pgn_structure.h): packed task descriptors {ebase/32 | rbase << 16, K | nrows << 8 | sh << 16 | flags << 24}
     const uint2 *sol_task, *fac_task, *inv_task;
-    const uint16_t *sol_ph_ptr, *sol_orow, *fidx;
+    const uint16_t *sol_orow, *fidx;
     const uint32_t* bent;
     const uint32_t *fac_lvl_ptr, *fac_tgt, *inv_lvl_ptr, *inv_tgt;
     const unsigned long long *fac_ent, *inv_ent;
-    int nslots, zslot, lvl0_end, n_fwd_ph, n_bwd_ph, n_sol_task, n_fac_task, n_inv_task, n_bent, n_orow, n_inv_levels;
-    int tail_level, tail_start, tail_dim, n_tl;
-    const uint16_t *tl_src, *tl_dst, *tl_col;
+    int nslots, zslot, rhs_tmp_end, n_fwd_ph, n_bwd_ph, n_sol_task, n_fac_task, n_inv_task, n_bent, n_orow, n_fac_lvl, n_inv_levels;
+    int tail_level, tail_start, tail_dim;
     const double* ctab;      // [CT_LEN]
     const double* wtab;      // [W_LEN] cost weights
     int n_hji;               // N_HJI

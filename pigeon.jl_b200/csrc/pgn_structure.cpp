@@ -266,14 +266,14 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     for (int j = 0; j < n; j++) { Q.pos_var[j] = (uint16_t)pos2[j]; Q.pos2idx[pos2[j]] = (uint16_t)j; }
     for (int i = 0; i < m; i++) { Q.pos_con[i] = (uint16_t)pos2[n + i]; Q.is_con[pos2[n + i]] = 1; Q.pos2idx[pos2[n + i]] = (uint16_t)i; }
 
-    // dense tail: trailing levels of width <= 4 (the top separators of the nested dissection), at most 64 positions and small enough
-    // for its packed dense copy to fit the 2*Nk-double scratch region of the kernel
+    // dense tail: trailing levels of width <= 4 (the top separators of the nested dissection), at most 64 positions.  Its Schur
+    // complement is formed by one gather pass and inverted densely (symmetric sweep) on chip
     {
         int Lt = nlev;
         while (Lt > 1) {
             int w = Q.lvl_ptr[Lt] - Q.lvl_ptr[Lt - 1];
             int D = Nk - Q.lvl_ptr[Lt - 1];
-            if (w > 4 || D > 64 || D * (D - 1) / 2 > 2 * Nk - 8) break;
+            if (w > 4 || D > 64) break;
             Lt--;
         }
         if (nlev - Lt < 4) Lt = nlev;      // not worth it
@@ -281,7 +281,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     }
     std::vector<std::vector<int>> rows(Nk);
     for (int k = 0; k < Nk; k++) for (int i : cs[k]) rows[i].push_back(k);   // ascending k by construction
-    // level ranges of the sparse part [1, tail_level): the unit lower block L[range, range] is replaced, after every numeric
+    // level ranges of the sparse part [0, tail_level): the unit lower block L[range, range] is replaced, after every numeric
     // factorisation, by its explicit inverse (same pattern once padded with the transitive closure), so a whole range costs two
     // parallel steps in the triangular solves instead of one step per level.  Ranges grow greedily while the closure adds
     // little fill.
@@ -296,7 +296,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
                 maxin = std::max(maxin, (int)M[r - pa].size());
             }
         };
-        int la = 1;
+        int la = 0;
         Q.range_lvl.clear();
         while (la < Q.tail_level) {
             int lb = la + 1;
@@ -306,7 +306,9 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
             while (lb < Q.tail_level) {
                 long s2, c2; int mi2;
                 closure(la, lb + 1, M2, s2, c2, mi2);
-                if (c2 <= s2 + s2 / 4 + 32 && mi2 <= 96) { lb++; M.swap(M2); snz = s2; cnz = c2; mi = mi2; }
+                // the first range (the stage-local eliminations above level 0) may double its entries: every range saved is two phases per solve
+                const long budget = la == 0 ? 2 * s2 + 64 : s2 + s2 / 4 + 32;
+                if (c2 <= budget && mi2 <= 96) { lb++; M.swap(M2); snz = s2; cnz = c2; mi = mi2; }
                 else break;
             }
             const int pa = Q.lvl_ptr[la];
@@ -376,7 +378,10 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     std::vector<int> range_pa, range_pb;
     for (size_t k = 0; k + 1 < Q.range_lvl.size(); k += 2) { range_pa.push_back(Q.lvl_ptr[Q.range_lvl[k]]); range_pb.push_back(Q.lvl_ptr[Q.range_lvl[k + 1]]); }
     const int nr = (int)range_pa.size();
-    Q.lvl0_end = Q.lvl_ptr[1];
+    // the ranges tile [0, tail_start); the right-hand side of the first range is written to the scratch vector (its only forward phase is
+    // the in-range one, scratch -> solution)
+    if (nr == 0 || range_pa[0] != 0 || range_pb[nr - 1] != Q.tail_start) return fail("internal: level ranges do not tile the sparse part");
+    Q.rhs_tmp_end = range_pb[0];
     std::vector<int> slot(nnzL, -1);          // CSR entry -> L slot
     // -- forward solve: L slots are allocated in the order the forward phases consume them
     Q.sol_ph_ptr.assign(1, 0);
@@ -412,13 +417,12 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         Q.sol_ph_ptr.push_back((uint16_t)(Q.sol_task.size() / 4));
     };
     for (int k = 0; k < nr; k++) {
-        fwd_phase(range_pa[k], range_pb[k], 0, range_pa[k], TASK_DST_TMP);                                         // t = b - W_ext y^           (sol -> tmp)
+        if (k > 0) fwd_phase(range_pa[k], range_pb[k], 0, range_pa[k], TASK_DST_TMP);                                         // t = b - W_ext y^           (sol -> tmp)
         fwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD | TASK_SCALE_OUT);   // y^ = (t + M t) / d         (tmp -> sol)
     }
     if (Q.tail_dim > 0) fwd_phase(Q.tail_start, Nk, 0, Q.tail_start, TASK_DST_TMP);                               // tail stage 1               (sol -> tmp)
     Q.n_fwd_ph = (int)Q.sol_ph_ptr.size() - 1;
-    for (int e = 0; e < (int)nnzL; e++) if (slot[e] < 0) slot[e] = nslots++;     // entries inside the dense tail block: no solve phase reads them
-    Q.zslot = nslots++;
+    Q.zslot = nslots++;                       // entries inside the dense tail block get no slot: they live in the dense Schur complement
     nslots = (nslots + 31) & ~31;
     Q.nslots = nslots;
     Q.fidx.resize(nslots, (uint16_t)Nk);
@@ -450,18 +454,16 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         bwd_phase(range_pa[k], range_pb[k], range_pb[k], Nk, TASK_DST_TMP | TASK_SCALE_ACC);                       // v = y^ - (W_below' x) / d  (sol -> tmp)
         bwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD);                    // x = v + M' v               (tmp -> sol)
     }
-    bwd_phase(0, Q.lvl_ptr[1], 0, Nk, TASK_SCALE_ACC);                                                             // level 0: x = y^ - (W' x) / d   (sol -> sol)
     Q.n_bwd_ph = (int)Q.sol_ph_ptr.size() - 1 - Q.n_fwd_ph;
 
+    // A entries -> L slot, or (both ends in the tail) nslots + packed lower index i (i + 1) / 2 + j of the dense Schur complement
     Q.a_slot.resize(Q.nnzA);
-    for (int e = 0; e < Q.nnzA; e++) Q.a_slot[e] = (uint16_t)slot[Q.a_lpos[e]];
-    // dense tail tables: entries of L[tail, tail] -> packed strictly-lower dense index
-    for (int i = Q.tail_start; i < Nk; i++)
-        for (int x = Q.lrow_ptr[i]; x < Q.lrow_ptr[i + 1]; x++)
-            if (Q.lrow_col[x] >= Q.tail_start) {
-                int ii = i - Q.tail_start, jj = Q.lrow_col[x] - Q.tail_start;
-                Q.tl_src.push_back((uint16_t)slot[x]); Q.tl_dst.push_back((uint16_t)(ii * (ii - 1) / 2 + jj)); Q.tl_col.push_back(Q.lrow_col[x]);
-            }
+    for (int e = 0; e < Q.nnzA; e++) {
+        const int hi = std::max(Q.a_rowpos[e], Q.a_colpos[e]), lo = std::min(Q.a_rowpos[e], Q.a_colpos[e]);
+        if (lo >= Q.tail_start) { const int ii = hi - Q.tail_start, jj = lo - Q.tail_start; Q.a_slot[e] = (uint16_t)(nslots + ii * (ii + 1) / 2 + jj); }
+        else Q.a_slot[e] = (uint16_t)slot[Q.a_lpos[e]];
+    }
+    if (nslots + Q.tail_dim * (Q.tail_dim + 1) / 2 >= 32768) return fail("L slots exceed the index range of the gather programs");
 
     // generic emitter for the gather programs (factorisation, range inverses): targets with (a, b, k) entry lists
     struct Tgt { uint32_t tgt; std::vector<uint64_t> ents; };
@@ -482,16 +484,18 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         lvl_ptr.push_back((uint32_t)(tasks.size() / 4));
     };
     auto ent3 = [](int a, int b, int k) { return (uint64_t)a | ((uint64_t)b << 16) | ((uint64_t)k << 32); };
-    // numeric factorisation program (left-looking gathers, level scheduled), unscaled form W = L D
+    // numeric factorisation program (left-looking gathers, level scheduled), unscaled form W = L D.  Targets: PIVOT | position, or a slot
+    // (L slot, or nslots + packed index of the dense tail Schur complement S = K_TT - sum_{k < tail} W_Tk W_Tk' / d_k, gathered by one
+    // extra pass after the last sparse level)
     Q.fac_lvl_ptr.assign(1, 0);
-    for (int l = 0; l < nlev; l++) {
+    for (int l = 0; l < Q.tail_level; l++) {
         std::vector<Tgt> tg;
         for (int j = Q.lvl_ptr[l]; j < Q.lvl_ptr[l + 1]; j++) {
-            Tgt d; d.tgt = (uint32_t)(nslots + j) | ((uint32_t)j << 16);
+            Tgt d; d.tgt = FAC_TGT_PIVOT | (uint32_t)j;
             for (int kk : rows[j]) { int a = slot[lidx(j, kk)]; d.ents.push_back(ent3(a, a, kk)); }
             tg.push_back(std::move(d));
             for (int i : cs[j]) {
-                Tgt o; o.tgt = (uint32_t)slot[lidx(i, j)] | ((uint32_t)j << 16);
+                Tgt o; o.tgt = (uint32_t)slot[lidx(i, j)];
                 const auto &ri = rows[i], &rj = rows[j];
                 size_t x = 0, y = 0;
                 while (x < ri.size() && y < rj.size()) {
@@ -503,6 +507,23 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
                 if (!o.ents.empty()) tg.push_back(std::move(o));      // W_ij = K_ij needs no work
             }
         }
+        emit_level(tg, Q.fac_task, Q.fac_lvl_ptr, Q.fac_tgt, Q.fac_ent);
+    }
+    if (Q.tail_dim > 0) {
+        std::vector<Tgt> tg;
+        for (int i = Q.tail_start; i < Nk; i++)
+            for (int j = Q.tail_start; j <= i; j++) {
+                const int ii = i - Q.tail_start, jj = j - Q.tail_start;
+                Tgt o; o.tgt = (uint32_t)(nslots + ii * (ii + 1) / 2 + jj);
+                const auto &ri = rows[i], &rj = rows[j];
+                size_t x = 0, y = 0;
+                while (x < ri.size() && y < rj.size() && ri[x] < Q.tail_start && rj[y] < Q.tail_start) {
+                    if (ri[x] == rj[y]) { o.ents.push_back(ent3(slot[Q.lrow_ptr[i] + (int)x], slot[Q.lrow_ptr[j] + (int)y], ri[x])); x++; y++; }
+                    else if (ri[x] < rj[y]) x++;
+                    else y++;
+                }
+                if (!o.ents.empty()) tg.push_back(std::move(o));
+            }
         emit_level(tg, Q.fac_task, Q.fac_lvl_ptr, Q.fac_tgt, Q.fac_ent);
     }
     // inverse program: for every range, level by level, each in-range entry (i,j) becomes  M_ij = -(W_ij/d_j + sum_{j<k<i} W_ik/d_k M_kj)

@@ -22,6 +22,9 @@
 
 // in-place range inverse: a warp keeps the results of at most this many tasks of one level in registers before writing them back
 #define INV_MAX_TASKS_PER_WARP 4
+#define FAC_TGT_PIVOT 0x80000000u
+// solve phases (two per level range and direction) whose task ranges travel in the kernel parameters
+#define ADMM_MAX_PHASES 48
 
 namespace pgn {
 
@@ -90,9 +93,9 @@ struct QpTables {
     std::vector<uint16_t> sol_orow;                    // output position per (task, row)
     std::vector<uint16_t> fidx;                        // forward: source position per L slot (size nslots)
     std::vector<uint32_t> bent;                        // backward entries in program order: L slot | source position << 16
-    int lvl0_end;                                      // positions [0, lvl0_end) are level 0: y^_r = b_r / d_r is folded into the rhs
-    // numeric factorisation: per level a list of tasks; target (id | col << 16): id < nslots an L slot, id >= nslots the pivot of
-    // position id - nslots; entry: a | b << 16 | k << 32  (product W[a] * W[b] / d_k)
+    int rhs_tmp_end;                                   // positions [0, rhs_tmp_end) = first range: their right-hand side goes to the scratch vector
+    // numeric factorisation: per level a list of tasks; target: FAC_TGT_PIVOT | position, or a slot (an L slot, or nslots + packed lower
+    // index of the dense tail Schur complement, gathered by the last pass); entry: a | b << 16 | k << 32  (product W[a] * W[b] / d_k)
     std::vector<uint32_t> fac_task, fac_lvl_ptr, fac_tgt;
     std::vector<uint64_t> fac_ent;
     // in-place inversion of the range blocks (unit lower M = L_RR^-1), level by level: target (slot | col << 16),
@@ -102,10 +105,10 @@ struct QpTables {
     int inv_max_tasks_per_warp;
     // A entries -> L slot
     std::vector<uint16_t> a_slot;
-    // dense tail: the last `tail_dim` positions (levels >= tail_level) form a (nearly dense) unit lower triangular block whose explicit
-    // inverse is rebuilt after every numeric factorisation; it replaces tail_dim narrow levels by two dense mat-vec levels
+    // dense tail: the Schur complement of the last `tail_dim` positions (levels >= tail_level, the top separators) is formed densely
+    // (packed lower, with diagonal) and inverted on chip by a symmetric sweep after every numeric factorisation; in the solves it
+    // replaces tail_dim narrow levels by one dense symmetric mat-vec
     int tail_level, tail_start, tail_dim;
-    std::vector<uint16_t> tl_src, tl_dst, tl_col;       // L slot -> packed strictly-lower dense index i*(i-1)/2 + j; column position (for 1/d)
     // where the solution components consumed by the host-side API live
     int var_u1_delta, var_u1_fx;                        // variable indices of u[:,2] (node 2)
 };

@@ -28,9 +28,14 @@ int main(int argc, char** argv) {
     for (int e = 0; e < Q.nnzA; e++) { int r = Q.a_rowpos[e], c = Q.a_colpos[e]; K[(size_t)r * Nk + c] = Aval[e]; K[(size_t)c * Nk + r] = Aval[e]; }
     // emulate the kernel factorisation (unscaled form W = L D, one gather pass per level, no scaling pass)
     const int NS = Q.nslots;
-    std::vector<double> L(NS, 0.0), Dinv(Nk);
+    const int ts = Q.tail_start, Dm = Q.tail_dim, npk = Dm * (Dm + 1) / 2;
+    std::vector<double> L(NS + npk, 0.0), Dinv(Nk);                      // L slots followed by the packed lower dense tail block
     for (int e = 0; e < Q.nnzA; e++) L[Q.a_slot[e]] = Aval[e];
-    for (int p = 0; p < Nk; p++) Dinv[p] = Q.is_con[p] ? -rhoinv[Q.pos2idx[p]] : Pd[Q.pos2idx[p]];      // holds K_pp until the pivot is formed
+    for (int p = 0; p < Nk; p++) {
+        const double kpp = Q.is_con[p] ? -rhoinv[Q.pos2idx[p]] : Pd[Q.pos2idx[p]];
+        if (p >= ts && Dm > 0) { const int i = p - ts; L[NS + i * (i + 1) / 2 + i] = kpp; Dinv[p] = 0.0; }
+        else Dinv[p] = kpp;                                              // holds K_pp until the pivot is formed
+    }
     size_t npairs = 0;
     // a task list executed the way the warps do: every lane accumulates its K slots, the lanes of a row are summed, lane 0 of the row applies the result
     auto run_gather = [&](const std::vector<uint32_t>& tasks, uint32_t t0, uint32_t t1, const std::vector<uint32_t>& tgts, const std::vector<uint64_t>& ents,
@@ -53,13 +58,12 @@ int main(int argc, char** argv) {
             for (int lane = nrows << sh; lane < 32; lane++) for (int k = 0; k < K; k++) { const uint64_t e = ents[ebase + k * 32 + lane]; if ((int)(e & 0xffff) != Q.zslot) { printf("FAIL pad\n"); exit(3); } }
         }
     };
-    for (int l = 0; l < Q.nlev; l++) {
+    for (size_t l = 0; l + 1 < Q.fac_lvl_ptr.size(); l++) {
         std::vector<std::pair<uint32_t, double>> res;
         run_gather(Q.fac_task, Q.fac_lvl_ptr[l], Q.fac_lvl_ptr[l + 1], Q.fac_tgt, Q.fac_ent, res);
         for (auto& r : res) {
-            const int id = r.first & 0xffff;
-            if (id >= NS) { const int j = id - NS; Dinv[j] = 1.0 / (Dinv[j] - r.second); }
-            else L[id] -= r.second;
+            if (r.first & FAC_TGT_PIVOT) { const int j = r.first & 0x7fffffff; Dinv[j] = 1.0 / (Dinv[j] - r.second); }
+            else L[r.first & 0xffff] -= r.second;
         }
     }
     // range inverses in place (two-phase per level, as in the kernel)
@@ -69,20 +73,28 @@ int main(int argc, char** argv) {
         for (auto& r : res) { const int id = r.first & 0xffff, col = r.first >> 16; r.second = -(L[id] * Dinv[col] + r.second); }
         for (auto& r : res) L[r.first & 0xffff] = r.second;
     }
-    // dense tail: packed copy of the unit lower L[tail, tail] = W / d_col and its explicit inverse (column-wise forward substitution), as in the kernel
-    const int ts = Q.tail_start, Dm = Q.tail_dim;
-    std::vector<double> Ld(Dm * (Dm - 1) / 2 + 1, 0.0), Ti(Dm * (Dm - 1) / 2 + 1, 0.0);
-    for (size_t e = 0; e < Q.tl_src.size(); e++) Ld[Q.tl_dst[e]] = L[Q.tl_src[e]] * Dinv[Q.tl_col[e]];
-    for (int j = 0; j < Dm; j++) for (int r = j + 1; r < Dm; r++) {
-        double acc = 0; int rb = r * (r - 1) / 2;
-        for (int k = j + 1; k < r; k++) acc += Ld[rb + k] * Ti[k * (k - 1) / 2 + j];
-        Ti[rb + j] = -(Ld[rb + j] + acc);
+    // dense tail: symmetric sweep of the packed lower Schur complement over all pivots -> -S^-1 (as in the kernel: the pivot column is staged
+    // in a small buffer one step ahead)
+    double* S = L.data() + NS;
+    auto PK = [](int i, int k) { return i >= k ? i * (i + 1) / 2 + k : k * (k + 1) / 2 + i; };
+    for (int p = 0; p < Dm; p++) {
+        std::vector<double> col(Dm);
+        for (int i = 0; i < Dm; i++) col[i] = S[PK(i, p)];
+        const double dinv = 1.0 / col[p];
+        for (int i = 0; i < Dm; i++)
+            for (int k = 0; k <= i; k++) {
+                double& v = S[PK(i, k)];
+                if (i == p && k == p) v = -dinv;
+                else if (i == p) v = col[k] * dinv;
+                else if (k == p) v = col[i] * dinv;
+                else v -= col[i] * col[k] * dinv;
+            }
     }
     if (L[Q.zslot] != 0.0) { printf("FAIL zslot written\n"); return 3; }
     // solve K x = b with the solve programs
     std::vector<double> b(Nk), x(Nk + 1, 0.0), tmp(Nk + 1, 0.0);
     for (auto& v : b) v = U(rng);
-    for (int p = 0; p < Nk; p++) x[p] = p < Q.lvl0_end ? b[p] * Dinv[p] : b[p];        // level 0 folded into the right-hand side
+    for (int p = 0; p < Nk; p++) (p < Q.rhs_tmp_end ? tmp : x)[p] = b[p];       // the first range reads its right-hand side from the scratch vector
     std::vector<char> written(Nk, 0);
     auto run_phase = [&](int ph, bool bwd) {
         std::vector<std::pair<int, double>> outs;
@@ -110,10 +122,7 @@ int main(int argc, char** argv) {
         for (auto& o : outs) { (dst_tmp ? tmp : x)[o.first] = o.second; if (!dst_tmp) written[o.first]++; }
     };
     for (int ph = 0; ph < Q.n_fwd_ph; ph++) run_phase(ph, false);
-    std::vector<double> t2(Nk);
-    for (int rr = 0; rr < Dm; rr++) { double s = tmp[ts + rr]; for (int k = 0; k < rr; k++) s += Ti[rr * (rr - 1) / 2 + k] * tmp[ts + k]; x[ts + rr] = s * Dinv[ts + rr]; }
-    for (int rr = 0; rr < Dm; rr++) { double s = x[ts + rr]; for (int k = rr + 1; k < Dm; k++) s += Ti[k * (k - 1) / 2 + rr] * x[ts + k]; t2[ts + rr] = s; }
-    for (int rr = 0; rr < Dm; rr++) x[ts + rr] = t2[ts + rr];
+    for (int i = 0; i < Dm; i++) { double acc = 0; for (int k = 0; k < Dm; k++) acc += S[PK(i, k)] * tmp[ts + k]; x[ts + i] = -acc; }
     for (int ph = Q.n_fwd_ph; ph < Q.n_fwd_ph + Q.n_bwd_ph; ph++) run_phase(ph, true);
     if (x[Nk] != 0.0 || tmp[Nk] != 0.0) { printf("FAIL zero element written\n"); return 3; }
     // residual ||K x - b||_inf and the kadj product against the dense one
