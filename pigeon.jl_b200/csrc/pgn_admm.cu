@@ -142,48 +142,42 @@ struct RhoInv { double in, eq, loose; };
 __device__ __forceinline__ RhoInv make_rho_inv(double rho) { RhoInv r; r.in = 1.0 / rho; r.eq = 1.0 / (1e3 * rho); r.loose = 1.0 / 1e-6; return r; }
 __device__ __forceinline__ double rinv_of(uint8_t flag, const RhoInv& r) { return flag == 2 ? r.eq : (flag == 3 ? r.loose : r.in); }
 
-// sum over the g (power of two) adjacent lanes of a group; every lane of the warp must call
-__device__ __forceinline__ double group_sum(double v, int g) {
-    switch (g) {      // warp-uniform; falls through the remaining butterfly steps
-        case 32: v += __shfl_xor_sync(0xffffffffu, v, 16);
-        case 16: v += __shfl_xor_sync(0xffffffffu, v, 8);
-        case 8: v += __shfl_xor_sync(0xffffffffu, v, 4);
-        case 4: v += __shfl_xor_sync(0xffffffffu, v, 2);
-        case 2: v += __shfl_xor_sync(0xffffffffu, v, 1);
-        default: break;
-    }
+// sum over the 2^sh adjacent lanes of a group (sh warp-uniform); every lane of the warp must call.  A plain loop: a switch here becomes
+// a jump table (LDC + BRX), which costs a lone warp far more than the shuffles themselves.
+__device__ __forceinline__ double group_sum_sh(double v, int sh) {
+#pragma unroll 1
+    for (int o = (1 << sh) >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ double group_sum_sh(double v, int sh) {     // sh is warp-uniform
-    if (sh > 4) v += __shfl_xor_sync(0xffffffffu, v, 16);
-    if (sh > 3) v += __shfl_xor_sync(0xffffffffu, v, 8);
-    if (sh > 2) v += __shfl_xor_sync(0xffffffffu, v, 4);
-    if (sh > 1) v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (sh > 0) v += __shfl_xor_sync(0xffffffffu, v, 1);
+template <int G>
+__device__ __forceinline__ double group_sum_c(double v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
 // One warp task of a gather program (factorisation / range inverse): returns, in the lanes with sub == 0, the sum over the row's
-// entries of W[a] * W[b] / d_k.  Entries stream from global memory (static, coalesced: slot k of lane l is at ebase + 32 k + l); loads are
-// issued in batches of four so that their latencies overlap.
+// entries of W[a] * W[b] / d_k.  Entries stream from global memory (static, coalesced: slot k of lane l is at ebase + 32 k + l) in batches
+// of four; the last (partial) batch reads up to three slots past the task — always inside the padded array — and replaces them by the
+// zero entry, so the task runs without data-dependent branches.
 #define GATHER_TERM(e) (s.Lval[(e) & 0xffff] * s.Lval[((e) >> 16) & 0xffff] * s.Dinv[(e) >> 32])
-__device__ __forceinline__ double gather_task(const Smem& s, const uint2 d, const unsigned long long* __restrict__ ents, int lane) {
+__device__ __forceinline__ double gather_task(const Smem& s, const uint2 d, const unsigned long long* __restrict__ ents, int lane, unsigned long long pad) {
     const int K = d.y & 0xff, sh = (d.y >> 16) & 0xff;
     const unsigned long long* e = ents + ((size_t)(d.x & 0xffff) << 5) + lane;
     double acc0 = 0.0, acc1 = 0.0;
     int k = 0;
-    for (; k + 4 <= K; k += 4) {
-        const unsigned long long e0 = __ldg(e + k * 32), e1 = __ldg(e + k * 32 + 32), e2 = __ldg(e + k * 32 + 64), e3 = __ldg(e + k * 32 + 96);
+#pragma unroll 1
+    for (; k + 4 <= K; k += 4, e += 128) {
+        const unsigned long long e0 = __ldg(e), e1 = __ldg(e + 32), e2 = __ldg(e + 64), e3 = __ldg(e + 96);
         const double t0 = GATHER_TERM(e0), t1 = GATHER_TERM(e1), t2 = GATHER_TERM(e2), t3 = GATHER_TERM(e3);
         acc0 += t0; acc1 += t1; acc0 += t2; acc1 += t3;
     }
-    const int r = K - k;
-    if (r > 0) {
-        const unsigned long long e0 = __ldg(e + k * 32), e1 = __ldg(e + (r > 1 ? k + 1 : k) * 32), e2 = __ldg(e + (r > 2 ? k + 2 : k) * 32);
+    {
+        const int rem = K - k;
+        unsigned long long e0 = __ldg(e), e1 = __ldg(e + 32), e2 = __ldg(e + 64);
+        e0 = rem > 0 ? e0 : pad; e1 = rem > 1 ? e1 : pad; e2 = rem > 2 ? e2 : pad;
         const double t0 = GATHER_TERM(e0), t1 = GATHER_TERM(e1), t2 = GATHER_TERM(e2);
-        acc0 += t0;
-        if (r > 1) acc1 += t1;
-        if (r > 2) acc0 += t2;
+        acc0 += t0; acc1 += t1; acc0 += t2;
     }
     return group_sum_sh(acc0 + acc1, sh);
 }
@@ -203,6 +197,7 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long t_lvl = clock64();
     const RhoInv ri = make_rho_inv(rho);
+    const unsigned long long pad = (unsigned long long)q.zslot | ((unsigned long long)q.zslot << 16);      // 0 * 0 / d_0
     const int ts = q.tail_start, Dm = q.tail_dim, npk = Dm * (Dm + 1) / 2;
     for (int e = tid; e < q.nslots + npk; e += ADMM_THREADS) s.Lval[e] = 0.0;
     __syncthreads();
@@ -223,7 +218,7 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
             const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
             uint32_t tg = 0;
             if (writer) tg = __ldg(q.fac_tgt + (d.x >> 16) + rr);          // issued before the gather: its latency overlaps the entry stream
-            const double acc = gather_task(s, d, q.fac_ent, lane);
+            const double acc = gather_task(s, d, q.fac_ent, lane, pad);
             if (writer) {
                 if (tg & FAC_TGT_PIVOT) { const int j = tg & 0x7fffffff; s.Dinv[j] = 1.0 / (s.Dinv[j] - acc); }
                 else s.Lval[tg] -= acc;
@@ -248,7 +243,7 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
                 const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
                 uint32_t tg = 0;
                 if (writer) tg = __ldg(q.inv_tgt + (d.x >> 16) + rr);
-                const double acc = gather_task(s, d, q.inv_ent, lane);
+                const double acc = gather_task(s, d, q.inv_ent, lane, pad);
                 if (writer) {
                     id[k] = tg & 0xffff;
                     v[k] = -(s.Lval[id[k]] * s.Dinv[tg >> 16] + acc);
@@ -308,73 +303,80 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
 // One phase of a triangular solve: warp w runs tasks t0 + w, t0 + w + NW, ... < t1,   out[r] = f(in[r], sum_e W_e * in[c_e])  with the
 // phase's flags FL known at compile time (pgn_structure.h).  Forward phases read the L values in slot order (conflict-free); backward
 // phases gather them through (slot, source) pairs.  Loads are issued in batches of four so that their latencies overlap.
+#ifdef PGN_PHASE_PROBE
+#define PROBE(i) do { if (probe && threadIdx.x == 0) { const long long n__ = clock64(); probe[i] += (unsigned int)(n__ - tp); tp = n__; } } while (0)
+#else
+#define PROBE(i)
+#endif
 template <int FL, bool BWD>
-__device__ __forceinline__ void run_phase(const Smem& s, int t0, int t1) {
+__device__ __forceinline__ void run_phase(const Smem& s, int t0, int t1, int zidx, uint32_t zpair, unsigned int* probe = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef PGN_PHASE_PROBE
+    long long tp = clock64();
+#endif
     const double* __restrict__ in = (FL & TASK_SRC_TMP) ? s.dxy : s.sol;
     double* __restrict__ out = (FL & TASK_DST_TMP) ? s.dxy : s.sol;
     for (int t = t0 + warp; t < t1; t += NW) {
+        // straight-line on purpose: with one or two live warps per scheduler every branch costs a full resolve latency
         const uint2 d = s.sol_task[t];
-        const int K = d.y & 0xff, sh = (d.y >> 16) & 0xff;
+        PROBE(0);
+        const int K = d.y & 0xff, nrows = (d.y >> 8) & 0xff, sh = (d.y >> 16) & 0xff;
         const int rr = lane >> sh;
-        const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
-        int r = 0;
-        double x = 0.0, di = 0.0;
-        if (writer) {                      // issued ahead of the gather
-            r = s.orow[(d.x >> 16) + rr];
-            x = in[r];
-            if (FL & (TASK_SCALE_ACC | TASK_SCALE_OUT)) di = s.Dinv[r];
-        }
+        const bool writer = ((lane & ((1 << sh) - 1)) == 0) & (rr < nrows);
+        const int r = s.orow[(d.x >> 16) + min(rr, nrows - 1)];
+        double x = in[r];
+        const double di = (FL & (TASK_SCALE_ACC | TASK_SCALE_OUT)) ? s.Dinv[r] : 0.0;
         const int e = ((d.x & 0xffff) << 5) + lane;
         double acc0 = 0.0, acc1 = 0.0;
+        // full batches of four with constant offsets, then one partial batch that reads up to three slots past the task (always inside
+        // the padded arrays) and redirects them to the zero entries: no data-dependent branches
         int k = 0;
         if (!BWD) {
             const double* lv = s.Lval + e;
             const uint16_t* ix = s.fidx + e;
-            for (; k + 4 <= K; k += 4) {
-                const int i0 = ix[k * 32], i1 = ix[k * 32 + 32], i2 = ix[k * 32 + 64], i3 = ix[k * 32 + 96];
-                const double l0 = lv[k * 32], l1 = lv[k * 32 + 32], l2 = lv[k * 32 + 64], l3 = lv[k * 32 + 96];
+#pragma unroll 1
+            for (; k + 4 <= K; k += 4, lv += 128, ix += 128) {
+                const int i0 = ix[0], i1 = ix[32], i2 = ix[64], i3 = ix[96];
+                const double l0 = lv[0], l1 = lv[32], l2 = lv[64], l3 = lv[96];
                 const double x0 = in[i0], x1 = in[i1], x2 = in[i2], x3 = in[i3];
                 acc0 += l0 * x0; acc1 += l1 * x1; acc0 += l2 * x2; acc1 += l3 * x3;
             }
             const int rem = K - k;
-            if (rem > 0) {
-                const int k1 = rem > 1 ? k + 1 : k, k2 = rem > 2 ? k + 2 : k;
-                const int i0 = ix[k * 32], i1 = ix[k1 * 32], i2 = ix[k2 * 32];
-                const double l0 = lv[k * 32], l1 = lv[k1 * 32], l2 = lv[k2 * 32];
-                const double x0 = in[i0], x1 = in[i1], x2 = in[i2];
-                acc0 += l0 * x0;
-                if (rem > 1) acc1 += l1 * x1;
-                if (rem > 2) acc0 += l2 * x2;
-            }
+            int i0 = ix[0], i1 = ix[32], i2 = ix[64];
+            double l0 = lv[0], l1 = lv[32], l2 = lv[64];
+            i0 = rem > 0 ? i0 : zidx; i1 = rem > 1 ? i1 : zidx; i2 = rem > 2 ? i2 : zidx;
+            l0 = rem > 0 ? l0 : 0.0; l1 = rem > 1 ? l1 : 0.0; l2 = rem > 2 ? l2 : 0.0;
+            const double x0 = in[i0], x1 = in[i1], x2 = in[i2];
+            acc0 += l0 * x0; acc1 += l1 * x1; acc0 += l2 * x2;
         } else {
             const uint32_t* be = s.bent + e;
-            for (; k + 4 <= K; k += 4) {
-                const uint32_t b0 = be[k * 32], b1 = be[k * 32 + 32], b2 = be[k * 32 + 64], b3 = be[k * 32 + 96];
+#pragma unroll 1
+            for (; k + 4 <= K; k += 4, be += 128) {
+                const uint32_t b0 = be[0], b1 = be[32], b2 = be[64], b3 = be[96];
                 const double l0 = s.Lval[b0 & 0xffff], l1 = s.Lval[b1 & 0xffff], l2 = s.Lval[b2 & 0xffff], l3 = s.Lval[b3 & 0xffff];
                 const double x0 = in[b0 >> 16], x1 = in[b1 >> 16], x2 = in[b2 >> 16], x3 = in[b3 >> 16];
                 acc0 += l0 * x0; acc1 += l1 * x1; acc0 += l2 * x2; acc1 += l3 * x3;
             }
             const int rem = K - k;
-            if (rem > 0) {
-                const uint32_t b0 = be[k * 32], b1 = be[(rem > 1 ? k + 1 : k) * 32], b2 = be[(rem > 2 ? k + 2 : k) * 32];
-                const double l0 = s.Lval[b0 & 0xffff], l1 = s.Lval[b1 & 0xffff], l2 = s.Lval[b2 & 0xffff];
-                const double x0 = in[b0 >> 16], x1 = in[b1 >> 16], x2 = in[b2 >> 16];
-                acc0 += l0 * x0;
-                if (rem > 1) acc1 += l1 * x1;
-                if (rem > 2) acc0 += l2 * x2;
-            }
+            uint32_t b0 = be[0], b1 = be[32], b2 = be[64];
+            b0 = rem > 0 ? b0 : zpair; b1 = rem > 1 ? b1 : zpair; b2 = rem > 2 ? b2 : zpair;
+            const double l0 = s.Lval[b0 & 0xffff], l1 = s.Lval[b1 & 0xffff], l2 = s.Lval[b2 & 0xffff];
+            const double x0 = in[b0 >> 16], x1 = in[b1 >> 16], x2 = in[b2 >> 16];
+            acc0 += l0 * x0; acc1 += l1 * x1; acc0 += l2 * x2;
         }
         double acc = acc0 + acc1;
-        if (sh) acc = group_sum_sh(acc, sh);
-        if (writer) {
-            if (FL & TASK_SCALE_ACC) acc *= di;
-            x = (FL & TASK_ADD) ? x + acc : x - acc;
-            if (FL & TASK_SCALE_OUT) x *= di;
-            out[r] = x;
-        }
+        PROBE(1);
+        acc = group_sum_sh(acc, sh);
+        PROBE(2);
+        if (FL & TASK_SCALE_ACC) acc *= di;
+        x = (FL & TASK_ADD) ? x + acc : x - acc;
+        if (FL & TASK_SCALE_OUT) x *= di;
+        if (writer) out[r] = x;
+        PROBE(3);
     }
+    PROBE(4);
     __syncthreads();
+    PROBE(5);
 }
 
 #define LVL_T(idx)                                                                         \
@@ -392,9 +394,11 @@ __device__ __forceinline__ void kkt_solve(const AdmmArgs& a, const Smem& s, unsi
     const QpDev& q = a.q;
     const int tid = threadIdx.x;
     long long t_lvl = clock64();
+    const int zidx = q.Nk;                                                    // the always-zero vector element
+    const uint32_t zpair = (uint32_t)q.zslot | ((uint32_t)q.Nk << 16);       // (always-zero L slot, always-zero vector element)
     for (int ph = 0; ph < q.n_fwd_ph; ph++) {
-        if (ph & 1) run_phase<TASK_DST_TMP, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1]);                                   // t = b - W_ext y^
-        else run_phase<TASK_SRC_TMP | TASK_ADD | TASK_SCALE_OUT, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1]);              // y^ = (t + M t) / d
+        if (ph & 1) run_phase<TASK_DST_TMP, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1], zidx, zpair, (lvl_cyc && blockIdx.x == 0 && ph == 1) ? lvl_cyc + 200 : nullptr);      // t = b - W_ext y^
+        else run_phase<TASK_SRC_TMP | TASK_ADD | TASK_SCALE_OUT, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1], zidx, zpair);              // y^ = (t + M t) / d
         LVL_T(ph);
     }
     const int ts = q.tail_start, Dm = q.tail_dim;
@@ -410,7 +414,7 @@ __device__ __forceinline__ void kkt_solve(const AdmmArgs& a, const Smem& s, unsi
                 for (; k <= i; k += 8) acc += row[k] * tv[k];
                 for (; k < Dm; k += 8) acc += s.S[k * (k + 1) / 2 + i] * tv[k];
             }
-            acc = group_sum(acc, 8);
+            acc = group_sum_c<8>(acc);
             if (i < Dm && sub == 0) s.sol[ts + i] = -acc;
         }
         __syncthreads();
@@ -418,8 +422,8 @@ __device__ __forceinline__ void kkt_solve(const AdmmArgs& a, const Smem& s, unsi
     }
     for (int ph = 0; ph < q.n_bwd_ph; ph++) {
         const int pp = q.n_fwd_ph + ph;
-        if (ph & 1) run_phase<TASK_SRC_TMP | TASK_ADD, true>(s, a.ph_ptr[pp], a.ph_ptr[pp + 1]);                         // x = v + M' v
-        else run_phase<TASK_DST_TMP | TASK_SCALE_ACC, true>(s, a.ph_ptr[pp], a.ph_ptr[pp + 1]);                          // v = y^ - (W_below' x) / d
+        if (ph & 1) run_phase<TASK_SRC_TMP | TASK_ADD, true>(s, a.ph_ptr[pp], a.ph_ptr[pp + 1], zidx, zpair);                         // x = v + M' v
+        else run_phase<TASK_DST_TMP | TASK_SCALE_ACC, true>(s, a.ph_ptr[pp], a.ph_ptr[pp + 1], zidx, zpair);                          // v = y^ - (W_below' x) / d
         LVL_T(pp);
     }
 }

@@ -71,13 +71,15 @@ __device__ __forceinline__ TrajNode traj_at_s(const TrajView& tv, int base, doub
 }
 // path_coordinates (trajectories.jl:71-93): closest segment by an O(n_nodes) scan (first minimum wins), then (s, e).
 // Deviation: the sqrt argument is floored at 0 (the reference raises a DomainError on negative round-off).
-__device__ __forceinline__ void path_coordinates(const TrajView& tv, int base, double x, double y, double& s_out, double& e_out) {
+// The scan is spread over the 32 lanes of a warp (segment i on lane i mod 32), followed by a butterfly arg-min whose tie-break keeps the
+// smallest segment index, i.e. exactly the serial first-minimum-wins result.  Every lane returns (s, e).
+__device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int base, double x, double y, int lane, double& s_out, double& e_out) {
     const int nn = tv.n_nodes;
     const double *E = tv.f[4] + base, *Nn = tv.f[5] + base;
     double d2min = INFINITY;
-    int imin = 0;
-    double ax = __ldg(E), ay = __ldg(Nn);
-    for (int i = 0; i < nn - 1; i++) {
+    int imin = 0x7fffffff;
+    for (int i = lane; i < nn - 1; i += 32) {
+        const double ax = __ldg(E + i), ay = __ldg(Nn + i);
         const double bx = __ldg(E + i + 1), by = __ldg(Nn + i + 1);
         const double vx = bx - ax, vy = by - ay;
         double lam = (vx * (x - ax) + vy * (y - ay)) / (vx * vx + vy * vy);
@@ -85,9 +87,14 @@ __device__ __forceinline__ void path_coordinates(const TrajView& tv, int base, d
         const double px = (1 - lam) * ax + lam * bx, py = (1 - lam) * ay + lam * by;
         const double d2 = (px - x) * (px - x) + (py - y) * (py - y);
         if (d2 < d2min) { d2min = d2; imin = i; }
-        ax = bx; ay = by;
     }
-    const int i = imin;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double d2o = __shfl_xor_sync(0xffffffffu, d2min, o);
+        const int io = __shfl_xor_sync(0xffffffffu, imin, o);
+        if (d2o < d2min || (d2o == d2min && io < imin)) { d2min = d2o; imin = io; }
+    }
+    const int i = imin == 0x7fffffff ? 0 : imin;      // all distances NaN: the serial scan keeps segment 0
     const double ex = __ldg(E + i), ey = __ldg(Nn + i);
     const double vx = __ldg(E + i + 1) - ex, vy = __ldg(Nn + i + 1) - ey;
     const double wx = x - ex, wy = y - ey;
@@ -125,8 +132,10 @@ struct NodeArgs {
     double *qs, *us, *ps;
 };
 
+// One warp per vehicle: the lanes share the closest-segment scan and, on warm steps, take one horizon node each; the cold rollout
+// (a recurrence over the nodes) runs on lane 0.
 __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (v >= a.B) return;
     const int B = a.B, N = a.N, Ns = a.Ns;
     const VehParams& P = a.P;
@@ -145,21 +154,23 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
     double* ps = a.ps + (size_t)v * N * 4;
 
     double s0, e0;
-    path_coordinates(a.tv, base, E0, N0, s0, e0);
+    path_coordinates_warp(a.tv, base, E0, N0, lane, s0, e0);
 
     if (a.kind == PGN_COUPLED) {
         TrajNode tj = traj_at_s(a.tv, base, s0);
         double ds = s0 - traj_at_time(a.tv, base, ts[0]).s;
         const double dpsi = adiff(psi0, tj.psi);
-        qs[0] = ds; qs[1] = Ux0; qs[2] = Uy0; qs[3] = r0; qs[4] = dpsi; qs[5] = e0;
-        us[0] = d0; us[1] = Fx0;
-        ps[0] = tj.V; ps[1] = tj.kappa; ps[2] = 0; ps[3] = 0;
+        if (lane == 0) {
+            qs[0] = ds; qs[1] = Ux0; qs[2] = Uy0; qs[3] = r0; qs[4] = dpsi; qs[5] = e0;
+            us[0] = d0; us[1] = Fx0;
+            ps[0] = tj.V; ps[1] = tj.kappa; ps[2] = 0; ps[3] = 0;
+        }
         if (a.solved[v]) {
             // warm: previous QP solution interpolated in prev_ts (update_interpolations!, coupled_lat_long.jl:86-102,189-195)
             const double* pts = a.prev_ts + (size_t)v * N;
             const double* X = a.sol_x + (size_t)v * a.n_sol;
             const double tend = pts[N - 1];
-            for (int i = 1; i < N; i++) {
+            for (int i = 1 + lane; i < N; i += 32) {
                 const double t = ts[i];
                 const double tq = t < tend ? t : tend;
                 int k = 0;
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
                 tj = traj_at_s(a.tv, base, s);
                 ps[4 * i + 0] = tj.V; ps[4 * i + 1] = tj.kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
             }
-        } else {
+        } else if (lane == 0) {
             // cold: forward rollout of (V, s) with steady-state cornering estimates (coupled_lat_long.jl:103-141)
             double s = s0, sp, cp;
             sincos(dpsi, &sp, &cp);
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
                 s = s + V * tau + A * tau * tau / 2;
             }
         }
-    } else {
+    } else if (lane == 0) {
         // decoupled: always the steady-state rollout (decoupled_lat_long.jl:65-103)
         double s = s0;
         double V = hypot(Ux0, Uy0);
@@ -331,7 +342,7 @@ void launch_nodes(pgn_handle* h) {
     a.state = h->d_state; a.control = h->d_control; a.toff = h->d_toff; a.solved = h->d_solved; a.traj_id = h->d_traj_id;
     a.ts = h->d_ts; a.dt = h->d_dt; a.prev_ts = h->d_prev_ts; a.sol_x = h->d_sol_x;
     a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps;
-    k_nodes<<<(h->B + 127) / 128, 128, 0, h->stream>>>(a);
+    k_nodes<<<(h->B + 3) / 4, 128, 0, h->stream>>>(a);
     h->launches++;
 }
 void launch_controls(pgn_handle* h, double* d_out) {

@@ -32,3 +32,4 @@ print("  sum per solve %.0f" % (lv[:110].sum() / (per * n_solves)))
 print("factor of CTA 0 (cycles per factorisation, %.1f vehicles):" % per)
 print("  init %.0f  levels %.0f  range inverses %.0f  tail %.0f" % (lv[110] / per, lv[120:220].sum() / per, lv[111] / per, lv[112] / per))
 print("  per level:", [int(x / per) for x in lv[120:120 + min(g.n_levels, 100)]])
+print("probe of forward phase 1 on warp 0 (cycles per solve): task load %.0f  gather loop %.0f  reduce %.0f  epilogue %.0f  loop exit %.0f  barrier %.0f" % tuple(lv[200 + i] / (per * n_solves) for i in range(6)))
