@@ -261,37 +261,38 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
     // Pivot p: S_ik -= S_ip S_kp / d,  S_ip <- S_ip / d,  S_pp <- -1 / d.  The pivot column (and 1/d) of step p+1 is staged into a small
     // buffer by the threads that produce it during step p, so one barrier per pivot suffices.
     if (Dm > 0) {
-        double* col = s.red;                 // [2][64] columns + [2] reciprocal pivots
-        double* dinvb = s.red + 128;
+        double* col = s.red;                 // [2][64] pivot columns + [2] pivots
+        double* dpiv = s.red + 128;
+        const int ept = (npk + ADMM_THREADS - 1) / ADMM_THREADS;
         int ei[SWEEP_EPT], ek[SWEEP_EPT];
 #pragma unroll
         for (int x = 0; x < SWEEP_EPT; x++) {
-            const int e = tid + x * ADMM_THREADS;
+            const int e = min(tid + x * ADMM_THREADS, npk - 1);          // surplus threads shadow the last element (their stores are masked)
             int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-            while ((i + 1) * (i + 2) / 2 <= e) i++;
-            while (i * (i + 1) / 2 > e) i--;
-            ei[x] = e < npk ? i : -1; ek[x] = e - i * (i + 1) / 2;
+            i += ((i + 1) * (i + 2) / 2 <= e);
+            i -= (i * (i + 1) / 2 > e);
+            ei[x] = i; ek[x] = e - i * (i + 1) / 2;
         }
         if (tid < Dm) col[tid] = s.S[tid * (tid + 1) / 2];
-        if (tid == 0) dinvb[0] = 1.0 / s.S[0];
+        if (tid == 0) dpiv[0] = s.S[0];
         __syncthreads();
         for (int p = 0; p < Dm; p++) {
             const double* cc = col + (p & 1) * 64;
             double* cn = col + ((p + 1) & 1) * 64;
-            const double dinv = dinvb[p & 1];
+            const double dinv = 1.0 / dpiv[p & 1];           // every thread forms the reciprocal itself: no serial hand-off through one lane
 #pragma unroll
             for (int x = 0; x < SWEEP_EPT; x++) {
-                const int i = ei[x], k = ek[x];
-                if (i >= 0) {
-                    const int e = tid + x * ADMM_THREADS;
-                    const double ci = cc[i], ck = cc[k];
-                    double v;
-                    if (i == p) v = (k == p) ? -dinv : ck * dinv;
-                    else if (k == p) v = ci * dinv;
-                    else v = s.S[e] - ci * ck * dinv;
-                    s.S[e] = v;
-                    if (k == p + 1) { cn[i] = v; if (i == p + 1) dinvb[(p + 1) & 1] = 1.0 / v; }
-                    else if (i == p + 1) cn[k] = v;
+                if (x < ept) {                                // uniform
+                    const int i = ei[x], k = ek[x], e = tid + x * ADMM_THREADS;
+                    const bool live = e < npk;
+                    const double ci = cc[i], ck = cc[k], old = s.S[live ? e : 0];
+                    const double upd = old - ci * ck * dinv;
+                    const double onrow = (k == p) ? -dinv : ck * dinv;       // i == p
+                    const double v = (i == p) ? onrow : ((k == p) ? ci * dinv : upd);
+                    if (live) s.S[e] = v;
+                    if (live && k == p + 1) cn[i] = v;                        // column p+1 below (and on) the diagonal ...
+                    if (live && i == p + 1) cn[k] = v;                        // ... and its mirror image left of the diagonal
+                    if (live && i == p + 1 && k == p + 1) dpiv[(p + 1) & 1] = v;
                 }
             }
             __syncthreads();
@@ -406,14 +407,20 @@ __device__ __forceinline__ void kkt_solve(const AdmmArgs& a, const Smem& s, unsi
         // x_T = S^-1 t_T with the packed lower -S^-1: 8 lanes per row
         for (int i8 = tid; i8 < ((Dm * 8 + 31) & ~31); i8 += ADMM_THREADS) {
             const int i = i8 >> 3, sub = i8 & 7;
-            double acc = 0.0;
-            if (i < Dm) {
+            double acc0 = 0.0, acc1 = 0.0;
+            {
                 const double* tv = s.dxy + ts;
-                const double* row = s.S + i * (i + 1) / 2;
-                int k = sub;
-                for (; k <= i; k += 8) acc += row[k] * tv[k];
-                for (; k < Dm; k += 8) acc += s.S[k * (k + 1) / 2 + i] * tv[k];
+                const int ii = min(i, Dm - 1), rb = ii * (ii + 1) / 2;
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {             // tail_dim <= 64: eight columns per lane, all loads in flight together
+                    const int k0 = sub + 8 * j, k1 = k0 + 8;
+                    const int c0 = min(k0, Dm - 1), c1 = min(k1, Dm - 1);
+                    const double a0 = s.S[c0 <= ii ? rb + c0 : c0 * (c0 + 1) / 2 + ii], a1 = s.S[c1 <= ii ? rb + c1 : c1 * (c1 + 1) / 2 + ii];
+                    const double t0 = tv[c0], t1 = tv[c1];
+                    acc0 += (k0 < Dm ? a0 : 0.0) * t0; acc1 += (k1 < Dm ? a1 : 0.0) * t1;
+                }
             }
+            double acc = acc0 + acc1;
             acc = group_sum_c<8>(acc);
             if (i < Dm && sub == 0) s.sol[ts + i] = -acc;
         }
@@ -621,14 +628,36 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
 
         // ---- 2. modified Ruiz equilibration (scale_data of OSQP) -------------------------------------------------------
         for (int it = 0; it < st.scaling; it++) {
+            // inf-norms of the KKT columns (variables: P_jj and column j of A; constraints: row i of A), four gathers in flight per thread
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
-                double nrm = s.flag[p] ? 0.0 : fabs(s.lo[p]);
+                double n0 = s.flag[p] ? 0.0 : fabs(s.lo[p]), n1 = 0.0;
+                int e = s.kptr[p];
                 const int e1 = s.kptr[p + 1];
-                for (int e = s.kptr[p]; e < e1; e++) nrm = fmax(nrm, fabs(s.Aval[s.ke[e]]));
-                s.sol[p] = 1.0 / sqrt(limit_scaling(nrm));
+#pragma unroll 1
+                for (; e + 4 <= e1; e += 4) {
+                    const int j0 = s.ke[e], j1 = s.ke[e + 1], j2 = s.ke[e + 2], j3 = s.ke[e + 3];
+                    const double a0 = s.Aval[j0], a1 = s.Aval[j1], a2 = s.Aval[j2], a3 = s.Aval[j3];
+                    n0 = fmax(n0, fmax(fabs(a0), fabs(a1))); n1 = fmax(n1, fmax(fabs(a2), fabs(a3)));
+                }
+                if (e < e1) {
+                    const int last = e1 - 1;
+                    const int j0 = s.ke[e], j1 = s.ke[min(e + 1, last)], j2 = s.ke[min(e + 2, last)];
+                    const double a0 = s.Aval[j0], a1 = s.Aval[j1], a2 = s.Aval[j2];
+                    n0 = fmax(n0, fmax(fabs(a0), fabs(a1))); n1 = fmax(n1, fabs(a2));
+                }
+                s.sol[p] = 1.0 / sqrt(limit_scaling(fmax(n0, n1)));
             }
             __syncthreads();
-            for (int e = tid; e < q.nnzA; e += ADMM_THREADS) { const uint32_t rc = s.arc[e]; s.Aval[e] *= s.sol[rc & 0xffff] * s.sol[rc >> 16]; }
+            {
+                int e = tid;
+                for (; e + ADMM_THREADS < q.nnzA; e += 2 * ADMM_THREADS) {       // two independent entries per trip
+                    const uint32_t rc0 = s.arc[e], rc1 = s.arc[e + ADMM_THREADS];
+                    const double f0 = s.sol[rc0 & 0xffff] * s.sol[rc0 >> 16], f1 = s.sol[rc1 & 0xffff] * s.sol[rc1 >> 16];
+                    const double a0 = s.Aval[e], a1 = s.Aval[e + ADMM_THREADS];
+                    s.Aval[e] = a0 * f0; s.Aval[e + ADMM_THREADS] = a1 * f1;
+                }
+                if (e < q.nnzA) { const uint32_t rc = s.arc[e]; s.Aval[e] *= s.sol[rc & 0xffff] * s.sol[rc >> 16]; }
+            }
             double sumP = 0.0, maxq = 0.0;   // sum |P_jj|, max |q_j|
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
                 const double d = s.sol[p];
