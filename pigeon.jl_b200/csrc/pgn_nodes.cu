@@ -1,5 +1,5 @@
-// pgn_nodes.cu — time steps, linearisation-node generation, control extraction and plant rollout; one vehicle per thread over
-// SoA HBM arrays.
+// pgn_nodes.cu — time steps, linearisation-node generation (one warp per vehicle), control extraction and plant rollout (one vehicle
+// per thread) over SoA HBM arrays.
 //   compute_time_steps!            reference src/model_predictive_control.jl:17-30
 //   compute_linearization_nodes!   src/coupled_lat_long.jl:62-142, src/decoupled_lat_long.jl:52-104
 //   trajectory lookups             src/trajectories.jl:47-94, src/math.jl:4-9
