@@ -285,6 +285,19 @@ def run_gpu(args):
                 "fp64": {"achieved_tflops": B * flop_qp / (admm_ms * 1e-3) / 1e12, "nominal_peak_tflops": 37.0, "flop_per_qp": flop_qp},
                 "note": "one QP per CTA; the solve is a chain of dependent sparse triangular solves in shared memory: latency/occupancy-bound, neither HBM- nor tensor-bound (SURVEY.md 8d)"}
         roof["frac"] = roof["achieved"] / roof["peak"]
+        # DRAM traffic of one launch from the committed `ncu --set full` capture of the same workload (read + written bytes)
+        try:
+            import re
+            txt = open(os.path.join(ROOT, "profiles", "r1_admm_ncu_full.md")).read()
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = re.search(r"dram__bytes_read.sum`\) \| ([0-9.]+) \| (\w+)", txt); wr = re.search(r"dram__bytes_write.sum`\) \| ([0-9.]+) \| (\w+)", txt)
+            wf = re.search(r"l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed`\) \| ([0-9.]+)", txt)
+            roof["traffic"] = float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)]
+            roof["traffic_source"] = "profiles/r1_admm_ncu_full.md (B = 1024; below the algorithmic bytes because the records and iterates of 1024 vehicles stay in the 126 MB L2)"
+            if wf:
+                roof["smem"] = {"pct_of_peak_wavefronts": float(wf.group(1)), "source": "profiles/r1_admm_ncu_full.md: the most loaded unit of the kernel is the shared-memory pipe"}
+        except Exception:
+            pass
         roof["fp64"]["frac"] = roof["fp64"]["achieved_tflops"] / 37.0
         ncpu = min(B, 256)
         cpu = cpu_baseline(ncpu, 3, 1) if not args.no_cpu else None

@@ -327,3 +327,98 @@ def test_smoke_scenario_known_answers(p):
         if kind == 1:
             assert u[0, 2] == pytest.approx(366.5, rel=0.05)        # drag equilibrium Cd0 + Cd1*Ux
         g.close()
+
+
+# ---- size-independent properties at BASELINE.json's larger batches (the oracle only checks a subsample) -----------------------------
+def _scenario(p, B, seed=5):
+    trajs = p.synthetic.synthetic_trajectories(n_traj=16, n_nodes=600)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B, seed=p.synthetic.SEED + seed)
+    rng = np.random.default_rng(seed)
+    other = np.zeros((B, 4))
+    rad = rng.uniform(0.5, 9.0, B); ang = rng.uniform(-np.pi, np.pi, B)
+    other[:, 0] = state[:, 0] + rad * np.cos(ang); other[:, 1] = state[:, 1] + rad * np.sin(ang)
+    other[:, 2] = state[:, 2] + rng.normal(0, 0.5, B); other[:, 3] = rng.uniform(1.5, 12, B)
+    other[::10, 0] += 500.0                      # 10 % outside the grid
+    return trajs, tid, state, control, t0, other
+
+
+def test_scale_coupled_hji_batch_permutation_invariance_and_subsample_parity(p):
+    """configs[3] in miniature-by-oracle: B = 4096 scenarios with the HJI constraint active for about half of them.  (a) vehicles are
+    independent: permuting the batch permutes the outputs bit for bit; (b) a 24-vehicle subsample matches the oracle."""
+    B, steps = 4096, 3
+    knots, V, gV = p.synthetic.analytic_hji_grid((13, 13, 7, 7, 5, 7, 5))
+    trajs, tid, state, control, t0, other = _scenario(p, B)
+    perm = np.random.default_rng(11).permutation(B)
+    outs = []
+    for order in (np.arange(B), perm):
+        g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid[order])
+        g.set_HJI_cache(p.HJICache(knots, V, gV))
+        g.set_state(state[order], control[order], other[order])
+        us, its = [], []
+        for k in range(steps):
+            us.append(g.step(t0[order] + 0.01 * k)); its.append(g.stats()["iters"].copy())
+            g.rollout(0.01)
+        hji = g.qp_data()["hji"]
+        outs.append((np.array(us), np.array(its), hji))
+        g.close()
+    (u0, i0, h0), (u1, i1, h1) = outs
+    assert np.array_equal(u0[:, perm], u1, equal_nan=True) and np.array_equal(i0[:, perm], i1) and np.array_equal(h0[perm], h1, equal_nan=True)
+    active = ~((h0[:, 0] == 0) & (h0[:, 1] == 0) & (h0[:, 2] == 1.0))
+    assert 0.2 * B < active.sum() < 0.8 * B
+    ok = np.all(np.isfinite(u0), axis=(0, 2))          # an other car half a metre away can make a QP infeasible: NaN controls, as OSQP reports
+    assert ok.mean() > 0.9
+    # subsample against the oracle (closed loop driven by the oracle's own controls)
+    sub = np.random.default_rng(3).choice(np.flatnonzero(ok), 24, replace=False)
+    ms = oracles_for(0, trajs, tid[sub], state[sub], control[sub], other[sub], hji=o.HjiCache(knots, V, gV))
+    for k in range(steps):
+        for j, m in enumerate(ms):
+            uo = m.step(t0[sub[j]] + 0.01 * k)
+            assert np.max(np.abs(u0[k, sub[j]] - uo) / U_RANGE) < 1e-4, (k, j)
+            assert i0[k, sub[j]] == m.stats()["iter"]
+            q, u = m.get_state()
+            m.set_state(o.flow(o.MODEL_BICYCLE, m.vp, q, 0.01, [u[0], u[1] + u[2], 0, 0, 0, 0]), uo, other4=other[sub[j]])
+
+
+def test_scale_decoupled_batch_size_independence(p):
+    """configs[2] per GPU (8192 vehicles): a vehicle's lateral QP and feed-forward force do not depend on the batch it is solved in."""
+    B, small = 8192, 64
+    trajs, tid, state, control, t0, other = _scenario(p, B, seed=9)
+    res = []
+    for n in (B, small):
+        g = p.BatchedDecoupledTrajectoryTrackingMPC(p.X1(), trajs, n, trajectory_index=tid[:n])
+        g.set_state(state[:n], control[:n], other[:n])
+        u = [g.step(t0[:n] + 0.01 * k) for k in range(2)]
+        res.append((np.array(u), g.stats()["iters"].copy(), g.stats()["status"].copy()))
+        g.close()
+    assert np.array_equal(res[0][0][:, :small], res[1][0]) and np.array_equal(res[0][1][:small], res[1][1])
+    assert (res[0][2] == 1).mean() > 0.99
+    m = oracles_for(1, trajs, tid[:4], state[:4], control[:4], other[:4])
+    for j, mm in enumerate(m):
+        assert np.max(np.abs(res[0][0][0, j] - mm.step(t0[j])) / U_RANGE) < 1e-4
+
+
+def test_scale_closed_loop_monte_carlo_on_device(p):
+    """configs[4] in miniature: the fully on-device closed loop (pgn_simulate: linearise -> QP -> rollout, no host round trips) over 2048
+    perturbed initial states x 40 steps equals the same loop driven step by step through the host API, and the tracking error stays bounded."""
+    B, steps = 2048, 40
+    trajs, tid, state, control, t0, other = _scenario(p, B, seed=21)
+    far = np.tile(FAR, (B, 1))
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g.set_state(state, control, far)
+    g.simulate_device(t0, 0.01, steps)
+    q_dev, u_dev = g.get_state()
+    it_dev = g.stats()["iters"].copy()
+    g.reset_solver(); g.reset_solved()
+    g.set_state(state, control, far)
+    for k in range(steps):
+        g.step(t0 + 0.01 * k); g.rollout(0.01)
+    q_host, u_host = g.get_state()
+    assert np.array_equal(it_dev, g.stats()["iters"])
+    assert np.array_equal(q_dev, q_host, equal_nan=True) and np.array_equal(u_dev, u_host, equal_nan=True)
+    assert np.isfinite(q_dev).all(axis=1).mean() > 0.99       # an infeasible QP returns NaN controls (OSQP semantics); the ROS layer of the reference handles that
+    qs, _, _ = g.nodes()                                    # node 1 = current state in path coordinates: (ds, Ux, Uy, r, dpsi, e)
+    g0 = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g0.set_state(state, control, far); g0.compute_time_steps(t0); g0.compute_linearization_nodes()
+    qs0, _, _ = g0.nodes()
+    assert np.nanmedian(np.abs(qs[:, 0, 5])) < 1.05 * np.median(np.abs(qs0[:, 0, 5])) and np.nanmax(np.abs(qs[:, 0, 5])) < 3.0      # no divergence in 0.4 s
+    g.close(); g0.close()
