@@ -102,6 +102,13 @@ PGN_API int pgn_reset_solved(pgn_handle* h, const uint8_t* mask /*[B]*/);
 /* Parametron.initialize!(mpc.model) (ros_integration.jl:146): cold ADMM iterates, rho back to its setting */
 PGN_API int pgn_reset_solver(pgn_handle* h, const uint8_t* mask /*[B]*/);
 
+/* Per-vehicle guards of the reference's callback (src/ros_integration.jl:84-87 and 134-147), off by default (`simulate` has none):
+ *   pause_below_speed > 0: a vehicle with current_state.Ux < pause_below_speed skips the step (the callback returns early): its QP is
+ *                          not solved, solver state and mpc.solved stay as they are, the control output is the current control;
+ *   nan_fallback != 0    : NaN in (delta, Fxf, Fxr) => the output is the current control, the vehicle's ADMM iterates / rho are
+ *                          re-initialised (Parametron.initialize!) and mpc.solved = false (cold node generation next step). */
+PGN_API int pgn_set_guards(pgn_handle* h, int32_t nan_fallback, double pause_below_speed);
+
 /* --- the 5-call step API (model_predictive_control.jl:70-78) ------------------------------------------------------ */
 PGN_API int pgn_compute_time_steps(pgn_handle* h, const double* t0 /*[B]*/);           /* compute_time_steps!(mpc, t0) */
 PGN_API int pgn_compute_linearization_nodes(pgn_handle* h);                            /* compute_linearization_nodes!(mpc) */

@@ -173,6 +173,9 @@ _mask(m) = m === nothing ? Ptr{UInt8}(C_NULL) : pointer(m)
 "mpc.solved = false (per vehicle)"
 reset_solved!(mpc, mask::Union{Nothing,Vector{UInt8}}=nothing) = GC.@preserve mask check(ccall((:pgn_reset_solved, libpigeon), Cint, (Ptr{Cvoid}, Ptr{UInt8}), mpc.handle, _mask(mask)))
 "Parametron.initialize!(mpc.model) (ros_integration.jl:146), per vehicle"
+# guards of the ROS callback (src/ros_integration.jl:84-87, 134-147): pause below a speed, previous control + re-initialisation on NaN
+set_guards!(mpc; nan_fallback::Bool=false, pause_below_speed::Float64=0.0) =
+    check(ccall((:pgn_set_guards, libpigeon), Cint, (Ptr{Cvoid}, Int32, Float64), mpc.handle, Int32(nan_fallback), pause_below_speed))
 reset_solver!(mpc, mask::Union{Nothing,Vector{UInt8}}=nothing) = GC.@preserve mask check(ccall((:pgn_reset_solver, libpigeon), Cint, (Ptr{Cvoid}, Ptr{UInt8}), mpc.handle, _mask(mask)))
 
 # ---- the 5-call step API (src/model_predictive_control.jl:70-78) --------------------------------------------------------------

@@ -25,7 +25,7 @@ class PgnConfig(C.Structure):
 # every symbol declared in include/pigeon_b200.h
 SYMBOLS = ["pgn_default_config", "pgn_x1_vehicle_params", "pgn_default_control_params", "pgn_create", "pgn_destroy", "pgn_last_error", "pgn_set_stream",
            "pgn_synchronize", "pgn_set_vehicle_params", "pgn_set_control_params", "pgn_set_trajectories", "pgn_assign_trajectories", "pgn_set_hji_cache",
-           "pgn_set_state", "pgn_reset_solved", "pgn_reset_solver", "pgn_compute_time_steps", "pgn_compute_linearization_nodes", "pgn_update_qp",
+           "pgn_set_state", "pgn_reset_solved", "pgn_reset_solver", "pgn_set_guards", "pgn_compute_time_steps", "pgn_compute_linearization_nodes", "pgn_update_qp",
            "pgn_solve", "pgn_get_next_control", "pgn_step", "pgn_step_device", "pgn_simulate", "pgn_rollout", "pgn_qp_dims", "pgn_get_state",
            "pgn_get_time_steps", "pgn_get_nodes", "pgn_set_nodes", "pgn_get_qp_data", "pgn_get_solution", "pgn_get_stats", "pgn_hji_lookup",
            "pgn_hji_lookup_device", "pgn_device_controls", "pgn_device_stats", "pgn_set_profiling", "pgn_get_stage_ms", "pgn_get_admm_cycles"]
@@ -50,6 +50,7 @@ def load():
     lib.pgn_create.argtypes = [C.POINTER(PgnConfig), C.POINTER(C.c_void_p)]
     lib.pgn_simulate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int32]
     lib.pgn_rollout.argtypes = [C.c_void_p, C.c_double]
+    lib.pgn_set_guards.argtypes = [C.c_void_p, C.c_int32, C.c_double]
     _lib = lib
     return lib
 

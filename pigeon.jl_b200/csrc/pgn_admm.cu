@@ -36,6 +36,8 @@ struct AdmmArgs {
     uint8_t* solved;
     int* counter;
     const int32_t* order;          // ticket -> vehicle (longest previous solve first)
+    const uint8_t* skip;           // guard: paused vehicles are not solved (nullptr = guard off)
+    uint8_t* cold;                 // guard: vehicles whose iterates / rho start from scratch (Parametron.initialize! after a NaN)
     uint16_t ph_ptr[ADMM_MAX_PHASES + 1];   // first task of every solve phase (forward phases, then backward phases): uniform constant-bank reads
     unsigned long long* cycles;   // optional per-phase cycle counters (profiling builds of the host call): gather, ruiz, factor, solve, update, check, store
 };
@@ -575,6 +577,11 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         __syncthreads();
         if (ticket >= a.B) break;
         const int v = a.order[ticket];
+        if (a.skip && a.skip[v]) {                                  // CTA-uniform: every thread reads the same flag
+            if (tid == 0) { a.iters[v] = 0; a.status[v] = PGN_QP_UNSOLVED; }
+            continue;
+        }
+        const bool warm = st.warm_start && !a.cold[v];
         const double* rec = a.rec + (size_t)v * q.rec_len;
         PHASE(7);
 
@@ -605,7 +612,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                 s.lo[p] = fmax(b[0], -OSQP_INFTY);
                 s.hi[p] = fmin(b[1], OSQP_INFTY);
                 s.flag[p] = 1;
-                s.yq[p] = st.warm_start ? a.ws_y[(size_t)v * q.Nk + p] : 0.0;
+                s.yq[p] = warm ? a.ws_y[(size_t)v * q.Nk + p] : 0.0;
             } else {
                 const int pm = __ldg(q.P_mode + idx), qm = __ldg(q.q_mode + idx);
                 double Pv = 0.0, qv = 0.0;
@@ -619,9 +626,9 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                 s.flag[p] = 0;
             }
             s.sc[p] = 1.0;         // D_j | E_i
-            s.xz[p] = st.warm_start ? a.ws_xz[(size_t)v * q.Nk + p] : 0.0;
+            s.xz[p] = warm ? a.ws_xz[(size_t)v * q.Nk + p] : 0.0;
         }
-        double rho = st.warm_start ? a.rho[v] : st.rho;
+        double rho = warm ? a.rho[v] : st.rho;
         double c = 1.0;
         __syncthreads();
         PHASE(0);
@@ -799,6 +806,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
             a.iters[v] = iter; a.status[v] = status; a.rho_updates[v] = n_rho_upd;
             a.pri_res[v] = pri_res; a.dua_res[v] = dua_res;
             a.solved[v] = 1;
+            a.cold[v] = 0;
         }
         __syncthreads();
         PHASE(6);
@@ -845,6 +853,7 @@ void launch_admm(pgn_handle* h) {
     k_admm_order<<<1, 1024, 0, h->stream>>>(h->d_iters, h->d_order, h->B);
     h->launches++;
     a.order = h->d_order;
+    a.skip = h->guard_pause > 0.0 ? h->d_skip : nullptr; a.cold = h->d_cold;
     for (size_t i = 0; i < h->tab.sol_ph_ptr.size() && i <= ADMM_MAX_PHASES; i++) a.ph_ptr[i] = h->tab.sol_ph_ptr[i];
     int ctas_per_sm = 1;
     if (h->admm_smem_bytes * 2 + 2048 <= 227 * 1024) ctas_per_sm = 2;

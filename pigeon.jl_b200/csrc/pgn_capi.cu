@@ -270,12 +270,13 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_cycles, 512);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
     CK(cudaMemset(h->d_sol_x, 0, B * t.n * 8)); CK(cudaMemset(h->d_sol_y, 0, B * t.m * 8));
-    CK(cudaMemset(h->d_cycles, 0, 4096));
+    CK(cudaMemset(h->d_cycles, 0, 4096)); CK(cudaMemset(h->d_skip, 0, B)); CK(cudaMemset(h->d_cold, 0, B));
+    h->guard_nan = 0; h->guard_pause = 0.0;
     CK(cudaMemset(h->d_iters, 0, B * 4)); CK(cudaMemset(h->d_status, 0, B * 4)); CK(cudaMemset(h->d_rho_updates, 0, B * 4));
     CK(cudaMemset(h->d_rec, 0, B * (size_t)t.rec.rec_len * 8)); CK(cudaMemset(h->d_controls, 0, 3 * B * 8));
     {   // other car far away, time_offset = NaN (path mode), ts = 1..N (MPCTimeSteps ctor), rho = setting
@@ -378,6 +379,13 @@ int pgn_reset_solved(pgn_handle* h, const uint8_t* mask) {
     CK(cudaMemcpy(cur.data(), h->d_solved, h->B, cudaMemcpyDeviceToHost));
     for (int v = 0; v < h->B; v++) if (mask[v]) cur[v] = 0;
     CK(cudaMemcpy(h->d_solved, cur.data(), h->B, cudaMemcpyHostToDevice));
+    return PGN_OK;
+}
+int pgn_set_guards(pgn_handle* h, int32_t nan_fallback, double pause_below_speed) {
+    REQUIRE(h, "NULL handle");
+    REQUIRE(pause_below_speed >= 0.0, "pause_below_speed must be >= 0");
+    h->guard_nan = nan_fallback != 0; h->guard_pause = pause_below_speed;
+    if (pause_below_speed == 0.0) CK(cudaMemsetAsync(h->d_skip, 0, h->B, h->stream));
     return PGN_OK;
 }
 int pgn_reset_solver(pgn_handle* h, const uint8_t* mask) {

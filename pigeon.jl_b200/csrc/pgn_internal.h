@@ -97,6 +97,8 @@ struct pgn_handle {
     double *d_pri_res, *d_dua_res;
     double* d_controls;                                  // [3][B]
     double *d_t0, *d_t0_base;                            // [B]
+    uint8_t *d_skip, *d_cold;                            // guards: vehicle paused this step / ADMM iterates to be re-initialised
+    int guard_nan; double guard_pause;
     int32_t* d_order;                                    // ticket -> vehicle order of the ADMM launch
     int* d_counter;                                      // work-queue ticket for the persistent ADMM kernel
     unsigned long long* d_cycles;                        // [8] per-phase cycle counters of the ADMM kernel (profiling only)

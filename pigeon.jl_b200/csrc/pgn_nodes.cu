@@ -130,6 +130,7 @@ struct NodeArgs {
     const double *state, *control, *toff; const uint8_t* solved; const int32_t* traj_id;
     const double *ts, *dt, *prev_ts, *sol_x;
     double *qs, *us, *ps;
+    uint8_t* skip; double pause_below_speed;      // guard of src/ros_integration.jl:84-87
 };
 
 // One warp per vehicle: the lanes share the closest-segment scan and, on warm steps, take one horizon node each; the cold rollout
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
     const double d0 = a.control[0 * B + v], Fxf0 = a.control[1 * B + v], Fxr0 = a.control[2 * B + v];
     const double Fx0 = Fxf0 + Fxr0;
     const bool path_mode = isnan(a.toff[v]);
+    if (a.pause_below_speed > 0.0 && lane == 0) a.skip[v] = Ux0 < a.pause_below_speed;
     const int base = a.traj_id[v] * a.tv.n_nodes;
     const double* ts = a.ts + (size_t)v * N;
     const double* dt = a.dt + (size_t)v * (N - 1);
@@ -278,8 +280,12 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
 }
 
 // ---- get_next_control ------------------------------------------------------------------------------------------------
+// With the guards of src/ros_integration.jl: a paused vehicle (Ux below the threshold, :84-87) and a vehicle whose QP returned NaN
+// (:134-147) keep their current control; the latter is also re-initialised (cold ADMM iterates, mpc.solved = false).
 __global__ void k_controls(int B, int kind, int n_sol, int iv_delta, int iv_fx, double un0, double un1, VehParams P,
-                           const double* __restrict__ sol_x, const double* __restrict__ us, int N, double* __restrict__ out) {
+                           const double* __restrict__ sol_x, const double* __restrict__ us, int N, double* __restrict__ out,
+                           const double* __restrict__ control, const uint8_t* __restrict__ skip, int guard_nan, uint8_t* __restrict__ cold,
+                           uint8_t* __restrict__ solved) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= B) return;
     double d, Fx;
@@ -287,6 +293,10 @@ __global__ void k_controls(int B, int kind, int n_sol, int iv_delta, int iv_fx, 
     else { d = sol_x[(size_t)v * n_sol + iv_delta]; Fx = us[(size_t)v * N * 2 + 2 * 1 + 1]; }
     double Fxf, Fxr;
     if (Fx > 0) { Fxf = Fx * P.fwd_frac; Fxr = Fx * P.rwd_frac; } else { Fxf = Fx * P.fwb_frac; Fxr = Fx * P.rwb_frac; }
+    const bool paused = skip && skip[v];
+    const bool bad = guard_nan && !paused && (isnan(d) || isnan(Fxf) || isnan(Fxr));
+    if (paused || bad) { d = control[0 * B + v]; Fxf = control[1 * B + v]; Fxr = control[2 * B + v]; }
+    if (bad) { cold[v] = 1; solved[v] = 0; }
     out[0 * B + v] = d; out[1 * B + v] = Fxf; out[2 * B + v] = Fxr;
 }
 
@@ -342,13 +352,15 @@ void launch_nodes(pgn_handle* h) {
     a.state = h->d_state; a.control = h->d_control; a.toff = h->d_toff; a.solved = h->d_solved; a.traj_id = h->d_traj_id;
     a.ts = h->d_ts; a.dt = h->d_dt; a.prev_ts = h->d_prev_ts; a.sol_x = h->d_sol_x;
     a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps;
+    a.skip = h->d_skip; a.pause_below_speed = h->guard_pause;
     k_nodes<<<(h->B + 3) / 4, 128, 0, h->stream>>>(a);
     h->launches++;
 }
 void launch_controls(pgn_handle* h, double* d_out) {
     const int B = h->B;
     k_controls<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.kind, h->tab.n, h->tab.var_u1_delta, h->tab.var_u1_fx, h->un[0], h->un[1], h->veh,
-                                                       h->d_sol_x, h->d_us, h->N, d_out);
+                                                       h->d_sol_x, h->d_us, h->N, d_out, h->d_control, h->guard_pause > 0.0 ? h->d_skip : nullptr, h->guard_nan,
+                                                       h->d_cold, h->d_solved);
     h->launches++;
 }
 void launch_rollout(pgn_handle* h, double dt) {

@@ -222,6 +222,10 @@ class BatchedTrajectoryTrackingMPC:
         check(self._lib.pgn_reset_solver(self._h, dptr(m)))
 
     # ---- step API ----
+    def set_guards(self, nan_fallback=False, pause_below_speed=0.0):
+        """Per-vehicle guards of the reference's ROS callback (src/ros_integration.jl:84-87, 134-147); off by default."""
+        check(self._lib.pgn_set_guards(self._h, int(bool(nan_fallback)), C.c_double(float(pause_below_speed))))
+
     def _t0(self, t0):
         return f64(np.broadcast_to(np.asarray(t0, float), (self.B,)))
 

@@ -422,3 +422,46 @@ def test_scale_closed_loop_monte_carlo_on_device(p):
     qs0, _, _ = g0.nodes()
     assert np.nanmedian(np.abs(qs[:, 0, 5])) < 1.05 * np.median(np.abs(qs0[:, 0, 5])) and np.nanmax(np.abs(qs[:, 0, 5])) < 3.0      # no divergence in 0.4 s
     g.close(); g0.close()
+
+
+def test_guards_pause_and_nan_fallback(p):
+    """pgn_set_guards restates the per-vehicle guards of the reference's callback (src/ros_integration.jl:84-87, 134-147): a vehicle slower
+    than 1 m/s skips the step (current control kept, solver state untouched); a QP that returns NaN keeps the current control, and its
+    solver is re-initialised (next step: cold nodes, cold iterates, default rho) exactly like a fresh oracle controller."""
+    B = 16
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    state = state.copy()
+    state[2, 3] = 0.5                                  # paused vehicle
+    state[5, 4] = np.nan                               # a NaN lateral speed poisons this vehicle's QP data: NaN controls
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g.set_guards(nan_fallback=True, pause_below_speed=1.0)
+    g.set_state(state, control, other)
+    u1 = g.step(t0)
+    st = g.stats()
+    assert np.array_equal(u1[2], control[2]) and st["iters"][2] == 0                  # paused: current control, not solved
+    assert np.array_equal(u1[5], control[5])                                          # NaN: current control
+    assert np.all(np.isfinite(u1))
+    ms = oracles_for(0, trajs, tid, state, control, other)
+    for i in (0, 1, 3, 4, 6, 15):
+        assert np.max(np.abs(u1[i] - ms[i].step(t0[i])) / U_RANGE) < 1e-4
+    # second step: vehicle 5 gets a valid state again and must behave like a freshly constructed controller (cold start)
+    state2, _ = g.get_state()
+    state2[5] = state[6]; state2[2, 3] = 0.5
+    tid2 = tid.copy(); tid2[5] = tid[6]
+    g.assign_trajectories(tid2)
+    g.set_state(state2, u1, other)
+    u2 = g.step(t0 + 0.01)
+    fresh = o.Mpc(o.MPC_COUPLED)
+    fresh.set_trajectory(o.Trajectory(**{k: trajs[k][int(tid2[5])] for k in o.TRAJ_FIELDS}))
+    fresh.set_state(state2[5], u1[5], other4=other[5])
+    uf = fresh.step(t0[5] + 0.01)
+    assert np.max(np.abs(u2[5] - uf) / U_RANGE) < 1e-4 and g.stats()["iters"][5] == fresh.stats()["iter"]
+    assert np.array_equal(u2[2], u1[2])
+    # guards off (default): the NaN comes through, as from OSQP
+    g.set_guards(False, 0.0)
+    state3 = state2.copy(); state3[7, 4] = np.nan
+    g.set_state(state3, u2, other)
+    assert np.all(np.isnan(g.step(t0 + 0.02)[7]))
+    g.close()
