@@ -139,6 +139,16 @@ PGN_API int pgn_get_solution(pgn_handle* h, double* x /*[B][n]*/, double* y /*[B
 PGN_API int pgn_get_stats(pgn_handle* h, int32_t* iters, int32_t* status, double* pri_res, double* dua_res, double* rho, int32_t* rho_updates);
 /* stand-alone HJI lookup cache[x] (HJI_computation.jl:66-72); x [M][7] host, V [M], gradV [M][7] */
 PGN_API int pgn_hji_lookup(pgn_handle* h, int32_t M, const double* x, double* V, double* gradV);
+/* V and gradV of the last step's relative state HJIRelativeState(current_state, other_car_state) — what the callback logs and
+ * publishes (ros_integration.jl:57-58); (Inf, 0) outside the grid or before the first coupled step.  V [B], gradV [B][7] */
+PGN_API int pgn_get_hji_values(pgn_handle* h, double* V, double* gradV);
+/* optimal_control(dynamics, relative_state, gradV) (HJI_computation.jl:133-158, uMode = :max, N = 50): x [M][7], gradV [M][7] host,
+ * out [M][2] = (delta, Fx) */
+PGN_API int pgn_hji_optimal_control(pgn_handle* h, int32_t M, const double* x, const double* gradV, double* out);
+/* use_HJI_policy[] of the callback (ros_integration.jl:47,115-118), coupled controllers only: when on, a vehicle whose V <= HJI_eps
+ * gets BicycleControl(longitudinal_params, optimal_control(...)) from get_next_control / step instead of the QP's node-2 control
+ * (the QP is still solved, as in the callback).  Off by default. */
+PGN_API int pgn_set_hji_policy(pgn_handle* h, int32_t on);
 /* device variant for the HBM roofline micro-benchmark: d_x [7][M] field-major, d_V [M], d_gradV [7][M] */
 PGN_API int pgn_hji_lookup_device(pgn_handle* h, int32_t M, const double* d_x, double* d_V, double* d_gradV);
 /* device pointers of library-owned buffers (for zero-copy gathers through torch.distributed / NCCL) */

@@ -176,6 +176,20 @@ reset_solved!(mpc, mask::Union{Nothing,Vector{UInt8}}=nothing) = GC.@preserve ma
 # guards of the ROS callback (src/ros_integration.jl:84-87, 134-147): pause below a speed, previous control + re-initialisation on NaN
 set_guards!(mpc; nan_fallback::Bool=false, pause_below_speed::Float64=0.0) =
     check(ccall((:pgn_set_guards, libpigeon), Cint, (Ptr{Cvoid}, Int32, Float64), mpc.handle, Int32(nan_fallback), pause_below_speed))
+# use_HJI_policy[] of the callback (src/ros_integration.jl:47,115-118): V <= HJI_ϵ => BicycleControl(LP, optimal_control(...))
+set_hji_policy!(mpc, on::Bool) = check(ccall((:pgn_set_hji_policy, libpigeon), Cint, (Ptr{Cvoid}, Int32), mpc.handle, Int32(on)))
+"(V, ∇V) of the last step's HJIRelativeState(current_state, other_car_state) (src/ros_integration.jl:57-58); ∇V is 7×B"
+function hji_values(mpc)
+    V = Vector{Float64}(undef, mpc.B); g = Matrix{Float64}(undef, 7, mpc.B)
+    check(ccall((:pgn_get_hji_values, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), mpc.handle, V, g))
+    V, g
+end
+"optimal_control(dynamics, relative_state, ∇V) (src/HJI_computation.jl:133-158) for 7×M relative states / gradients -> 2×M (δ, Fx)"
+function optimal_control(mpc, relative_state::Matrix{Float64}, gradV::Matrix{Float64})
+    M = size(relative_state, 2); out = Matrix{Float64}(undef, 2, M)
+    check(ccall((:pgn_hji_optimal_control, libpigeon), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), mpc.handle, Int32(M), relative_state, gradV, out))
+    out
+end
 reset_solver!(mpc, mask::Union{Nothing,Vector{UInt8}}=nothing) = GC.@preserve mask check(ccall((:pgn_reset_solver, libpigeon), Cint, (Ptr{Cvoid}, Ptr{UInt8}), mpc.handle, _mask(mask)))
 
 # ---- the 5-call step API (src/model_predictive_control.jl:70-78) --------------------------------------------------------------

@@ -2,7 +2,7 @@
 // grid file deps/BicycleCAvoid.jld2 is a network download, /root/reference/deps/build.jl:1-4, and is absent).
 //
 // CPU restatement of /root/reference/src/HJI_computation.jl:20-24 (HJIRelativeState), :26-37,66-72 (HJICache lookup),
-// :74-88 (relative_dynamics), :90-131 (optimal_disturbance), :160-170 (compute_reachability_constraint).
+// :74-88 (relative_dynamics), :90-131 (optimal_disturbance), :133-158 (optimal_control), :160-170 (compute_reachability_constraint).
 // Interpolations.jl 0.11.2 `Gridded(Linear())` on Float32 tables with Float64 queries (not vendored) is restated as
 // per-dimension knot search + nested (dimension-1-innermost) linear interpolation with Float64 weights.
 #pragma once
@@ -124,6 +124,29 @@ inline void optimal_disturbance(const VehicleParams& P, const double* x7, const 
             uH2[0] = desAy / V; uH2[1] = maxAx; return;
         }
     }
+}
+
+// optimal_control (HJI_computation.jl:133-158), uMode = :max, N = 50: the "hammer" policy of the callback (ros_integration.jl:115-118).
+// delta at the limit chosen by the sign of B = gV5/m + a gV7/Izz, Fx by a 50-point grid search of A Fx + B Fyf + C Fyr over [Fx_min, Fx_max]
+// (first maximum wins: strict >), tire forces from lateral_tire_forces(BM, fake_qR, uR) with the raw drive/brake split (no control limits).
+inline void optimal_control(const VehicleParams& P, const double* x7, const double* gV7, double* uR2, int N = 50) {
+    double fake_q[6] = {0.0, 0.0, 0.0, x7[3], x7[4], x7[6]};
+    double A = gV7[3] / P.m;
+    double B = gV7[4] / P.m + P.a * gV7[6] / P.Izz;
+    double C = gV7[4] / P.m - P.b * gV7[6] / P.Izz;
+    double d_opt = (B >= 0) ? P.delta_max : -P.delta_max;
+    double V_opt = -INFINITY, Fx_opt = 0.0;
+    for (int n = 0; n < N; n++) {
+        double frac = (double)n / (double)(N - 1);
+        double Fx = frac * P.Fx_max + (1 - frac) * P.Fx_min;
+        double u3[3] = {d_opt, 0, 0};
+        longitudinal_tire_forces<double>(P, Fx, u3[1], u3[2]);
+        double Fyf, Fyr;
+        lateral_tire_forces_qu(P, fake_q, u3, Fyf, Fyr);
+        double V = A * Fx + B * Fyf + C * Fyr;
+        if (V > V_opt) { Fx_opt = Fx; V_opt = V; }
+    }
+    uR2[0] = d_opt; uR2[1] = Fx_opt;
 }
 
 // compute_reachability_constraint (HJI_computation.jl:160-170) with uR_lin = BicycleControl2(current_control)

@@ -67,6 +67,7 @@ public:
     bool solved = false;
     HjiCache hji = placeholder_hji();
     double hji_eps = 0.05;
+    bool use_hji_policy = false;   // use_HJI_policy[] of ros_integration.jl:47
     int N, T, Ns, nx, nu;          // nodes, intervals, short steps, state dim (6|4), QP control dim (2|1)
     std::vector<double> qs, us, ps;  // nodes: qs[N*nx], us[N*2], ps[N*4]
     // QP pieces (per interval t), kept for introspection / parity tests
@@ -148,9 +149,15 @@ public:
     // Parametron.initialize! equivalent: fresh OSQP workspace (cold iterates, rho back to its setting)
     void reset_solver() { solver_ready = false; }
     // ---- get_next_control ----
+    // use_hji_policy: the callback's override (ros_integration.jl:115-118): V <= HJI_eps => BicycleControl(LP, optimal_control(...))
     void get_next_control(double* out3) const {
         double d, Fx;
-        if (kind == MPC_COUPLED) { d = solver.sol_x[vu(0, 1)] * un[0]; Fx = solver.sol_x[vu(1, 1)] * un[1]; }
+        if (kind == MPC_COUPLED && use_hji_policy && hji_V <= hji_eps) {
+            double x7[7], u2[2];
+            hji_relative_state(state, other_car, x7);
+            optimal_control(veh, x7, hji_gradV, u2);
+            d = u2[0]; Fx = u2[1];
+        } else if (kind == MPC_COUPLED) { d = solver.sol_x[vu(0, 1)] * un[0]; Fx = solver.sol_x[vu(1, 1)] * un[1]; }
         else { d = solver.sol_x[vu(0, 1)]; Fx = us[2 * 1 + 1]; }
         out3[0] = d;
         longitudinal_tire_forces<double>(veh, Fx, out3[1], out3[2]);

@@ -131,6 +131,7 @@ void orc_hji_lookup(void* h, int M, const double* x7, double* V, double* gV7) {
 }
 void orc_hji_relative_state(const double* us6, const double* them4, double* x7) { hji_relative_state(us6, them4, x7); }
 void orc_optimal_disturbance(const double* vp, const double* x7, const double* gV7, double* uH2) { optimal_disturbance(vp_from(vp), x7, gV7, uH2); }
+void orc_optimal_control(const double* vp, const double* x7, const double* gV7, double* uR2) { optimal_control(vp_from(vp), x7, gV7, uR2); }
 void orc_reachability_constraint(const double* vp, void* h, const double* x7, double eps, const double* uR2, double* M2, double* b) {
     reachability_constraint(vp_from(vp), *(HjiCache*)h, x7, eps, uR2, M2, *b);
 }
@@ -176,6 +177,8 @@ void orc_mpc_free(void* h) { delete (Mpc*)h; }
 void orc_mpc_dims(void* h, int* out) { Mpc* M = (Mpc*)h; out[0] = M->N; out[1] = M->nx; out[2] = M->nu; out[3] = M->n; out[4] = M->m; out[5] = (int)M->Am.x.size(); }
 void orc_mpc_set_trajectory(void* h, void* traj) { ((Mpc*)h)->traj = *(TrajectoryTube*)traj; }
 void orc_mpc_set_hji(void* h, void* hji, double eps) { ((Mpc*)h)->hji = *(HjiCache*)hji; ((Mpc*)h)->hji_eps = eps; }
+void orc_mpc_set_hji_policy(void* h, int on) { ((Mpc*)h)->use_hji_policy = on != 0; }
+void orc_mpc_get_hji_values(void* h, double* V, double* gV7) { Mpc* M = (Mpc*)h; *V = M->hji_V; std::memcpy(gV7, M->hji_gradV, 56); }
 void orc_mpc_set_state(void* h, const double* q6, const double* u3, const double* other4, double time_offset) {
     Mpc* M = (Mpc*)h;
     if (q6) std::memcpy(M->state, q6, 48);

@@ -244,6 +244,13 @@ def optimal_disturbance(vp, x7, gV7):
     return o
 
 
+def optimal_control(vp, x7, gV7):
+    """optimal_control (HJI_computation.jl:133-158), uMode = :max, N = 50 -> (delta, Fx)"""
+    o, op = _out(2)
+    lib().orc_optimal_control(_d(vp)[1], _d(x7)[1], _d(gV7)[1], op)
+    return o
+
+
 def reachability_constraint(vp, cache, x7, eps, uR2):
     M, Mp = _out(2)
     b = C.c_double(0)
@@ -318,6 +325,16 @@ class Mpc:
 
     def set_hji(self, cache, eps=0.05):
         lib().orc_mpc_set_hji(self.h, cache.h, C.c_double(eps))
+
+    def set_hji_policy(self, on):
+        """use_HJI_policy[] of the callback (ros_integration.jl:47,115-118)"""
+        lib().orc_mpc_set_hji_policy(self.h, C.c_int(int(bool(on))))
+
+    def hji_values(self):
+        V = C.c_double(0)
+        g, gp = _out(7)
+        lib().orc_mpc_get_hji_values(self.h, C.byref(V), gp)
+        return V.value, g
 
     def set_state(self, q6, u3, other4=None, time_offset=float("nan")):
         o = None if other4 is None else _d(other4)[1]

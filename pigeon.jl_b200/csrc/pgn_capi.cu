@@ -270,13 +270,18 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
     CK(cudaMemset(h->d_sol_x, 0, B * t.n * 8)); CK(cudaMemset(h->d_sol_y, 0, B * t.m * 8));
     CK(cudaMemset(h->d_cycles, 0, 4096)); CK(cudaMemset(h->d_skip, 0, B)); CK(cudaMemset(h->d_cold, 0, B));
-    h->guard_nan = 0; h->guard_pause = 0.0;
+    h->guard_nan = 0; h->guard_pause = 0.0; h->hji_policy = 0;
+    {   // no step yet: cache[x] = (Inf, 0)
+        std::vector<double> hv(8 * B, 0.0);
+        for (size_t v = 0; v < B; v++) hv[7 * B + v] = INFINITY;
+        CK(cudaMemcpy(h->d_hji_val, hv.data(), 8 * B * 8, cudaMemcpyHostToDevice));
+    }
     CK(cudaMemset(h->d_iters, 0, B * 4)); CK(cudaMemset(h->d_status, 0, B * 4)); CK(cudaMemset(h->d_rho_updates, 0, B * 4));
     CK(cudaMemset(h->d_rec, 0, B * (size_t)t.rec.rec_len * 8)); CK(cudaMemset(h->d_controls, 0, 3 * B * 8));
     {   // other car far away, time_offset = NaN (path mode), ts = 1..N (MPCTimeSteps ctor), rho = setting
@@ -570,6 +575,32 @@ int pgn_hji_lookup(pgn_handle* h, int32_t M, const double* x, double* V, double*
     cudaFree(dx); cudaFree(dV); cudaFree(dg);
     if (e != cudaSuccess) return set_err(PGN_ECUDA, "hji lookup failed: %s", cudaGetErrorString(e));
     for (int i = 0; i < M; i++) for (int d = 0; d < 7; d++) gradV[(size_t)i * 7 + d] = gt[(size_t)d * M + i];
+    return PGN_OK;
+}
+int pgn_set_hji_policy(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->hji_policy = on != 0; return PGN_OK; }
+int pgn_get_hji_values(pgn_handle* h, double* V, double* gradV) {
+    REQUIRE(h && V && gradV, "NULL argument");
+    const size_t B = h->B;
+    std::vector<double> hv(8 * B);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(hv.data(), h->d_hji_val, 8 * B * 8, cudaMemcpyDeviceToHost));
+    for (size_t v = 0; v < B; v++) {
+        V[v] = hv[7 * B + v];
+        for (int k = 0; k < 7; k++) gradV[v * 7 + k] = hv[k * B + v];
+    }
+    return PGN_OK;
+}
+int pgn_hji_optimal_control(pgn_handle* h, int32_t M, const double* x, const double* gradV, double* out) {
+    REQUIRE(h && x && gradV && out && M >= 0, "bad argument");
+    if (M == 0) return PGN_OK;
+    double *dx = nullptr, *dg = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&dx, (size_t)M * 7 * 8)); CK(cudaMalloc(&dg, (size_t)M * 7 * 8)); CK(cudaMalloc(&dout, (size_t)M * 2 * 8));
+    cudaError_t e = cudaMemcpy(dx, x, (size_t)M * 7 * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dg, gradV, (size_t)M * 7 * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { launch_hji_optimal_control(h, M, dx, dg, dout); e = cudaStreamSynchronize(h->stream); }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)M * 2 * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dg); cudaFree(dout);
+    if (e != cudaSuccess) return set_err(PGN_ECUDA, "hji optimal control failed: %s", cudaGetErrorString(e));
     return PGN_OK;
 }
 int pgn_device_controls(pgn_handle* h, double** d_out) { REQUIRE(h && d_out, "NULL argument"); *d_out = h->d_controls; return PGN_OK; }

@@ -121,6 +121,35 @@ PGN_HD void lateral_tire_forces(const VehParams& B, const T& af, const T& ar, co
     Fyr = fiala_tan(tanr, B.Car, B.mu, Fxr, Fzr);
 }
 
+#ifdef __CUDACC__
+// optimal_control (HJI_computation.jl:133-158), uMode = :max, N = 50 — the callback's "hammer" policy (ros_integration.jl:115-118):
+// steering at the limit picked by the sign of B = gV5/m + a gV7/Izz, Fx by a 50-point grid search of A Fx + B Fyf + C Fyr (first
+// maximum wins), tire forces from lateral_tire_forces(BM, (0,0,0,Ux,Uy,r), (delta, raw drive/brake split of Fx)).
+// The slip angles and the steering sincos do not depend on Fx and are formed once.
+__device__ __forceinline__ void hji_optimal_control(const VehParams& P, double Ux, double Uy, double r, const double* g /*gradV[7]*/, double& d_opt, double& Fx_opt) {
+    const double A = g[3] / P.m;
+    const double Bc = g[4] / P.m + P.a * g[6] / P.Izz;
+    const double Cc = g[4] / P.m - P.b * g[6] / P.Izz;
+    d_opt = (Bc >= 0) ? P.delta_max : -P.delta_max;
+    double sd, cd;
+    sincos(d_opt, &sd, &cd);
+    const double af = atan2(Uy + P.a * r, Ux) - d_opt, ar = atan2(Uy - P.b * r, Ux);
+    double V_opt = -INFINITY;
+    Fx_opt = 0.0;
+    const int N = 50;
+    for (int n = 0; n < N; n++) {
+        const double frac = (double)n / (double)(N - 1);
+        const double Fx = __dadd_rn(__dmul_rn(frac, P.Fx_max), __dmul_rn(1.0 - frac, P.Fx_min));     // no FMA contraction: Fx_opt is returned verbatim
+        double Fxf, Fxr;
+        if (Fx > 0) { Fxf = Fx * P.fwd_frac; Fxr = Fx * P.rwd_frac; } else { Fxf = Fx * P.fwb_frac; Fxr = Fx * P.rwb_frac; }
+        double Fyf, Fyr;
+        lateral_tire_forces<double>(P, af, ar, Fxf, Fxr, sd, cd, Fyf, Fyr);
+        const double V = A * Fx + Bc * Fyf + Cc * Fyr;
+        if (V > V_opt) { Fx_opt = Fx; V_opt = V; }
+    }
+}
+#endif
+
 enum { MODEL_BICYCLE = 0, MODEL_TRACKING = 1, MODEL_LATERAL = 2 };
 
 // VehicleModel call (vehicle_dynamics.jl:293-316): control limits (Ux de-dualised), drive/brake split, then the bicycle

@@ -61,6 +61,18 @@ __device__ __forceinline__ void hji_interp(const HjiView& H, const HjiCell& c, d
     for (int k = 0; k < 8; k++) out[k] = acc[k];
 }
 
+// stand-alone policy evaluation: x [M][7] relative states, gV [M][7], out [M][2] = (delta, Fx)
+__global__ void __launch_bounds__(128) k_hji_optimal_control(VehParams P, int M, const double* __restrict__ x, const double* __restrict__ gV, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double g[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) g[k] = gV[(size_t)i * 7 + k];
+    double d, Fx;
+    hji_optimal_control(P, x[(size_t)i * 7 + 3], x[(size_t)i * 7 + 4], x[(size_t)i * 7 + 6], g, d, Fx);
+    out[(size_t)i * 2] = d; out[(size_t)i * 2 + 1] = Fx;
+}
+
 // stand-alone lookup: x [7][M] field-major, V [M], gradV [7][M]
 __global__ void __launch_bounds__(128) k_hji_lookup(HjiView H, int M, const double* __restrict__ x, double* __restrict__ V, double* __restrict__ gV) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,7 +96,7 @@ __global__ void __launch_bounds__(128) k_hji_lookup(HjiView H, int M, const doub
 // reachability constraint M u + b >= -sigma for every vehicle; writes (M1*un1, M2*un2, b) into the record
 __global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, VehParams P, double eps, double un0, double un1, const double* __restrict__ state,
                                                         const double* __restrict__ control, const double* __restrict__ other, double* __restrict__ rec,
-                                                        int rec_len, int o_hji) {
+                                                        int rec_len, int o_hji, double* __restrict__ hji_val /*[8][B]: gradV[0..6], V*/) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= B) return;
     const double E = state[0 * B + v], N = state[1 * B + v], psi = state[2 * B + v], Ux = state[3 * B + v], Uy = state[4 * B + v], r = state[5 * B + v];
@@ -99,12 +111,14 @@ __global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, VehPar
     x7[2] = adiff(opsi, psi);
     x7[3] = Ux; x7[4] = Uy; x7[5] = oV; x7[6] = r;
     double M0 = 0, M1 = 0, b = 1.0;
-    double g[8];
+    double g[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, INFINITY};      // cache[x] outside the grid: (V = Inf, gradV = 0)
     bool active = false;
     if (H.valid) {
         HjiCell c = hji_locate(H, x7);
         if (c.inside) { hji_interp(H, c, g); active = !(g[7] > eps); }
     }
+#pragma unroll
+    for (int k = 0; k < 8; k++) hji_val[(size_t)k * B + v] = g[k];    // V, gradV of this step: published by the callback, read by the policy override
     if (active) {
         // optimal_disturbance (dMode = :min). Deviation: other-car speed <= 0 gives (0,0) instead of NaN
         double uH0 = 0, uH1 = 0;
@@ -149,7 +163,11 @@ __global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, VehPar
 void launch_hji_constraint(pgn_handle* h) {
     const int B = h->B;
     k_hji_constraint<<<(B + 127) / 128, 128, 0, h->stream>>>(h->hji, B, h->veh, h->cfg.hji_eps, h->un[0], h->un[1], h->d_state, h->d_control, h->d_other,
-                                                             h->d_rec, h->tab.rec.rec_len, h->tab.rec.o_hji);
+                                                             h->d_rec, h->tab.rec.rec_len, h->tab.rec.o_hji, h->d_hji_val);
+    h->launches++;
+}
+void launch_hji_optimal_control(pgn_handle* h, int M, const double* d_x, const double* d_gV, double* d_out) {
+    k_hji_optimal_control<<<(M + 127) / 128, 128, 0, h->stream>>>(h->veh, M, d_x, d_gV, d_out);
     h->launches++;
 }
 void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV) {

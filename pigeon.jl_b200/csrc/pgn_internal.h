@@ -97,6 +97,8 @@ struct pgn_handle {
     double *d_pri_res, *d_dua_res;
     double* d_controls;                                  // [3][B]
     double *d_t0, *d_t0_base;                            // [B]
+    double* d_hji_val;                                   // [8][B]: gradV[0..6], V of the step's relative state (written by the HJI constraint kernel)
+    int hji_policy;                                      // use_HJI_policy[] (ros_integration.jl:47): V <= HJI_eps => optimal_control replaces the QP control
     uint8_t *d_skip, *d_cold;                            // guards: vehicle paused this step / ADMM iterates to be re-initialised
     int guard_nan; double guard_pause;
     int32_t* d_order;                                    // ticket -> vehicle order of the ADMM launch
@@ -121,6 +123,7 @@ void launch_hji_constraint(pgn_handle* h);
 void launch_admm(pgn_handle* h);
 void launch_controls(pgn_handle* h, double* d_out);
 void launch_rollout(pgn_handle* h, double dt);
+void launch_hji_optimal_control(pgn_handle* h, int M, const double* d_x, const double* d_gV, double* d_out);   // [M][7], [M][7] -> [M][2]
 void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV);
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]

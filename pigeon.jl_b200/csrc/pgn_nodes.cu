@@ -285,11 +285,17 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
 __global__ void k_controls(int B, int kind, int n_sol, int iv_delta, int iv_fx, double un0, double un1, VehParams P,
                            const double* __restrict__ sol_x, const double* __restrict__ us, int N, double* __restrict__ out,
                            const double* __restrict__ control, const uint8_t* __restrict__ skip, int guard_nan, uint8_t* __restrict__ cold,
-                           uint8_t* __restrict__ solved) {
+                           uint8_t* __restrict__ solved, const double* __restrict__ hji_val, double hji_eps, const double* __restrict__ state) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= B) return;
     double d, Fx;
-    if (kind == PGN_COUPLED) { d = sol_x[(size_t)v * n_sol + iv_delta] * un0; Fx = sol_x[(size_t)v * n_sol + iv_fx] * un1; }
+    if (hji_val && hji_val[(size_t)7 * B + v] <= hji_eps) {
+        // use_HJI_policy && V <= HJI_eps (ros_integration.jl:115-118): optimal_control replaces the QP's control
+        double g[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) g[k] = hji_val[(size_t)k * B + v];
+        hji_optimal_control(P, state[3 * B + v], state[4 * B + v], state[5 * B + v], g, d, Fx);
+    } else if (kind == PGN_COUPLED) { d = sol_x[(size_t)v * n_sol + iv_delta] * un0; Fx = sol_x[(size_t)v * n_sol + iv_fx] * un1; }
     else { d = sol_x[(size_t)v * n_sol + iv_delta]; Fx = us[(size_t)v * N * 2 + 2 * 1 + 1]; }
     double Fxf, Fxr;
     if (Fx > 0) { Fxf = Fx * P.fwd_frac; Fxr = Fx * P.rwd_frac; } else { Fxf = Fx * P.fwb_frac; Fxr = Fx * P.rwb_frac; }
@@ -360,7 +366,7 @@ void launch_controls(pgn_handle* h, double* d_out) {
     const int B = h->B;
     k_controls<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.kind, h->tab.n, h->tab.var_u1_delta, h->tab.var_u1_fx, h->un[0], h->un[1], h->veh,
                                                        h->d_sol_x, h->d_us, h->N, d_out, h->d_control, h->guard_pause > 0.0 ? h->d_skip : nullptr, h->guard_nan,
-                                                       h->d_cold, h->d_solved);
+                                                       h->d_cold, h->d_solved, (h->hji_policy && h->cfg.kind == PGN_COUPLED) ? h->d_hji_val : nullptr, h->cfg.hji_eps, h->d_state);
     h->launches++;
 }
 void launch_rollout(pgn_handle* h, double dt) {

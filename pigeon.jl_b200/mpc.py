@@ -303,6 +303,25 @@ class BatchedTrajectoryTrackingMPC:
         check(self._lib.pgn_hji_lookup(self._h, M, dptr(x), dptr(V), dptr(g)))
         return V, g
 
+    def hji_values(self):
+        """(V, gradV) of the last step's HJIRelativeState(current_state, other_car_state): what the callback logs (ros_integration.jl:57-58)."""
+        V, g = np.zeros(self.B), np.zeros((self.B, 7))
+        check(self._lib.pgn_get_hji_values(self._h, dptr(V), dptr(g)))
+        return V, g
+
+    def optimal_control(self, relative_state, gradV):
+        """optimal_control(dynamics, relative_state, gradV) (src/HJI_computation.jl:133-158) -> (M, 2) array of (delta, Fx)."""
+        x, g = f64(np.atleast_2d(relative_state)), f64(np.atleast_2d(gradV))
+        if x.shape != g.shape or x.shape[1] != 7:
+            raise ValueError("relative_state and gradV must both have shape (M, 7)")
+        out = np.zeros((x.shape[0], 2))
+        check(self._lib.pgn_hji_optimal_control(self._h, x.shape[0], dptr(x), dptr(g), dptr(out)))
+        return out
+
+    def set_hji_policy(self, on):
+        """use_HJI_policy[] of the callback (src/ros_integration.jl:47,115-118): V <= HJI_eps => the "hammer" control."""
+        check(self._lib.pgn_set_hji_policy(self._h, int(bool(on))))
+
     def hji_lookup_device(self, M, d_x, d_V, d_g):
         check(self._lib.pgn_hji_lookup_device(self._h, int(M), C.c_void_p(d_x), C.c_void_p(d_V), C.c_void_p(d_g)))
 

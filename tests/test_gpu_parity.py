@@ -465,3 +465,58 @@ def test_guards_pause_and_nan_fallback(p):
     g.set_state(state3, u2, other)
     assert np.all(np.isnan(g.step(t0 + 0.02)[7]))
     g.close()
+
+
+def test_hji_hammer_policy_parity(p):
+    """optimal_control (HJI_computation.jl:133-158) stand-alone and as the callback's override (ros_integration.jl:115-118)."""
+    knots, V, gV = p.synthetic.analytic_hji_grid((13, 13, 7, 7, 5, 7, 5))
+    cache_o = o.HjiCache(knots, V, gV)
+    B = 192
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    rng = np.random.default_rng(7)
+    other = np.zeros((B, 4))
+    rad = rng.uniform(0.5, 9.0, B); ang = rng.uniform(-np.pi, np.pi, B)
+    other[:, 0] = state[:, 0] + rad * np.cos(ang); other[:, 1] = state[:, 1] + rad * np.sin(ang)
+    other[:, 2] = state[:, 2] + rng.normal(0, 0.5, B); other[:, 3] = rng.uniform(1.5, 12, B)
+    other[::9, 0] += 500.0
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g.set_HJI_cache(p.HJICache(knots, V, gV))
+    # stand-alone: random relative states / gradients, plus the degenerate zero gradient
+    M = 4096
+    x7 = np.column_stack([rng.uniform(-10, 10, M), rng.uniform(-10, 10, M), rng.uniform(-3, 3, M), rng.uniform(1, 15, M), rng.uniform(-1.5, 1.5, M),
+                          rng.uniform(1, 12, M), rng.uniform(-0.8, 0.8, M)])
+    gv = rng.normal(0, 1, (M, 7)) * np.array([1, 1, 1, 0.5, 1, 1, 2.0])
+    gv[0] = 0.0
+    ug = g.optimal_control(x7, gv)
+    vp = o.x1()
+    uo = np.array([o.optimal_control(vp, x7[i], gv[i]) for i in range(M)])
+    assert np.array_equal(ug[:, 0], uo[:, 0])
+    same = ug[:, 1] == uo[:, 1]
+    assert same.mean() > 0.999          # the argmax of a 50-point grid may flip on a last-bit near-tie; everything else is bit-exact
+    assert ug[0, 0] == vp[20] and ug[0, 1] == vp[18]
+    # as the override inside the step
+    g.set_state(state, control, other)
+    g.set_hji_policy(True)
+    ms = oracles_for(0, trajs, tid, state, control, other, hji=cache_o)
+    for m in ms:
+        m.set_hji_policy(True)
+    u_gpu = g.step(t0)
+    Vg, gg = g.hji_values()
+    u_cpu = np.array([m.step(t0[i]) for i, m in enumerate(ms)])
+    Vo = np.array([m.hji_values()[0] for m in ms]); go = np.array([m.hji_values()[1] for m in ms])
+    fin = np.isfinite(Vo)
+    assert np.array_equal(np.isinf(Vg), ~fin) and np.allclose(Vg[fin], Vo[fin], rtol=0, atol=1e-6) and np.allclose(gg, go, rtol=0, atol=1e-6)
+    hammer = Vo <= 0.05
+    assert 30 < hammer.sum() < B - 30
+    scale = np.array([0.314, 16793.7, 16793.7])
+    assert np.array_equal(np.abs(u_gpu[hammer, 0]), np.full(hammer.sum(), vp[20]))       # hammer: steering at the limit
+    assert (np.max(np.abs(u_gpu[hammer] - u_cpu[hammer]) / scale, axis=1) < 1e-9).mean() > 0.98
+    assert np.max(np.abs(u_gpu[~hammer] - u_cpu[~hammer]) / scale) < 1e-4
+    # policy off: same vehicles get the QP control again
+    g.set_hji_policy(False)
+    g.reset_solver(); g.reset_solved(); g.set_state(state, control, other)
+    u_off = g.step(t0)
+    assert np.max(np.abs(u_off[hammer, 0])) < vp[20] or not np.array_equal(u_off[hammer], u_gpu[hammer])
+    assert np.max(np.abs(u_off[~hammer] - u_gpu[~hammer]) / scale) < 1e-12
+    g.close()

@@ -114,3 +114,67 @@ def test_optimal_disturbance_branches(vp):
     assert uH[1] == pytest.approx(min(5600 / 1964, 75e3 / 1964 / 6.0))
     x0 = x7.copy(); x0[5] = 0.0
     assert np.all(o.optimal_disturbance(vp, x0, g) == 0)                     # documented deviation: V_other = 0
+
+
+def _optimal_control_numpy(vp, x7, g, N=50):
+    """optimal_control (HJI_computation.jl:133-158, uMode = :max) written out with numpy over the whole Fx grid; the tire forces come
+    from the oracle's lateral_tire_forces(q, u) (pinned in test_oracle_primitives.py)."""
+    P = dict(zip(["L", "a", "b", "h", "G", "m", "Izz", "mu", "Caf", "Car", "Cd0", "Cd1", "Cd2", "fwd", "rwd", "fwb", "rwb", "Fx_max", "Fx_min", "Px_max",
+                  "delta_max", "kappa_max", "corr"], vp))
+    A = g[3] / P["m"]; B = g[4] / P["m"] + P["a"] * g[6] / P["Izz"]; Cc = g[4] / P["m"] - P["b"] * g[6] / P["Izz"]
+    d_opt = P["delta_max"] if B >= 0 else -P["delta_max"]
+    frac = np.arange(N) / (N - 1)
+    Fx = frac * P["Fx_max"] + (1 - frac) * P["Fx_min"]
+    q = np.array([0, 0, 0, x7[3], x7[4], x7[6]], float)
+    val = np.empty(N)
+    for n in range(N):
+        u3 = [d_opt, Fx[n] * (P["fwd"] if Fx[n] > 0 else P["fwb"]), Fx[n] * (P["rwd"] if Fx[n] > 0 else P["rwb"])]
+        Fyf, Fyr = o.lateral_tire_forces(vp, q, u3)
+        val[n] = A * Fx[n] + B * Fyf + Cc * Fyr
+    return np.array([d_opt, Fx[int(np.argmax(val))]]), val     # argmax = first maximum, as the strict > of the reference loop
+
+
+def test_optimal_control_hammer_policy():
+    vp = o.x1()
+    rng = np.random.default_rng(3)
+    for k in range(200):
+        x7 = np.array([rng.uniform(-10, 10), rng.uniform(-10, 10), rng.uniform(-3, 3), rng.uniform(1, 15), rng.uniform(-1.5, 1.5), rng.uniform(1, 12), rng.uniform(-0.8, 0.8)])
+        g = rng.normal(0, 1, 7) * np.array([1, 1, 1, 0.5, 1, 1, 2.0])
+        u = o.optimal_control(vp, x7, g)
+        ref, val = _optimal_control_numpy(vp, x7, g)
+        assert abs(u[0]) == vp[20] and u[0] == ref[0]                      # steering at the limit, sign of B
+        assert vp[18] <= u[1] <= vp[17]
+        assert u[1] == ref[1], (k, u, ref)
+    # known answers: zero gradient => B = 0 >= 0 => +delta_max, all grid values tie at 0 => the first one (Fx_min) wins
+    u = o.optimal_control(vp, np.array([0, 0, 0, 8.0, 0, 5.0, 0]), np.zeros(7))
+    assert u[0] == vp[20] and u[1] == vp[18]
+    # only dV/dUx > 0 => maximise A * Fx => Fx_max; < 0 => Fx_min
+    assert o.optimal_control(vp, np.array([0, 0, 0, 8.0, 0, 5.0, 0]), np.array([0, 0, 0, 1.0, 0, 0, 0]))[1] == vp[17]
+    assert o.optimal_control(vp, np.array([0, 0, 0, 8.0, 0, 5.0, 0]), np.array([0, 0, 0, -1.0, 0, 0, 0]))[1] == vp[18]
+
+
+def test_mpc_hji_policy_override(grid):
+    """use_HJI_policy (ros_integration.jl:115-118): V <= eps => get_next_control returns BicycleControl(LP, optimal_control(...))."""
+    knots, V, gV = synthetic.analytic_hji_grid((13, 13, 7, 7, 5, 7, 5))
+    cache = o.HjiCache(knots, V, gV)
+    trajs = synthetic.synthetic_trajectories(n_traj=1, n_nodes=300)
+    tid, state, control, t0 = synthetic.synthetic_batch(trajs, 2)
+    tr = o.Trajectory(**{k: trajs[k][0] for k in o.TRAJ_FIELDS})
+    outs = []
+    for i, other in enumerate([np.array([state[0, 0] + 1.0, state[0, 1] + 0.5, state[0, 2], 6.0]), np.array([1e4, 1e4, 0.0, 5.0])]):
+        res = []
+        for pol in (False, True):
+            m = o.Mpc(o.MPC_COUPLED)
+            m.set_trajectory(tr); m.set_hji(cache); m.set_hji_policy(pol)
+            m.set_state(state[0], control[0], other4=other)
+            res.append((m.step(t0[0]), m.hji_values()))
+        outs.append(res)
+    (u_qp, (V0, g0)), (u_pol, _) = outs[0]
+    assert V0 <= 0.05                                    # other car 1 m away: inside the unsafe set
+    vp = o.x1()
+    x7 = o.hji_relative_state(state[0], np.array([state[0, 0] + 1.0, state[0, 1] + 0.5, state[0, 2], 6.0]))
+    d, Fx = o.optimal_control(vp, x7, g0)
+    exp = np.array([d, Fx * (vp[13] if Fx > 0 else vp[15]), Fx * (vp[14] if Fx > 0 else vp[16])])
+    assert np.array_equal(u_pol, exp) and not np.allclose(u_pol, u_qp)
+    (u_qp_far, (Vf, _)), (u_pol_far, _) = outs[1]
+    assert np.isinf(Vf) and np.array_equal(u_qp_far, u_pol_far)        # out of grid: policy inactive
