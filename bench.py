@@ -248,6 +248,37 @@ def run_gpu(args):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / (float(t_e.item()) * 1e-3)
 
+    # ---------------- per-call latency (BASELINE.json: "p50 per-step latency"): host wall clock around one C-ABI call, host buffers ----------------
+    latency = None
+    if rank == 0 and not args.no_latency:
+        def pct(fn, n=200, warm=20):
+            for i in range(warm):
+                fn(i)
+            ts_ = []
+            for i in range(n):
+                a_ = time.perf_counter(); fn(warm + i); ts_.append((time.perf_counter() - a_) * 1e3)
+            return {"p50_ms": float(np.percentile(ts_, 50)), "p99_ms": float(np.percentile(ts_, 99)), "calls": n}
+        # (a) the batched step of this workload: pgn_set_state + pgn_step on the settled closed loop (states replayed cyclically)
+        lo, hi = SETTLE + W, SETTLE + W + K
+        latency = {"batched_step": dict(pct(lambda i: e2e_step(lo + i % (hi - lo))), batch=B, call="pgn_set_state + pgn_step (host buffers)")}
+        # (b) the reference's deployment point: ONE vehicle through the callback entry point (one packed copy in, one CUDA graph, one copy out)
+        one = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, 1, trajectory_index=tid[:1], device=local)
+        one.set_stream(stream.cuda_stream)
+        one.set_state(state[:1], control[:1], other[:1])
+        q1 = np.ascontiguousarray(np.stack(rec_states)[:, :1]); u1 = np.ascontiguousarray(np.stack(rec_controls)[:, :1])
+        o5 = np.zeros((1, 5)); st1 = np.zeros(1)
+        def cb(i):
+            k_ = min(i, nrec - 1)
+            lib.pgn_from_autobox(one._h, C.c_void_p(q1[k_].ctypes.data), C.c_void_p(u1[k_].ctypes.data), None, C.c_void_p(st1.ctypes.data), C.c_void_p(o5.ctypes.data))
+        latency["single_vehicle_callback"] = dict(pct(cb), batch=1, call="pgn_from_autobox (path-tracking mode; CUDA graph)")
+        def five(i):
+            k_ = min(i, nrec - 1)
+            lib.pgn_set_state(one._h, C.c_void_p(q1[k_].ctypes.data), C.c_void_p(u1[k_].ctypes.data), None, None)
+            lib.pgn_step(one._h, C.c_void_p(tn[k_][:1].copy().ctypes.data), C.c_void_p(o5.ctypes.data))
+        one.reset_solver(); one.reset_solved()
+        latency["single_vehicle_step"] = dict(pct(five), batch=1, call="pgn_set_state + pgn_step (stream launches)")
+        one.close()
+
     # ---------------- final gather of controls + statistics (NCCL over NVLink, outside the timed region) ----------------
     gathered = None
     if dist is not None:
@@ -313,7 +344,7 @@ def run_gpu(args):
                          "pct_not_solved": float((st["status"] != 1).mean() * 100)},
                 "stage_ms_per_step": {k: stage[k] / nprof for k in ("nodes", "linearize", "hji", "admm", "controls", "rollout")},
                 "admm_phase_share": {k: v / max(1.0, sum(cyc.values())) for k, v in cyc.items()},
-                "p50_latency_ms_per_batched_step": ms_max / K, "gather": gathered,
+                "latency": latency, "gather": gathered,
                 "cold_start": {"steps": SETTLE, "value": B * SETTLE / (cold_ms * 1e-3), "unit": UNIT + " (rank 0, device-resident)", "ms_per_step": cold_ms / SETTLE,
                                "note": "first %d closed-loop steps from the perturbed cold start; a few QPs per step run to thousands of iterations (max_iter 4000) and one QP occupies one SM, so single stragglers set the launch time" % SETTLE}}
         print(json.dumps(line), flush=True)
@@ -331,6 +362,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="vehicles per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-latency", action="store_true", help="skip the per-call latency leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

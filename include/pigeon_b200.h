@@ -117,6 +117,14 @@ PGN_API int pgn_solve(pgn_handle* h);                                           
 PGN_API int pgn_get_next_control(pgn_handle* h, double* out /*[B][3] = (delta, Fxf, Fxr)*/);  /* get_next_control(mpc) */
 /* the five calls fused (host buffers; copies inside) */
 PGN_API int pgn_step(pgn_handle* h, const double* t0 /*[B]*/, double* out /*[B][3]*/);
+/* from_autobox_callback (ros_integration.jl:48-151) for the whole batch in ONE call — the low-latency entry point (B = 1 is the
+ * reference's deployment).  Writes current_state q [B][6] and current_control u [B][3] (and other_car_state [B][4] unless NULL), picks
+ * the MPC time per vehicle: stamp[v] - time_offset[v], or the path_coordinates time when time_offset is NaN (path-tracking mode,
+ * :72-75); a vehicle whose time lies outside [0, trajectory.t[end]] (:77-80), or that is paused by pgn_set_guards (:84-87), returns
+ * early: no solve, output = current control.  Then the five step calls and out [B][5] = (delta, Fxf, Fxr, s_m, e_m) (:110-116), with
+ * the NaN fallback of pgn_set_guards and the policy of pgn_set_hji_policy applied.  Internally one packed H2D copy from pinned
+ * memory, one CUDA-graph launch of all kernels, one D2H copy. */
+PGN_API int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const double* other_car, const double* stamp, double* out /*[B][5]*/);
 /* same with inputs already resident: t0 and out are DEVICE pointers ([B] and [3][B] field-major); out may be NULL */
 PGN_API int pgn_step_device(pgn_handle* h, const double* d_t0, double* d_out);
 /* simulate (model_predictive_control.jl:80-100): n_steps closed-loop steps fully on the device:

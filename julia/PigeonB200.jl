@@ -176,6 +176,15 @@ reset_solved!(mpc, mask::Union{Nothing,Vector{UInt8}}=nothing) = GC.@preserve ma
 # guards of the ROS callback (src/ros_integration.jl:84-87, 134-147): pause below a speed, previous control + re-initialisation on NaN
 set_guards!(mpc; nan_fallback::Bool=false, pause_below_speed::Float64=0.0) =
     check(ccall((:pgn_set_guards, libpigeon), Cint, (Ptr{Cvoid}, Int32, Float64), mpc.handle, Int32(nan_fallback), pause_below_speed))
+"from_autobox_callback (src/ros_integration.jl:48-151) for the whole batch: returns 5×B (δ, Fxf, Fxr, s_m, e_m)"
+function from_autobox!(mpc, current_state::Matrix{Float64}, current_control::Matrix{Float64}, stamp::Vector{Float64};
+                       other_car_state::Union{Nothing,Matrix{Float64}}=nothing)
+    out = Matrix{Float64}(undef, 5, mpc.B)
+    po = other_car_state === nothing ? Ptr{Float64}(C_NULL) : pointer(other_car_state)
+    GC.@preserve other_car_state check(ccall((:pgn_from_autobox, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                                             mpc.handle, current_state, current_control, po, stamp, out))
+    out
+end
 # use_HJI_policy[] of the callback (src/ros_integration.jl:47,115-118): V <= HJI_ϵ => BicycleControl(LP, optimal_control(...))
 set_hji_policy!(mpc, on::Bool) = check(ccall((:pgn_set_hji_policy, libpigeon), Cint, (Ptr{Cvoid}, Int32), mpc.handle, Int32(on)))
 "(V, ∇V) of the last step's HJIRelativeState(current_state, other_car_state) (src/ros_integration.jl:57-58); ∇V is 7×B"

@@ -162,6 +162,36 @@ public:
         out3[0] = d;
         longitudinal_tire_forces<double>(veh, Fx, out3[1], out3[2]);
     }
+    // from_autobox_callback (ros_integration.jl:48-151) without the ROS plumbing.  Returns false where the callback returns early
+    // (time outside the trajectory :77-80, Ux < pause_speed :84-87; the reference hard-codes 1 m/s, 0 disables the check here);
+    // out5 = (delta, Fxf, Fxr, s, e); on an early return the control part is the current control.
+    bool from_autobox(const double* q6, const double* u3, const double* other4, double stamp, double pause_speed, bool nan_fallback, double* out5) {
+        for (int i = 0; i < 6; i++) state[i] = q6[i];
+        for (int i = 0; i < 3; i++) control[i] = u3[i];
+        if (other4) for (int i = 0; i < 4; i++) other_car[i] = other4[i];
+        double s, e, tp;
+        traj.path_coordinates(state[0], state[1], s, e, tp);
+        out5[0] = control[0]; out5[1] = control[1]; out5[2] = control[2]; out5[3] = s; out5[4] = e;
+        double t = tp;                                                  // path tracking mode (:72-75)
+        if (!std::isnan(time_offset)) {
+            t = stamp - time_offset;
+            if (t < 0 || t > traj.t.back()) return false;
+        }
+        if (pause_speed > 0 && state[3] < pause_speed) return false;
+        compute_time_steps(t);
+        compute_linearization_nodes();
+        update_qp();
+        solve();
+        double u[3];
+        get_next_control(u);
+        if (nan_fallback && (std::isnan(u[0]) || std::isnan(u[1]) || std::isnan(u[2]))) {      // :134-147
+            reset_solver();
+            solved = false;
+            return true;
+        }
+        out5[0] = u[0]; out5[1] = u[1]; out5[2] = u[2];
+        return true;
+    }
     // one closed-loop step of simulate() (model_predictive_control.jl:87-98)
     void simulate_step(double t, double dt_sim) {
         compute_time_steps(t);

@@ -177,6 +177,9 @@ void orc_mpc_free(void* h) { delete (Mpc*)h; }
 void orc_mpc_dims(void* h, int* out) { Mpc* M = (Mpc*)h; out[0] = M->N; out[1] = M->nx; out[2] = M->nu; out[3] = M->n; out[4] = M->m; out[5] = (int)M->Am.x.size(); }
 void orc_mpc_set_trajectory(void* h, void* traj) { ((Mpc*)h)->traj = *(TrajectoryTube*)traj; }
 void orc_mpc_set_hji(void* h, void* hji, double eps) { ((Mpc*)h)->hji = *(HjiCache*)hji; ((Mpc*)h)->hji_eps = eps; }
+int orc_mpc_from_autobox(void* h, const double* q6, const double* u3, const double* other4, double stamp, double pause_speed, int nan_fallback, double* out5) {
+    return ((Mpc*)h)->from_autobox(q6, u3, other4, stamp, pause_speed, nan_fallback != 0, out5) ? 1 : 0;
+}
 void orc_mpc_set_hji_policy(void* h, int on) { ((Mpc*)h)->use_hji_policy = on != 0; }
 void orc_mpc_get_hji_values(void* h, double* V, double* gV7) { Mpc* M = (Mpc*)h; *V = M->hji_V; std::memcpy(gV7, M->hji_gradV, 56); }
 void orc_mpc_set_state(void* h, const double* q6, const double* u3, const double* other4, double time_offset) {

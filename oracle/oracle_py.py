@@ -326,6 +326,13 @@ class Mpc:
     def set_hji(self, cache, eps=0.05):
         lib().orc_mpc_set_hji(self.h, cache.h, C.c_double(eps))
 
+    def from_autobox(self, q6, u3, stamp, other4=None, pause_speed=0.0, nan_fallback=False):
+        """from_autobox_callback (ros_integration.jl:48-151): returns (published, out5 = (delta, Fxf, Fxr, s, e))"""
+        o, op = _out(5)
+        ot = None if other4 is None else _d(other4)[1]
+        r = lib().orc_mpc_from_autobox(self.h, _d(q6)[1], _d(u3)[1], ot, C.c_double(stamp), C.c_double(pause_speed), C.c_int(int(nan_fallback)), op)
+        return bool(r), o
+
     def set_hji_policy(self, on):
         """use_HJI_policy[] of the callback (ros_integration.jl:47,115-118)"""
         lib().orc_mpc_set_hji_policy(self.h, C.c_int(int(bool(on))))

@@ -853,7 +853,7 @@ void launch_admm(pgn_handle* h) {
     k_admm_order<<<1, 1024, 0, h->stream>>>(h->d_iters, h->d_order, h->B);
     h->launches++;
     a.order = h->d_order;
-    a.skip = h->guard_pause > 0.0 ? h->d_skip : nullptr; a.cold = h->d_cold;
+    a.skip = (h->guard_pause > 0.0 || h->in_callback) ? h->d_skip : nullptr; a.cold = h->d_cold;
     for (size_t i = 0; i < h->tab.sol_ph_ptr.size() && i <= ADMM_MAX_PHASES; i++) a.ph_ptr[i] = h->tab.sol_ph_ptr[i];
     int ctas_per_sm = 1;
     if (h->admm_smem_bytes * 2 + 2048 <= 227 * 1024) ctas_per_sm = 2;

@@ -270,13 +270,19 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_se, 2 * B); AL(d_tskip, B);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
     CK(cudaMemset(h->d_sol_x, 0, B * t.n * 8)); CK(cudaMemset(h->d_sol_y, 0, B * t.m * 8));
     CK(cudaMemset(h->d_cycles, 0, 4096)); CK(cudaMemset(h->d_skip, 0, B)); CK(cudaMemset(h->d_cold, 0, B));
     h->guard_nan = 0; h->guard_pause = 0.0; h->hji_policy = 0;
+    h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
+    CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
+    {
+        cudaError_t e = cudaMallocHost((void**)&h->h_io, (1 + 19 * B) * sizeof(double));
+        if (e != cudaSuccess) return bail(set_err(PGN_ENOMEM, "cudaMallocHost failed: %s", cudaGetErrorString(e)));
+    }
     {   // no step yet: cache[x] = (Inf, 0)
         std::vector<double> hv(8 * B, 0.0);
         for (size_t v = 0; v < B; v++) hv[7 * B + v] = INFINITY;
@@ -320,22 +326,26 @@ int pgn_destroy(pgn_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void* p : h->allocs) cudaFree(p);
+    if (h->cb_has_exec) { cudaGraphExecDestroy(h->cb_exec); cudaGraphDestroy(h->cb_graph); }
+    if (h->h_io) cudaFreeHost(h->h_io);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaEventDestroy(h->ev[0]); cudaEventDestroy(h->ev[1]);
     delete h;
     return PGN_OK;
 }
 
-int pgn_set_stream(pgn_handle* h, void* s) { REQUIRE(h, "NULL handle"); h->stream = s ? (cudaStream_t)s : h->own_stream; return PGN_OK; }
+int pgn_set_stream(pgn_handle* h, void* s) { REQUIRE(h, "NULL handle"); h->epoch++; h->stream = s ? (cudaStream_t)s : h->own_stream; return PGN_OK; }
 int pgn_synchronize(pgn_handle* h) { REQUIRE(h, "NULL handle"); CK(cudaStreamSynchronize(h->stream)); return PGN_OK; }
 
 int pgn_set_vehicle_params(pgn_handle* h, const double* vp) {
     REQUIRE(h && vp, "NULL argument");
+    h->epoch++;
     memcpy(&h->veh, vp, sizeof(double) * PGN_VEHICLE_PARAMS_LEN);
     return upload_constants(h);
 }
 int pgn_set_control_params(pgn_handle* h, const double* cp) {
     REQUIRE(h && cp, "NULL argument");
+    h->epoch++;
     memcpy(&h->ctl, cp, sizeof(double) * PGN_CONTROL_PARAMS_LEN);
     REQUIRE(h->ctl.N_HJI >= 0 && h->ctl.N_HJI <= h->cfg.N_short, "N_HJI must be within [0, N_short]");
     return upload_constants(h);
@@ -345,6 +355,13 @@ int pgn_set_trajectories(pgn_handle* h, int32_t n_traj, int32_t n_nodes, const d
     REQUIRE(n_traj >= 1 && n_nodes >= 2, "need n_traj >= 1 and n_nodes >= 2");
     const size_t cnt = (size_t)n_traj * n_nodes;
     double* base = nullptr;
+    h->epoch++;
+    if (h->have_traj && h->traj.f[0]) {      // latest_trajectory[] is replaced at run time (ros_integration.jl:19,53): release the previous tables
+        CK(cudaStreamSynchronize(h->stream));
+        void* old = (void*)h->traj.f[0];
+        for (size_t i = 0; i < h->allocs.size(); i++) if (h->allocs[i] == old) { h->allocs.erase(h->allocs.begin() + i); cudaFree(old); break; }
+        h->traj.f[0] = nullptr;
+    }
     int rc = dev_alloc(h, &base, 12 * cnt);
     if (rc) return rc;
     for (int k = 0; k < 12; k++) {
@@ -365,6 +382,7 @@ int pgn_assign_trajectories(pgn_handle* h, const int32_t* traj_id) {
 }
 int pgn_set_hji_cache(pgn_handle* h, const int32_t dims[7], const float* knots, const float* V, const float* gradV) {
     REQUIRE(h && dims && knots && V && gradV, "NULL argument");
+    h->epoch++;
     return set_hji_internal(h, dims, knots, V, gradV);
 }
 int pgn_set_state(pgn_handle* h, const double* q, const double* u, const double* other, const double* toff) {
@@ -389,6 +407,7 @@ int pgn_reset_solved(pgn_handle* h, const uint8_t* mask) {
 int pgn_set_guards(pgn_handle* h, int32_t nan_fallback, double pause_below_speed) {
     REQUIRE(h, "NULL handle");
     REQUIRE(pause_below_speed >= 0.0, "pause_below_speed must be >= 0");
+    h->epoch++;
     h->guard_nan = nan_fallback != 0; h->guard_pause = pause_below_speed;
     if (pause_below_speed == 0.0) CK(cudaMemsetAsync(h->d_skip, 0, h->B, h->stream));
     return PGN_OK;
@@ -454,6 +473,60 @@ int pgn_step(pgn_handle* h, const double* t0, double* out) {
     if (rc) return rc;
     if (out) return download_aos(h, h->d_controls, out, 3);
     CK(cudaStreamSynchronize(h->stream));
+    return PGN_OK;
+}
+// from_autobox_callback (ros_integration.jl:48-151): the whole callback for B vehicles as one packed H2D copy, one graph launch
+// (unpack + time selection + the five step stages + pack) and one D2H copy.
+static int callback_enqueue(pgn_handle* h) {
+    const size_t B = h->B;
+    CK(cudaMemcpyAsync(h->d_io, h->h_io, (1 + 14 * B) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_callback_in(h);
+    h->in_callback = 1;
+    step_time_steps_dev(h, h->d_t0);
+    step_nodes(h);
+    step_update(h);
+    step_solve(h);
+    step_controls(h, h->d_controls);
+    h->in_callback = 0;
+    launch_callback_out(h);
+    CK(cudaMemcpyAsync(h->h_io + 1 + 14 * B, h->d_io + 1 + 14 * B, 5 * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return PGN_OK;
+}
+int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const double* other, const double* stamp, double* out) {
+    REQUIRE(h && q && u && stamp && out, "NULL argument");
+    REQUIRE(h->have_traj, "no trajectory set");
+    const size_t B = h->B;
+    double* io = h->h_io;
+    io[0] = other ? 1.0 : 0.0;
+    memcpy(io + 1, q, 6 * B * 8); memcpy(io + 1 + 6 * B, u, 3 * B * 8);
+    if (other) memcpy(io + 1 + 9 * B, other, 4 * B * 8);
+    memcpy(io + 1 + 13 * B, stamp, B * 8);
+    int rc = PGN_OK;
+    if (h->profiling) {
+        rc = callback_enqueue(h);          // stage timers synchronise: no capture
+    } else {
+        if (!h->cb_has_exec || h->cb_epoch != h->epoch || h->cb_stream != h->stream) {
+            if (h->cb_has_exec) { cudaGraphExecDestroy(h->cb_exec); cudaGraphDestroy(h->cb_graph); h->cb_has_exec = 0; }
+            const long long l0 = h->launches;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            rc = callback_enqueue(h);
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+            h->in_callback = 0;
+            h->cb_launches = h->launches - l0; h->launches = l0;
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return set_err(PGN_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&h->cb_exec, g, 0);
+            if (e != cudaSuccess) { cudaGraphDestroy(g); return set_err(PGN_ECUDA, "graph instantiation failed: %s", cudaGetErrorString(e)); }
+            h->cb_graph = g; h->cb_has_exec = 1; h->cb_epoch = h->epoch; h->cb_stream = h->stream;
+        }
+        CK(cudaGraphLaunch(h->cb_exec, h->stream));
+        h->launches += h->cb_launches;
+    }
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    memcpy(out, io + 1 + 14 * B, 5 * B * 8);
     return PGN_OK;
 }
 int pgn_rollout(pgn_handle* h, double dt) {
@@ -577,7 +650,7 @@ int pgn_hji_lookup(pgn_handle* h, int32_t M, const double* x, double* V, double*
     for (int i = 0; i < M; i++) for (int d = 0; d < 7; d++) gradV[(size_t)i * 7 + d] = gt[(size_t)d * M + i];
     return PGN_OK;
 }
-int pgn_set_hji_policy(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->hji_policy = on != 0; return PGN_OK; }
+int pgn_set_hji_policy(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->epoch++; h->hji_policy = on != 0; return PGN_OK; }
 int pgn_get_hji_values(pgn_handle* h, double* V, double* gradV) {
     REQUIRE(h && V && gradV, "NULL argument");
     const size_t B = h->B;
@@ -610,7 +683,7 @@ int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_status) {
     if (d_status) *d_status = h->d_status;
     return PGN_OK;
 }
-int pgn_set_profiling(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->profiling = on; return PGN_OK; }
+int pgn_set_profiling(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->epoch++; h->profiling = on; return PGN_OK; }
 int pgn_get_admm_cycles(pgn_handle* h, double* out, int32_t reset) {
     REQUIRE(h && out, "NULL argument");
     unsigned long long c[512];

@@ -101,6 +101,10 @@ struct pgn_handle {
     int hji_policy;                                      // use_HJI_policy[] (ros_integration.jl:47): V <= HJI_eps => optimal_control replaces the QP control
     uint8_t *d_skip, *d_cold;                            // guards: vehicle paused this step / ADMM iterates to be re-initialised
     int guard_nan; double guard_pause;
+    // callback entry point (pgn_from_autobox): packed message buffer (pinned host + device), time-interval flags, path coordinates,
+    // and the CUDA graph of the whole call (H2D copy, unpack, the five step stages, pack, D2H copy), re-captured when a setter bumps `epoch`
+    double *h_io, *d_io, *d_se; uint8_t* d_tskip; int in_callback;
+    cudaGraph_t cb_graph; cudaGraphExec_t cb_exec; long long epoch, cb_epoch, cb_launches; cudaStream_t cb_stream; int cb_has_exec;
     int32_t* d_order;                                    // ticket -> vehicle order of the ADMM launch
     int* d_counter;                                      // work-queue ticket for the persistent ADMM kernel
     unsigned long long* d_cycles;                        // [8] per-phase cycle counters of the ADMM kernel (profiling only)
@@ -122,6 +126,8 @@ void launch_linearize(pgn_handle* h);
 void launch_hji_constraint(pgn_handle* h);
 void launch_admm(pgn_handle* h);
 void launch_controls(pgn_handle* h, double* d_out);
+void launch_callback_in(pgn_handle* h);
+void launch_callback_out(pgn_handle* h);
 void launch_rollout(pgn_handle* h, double dt);
 void launch_hji_optimal_control(pgn_handle* h, int M, const double* d_x, const double* d_gV, double* d_out);   // [M][7], [M][7] -> [M][2]
 void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV);

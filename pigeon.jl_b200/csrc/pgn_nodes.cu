@@ -73,7 +73,7 @@ __device__ __forceinline__ TrajNode traj_at_s(const TrajView& tv, int base, doub
 // Deviation: the sqrt argument is floored at 0 (the reference raises a DomainError on negative round-off).
 // The scan is spread over the 32 lanes of a warp (segment i on lane i mod 32), followed by a butterfly arg-min whose tie-break keeps the
 // smallest segment index, i.e. exactly the serial first-minimum-wins result.  Every lane returns (s, e).
-__device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int base, double x, double y, int lane, double& s_out, double& e_out) {
+__device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int base, double x, double y, int lane, double& s_out, double& e_out, double* t_out = nullptr) {
     const int nn = tv.n_nodes;
     const double *E = tv.f[4] + base, *Nn = tv.f[5] + base;
     double d2min = INFINITY;
@@ -102,6 +102,12 @@ __device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int ba
     const double ds = sqrt(arg > 0 ? arg : 0.0);
     s_out = __ldg(tv.f[1] + base + i) + ds;
     e_out = sqrt(d2min) * sign_(vx * wy - vy * wx);
+    if (t_out) {      // third return value of path_coordinates (trajectories.jl:85-92): time at which the trajectory passes the closest point
+        const double Vi = __ldg(tv.f[2] + base + i), ti = __ldg(tv.f[0] + base + i);
+        const double A = (__ldg(tv.f[2] + base + i + 1) - Vi) / (__ldg(tv.f[0] + base + i + 1) - ti);
+        const double dt = fabs(A) < 1e-3 ? ds / Vi : (sqrt(2 * A * ds + Vi * Vi) - Vi) / A;
+        *t_out = ti + dt;
+    }
 }
 
 // ---- compute_time_steps! ---------------------------------------------------------------------------------------------
@@ -131,6 +137,7 @@ struct NodeArgs {
     const double *ts, *dt, *prev_ts, *sol_x;
     double *qs, *us, *ps;
     uint8_t* skip; double pause_below_speed;      // guard of src/ros_integration.jl:84-87
+    const uint8_t* tskip;                         // callback entry point only: time outside the trajectory interval (src/ros_integration.jl:77-80)
 };
 
 // One warp per vehicle: the lanes share the closest-segment scan and, on warm steps, take one horizon node each; the cold rollout
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
     const double d0 = a.control[0 * B + v], Fxf0 = a.control[1 * B + v], Fxr0 = a.control[2 * B + v];
     const double Fx0 = Fxf0 + Fxr0;
     const bool path_mode = isnan(a.toff[v]);
-    if (a.pause_below_speed > 0.0 && lane == 0) a.skip[v] = Ux0 < a.pause_below_speed;
+    if ((a.pause_below_speed > 0.0 || a.tskip) && lane == 0) a.skip[v] = (a.pause_below_speed > 0.0 && Ux0 < a.pause_below_speed) || (a.tskip && a.tskip[v]);
     const int base = a.traj_id[v] * a.tv.n_nodes;
     const double* ts = a.ts + (size_t)v * N;
     const double* dt = a.dt + (size_t)v * (N - 1);
@@ -324,6 +331,43 @@ __global__ void __launch_bounds__(128) k_rollout(int B, VehParams P, double dt, 
     }
 }
 
+// ---- from_autobox_callback (src/ros_integration.jl:48-151) as one batched entry point ------------------------------------------------
+// io buffer (doubles): [0] has_other, then q [B][6], u [B][3], other [B][4], stamp [B]  |  out [B][5] = (delta, Fxf, Fxr, s, e)
+// One warp per vehicle: scatter the message fields into the SoA state, pick the MPC time (stamp - time_offset, or the path_coordinates
+// time in path-tracking mode, :72-75), flag vehicles whose time lies outside the trajectory (:77-80) and keep (s, e) for the reply (:110).
+__global__ void __launch_bounds__(128) k_callback_in(int B, TrajView tv, const int32_t* __restrict__ traj_id, const double* __restrict__ io,
+                                                     const double* __restrict__ toff, double* __restrict__ state, double* __restrict__ control,
+                                                     double* __restrict__ other, double* __restrict__ t0, uint8_t* __restrict__ tskip, double* __restrict__ se) {
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= B) return;
+    const double* q = io + 1 + (size_t)v * 6;
+    const double* u = io + 1 + (size_t)B * 6 + (size_t)v * 3;
+    const double* o = io + 1 + (size_t)B * 9 + (size_t)v * 4;
+    const double stamp = io[1 + (size_t)B * 13 + v];
+    if (lane < 6) state[(size_t)lane * B + v] = q[lane];
+    if (lane < 3) control[(size_t)lane * B + v] = u[lane];
+    if (io[0] != 0.0 && lane < 4) other[(size_t)lane * B + v] = o[lane];
+    double s, e, tp;
+    path_coordinates_warp(tv, traj_id[v] * tv.n_nodes, q[0], q[1], lane, s, e, &tp);
+    if (lane == 0) {
+        const double off = toff[v];
+        double t = tp;
+        bool out_of_interval = false;
+        if (!isnan(off)) {
+            t = stamp - off;
+            out_of_interval = t < 0 || t > __ldg(tv.f[0] + traj_id[v] * tv.n_nodes + tv.n_nodes - 1);
+        }
+        t0[v] = t; tskip[v] = out_of_interval;
+        se[v] = s; se[B + v] = e;
+    }
+}
+__global__ void k_callback_out(int B, const double* __restrict__ controls, const double* __restrict__ se, double* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    out[(size_t)v * 5 + 0] = controls[v]; out[(size_t)v * 5 + 1] = controls[B + v]; out[(size_t)v * 5 + 2] = controls[2 * B + v];
+    out[(size_t)v * 5 + 3] = se[v]; out[(size_t)v * 5 + 4] = se[B + v];
+}
+
 // ---- layout helpers --------------------------------------------------------------------------------------------------
 __global__ void k_transpose_in(int B, int k, const double* __restrict__ aos, double* __restrict__ soa) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -358,14 +402,22 @@ void launch_nodes(pgn_handle* h) {
     a.state = h->d_state; a.control = h->d_control; a.toff = h->d_toff; a.solved = h->d_solved; a.traj_id = h->d_traj_id;
     a.ts = h->d_ts; a.dt = h->d_dt; a.prev_ts = h->d_prev_ts; a.sol_x = h->d_sol_x;
     a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps;
-    a.skip = h->d_skip; a.pause_below_speed = h->guard_pause;
+    a.skip = h->d_skip; a.pause_below_speed = h->guard_pause; a.tskip = h->in_callback ? h->d_tskip : nullptr;
     k_nodes<<<(h->B + 3) / 4, 128, 0, h->stream>>>(a);
+    h->launches++;
+}
+void launch_callback_in(pgn_handle* h) {
+    k_callback_in<<<(h->B + 3) / 4, 128, 0, h->stream>>>(h->B, h->traj, h->d_traj_id, h->d_io, h->d_toff, h->d_state, h->d_control, h->d_other, h->d_t0, h->d_tskip, h->d_se);
+    h->launches++;
+}
+void launch_callback_out(pgn_handle* h) {
+    k_callback_out<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, h->d_controls, h->d_se, h->d_io + 1 + (size_t)h->B * 14);
     h->launches++;
 }
 void launch_controls(pgn_handle* h, double* d_out) {
     const int B = h->B;
     k_controls<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.kind, h->tab.n, h->tab.var_u1_delta, h->tab.var_u1_fx, h->un[0], h->un[1], h->veh,
-                                                       h->d_sol_x, h->d_us, h->N, d_out, h->d_control, h->guard_pause > 0.0 ? h->d_skip : nullptr, h->guard_nan,
+                                                       h->d_sol_x, h->d_us, h->N, d_out, h->d_control, (h->guard_pause > 0.0 || h->in_callback) ? h->d_skip : nullptr, h->guard_nan,
                                                        h->d_cold, h->d_solved, (h->hji_policy && h->cfg.kind == PGN_COUPLED) ? h->d_hji_val : nullptr, h->cfg.hji_eps, h->d_state);
     h->launches++;
 }

@@ -226,6 +226,14 @@ class BatchedTrajectoryTrackingMPC:
         """Per-vehicle guards of the reference's ROS callback (src/ros_integration.jl:84-87, 134-147); off by default."""
         check(self._lib.pgn_set_guards(self._h, int(bool(nan_fallback)), C.c_double(float(pause_below_speed))))
 
+    def from_autobox(self, state, control, stamp, other_car=None):
+        """from_autobox_callback (src/ros_integration.jl:48-151) for the batch in one call: returns (B, 5) = (delta, Fxf, Fxr, s_m, e_m)."""
+        q, u = f64(state, (self.B, 6)), f64(control, (self.B, 3))
+        o = None if other_car is None else f64(other_car, (self.B, 4))
+        out = np.zeros((self.B, 5))
+        check(self._lib.pgn_from_autobox(self._h, dptr(q), dptr(u), dptr(o), dptr(self._t0(stamp)), dptr(out)))
+        return out
+
     def _t0(self, t0):
         return f64(np.broadcast_to(np.asarray(t0, float), (self.B,)))
 

@@ -520,3 +520,55 @@ def test_hji_hammer_policy_parity(p):
     assert np.max(np.abs(u_off[hammer, 0])) < vp[20] or not np.array_equal(u_off[hammer], u_gpu[hammer])
     assert np.max(np.abs(u_off[~hammer] - u_gpu[~hammer]) / scale) < 1e-12
     g.close()
+
+
+def test_from_autobox_callback_parity(p):
+    """pgn_from_autobox = from_autobox_callback (ros_integration.jl:48-151): same result as the oracle's restatement of the callback and,
+    step for step, as the explicit set_state + five-call sequence; early returns keep the current control; the CUDA graph is re-captured
+    after a setter."""
+    B = 24
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    toff = np.full(B, np.nan)
+    toff[B // 2:] = 50.0                                  # second half: trajectory-tracking mode, stamp = t + 50
+    stamp = np.where(np.isnan(toff), 777.0, t0 + 50.0)
+    t_end = np.array([trajs["t"][int(j)][-1] for j in tid])
+    stamp[B // 2] = 49.0                                  # t < 0
+    stamp[B // 2 + 1] = 50.0 + t_end[B // 2 + 1] + 1.0    # t > t_end
+    state = state.copy(); state[3, 3] = 0.5               # below the pause speed
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g.set_guards(nan_fallback=True, pause_below_speed=1.0)
+    g.set_state(state, control, other, time_offset=toff)
+    ms = oracles_for(0, trajs, tid, state, control, other)
+    for i, m in enumerate(ms):
+        m.set_state(state[i], control[i], other4=other[i], time_offset=toff[i])
+    early = {3, B // 2, B // 2 + 1}
+    q, u = state.copy(), control.copy()
+    for k in range(3):
+        out = g.from_autobox(q, u, stamp + 0.01 * k, other_car=other if k == 0 else None)
+        it = g.stats()["iters"]
+        for i, m in enumerate(ms):
+            pub, ref = m.from_autobox(q[i], u[i], stamp[i] + 0.01 * k, pause_speed=1.0, nan_fallback=True)
+            assert pub == (i not in early)
+            assert np.max(np.abs(out[i, :3] - ref[:3]) / U_RANGE) < 1e-4, (k, i)
+            assert abs(out[i, 3] - ref[3]) < 1e-9 and abs(out[i, 4] - ref[4]) < 1e-9
+            if pub:
+                assert it[i] == m.stats()["iter"]
+            else:
+                assert np.array_equal(out[i, :3], u[i]) and it[i] == 0
+        u = out[:, :3].copy()          # next message: same measured state, the reply as the current control (warm nodes, warm ADMM)
+        if k == 1:
+            g.set_guards(nan_fallback=True, pause_below_speed=1.0)      # bumps the epoch: the next call re-captures the graph
+    # the fused call equals the explicit sequence on a fresh handle
+    g2 = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g2.set_state(state, control, other, time_offset=np.full(B, np.nan))
+    o1 = g2.from_autobox(state, control, 0.0, other_car=other)
+    g3 = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    g3.set_state(state, control, other, time_offset=np.full(B, np.nan))
+    tp = np.array([o.Trajectory(**{kk: trajs[kk][int(tid[i])] for kk in o.TRAJ_FIELDS}).path_coordinates(state[i, 0], state[i, 1])[2] for i in range(B)])
+    o3 = g3.step(tp)
+    fin = np.isfinite(o3).all(axis=1)          # vehicle 3 (0.5 m/s, no pause guard on these handles) divides by a tiny Ux: NaN in both
+    assert np.array_equal(fin, np.isfinite(o1[:, :3]).all(axis=1)) and fin.sum() >= B - 1
+    assert np.max(np.abs(o1[fin, :3] - o3[fin]) / U_RANGE) < 1e-9
+    g.close(); g2.close(); g3.close()

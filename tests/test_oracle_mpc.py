@@ -140,3 +140,31 @@ def test_warm_nodes_interpolate_previous_solution():
             assert qs[i, c] == pytest.approx(np.interp(tq, prev, X[:, c]), rel=1e-12, abs=1e-14)
         for c in range(2):
             assert us[i, c] == pytest.approx(np.interp(tq, prev, U[:, c]) * un[c], rel=1e-12, abs=1e-12)
+
+
+def test_from_autobox_callback_semantics():
+    """from_autobox_callback (ros_integration.jl:48-151): time selection, early returns, reply fields."""
+    tr = world_trajectory("skidpadoval")
+    f = tr.fields
+    q = [f["E"][400], f["N"][400] + 0.2, f["psi"][400], 6, 0, 0.3]
+    u = [0.08, 0, 390.0]
+    s_e_t = tr.path_coordinates(q[0], q[1])
+    # path-tracking mode (time_offset NaN): the MPC time is the path_coordinates time; reply carries (s, e)
+    m = o.Mpc(o.MPC_COUPLED); m.set_trajectory(tr); m.set_state(q, u, other4=FAR)
+    pub, out = m.from_autobox(q, u, stamp=123.0, pause_speed=1.0)
+    assert pub and out[3] == s_e_t[0] and out[4] == s_e_t[1]
+    ref = o.Mpc(o.MPC_COUPLED); ref.set_trajectory(tr); ref.set_state(q, u, other4=FAR)
+    assert np.array_equal(out[:3], ref.step(s_e_t[2]))
+    # trajectory mode: t = stamp - time_offset; outside [0, t_end] the callback returns early and the control stays
+    m2 = o.Mpc(o.MPC_COUPLED); m2.set_trajectory(tr); m2.set_state(q, u, other4=FAR, time_offset=100.0)
+    pub, out = m2.from_autobox(q, u, stamp=99.0)
+    assert not pub and np.array_equal(out[:3], u) and m2.stats()["iter"] == 0
+    pub, out = m2.from_autobox(q, u, stamp=100.0 + f["t"][-1] + 1.0)
+    assert not pub
+    pub, out = m2.from_autobox(q, u, stamp=100.0 + f["t"][400])
+    ref2 = o.Mpc(o.MPC_COUPLED); ref2.set_trajectory(tr); ref2.set_state(q, u, other4=FAR, time_offset=100.0)
+    assert pub and np.array_equal(out[:3], ref2.step(f["t"][400]))
+    # paused below 1 m/s
+    qs = list(q); qs[3] = 0.4
+    pub, out = m2.from_autobox(qs, u, stamp=100.0 + f["t"][400], pause_speed=1.0)
+    assert not pub and np.array_equal(out[:3], u)
