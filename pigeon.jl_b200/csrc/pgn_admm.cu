@@ -189,12 +189,13 @@ __device__ __forceinline__ double gather_task(const Smem& s, const uint2 d, cons
 // then the explicit inverses of the level ranges (in place) and of the dense tail.
 #define FAC_T(idx)                                                                         \
     do {                                                                                   \
-        if (lvl_cyc && threadIdx.x == 0 && blockIdx.x == 0) {                              \
+        if (PROF && lvl_cyc && threadIdx.x == 0 && blockIdx.x == 0) {                              \
             const long long now__ = clock64();                                             \
             lvl_cyc[(idx)] += (unsigned int)(now__ - t_lvl);                               \
             t_lvl = now__;                                                                 \
         }                                                                                  \
     } while (0)
+template <bool PROF>
 __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, unsigned int* lvl_cyc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long t_lvl = clock64();
@@ -384,7 +385,7 @@ __device__ __forceinline__ void run_phase(const Smem& s, int t0, int t1, int zid
 
 #define LVL_T(idx)                                                                         \
     do {                                                                                   \
-        if (lvl_cyc && threadIdx.x == 0 && blockIdx.x == 0) {                              \
+        if (PROF && lvl_cyc && threadIdx.x == 0 && blockIdx.x == 0) {                              \
             const long long now__ = clock64();                                             \
             lvl_cyc[(idx)] += (unsigned int)(now__ - t_lvl);                               \
             t_lvl = now__;                                                                 \
@@ -393,6 +394,7 @@ __device__ __forceinline__ void run_phase(const Smem& s, int t0, int t1, int zid
 // sol <- K^-1 rhs (rhs in sol, except the first range whose rhs is in the scratch vector):  forward over the level ranges (first range:
 // in-range explicit inverse only; others: external part, then in-range inverse), the dense tail (external part as the last forward
 // phase, then one symmetric mat-vec with -S^-1), and the mirror image backwards.
+template <bool PROF>
 __device__ __forceinline__ void kkt_solve(const AdmmArgs& a, const Smem& s, unsigned int* lvl_cyc) {
     const QpDev& q = a.q;
     const int tid = threadIdx.x;
@@ -400,7 +402,7 @@ __device__ __forceinline__ void kkt_solve(const AdmmArgs& a, const Smem& s, unsi
     const int zidx = q.Nk;                                                    // the always-zero vector element
     const uint32_t zpair = (uint32_t)q.zslot | ((uint32_t)q.Nk << 16);       // (always-zero L slot, always-zero vector element)
     for (int ph = 0; ph < q.n_fwd_ph; ph++) {
-        if (ph & 1) run_phase<TASK_DST_TMP, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1], zidx, zpair, (lvl_cyc && blockIdx.x == 0 && ph == 1) ? lvl_cyc + 200 : nullptr);      // t = b - W_ext y^
+        if (ph & 1) run_phase<TASK_DST_TMP, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1], zidx, zpair, nullptr);      // t = b - W_ext y^
         else run_phase<TASK_SRC_TMP | TASK_ADD | TASK_SCALE_OUT, false>(s, a.ph_ptr[ph], a.ph_ptr[ph + 1], zidx, zpair);              // y^ = (t + M t) / d
         LVL_T(ph);
     }
@@ -539,13 +541,16 @@ __device__ bool dual_infeasible(const QpDev& q, const Smem& s, double eps, doubl
 
 #define PHASE(idx)                                                                  \
     do {                                                                            \
-        if (a.cycles && threadIdx.x == 0) {                                         \
+        if (PROF && a.cycles && threadIdx.x == 0) {                                         \
             const long long now__ = clock64();                                      \
             s_cyc[(idx)] += (unsigned int)(now__ - t_phase);                        \
             t_phase = now__;                                                        \
         }                                                                           \
     } while (0)
 
+// PROF: in-kernel cycle counters (profiling level 2).  A template parameter because even an untaken counter predicate (parameter load +
+// blockIdx read + compare) costs ~50 cycles per barrier interval (tools/ubench/sreg.cu).
+template <bool PROF>
 __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_vehicle;
@@ -699,7 +704,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
 
         PHASE(1);
         // ---- 3. factor ----------------------------------------------------------------------------------------------------
-        factor(q, s, st.sigma, rho, a.cycles ? s_cyc + 16 : nullptr);
+        factor<PROF>(q, s, st.sigma, rho, PROF ? s_cyc + 16 : nullptr);
         PHASE(2);
 
         // ---- 4. ADMM iterations ---------------------------------------------------------------------------------------------
@@ -719,7 +724,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
             const bool check = st.check_termination && (iter % st.check_termination == 0);
             const bool adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
             const bool need_delta = check || adapt;
-            kkt_solve(a, s, a.cycles ? s_cyc + 16 : nullptr);
+            kkt_solve<PROF>(a, s, PROF ? s_cyc + 16 : nullptr);
             PHASE(3);
             // x, z, y updates; on iterations without a residual check the next right-hand side is formed in the same pass
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
@@ -769,7 +774,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                     n_rho_upd++;
                     __syncthreads();
                     PHASE(5);
-                    factor(q, s, st.sigma, rho, a.cycles ? s_cyc + 16 : nullptr);
+                    factor<PROF>(q, s, st.sigma, rho, PROF ? s_cyc + 16 : nullptr);
                     PHASE(2);
                 }
             }
@@ -811,7 +816,7 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         __syncthreads();
         PHASE(6);
     }
-    if (a.cycles) {
+    if (PROF && a.cycles) {
         __syncthreads();
         for (int i = threadIdx.x; i < ADMM_NCYC; i += ADMM_THREADS)
             if (s_cyc[i]) atomicAdd(a.cycles + i, (unsigned long long)s_cyc[i]);
@@ -837,7 +842,8 @@ __global__ void __launch_bounds__(1024) k_admm_order(const int32_t* __restrict__
 int admm_configure(pgn_handle* h) {
     h->admm_smem_bytes = (int)admm_smem_bytes(h->tab);
     h->admm_threads = ADMM_THREADS;
-    cudaError_t e = cudaFuncSetAttribute(k_admm, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
     return (int)e;
 }
 
@@ -860,7 +866,8 @@ void launch_admm(pgn_handle* h) {
     if (h->admm_smem_bytes * 3 + 3072 <= 227 * 1024) ctas_per_sm = 3;
     int grid = h->num_sms * ctas_per_sm;
     if (grid > h->B) grid = h->B;
-    k_admm<<<grid, ADMM_THREADS, h->admm_smem_bytes, h->stream>>>(a);
+    if (a.cycles) k_admm<true><<<grid, ADMM_THREADS, h->admm_smem_bytes, h->stream>>>(a);
+    else k_admm<false><<<grid, ADMM_THREADS, h->admm_smem_bytes, h->stream>>>(a);
     h->launches++;
 }
 
