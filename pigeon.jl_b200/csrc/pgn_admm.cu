@@ -720,13 +720,51 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
         } while (0)
         for (int p = tid; p < q.Nk; p += ADMM_THREADS) { const uint8_t f = s.flag[p]; ADMM_RHS(p, f); }
         __syncthreads();
+        // iterations until the next residual check / rho estimate (countdowns: a run-time modulo is ~25 instructions on every warp)
+        int chk_left = st.check_termination > 0 ? st.check_termination : 0x7fffffff;
+        int adp_left = (st.adaptive_rho && st.adaptive_rho_interval > 0) ? st.adaptive_rho_interval : 0x7fffffff;
         for (iter = 1; iter <= st.max_iter; iter++) {
-            const bool check = st.check_termination && (iter % st.check_termination == 0);
-            const bool adapt = st.adaptive_rho && st.adaptive_rho_interval && (iter % st.adaptive_rho_interval == 0);
+            const bool check = --chk_left == 0, adapt = --adp_left == 0;
+            if (check) chk_left = st.check_termination;
+            if (adapt) adp_left = st.adaptive_rho_interval;
             const bool need_delta = check || adapt;
             kkt_solve<PROF>(a, s, PROF ? s_cyc + 16 : nullptr);
             PHASE(3);
-            // x, z, y updates; on iterations without a residual check the next right-hand side is formed in the same pass
+            if (!need_delta) {
+                // x, z, y updates fused with the next right-hand side.  Branch-free (both the constraint and the variable form are
+                // evaluated, selects pick one) with three positions per thread in flight: the pass is a latency chain of each warp's
+                // own instructions, so independent positions are interleaved instead of run one after the other.
+                for (int p0 = tid; p0 < q.Nk; p0 += 3 * ADMM_THREADS) {
+                    int pp[3]; bool ok[3]; uint8_t f[3];
+                    double xz[3], y[3], so[3], lo[3], hi[3];
+#pragma unroll
+                    for (int u = 0; u < 3; u++) {
+                        const int p = p0 + u * ADMM_THREADS;
+                        ok[u] = p < q.Nk; pp[u] = ok[u] ? p : p0;
+                        f[u] = s.flag[pp[u]]; xz[u] = s.xz[pp[u]]; y[u] = s.yq[pp[u]]; so[u] = s.sol[pp[u]]; lo[u] = s.lo[pp[u]]; hi[u] = s.hi[pp[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; u++) {
+                        const bool con = f[u] != 0;
+                        const double r = rho_of(f[u], rho), ri = rinv_of(f[u], rinv);
+                        const double zt = xz[u] + ri * (so[u] - y[u]);
+                        const double zr = alpha * zt + (1.0 - alpha) * xz[u];
+                        const double zn = fmin(fmax(zr + ri * y[u], lo[u]), hi[u]);
+                        const double dy = r * (zr - zn);
+                        const double xn = alpha * so[u] + (1.0 - alpha) * xz[u];
+                        const double nx = con ? zn : xn, ny = con ? y[u] + dy : y[u];
+                        const double b = con ? nx - ri * ny : st.sigma * nx - ny;
+                        if (ok[u]) {
+                            s.xz[pp[u]] = nx;
+                            if (con) s.yq[pp[u]] = ny;
+                            if (pp[u] < q.rhs_tmp_end) s.dxy[pp[u]] = b; else s.sol[pp[u]] = b;
+                        }
+                    }
+                }
+                __syncthreads();
+                PHASE(4);
+                continue;
+            }
             for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
                 const uint8_t f = s.flag[p];
                 if (f) {
@@ -738,18 +776,16 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
                     const double dy = r * (zr - zn);
                     s.xz[p] = zn;
                     s.yq[p] = y + dy;
-                    if (need_delta) s.dxy[p] = dy;
+                    s.dxy[p] = dy;
                 } else {
                     const double xp = s.xz[p];
                     const double xn = alpha * s.sol[p] + (1.0 - alpha) * xp;
                     s.xz[p] = xn;
-                    if (need_delta) s.dxy[p] = xn - xp;
+                    s.dxy[p] = xn - xp;
                 }
-                if (!need_delta) ADMM_RHS(p, f);
             }
             __syncthreads();
             PHASE(4);
-            if (!need_delta) continue;
             Resid R = residuals(q, s, cinv);
             pri_res = R.pri_res; dua_res = R.dua_res;
             if (check) {
