@@ -158,8 +158,7 @@ def run_gpu(args):
         if record:
             q, u = mpc.get_state()
             rec_states.append(q); rec_controls.append(u)
-        mpc.step_device(d_t0.data_ptr(), d_out.data_ptr())
-        mpc.rollout(dt)
+        mpc.step_rollout_device(d_t0.data_ptr(), d_out.data_ptr(), dt)      # step + plant rollout (launched beside the QP solve)
         d_t0.add_(dt)
 
     # pass 1 (untimed): record the closed-loop states of all SETTLE+W+K steps for the e2e replay

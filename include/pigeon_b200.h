@@ -127,6 +127,10 @@ PGN_API int pgn_step(pgn_handle* h, const double* t0 /*[B]*/, double* out /*[B][
 PGN_API int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const double* other_car, const double* stamp, double* out /*[B][5]*/);
 /* same with inputs already resident: t0 and out are DEVICE pointers ([B] and [3][B] field-major); out may be NULL */
 PGN_API int pgn_step_device(pgn_handle* h, const double* d_t0, double* d_out);
+/* pgn_step_device followed by pgn_rollout(dt), i.e. one iteration of the `simulate` loop (model_predictive_control.jl:87-98), with the plant
+ * step launched beside the QP solve: propagate() needs only the state and the control applied during the interval, both known before
+ * the solve, so it runs on a side stream into a shadow state and is committed together with the new control.  Same results as the two calls. */
+PGN_API int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d_out, double dt);
 /* simulate (model_predictive_control.jl:80-100): n_steps closed-loop steps fully on the device:
  * step at t0 + k*dt, plant rollout propagate(dynamics, state, StepControl(dt, control)), apply the new control */
 PGN_API int pgn_simulate(pgn_handle* h, const double* t0 /*[B]*/, double dt, int32_t n_steps);

@@ -206,6 +206,9 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     if (e != cudaSuccess) { delete h; return set_err(PGN_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
     h->stream = h->own_stream;
     cudaEventCreate(&h->ev[0]); cudaEventCreate(&h->ev[1]);
+    h->side_stream = nullptr;
+    cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     double vp[PGN_VEHICLE_PARAMS_LEN], cp[PGN_CONTROL_PARAMS_LEN];
     x1_params(vp); default_control(cfg->kind, cp);
     memcpy(&h->veh, vp, sizeof(vp)); memcpy(&h->ctl, cp, sizeof(cp));
@@ -270,7 +273,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_se, 2 * B); AL(d_tskip, B);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_se, 2 * B); AL(d_tskip, B);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
@@ -329,6 +332,8 @@ int pgn_destroy(pgn_handle* h) {
     if (h->cb_has_exec) { cudaGraphExecDestroy(h->cb_exec); cudaGraphDestroy(h->cb_graph); }
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
     cudaEventDestroy(h->ev[0]); cudaEventDestroy(h->ev[1]);
     delete h;
     return PGN_OK;
@@ -529,6 +534,30 @@ int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const doub
     memcpy(out, io + 1 + 14 * B, 5 * B * 8);
     return PGN_OK;
 }
+// step + plant rollout of `simulate` (model_predictive_control.jl:87-98) with the plant step beside the QP solve
+int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d_out, double dt) {
+    REQUIRE(h && d_t0, "NULL argument");
+    if (h->profiling || !h->side_stream) {            // stage timers synchronise: serial order
+        int rc = pgn_step_device(h, d_t0, d_out);
+        if (rc) return rc;
+        return pgn_rollout(h, dt);
+    }
+    step_time_steps_dev(h, d_t0);
+    step_nodes(h);
+    step_update(h);
+    // fork: the propagation reads state / current control only (nothing on the main stream writes them before the commit)
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    launch_propagate_shadow(h, dt, h->side_stream);
+    CK(cudaEventRecord(h->ev_join, h->side_stream));
+    step_solve(h);
+    step_controls(h, h->d_controls);
+    if (d_out) CK(cudaMemcpyAsync(d_out, h->d_controls, (size_t)h->B * 3 * 8, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    launch_commit_rollout(h);
+    CK(cudaGetLastError());
+    return PGN_OK;
+}
 int pgn_rollout(pgn_handle* h, double dt) {
     REQUIRE(h, "NULL handle");
     { StageTimer T(h, 5); launch_rollout(h, dt); }
@@ -540,9 +569,8 @@ int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
     CK(cudaMemcpyAsync(h->d_t0_base, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
     for (int k = 0; k < n_steps; k++) {
         launch_time_axpy(h, h->d_t0_base, (double)k, dt, h->d_t0, h->B);
-        int rc = pgn_step_device(h, h->d_t0, nullptr);
+        int rc = pgn_step_rollout_device(h, h->d_t0, nullptr, dt);
         if (rc) return rc;
-        { StageTimer T(h, 5); launch_rollout(h, dt); }
     }
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());

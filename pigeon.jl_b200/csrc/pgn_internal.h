@@ -103,6 +103,8 @@ struct pgn_handle {
     int guard_nan; double guard_pause;
     // callback entry point (pgn_from_autobox): packed message buffer (pinned host + device), time-interval flags, path coordinates,
     // and the CUDA graph of the whole call (H2D copy, unpack, the five step stages, pack, D2H copy), re-captured when a setter bumps `epoch`
+    // plant rollout beside the ADMM launch (pgn_step_rollout_device / pgn_simulate): shadow state, side stream, fork / join events
+    double* d_state_next; cudaStream_t side_stream; cudaEvent_t ev_fork, ev_join;
     double *h_io, *d_io, *d_se; uint8_t* d_tskip; int in_callback;
     cudaGraph_t cb_graph; cudaGraphExec_t cb_exec; long long epoch, cb_epoch, cb_launches; cudaStream_t cb_stream; int cb_has_exec;
     int32_t* d_order;                                    // ticket -> vehicle order of the ADMM launch
@@ -129,6 +131,8 @@ void launch_controls(pgn_handle* h, double* d_out);
 void launch_callback_in(pgn_handle* h);
 void launch_callback_out(pgn_handle* h);
 void launch_rollout(pgn_handle* h, double dt);
+void launch_propagate_shadow(pgn_handle* h, double dt, cudaStream_t side);
+void launch_commit_rollout(pgn_handle* h);
 void launch_hji_optimal_control(pgn_handle* h, int M, const double* d_x, const double* d_gV, double* d_out);   // [M][7], [M][7] -> [M][2]
 void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV);
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]

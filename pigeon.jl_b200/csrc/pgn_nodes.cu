@@ -426,6 +426,39 @@ void launch_rollout(pgn_handle* h, double dt) {
     k_rollout<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->veh, dt, h->cfg.rk4_substeps, h->d_state, h->d_control, h->d_controls);
     h->launches++;
 }
+// The plant step only needs the state and the control that was applied DURING the interval, both known before the QP is solved, so it
+// can run beside the ADMM launch: propagate into a shadow state on the side stream, commit (state <- shadow, control <- new control) on
+// the main stream once both are done.
+__global__ void __launch_bounds__(128) k_propagate_shadow(int B, VehParams P, double dt, int nsub, const double* __restrict__ state, const double* __restrict__ control,
+                                                          double* __restrict__ state_next) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    double x[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] = state[i * B + v];
+    double u[4] = {control[0 * B + v], control[1 * B + v] + control[2 * B + v], 0.0, 0.0};
+    flow_rk4<MODEL_BICYCLE, 6, double>(P, x, dt, u, u, nsub);
+#pragma unroll
+    for (int i = 0; i < 6; i++) state_next[i * B + v] = x[i];
+}
+__global__ void k_commit_rollout(int B, const double* __restrict__ state_next, const double* __restrict__ new_control, double* __restrict__ state, double* __restrict__ control) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+#pragma unroll
+    for (int i = 0; i < 6; i++) state[i * B + v] = state_next[i * B + v];
+#pragma unroll
+    for (int i = 0; i < 3; i++) control[i * B + v] = new_control[i * B + v];
+}
+void launch_propagate_shadow(pgn_handle* h, double dt, cudaStream_t side) {
+    const int B = h->B;
+    k_propagate_shadow<<<(B + 127) / 128, 128, 0, side>>>(B, h->veh, dt, h->cfg.rk4_substeps, h->d_state, h->d_control, h->d_state_next);
+    h->launches++;
+}
+void launch_commit_rollout(pgn_handle* h) {
+    const int B = h->B;
+    k_commit_rollout<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->d_state_next, h->d_controls, h->d_state, h->d_control);
+    h->launches++;
+}
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k) {
     const int n = h->B * k;
     k_transpose_in<<<(n + 255) / 256, 256, 0, h->stream>>>(h->B, k, d_aos, d_soa);

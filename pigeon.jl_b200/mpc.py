@@ -262,6 +262,10 @@ class BatchedTrajectoryTrackingMPC:
     def step_device(self, d_t0_ptr, d_out_ptr=None):
         check(self._lib.pgn_step_device(self._h, C.c_void_p(d_t0_ptr), C.c_void_p(d_out_ptr) if d_out_ptr else None))
 
+    def step_rollout_device(self, d_t0_ptr, d_out_ptr=None, dt=0.01):
+        """One iteration of the `simulate` loop on device-resident data: step, then plant rollout (launched beside the QP solve)."""
+        check(self._lib.pgn_step_rollout_device(self._h, C.c_void_p(d_t0_ptr), C.c_void_p(d_out_ptr) if d_out_ptr else None, float(dt)))
+
     def rollout(self, dt=0.01):
         check(self._lib.pgn_rollout(self._h, float(dt)))
 
