@@ -42,11 +42,11 @@ class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.stamps, self.proc, self.gpu = [], [], None, gpu_index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -56,8 +56,14 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
+            self.stamps.append(time.perf_counter())
 
-    def stop(self):
+    def stop(self, t_from=None):
+        """Samples taken at or after `t_from` (perf_counter); if none landed there, every sample of the loaded region."""
+        if t_from is not None:
+            keep = [r for r, t in zip(self.rows, self.stamps) if t >= t_from]
+            if keep:
+                self.rows = keep
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -168,6 +174,10 @@ def run_gpu(args):
     mpc.reset_solver(); mpc.reset_solved()
     mpc.set_state(state, control, other)
     d_t0.copy_(torch.tensor(t0, dtype=torch.float64, device=dev))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()           # nvidia-smi needs ~0.2 s to deliver its first sample: started before the settling pass, read over the whole loaded region
+        time.sleep(0.3)
     barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record(stream)
@@ -178,10 +188,8 @@ def run_gpu(args):
     cold_ms = c0.elapsed_time(c1)
     for _ in range(W):
         dev_step(False)
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    t_timed = time.perf_counter()      # clock samples from here on are the ones reported (the GPU is warm: settling + warm-up ran just before)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mpc.stage_ms(reset=True)
     ev0.record(stream)
@@ -191,7 +199,7 @@ def run_gpu(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = mpc.stage_ms(reset=True)["launches"]
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_timed) if rank == 0 else None
     st = mpc.stats()
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -323,9 +331,9 @@ def run_gpu(args):
             rd = re.search(r"dram__bytes_read.sum`\) \| ([0-9.]+) \| (\w+)", txt); wr = re.search(r"dram__bytes_write.sum`\) \| ([0-9.]+) \| (\w+)", txt)
             wf = re.search(r"l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed`\) \| ([0-9.]+)", txt)
             roof["traffic"] = float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)]
-            roof["traffic_source"] = "profiles/r1_admm_ncu_full.md (B = 1024; below the algorithmic bytes because the records and iterates of 1024 vehicles stay in the 126 MB L2)"
+            roof["traffic_source"] = "profiles/r1b_admm_ncu_full.md (B = 1024; below the algorithmic bytes because the records and iterates of 1024 vehicles stay in the 126 MB L2)"
             if wf:
-                roof["smem"] = {"pct_of_peak_wavefronts": float(wf.group(1)), "source": "profiles/r1_admm_ncu_full.md: the most loaded unit of the kernel is the shared-memory pipe"}
+                roof["smem"] = {"pct_of_peak_wavefronts": float(wf.group(1)), "source": "profiles/r1b_admm_ncu_full.md: the most loaded unit of the kernel is the shared-memory pipe"}
         except Exception:
             pass
         roof["fp64"]["frac"] = roof["fp64"]["achieved_tflops"] / 37.0

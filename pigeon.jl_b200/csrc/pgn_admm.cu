@@ -640,24 +640,35 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
 
         // ---- 2. modified Ruiz equilibration (scale_data of OSQP) -------------------------------------------------------
         for (int it = 0; it < st.scaling; it++) {
-            // inf-norms of the KKT columns (variables: P_jj and column j of A; constraints: row i of A), four gathers in flight per thread
-            for (int p = tid; p < q.Nk; p += ADMM_THREADS) {
-                double n0 = s.flag[p] ? 0.0 : fabs(s.lo[p]), n1 = 0.0;
-                int e = s.kptr[p];
-                const int e1 = s.kptr[p + 1];
+            // inf-norms of the KKT columns (variables: P_jj and column j of A; constraints: row i of A), four gathers in flight per thread;
+            // the square roots and reciprocals (~220 cycles each, serial) of a thread's positions are formed together after the scans
+            for (int p0 = tid; p0 < q.Nk; p0 += 3 * ADMM_THREADS) {
+                double nrm[3];
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const int p = p0 + u * ADMM_THREADS;
+                    if (p >= q.Nk) { nrm[u] = 1.0; continue; }
+                    double n0 = s.flag[p] ? 0.0 : fabs(s.lo[p]), n1 = 0.0;
+                    int e = s.kptr[p];
+                    const int e1 = s.kptr[p + 1];
 #pragma unroll 1
-                for (; e + 4 <= e1; e += 4) {
-                    const int j0 = s.ke[e], j1 = s.ke[e + 1], j2 = s.ke[e + 2], j3 = s.ke[e + 3];
-                    const double a0 = s.Aval[j0], a1 = s.Aval[j1], a2 = s.Aval[j2], a3 = s.Aval[j3];
-                    n0 = fmax(n0, fmax(fabs(a0), fabs(a1))); n1 = fmax(n1, fmax(fabs(a2), fabs(a3)));
+                    for (; e + 4 <= e1; e += 4) {
+                        const int j0 = s.ke[e], j1 = s.ke[e + 1], j2 = s.ke[e + 2], j3 = s.ke[e + 3];
+                        const double a0 = s.Aval[j0], a1 = s.Aval[j1], a2 = s.Aval[j2], a3 = s.Aval[j3];
+                        n0 = fmax(n0, fmax(fabs(a0), fabs(a1))); n1 = fmax(n1, fmax(fabs(a2), fabs(a3)));
+                    }
+                    if (e < e1) {
+                        const int last = e1 - 1;
+                        const int j0 = s.ke[e], j1 = s.ke[min(e + 1, last)], j2 = s.ke[min(e + 2, last)];
+                        const double a0 = s.Aval[j0], a1 = s.Aval[j1], a2 = s.Aval[j2];
+                        n0 = fmax(n0, fmax(fabs(a0), fabs(a1))); n1 = fmax(n1, fabs(a2));
+                    }
+                    nrm[u] = limit_scaling(fmax(n0, n1));
                 }
-                if (e < e1) {
-                    const int last = e1 - 1;
-                    const int j0 = s.ke[e], j1 = s.ke[min(e + 1, last)], j2 = s.ke[min(e + 2, last)];
-                    const double a0 = s.Aval[j0], a1 = s.Aval[j1], a2 = s.Aval[j2];
-                    n0 = fmax(n0, fmax(fabs(a0), fabs(a1))); n1 = fmax(n1, fabs(a2));
-                }
-                s.sol[p] = 1.0 / sqrt(limit_scaling(fmax(n0, n1)));
+                const double r0 = 1.0 / sqrt(nrm[0]), r1 = 1.0 / sqrt(nrm[1]), r2 = 1.0 / sqrt(nrm[2]);
+                s.sol[p0] = r0;
+                if (p0 + ADMM_THREADS < q.Nk) s.sol[p0 + ADMM_THREADS] = r1;
+                if (p0 + 2 * ADMM_THREADS < q.Nk) s.sol[p0 + 2 * ADMM_THREADS] = r2;
             }
             __syncthreads();
             {
@@ -689,8 +700,10 @@ __global__ void __launch_bounds__(ADMM_THREADS, 1) k_admm(const AdmmArgs a) {
             for (int p = tid; p < q.Nk; p += ADMM_THREADS)
                 if (!s.flag[p]) { s.lo[p] *= c_temp; s.yq[p] *= c_temp; }
             c *= c_temp;
-            __syncthreads();
+            // no barrier here: every thread owns the same positions p in all per-position loops, and the A values (scaled by other threads
+            // above) are fenced from the next pass's scans by the two barriers of the block reduction
         }
+        __syncthreads();
         const double cinv = 1.0 / c;
         // bounds scaled by E; constraint classes (set_rho_vec of OSQP)
         for (int p = tid; p < q.Nk; p += ADMM_THREADS)
