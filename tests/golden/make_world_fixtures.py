@@ -11,7 +11,7 @@ import yaml
 
 SRC = "/root/reference/test/path"
 DST = os.path.dirname(os.path.abspath(__file__))
-NAMES = ["skidpadoval", "vail", "westpaddock", "curvy"]
+NAMES = ["skidpadoval", "vail", "westpaddock", "curvy", "EastPaddock", "flidpadoval", "newskidpadoval", "paddockoval"]
 
 for name in NAMES:
     with open(os.path.join(SRC, name + ".world")) as f:

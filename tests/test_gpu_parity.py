@@ -572,3 +572,39 @@ def test_from_autobox_callback_parity(p):
     assert np.array_equal(fin, np.isfinite(o1[:, :3]).all(axis=1)) and fin.sum() >= B - 1
     assert np.max(np.abs(o1[fin, :3] - o3[fin]) / U_RANGE) < 1e-9
     g.close(); g2.close(); g3.close()
+
+
+@pytest.mark.parametrize("kind,Ns,Nl", [(0, 10, 20), (0, 5, 10), (1, 10, 20)])
+def test_all_world_fixtures_closed_loop_parity(p, kind, Ns, Nl):
+    """configs[0], secondary points: all eight test/path/*.world fixtures in one batch (one vehicle per fixture, started on
+    the path a quarter of the way in at the desired speed), default and deployed horizon, coupled and decoupled: closed-loop controls,
+    iteration counts and final states against the CPU oracle."""
+    golden = os.path.join(ROOT, "tests", "golden")
+    names = sorted(f[6:-4] for f in os.listdir(golden) if f.startswith("world_") and f.endswith(".npz"))
+    ws = [np.load(os.path.join(golden, f"world_{n}.npz")) for n in names]
+    tubes = [p.TrajectoryTube.from_path(w) for w in ws]
+    trajs = {k: np.stack([getattr(t, k) for t in tubes]) for k in o.TRAJ_FIELDS}
+    B = len(names)
+    tid = np.arange(B, dtype=np.int32)
+    k0 = 250
+    state = np.array([[w["posE_m"][k0], w["posN_m"][k0], w["psi_rad"][k0], max(float(w["UxDes_mps"][k0]), 3.0), 0.0, 0.0] for w in ws])
+    control = np.zeros((B, 3))
+    t0 = np.array([t.t[k0] for t in tubes])
+    other = np.tile(FAR, (B, 1))
+    cls = p.BatchedCoupledTrajectoryTrackingMPC if kind == 0 else p.BatchedDecoupledTrajectoryTrackingMPC
+    g = cls(p.X1(), trajs, B, trajectory_index=tid, N_short=Ns, N_long=Nl)
+    g.set_state(state, control, other)
+    ms = oracles_for(kind, trajs, tid, state, control, other, N_short=Ns, N_long=Nl)
+    for k in range(25):
+        ug = g.step(t0 + 0.01 * k)
+        g.rollout(0.01)
+        it = g.stats()["iters"]
+        for i, m in enumerate(ms):
+            m.simulate_step(t0[i] + 0.01 * k)
+            qo, uo = m.get_state()
+            assert it[i] == m.stats()["iter"], (names[i], k)
+            assert np.max(np.abs(ug[i] - uo) / U_RANGE) < 1e-4, (names[i], k)
+    qg, _ = g.get_state()
+    for i, m in enumerate(ms):
+        assert np.allclose(qg[i], m.get_state()[0], rtol=1e-8, atol=1e-7), names[i]
+    g.close()
