@@ -219,6 +219,10 @@ function step!(mpc::BatchedTrajectoryTrackingMPC, t0::Vector{Float64}, out::Matr
     out
 end
 
+"one iteration of the simulate loop (src/model_predictive_control.jl:87-98) on device-resident data: d_t0 / d_out are device pointers (CuPtr); the plant step runs beside the QP solve"
+step_rollout_device!(mpc::BatchedTrajectoryTrackingMPC, d_t0::Ptr{Float64}, d_out::Ptr{Float64}, dt::Float64=0.01) =
+    check(ccall((:pgn_step_rollout_device, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), mpc.handle, d_t0, d_out, dt))
+
 "simulate(mpc, q0, u0, dt) (src/model_predictive_control.jl:80-100) for the whole batch, entirely on the device; returns the final (state, control)."
 function simulate(mpc::BatchedTrajectoryTrackingMPC, q0::Matrix{Float64}, u0::Matrix{Float64}; dt=0.01, t0=zeros(mpc.B), n_steps::Integer)
     set_state!(mpc; current_state=q0, current_control=u0)
