@@ -106,10 +106,10 @@ PGN_HD double inv_fiala(double Fy, double Ca, double Fy_max, bool corrected) {
     return corrected ? r * (3 * Fy_max / Ca) : r;
 }
 // lateral_tire_forces (vehicle_dynamics.jl:64-76): 3 fixed-point iterations of longitudinal weight transfer, then the rear axle
+// The tire model only ever uses tan(alpha) (vehicle_dynamics.jl:35-47), so the core takes the tangents of the slip angles.
 template <class T>
-PGN_HD void lateral_tire_forces(const VehParams& B, const T& af, const T& ar, const T& Fxf, const T& Fxr, const T& sd, const T& cd,
-                                T& Fyf, T& Fyr, int num_iters = 3) {
-    T tanf = tan_(af), tanr = tan_(ar);
+PGN_HD void lateral_tire_forces_tan(const VehParams& B, const T& tanf, const T& tanr, const T& Fxf, const T& Fxr, const T& sd, const T& cd,
+                                    T& Fyf, T& Fyr, int num_iters = 3) {
     Fyf = T(0.0);
     T Fx = Fxf * cd - Fyf * sd + Fxr;
     for (int i = 0; i < num_iters; i++) {
@@ -119,6 +119,11 @@ PGN_HD void lateral_tire_forces(const VehParams& B, const T& af, const T& ar, co
     }
     T Fzr = (B.m * B.G * B.a + B.h * Fx) / B.L;
     Fyr = fiala_tan(tanr, B.Car, B.mu, Fxr, Fzr);
+}
+template <class T>
+PGN_HD void lateral_tire_forces(const VehParams& B, const T& af, const T& ar, const T& Fxf, const T& Fxr, const T& sd, const T& cd,
+                                T& Fyf, T& Fyr, int num_iters = 3) {
+    lateral_tire_forces_tan(B, tan_(af), tan_(ar), Fxf, Fxr, sd, cd, Fyf, Fyr, num_iters);
 }
 
 #ifdef __CUDACC__
@@ -168,10 +173,16 @@ PGN_HD void vehicle_model(const VehParams& P, const T* q, const T& delta_in, con
     else             { Fxf = Fx * P.fwb_frac; Fxr = Fx * P.rwb_frac; }
     T sd, cd;
     sincos_(d, sd, cd);
-    T af = atan2_(Uy + P.a * r, Ux) - d;
-    T ar = atan2_(Uy - P.b * r, Ux);
+    // slip angles alpha_f = atan(Uy + a r, Ux) - delta, alpha_r = atan(Uy - b r, Ux) (vehicle_dynamics.jl:118-119) enter the tire model only
+    // through their tangents: tan(alpha_r) = (Uy - b r) / Ux and tan(alpha_f) = (t - tan(delta)) / (1 + t tan(delta)), t = (Uy + a r) / Ux.
+    // Same function (and, through the dual numbers, same derivative) as tan(atan2(.) - delta) without the two atan2 and two tan
+    // evaluations, which were 47 % of the linearisation kernel's samples (profiles/r1b_linearize_ncu_full.md).
+    T iUx = 1.0 / Ux;
+    T tf = (Uy + P.a * r) * iUx, td = sd / cd;
+    T tanf = (tf - td) / (1.0 + tf * td);
+    T tanr = (Uy - P.b * r) * iUx;
     T Fyf, Fyr;
-    lateral_tire_forces(P, af, ar, Fxf, Fxr, sd, cd, Fyf, Fyr);
+    lateral_tire_forces_tan(P, tanf, tanr, Fxf, Fxr, sd, cd, Fyf, Fyr);
     T Fyf_t = Fyf * cd + Fxf * sd;
     T dUy = (Fyf_t + Fyr) / P.m - r * Ux;
     T dr = (P.a * Fyf_t - P.b * Fyr) / P.Izz;
