@@ -184,6 +184,34 @@ __device__ __forceinline__ double gather_task(const Smem& s, const uint2 d, cons
     return group_sum_sh(acc0 + acc1, sh);
 }
 
+// Same with the first four entries and the row's target already in registers (loaded before the previous level's barrier).
+__device__ __forceinline__ double gather_task_pre(const Smem& s, const uint2 d, const unsigned long long* __restrict__ ents, int lane, unsigned long long pad,
+                                                  unsigned long long p0, unsigned long long p1, unsigned long long p2, unsigned long long p3) {
+    const int K = d.y & 0xff, sh = (d.y >> 16) & 0xff;
+    const unsigned long long* e = ents + ((size_t)(d.x & 0xffff) << 5) + lane + 128;
+    p0 = K > 0 ? p0 : pad; p1 = K > 1 ? p1 : pad; p2 = K > 2 ? p2 : pad; p3 = K > 3 ? p3 : pad;
+    double acc0, acc1;
+    {
+        const double t0 = GATHER_TERM(p0), t1 = GATHER_TERM(p1), t2 = GATHER_TERM(p2), t3 = GATHER_TERM(p3);
+        acc0 = t0 + t2; acc1 = t1 + t3;
+    }
+    int k = 4;
+#pragma unroll 1
+    for (; k + 4 <= K; k += 4, e += 128) {
+        const unsigned long long e0 = __ldg(e), e1 = __ldg(e + 32), e2 = __ldg(e + 64), e3 = __ldg(e + 96);
+        const double t0 = GATHER_TERM(e0), t1 = GATHER_TERM(e1), t2 = GATHER_TERM(e2), t3 = GATHER_TERM(e3);
+        acc0 += t0; acc1 += t1; acc0 += t2; acc1 += t3;
+    }
+    if (k < K) {      // warp-uniform
+        const int rem = K - k;
+        unsigned long long e0 = __ldg(e), e1 = __ldg(e + 32), e2 = __ldg(e + 64);
+        e1 = rem > 1 ? e1 : pad; e2 = rem > 2 ? e2 : pad;
+        const double t0 = GATHER_TERM(e0), t1 = GATHER_TERM(e1), t2 = GATHER_TERM(e2);
+        acc0 += t0; acc1 += t1; acc0 += t2;
+    }
+    return group_sum_sh(acc0 + acc1, sh);
+}
+
 // numeric LDL' of K = [P + sigma I, A'; A, -1/rho] (position space) in the unscaled form W = L D with the static gather programs:
 //   d_j = K_jj - sum_k W_jk^2 / d_k,     W_ij = K_ij - sum_k W_ik W_jk / d_k        (one pass and one barrier per level)
 // then the explicit inverses of the level ranges (in place) and of the dense tail.
@@ -213,9 +241,40 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
     for (int e = tid; e < q.nnzA; e += ADMM_THREADS) s.Lval[__ldg(q.a_slot + e)] = s.Aval[e];
     __syncthreads();
     FAC_T(110);
+    // The static program of a level (task descriptor, the row's target, the first four entries: all in L2, ~300 cycles away) does not
+    // depend on the numbers: every warp fetches its first task of level l+1 before the barrier of level l, so the round trip overlaps
+    // the barrier wait instead of starting the level.
+    uint2 dn = make_uint2(0, 0);
+    unsigned long long pe0 = 0, pe1 = 0, pe2 = 0, pe3 = 0;
+    uint32_t tgn = 0;
+    bool have = false;
+#define FAC_PREFETCH(lvl)                                                                                   \
+    do {                                                                                                    \
+        const int t__ = s.fac_lvl[lvl] + warp;                                                              \
+        have = t__ < (int)s.fac_lvl[(lvl) + 1];                                                             \
+        if (have) {                                                                                         \
+            dn = s.fac_task[t__];                                                                           \
+            const unsigned long long* e__ = q.fac_ent + ((size_t)(dn.x & 0xffff) << 5) + lane;              \
+            pe0 = __ldg(e__); pe1 = __ldg(e__ + 32); pe2 = __ldg(e__ + 64); pe3 = __ldg(e__ + 96);          \
+            const int sh__ = (dn.y >> 16) & 0xff, rr__ = lane >> sh__;                                      \
+            tgn = __ldg(q.fac_tgt + (dn.x >> 16) + min(rr__, (int)((dn.y >> 8) & 0xff) - 1));               \
+        }                                                                                                   \
+    } while (0)
+    if (q.n_fac_lvl > 0) FAC_PREFETCH(0);
     for (int l = 0; l < q.n_fac_lvl; l++) {
         const int t1 = s.fac_lvl[l + 1];
-        for (int t = s.fac_lvl[l] + warp; t < t1; t += NW) {
+        if (have) {
+            const uint2 d = dn;
+            const int sh = (d.y >> 16) & 0xff, rr = lane >> sh;
+            const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
+            const uint32_t tg = tgn;
+            const double acc = gather_task_pre(s, d, q.fac_ent, lane, pad, pe0, pe1, pe2, pe3);
+            if (writer) {
+                if (tg & FAC_TGT_PIVOT) { const int j = tg & 0x7fffffff; s.Dinv[j] = 1.0 / (s.Dinv[j] - acc); }
+                else s.Lval[tg] -= acc;
+            }
+        }
+        for (int t = s.fac_lvl[l] + warp + NW; t < t1; t += NW) {
             const uint2 d = s.fac_task[t];
             const int sh = (d.y >> 16) & 0xff, rr = lane >> sh;
             const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
@@ -227,9 +286,11 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
                 else s.Lval[tg] -= acc;
             }
         }
+        if (l + 1 < q.n_fac_lvl) FAC_PREFETCH(l + 1); else have = false;
         __syncthreads();
         FAC_T(120 + (l < 100 ? l : 99));
     }
+#undef FAC_PREFETCH
     // level ranges: replace the in-range block of W by the explicit inverse M of the unit lower block L[range, range], level by level:
     //   M_ij = -(W_ij / d_j + sum_{j<k<i} W_ik / d_k M_kj)     (targets of one level are computed into registers before any is written)
     for (int l = 0; l < q.n_inv_levels; l++) {
