@@ -109,6 +109,12 @@ PGN_API int pgn_reset_solver(pgn_handle* h, const uint8_t* mask /*[B]*/);
  *                          re-initialised (Parametron.initialize!) and mpc.solved = false (cold node generation next step). */
 PGN_API int pgn_set_guards(pgn_handle* h, int32_t nan_fallback, double pause_below_speed);
 
+/* path_coordinates (trajectories.jl:71-94) scans every segment of the trajectory for the closest one.  half_width > 0 restricts the scan of
+ * a vehicle to the segments within half_width of the one found on its previous step (same result whenever the true closest segment lies
+ * inside the window — always for continuous motion along a path that does not pass close to itself); the first step after pgn_set_state
+ * with a new state, pgn_assign_trajectories, pgn_set_trajectories or this call scans everything.  0 (default) = the reference's full scan. */
+PGN_API int pgn_set_path_search_window(pgn_handle* h, int32_t half_width);
+
 /* --- the 5-call step API (model_predictive_control.jl:70-78) ------------------------------------------------------ */
 PGN_API int pgn_compute_time_steps(pgn_handle* h, const double* t0 /*[B]*/);           /* compute_time_steps!(mpc, t0) */
 PGN_API int pgn_compute_linearization_nodes(pgn_handle* h);                            /* compute_linearization_nodes!(mpc) */

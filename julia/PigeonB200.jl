@@ -185,6 +185,8 @@ function from_autobox!(mpc, current_state::Matrix{Float64}, current_control::Mat
                                              mpc.handle, current_state, current_control, po, stamp, out))
     out
 end
+# windowed closest-segment search of path_coordinates (src/trajectories.jl:71-80); 0 = full scan
+set_path_search_window!(mpc, half_width::Integer) = check(ccall((:pgn_set_path_search_window, libpigeon), Cint, (Ptr{Cvoid}, Int32), mpc.handle, Int32(half_width)))
 # use_HJI_policy[] of the callback (src/ros_integration.jl:47,115-118): V <= HJI_ϵ => BicycleControl(LP, optimal_control(...))
 set_hji_policy!(mpc, on::Bool) = check(ccall((:pgn_set_hji_policy, libpigeon), Cint, (Ptr{Cvoid}, Int32), mpc.handle, Int32(on)))
 "(V, ∇V) of the last step's HJIRelativeState(current_state, other_car_state) (src/ros_integration.jl:57-58); ∇V is 7×B"

@@ -273,13 +273,14 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_se, 2 * B); AL(d_tskip, B);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se, 2 * B); AL(d_tskip, B);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
     CK(cudaMemset(h->d_sol_x, 0, B * t.n * 8)); CK(cudaMemset(h->d_sol_y, 0, B * t.m * 8));
     CK(cudaMemset(h->d_cycles, 0, 4096)); CK(cudaMemset(h->d_skip, 0, B)); CK(cudaMemset(h->d_cold, 0, B));
     h->guard_nan = 0; h->guard_pause = 0.0; h->hji_policy = 0;
+    h->path_window = 0; CK(cudaMemset(h->d_last_seg, 0xff, B * 4));
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
     {
@@ -376,6 +377,7 @@ int pgn_set_trajectories(pgn_handle* h, int32_t n_traj, int32_t n_nodes, const d
     }
     h->traj.n_traj = n_traj; h->traj.n_nodes = n_nodes;
     h->have_traj = true;
+    CK(cudaMemset(h->d_last_seg, 0xff, (size_t)h->B * 4));
     CK(cudaMemset(h->d_traj_id, 0, (size_t)h->B * 4));
     return PGN_OK;
 }
@@ -383,6 +385,7 @@ int pgn_assign_trajectories(pgn_handle* h, const int32_t* traj_id) {
     REQUIRE(h && traj_id, "NULL argument");
     for (int v = 0; v < h->B; v++) REQUIRE(traj_id[v] >= 0 && traj_id[v] < h->traj.n_traj, "trajectory id out of range");
     CK(cudaMemcpy(h->d_traj_id, traj_id, (size_t)h->B * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->d_last_seg, 0xff, (size_t)h->B * 4));
     return PGN_OK;
 }
 int pgn_set_hji_cache(pgn_handle* h, const int32_t dims[7], const float* knots, const float* V, const float* gradV) {
@@ -393,6 +396,7 @@ int pgn_set_hji_cache(pgn_handle* h, const int32_t dims[7], const float* knots, 
 int pgn_set_state(pgn_handle* h, const double* q, const double* u, const double* other, const double* toff) {
     REQUIRE(h, "NULL handle");
     int rc;
+    if (q) CK(cudaMemsetAsync(h->d_last_seg, 0xff, (size_t)h->B * 4, h->stream));      // a new measured state may be anywhere on the path
     if (q && (rc = upload_aos(h, q, h->d_state, 6))) return rc;
     if (u && (rc = upload_aos(h, u, h->d_control, 3))) return rc;
     if (other && (rc = upload_aos(h, other, h->d_other, 4))) return rc;
@@ -676,6 +680,14 @@ int pgn_hji_lookup(pgn_handle* h, int32_t M, const double* x, double* V, double*
     cudaFree(dx); cudaFree(dV); cudaFree(dg);
     if (e != cudaSuccess) return set_err(PGN_ECUDA, "hji lookup failed: %s", cudaGetErrorString(e));
     for (int i = 0; i < M; i++) for (int d = 0; d < 7; d++) gradV[(size_t)i * 7 + d] = gt[(size_t)d * M + i];
+    return PGN_OK;
+}
+int pgn_set_path_search_window(pgn_handle* h, int32_t half_width) {
+    REQUIRE(h, "NULL handle");
+    REQUIRE(half_width >= 0, "half_width must be >= 0");
+    h->epoch++;
+    h->path_window = half_width;
+    CK(cudaMemsetAsync(h->d_last_seg, 0xff, (size_t)h->B * 4, h->stream));
     return PGN_OK;
 }
 int pgn_set_hji_policy(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->epoch++; h->hji_policy = on != 0; return PGN_OK; }

@@ -101,6 +101,7 @@ struct pgn_handle {
     int hji_policy;                                      // use_HJI_policy[] (ros_integration.jl:47): V <= HJI_eps => optimal_control replaces the QP control
     uint8_t *d_skip, *d_cold;                            // guards: vehicle paused this step / ADMM iterates to be re-initialised
     int guard_nan; double guard_pause;
+    int path_window; int32_t* d_last_seg;                // windowed closest-segment search: half-width in segments (0 = full scan), previous segment per vehicle (-1 = none)
     // callback entry point (pgn_from_autobox): packed message buffer (pinned host + device), time-interval flags, path coordinates,
     // and the CUDA graph of the whole call (H2D copy, unpack, the five step stages, pack, D2H copy), re-captured when a setter bumps `epoch`
     // plant rollout beside the ADMM launch (pgn_step_rollout_device / pgn_simulate): shadow state, side stream, fork / join events

@@ -73,12 +73,15 @@ __device__ __forceinline__ TrajNode traj_at_s(const TrajView& tv, int base, doub
 // Deviation: the sqrt argument is floored at 0 (the reference raises a DomainError on negative round-off).
 // The scan is spread over the 32 lanes of a warp (segment i on lane i mod 32), followed by a butterfly arg-min whose tie-break keeps the
 // smallest segment index, i.e. exactly the serial first-minimum-wins result.  Every lane returns (s, e).
-__device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int base, double x, double y, int lane, double& s_out, double& e_out, double* t_out = nullptr) {
+__device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int base, double x, double y, int lane, double& s_out, double& e_out, double* t_out = nullptr,
+                                                      int seg_lo = 0, int seg_hi = 0x7fffffff, int* seg_out = nullptr) {
     const int nn = tv.n_nodes;
     const double *E = tv.f[4] + base, *Nn = tv.f[5] + base;
     double d2min = INFINITY;
     int imin = 0x7fffffff;
-    for (int i = lane; i < nn - 1; i += 32) {
+    // [seg_lo, seg_hi): all segments by default; a window around the previous step's segment when the caller asked for one
+    const int i_end = min(nn - 1, seg_hi);
+    for (int i = max(seg_lo, 0) + lane; i < i_end; i += 32) {
         const double ax = __ldg(E + i), ay = __ldg(Nn + i);
         const double bx = __ldg(E + i + 1), by = __ldg(Nn + i + 1);
         const double vx = bx - ax, vy = by - ay;
@@ -94,7 +97,8 @@ __device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int ba
         const int io = __shfl_xor_sync(0xffffffffu, imin, o);
         if (d2o < d2min || (d2o == d2min && io < imin)) { d2min = d2o; imin = io; }
     }
-    const int i = imin == 0x7fffffff ? 0 : imin;      // all distances NaN: the serial scan keeps segment 0
+    const int i = imin == 0x7fffffff ? max(seg_lo, 0) : imin;      // all distances NaN: the serial scan keeps its first segment
+    if (seg_out) *seg_out = i;
     const double ex = __ldg(E + i), ey = __ldg(Nn + i);
     const double vx = __ldg(E + i + 1) - ex, vy = __ldg(Nn + i + 1) - ey;
     const double wx = x - ex, wy = y - ey;
@@ -137,6 +141,7 @@ struct NodeArgs {
     const double *ts, *dt, *prev_ts, *sol_x;
     double *qs, *us, *ps;
     uint8_t* skip; double pause_below_speed;      // guard of src/ros_integration.jl:84-87
+    int window; int32_t* last_seg;                // optional windowed closest-segment search (pgn_set_path_search_window)
     const uint8_t* tskip;                         // callback entry point only: time outside the trajectory interval (src/ros_integration.jl:77-80)
 };
 
@@ -163,7 +168,16 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
     double* ps = a.ps + (size_t)v * N * 4;
 
     double s0, e0;
-    path_coordinates_warp(a.tv, base, E0, N0, lane, s0, e0);
+    {
+        // with a window w > 0 only the segments within w of the previous step's closest segment are scanned (same result
+        // as the full scan of trajectories.jl:71-80 as long as the true closest segment lies in the window); a vehicle without a valid
+        // previous segment (first step, after pgn_set_state / pgn_assign_trajectories / pgn_reset_solved) scans everything
+        const int last = a.window > 0 ? a.last_seg[v] : -1;
+        int seg;
+        if (last >= 0) path_coordinates_warp(a.tv, base, E0, N0, lane, s0, e0, nullptr, last - a.window, last + a.window + 1, &seg);
+        else path_coordinates_warp(a.tv, base, E0, N0, lane, s0, e0, nullptr, 0, 0x7fffffff, &seg);
+        if (lane == 0) a.last_seg[v] = seg;
+    }
 
     if (a.kind == PGN_COUPLED) {
         TrajNode tj = traj_at_s(a.tv, base, s0);
@@ -337,7 +351,8 @@ __global__ void __launch_bounds__(128) k_rollout(int B, VehParams P, double dt, 
 // time in path-tracking mode, :72-75), flag vehicles whose time lies outside the trajectory (:77-80) and keep (s, e) for the reply (:110).
 __global__ void __launch_bounds__(128) k_callback_in(int B, TrajView tv, const int32_t* __restrict__ traj_id, const double* __restrict__ io,
                                                      const double* __restrict__ toff, double* __restrict__ state, double* __restrict__ control,
-                                                     double* __restrict__ other, double* __restrict__ t0, uint8_t* __restrict__ tskip, double* __restrict__ se) {
+                                                     double* __restrict__ other, double* __restrict__ t0, uint8_t* __restrict__ tskip, double* __restrict__ se,
+                                                     int window, int32_t* __restrict__ last_seg) {
     const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (v >= B) return;
     const double* q = io + 1 + (size_t)v * 6;
@@ -348,7 +363,13 @@ __global__ void __launch_bounds__(128) k_callback_in(int B, TrajView tv, const i
     if (lane < 3) control[(size_t)lane * B + v] = u[lane];
     if (io[0] != 0.0 && lane < 4) other[(size_t)lane * B + v] = o[lane];
     double s, e, tp;
-    path_coordinates_warp(tv, traj_id[v] * tv.n_nodes, q[0], q[1], lane, s, e, &tp);
+    {   // a stream of callbacks follows one vehicle: the window (if any) is centred on the previous callback's segment
+        const int last = window > 0 ? last_seg[v] : -1;
+        int seg;
+        if (last >= 0) path_coordinates_warp(tv, traj_id[v] * tv.n_nodes, q[0], q[1], lane, s, e, &tp, last - window, last + window + 1, &seg);
+        else path_coordinates_warp(tv, traj_id[v] * tv.n_nodes, q[0], q[1], lane, s, e, &tp, 0, 0x7fffffff, &seg);
+        if (lane == 0) last_seg[v] = seg;
+    }
     if (lane == 0) {
         const double off = toff[v];
         double t = tp;
@@ -403,11 +424,12 @@ void launch_nodes(pgn_handle* h) {
     a.ts = h->d_ts; a.dt = h->d_dt; a.prev_ts = h->d_prev_ts; a.sol_x = h->d_sol_x;
     a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps;
     a.skip = h->d_skip; a.pause_below_speed = h->guard_pause; a.tskip = h->in_callback ? h->d_tskip : nullptr;
+    a.window = h->path_window; a.last_seg = h->d_last_seg;
     k_nodes<<<(h->B + 3) / 4, 128, 0, h->stream>>>(a);
     h->launches++;
 }
 void launch_callback_in(pgn_handle* h) {
-    k_callback_in<<<(h->B + 3) / 4, 128, 0, h->stream>>>(h->B, h->traj, h->d_traj_id, h->d_io, h->d_toff, h->d_state, h->d_control, h->d_other, h->d_t0, h->d_tskip, h->d_se);
+    k_callback_in<<<(h->B + 3) / 4, 128, 0, h->stream>>>(h->B, h->traj, h->d_traj_id, h->d_io, h->d_toff, h->d_state, h->d_control, h->d_other, h->d_t0, h->d_tskip, h->d_se, h->path_window, h->d_last_seg);
     h->launches++;
 }
 void launch_callback_out(pgn_handle* h) {

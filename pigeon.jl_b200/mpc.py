@@ -330,6 +330,10 @@ class BatchedTrajectoryTrackingMPC:
         check(self._lib.pgn_hji_optimal_control(self._h, x.shape[0], dptr(x), dptr(g), dptr(out)))
         return out
 
+    def set_path_search_window(self, half_width):
+        """Windowed closest-segment search of path_coordinates (src/trajectories.jl:71-80); 0 = the reference's full scan."""
+        check(self._lib.pgn_set_path_search_window(self._h, int(half_width)))
+
     def set_hji_policy(self, on):
         """use_HJI_policy[] of the callback (src/ros_integration.jl:47,115-118): V <= HJI_eps => the "hammer" control."""
         check(self._lib.pgn_set_hji_policy(self._h, int(bool(on))))

@@ -608,3 +608,32 @@ def test_all_world_fixtures_closed_loop_parity(p, kind, Ns, Nl):
     for i, m in enumerate(ms):
         assert np.allclose(qg[i], m.get_state()[0], rtol=1e-8, atol=1e-7), names[i]
     g.close()
+
+
+def test_windowed_path_search_equals_full_scan(p):
+    """pgn_set_path_search_window: on a closed loop the windowed closest-segment search gives bit-identical nodes, controls and
+    states to the reference's full scan; a vehicle moved elsewhere through set_state falls back to the full scan."""
+    B = 96
+    trajs = p.synthetic.synthetic_trajectories(n_traj=4, n_nodes=600)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    ga = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    gb = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+    gb.set_path_search_window(12)
+    for g in (ga, gb):
+        g.set_state(state, control, other)
+        g.simulate_device(t0, 0.01, 30)
+    qa, ua = ga.get_state(); qb, ub = gb.get_state()
+    assert np.array_equal(qa, qb, equal_nan=True) and np.array_equal(ua, ub, equal_nan=True)      # (an infeasible QP gives NaN, unguarded here)
+    assert np.isfinite(qa).all(axis=1).mean() > 0.95
+    assert np.array_equal(ga.nodes()[0], gb.nodes()[0], equal_nan=True) and np.array_equal(ga.stats()["iters"], gb.stats()["iters"])
+    # callbacks: consecutive messages reuse the window; results equal the full scan
+    oa = ga.from_autobox(qa, ua, 0.0); ob = gb.from_autobox(qb, ub, 0.0)
+    oa2 = ga.from_autobox(qa, oa[:, :3], 0.0); ob2 = gb.from_autobox(qb, ob[:, :3], 0.0)
+    assert np.array_equal(oa, ob, equal_nan=True) and np.array_equal(oa2, ob2, equal_nan=True)
+    # teleport half the vehicles to their initial states: set_state invalidates the window
+    q2 = qb.copy(); q2[::2] = state[::2]
+    for g in (ga, gb):
+        g.set_state(q2, ub, other)
+    assert np.array_equal(ga.step(t0), gb.step(t0), equal_nan=True)
+    ga.close(); gb.close()
