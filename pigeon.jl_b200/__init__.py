@@ -8,3 +8,4 @@ from .mpc import (BatchedCoupledTrajectoryTrackingMPC, BatchedDecoupledTrajector
                   CoupledControlParams, DecoupledControlParams, HJICache, TrajectoryTube, X1, compute_linearization_nodes, compute_time_steps,
                   get_next_control, placeholder_HJICache, simulate, solve, straight_trajectory, update_QP)
 from .world import read_world, trajectory_from_world, write_world  # noqa: F401
+from .hji_io import load_hji_cache, save_hji_cache  # noqa: F401

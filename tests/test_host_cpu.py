@@ -192,3 +192,25 @@ def test_world_reader_round_trip_and_fixtures(p, tmp_path):
     p.write_world(bad, w)
     with pytest.raises(ValueError):
         p.read_world(bad)
+
+
+def test_hji_cache_file_round_trip(p, tmp_path):
+    """The flat PGNHJI1 file (julia/export_hji_cache.jl writes it from the reference's JLD2 objects) round-trips an HJICache bit for bit, in the
+    memory order pgn_set_hji_cache expects, and rejects truncated files."""
+    knots, V, gV = p.synthetic.analytic_hji_grid((5, 4, 5, 4, 3, 4, 3))
+    c = p.HJICache(knots, V, gV)
+    f = str(tmp_path / "cache.pgnhji")
+    p.save_hji_cache(f, c)
+    assert os.path.getsize(f) == 8 + 28 + 4 * (sum(len(k) for k in knots) + V.size + gV.size)
+    r = p.load_hji_cache(f)
+    assert all(np.array_equal(a, b) for a, b in zip(r.grid_knots, c.grid_knots))
+    assert np.array_equal(r.V, c.V) and np.array_equal(r.gradV, c.gradV)
+    raw = open(f, "rb").read()
+    # Julia memory order: V[i1, ...] with dimension 1 fastest; gradient components fastest
+    v0 = np.frombuffer(raw[36 + 4 * sum(len(k) for k in knots):][:8], dtype="<f4")
+    assert v0[0] == V[0, 0, 0, 0, 0, 0, 0] and v0[1] == V[1, 0, 0, 0, 0, 0, 0]
+    g0 = np.frombuffer(raw[36 + 4 * (sum(len(k) for k in knots) + V.size):][:32], dtype="<f4")
+    assert np.array_equal(g0[:7], gV[:, 0, 0, 0, 0, 0, 0, 0]) and g0[7] == gV[0, 1, 0, 0, 0, 0, 0, 0]
+    open(f, "wb").write(raw[:-5])
+    with pytest.raises(ValueError):
+        p.load_hji_cache(f)
