@@ -18,7 +18,8 @@ module PigeonB200
 export X1, CoupledControlParams, DecoupledControlParams, TrajectoryTube, straight_trajectory, HJICache, placeholder_HJICache,
        BatchedTrajectoryTrackingMPC, BatchedCoupledTrajectoryTrackingMPC, BatchedDecoupledTrajectoryTrackingMPC,
        compute_time_steps!, compute_linearization_nodes!, update_QP!, solve!, get_next_control, step!, simulate,
-       set_state!, set_HJI_cache!, reset_solved!, reset_solver!, solver_stats
+       set_state!, set_HJI_cache!, reset_solved!, reset_solver!, solver_stats, set_guards!, from_autobox!, set_hji_policy!, hji_values,
+       optimal_control, set_path_search_window!, step_rollout_device!
 
 const libpigeon = get(ENV, "PGN_LIB_PATH", joinpath(@__DIR__, "..", "pigeon.jl_b200", "libpigeon_b200.so"))
 
