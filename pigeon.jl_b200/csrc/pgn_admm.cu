@@ -184,30 +184,38 @@ __device__ __forceinline__ double gather_task(const Smem& s, const uint2 d, cons
     return group_sum_sh(acc0 + acc1, sh);
 }
 
-// Same with the first four entries and the row's target already in registers (loaded before the previous level's barrier).
+// Same with the first four entries and the row's target already in registers (loaded before the previous level's barrier).  The second
+// and third batch (K <= 12 covers every task but the Schur gather of the dense tail) are requested together before the first is
+// consumed, so a task pays at most one exposed L2 round trip; the branches are warp-uniform.
+#define GATHER_BATCH(b0, b1, b2, b3, kbase)                                                                            \
+    do {                                                                                                              \
+        const unsigned long long q0__ = (kbase) < K ? (b0) : pad, q1__ = (kbase) + 1 < K ? (b1) : pad;                  \
+        const unsigned long long q2__ = (kbase) + 2 < K ? (b2) : pad, q3__ = (kbase) + 3 < K ? (b3) : pad;              \
+        const double t0__ = GATHER_TERM(q0__), t1__ = GATHER_TERM(q1__), t2__ = GATHER_TERM(q2__), t3__ = GATHER_TERM(q3__); \
+        acc0 += t0__; acc1 += t1__; acc0 += t2__; acc1 += t3__;                                                         \
+    } while (0)
 __device__ __forceinline__ double gather_task_pre(const Smem& s, const uint2 d, const unsigned long long* __restrict__ ents, int lane, unsigned long long pad,
                                                   unsigned long long p0, unsigned long long p1, unsigned long long p2, unsigned long long p3) {
     const int K = d.y & 0xff, sh = (d.y >> 16) & 0xff;
     const unsigned long long* e = ents + ((size_t)(d.x & 0xffff) << 5) + lane + 128;
-    p0 = K > 0 ? p0 : pad; p1 = K > 1 ? p1 : pad; p2 = K > 2 ? p2 : pad; p3 = K > 3 ? p3 : pad;
-    double acc0, acc1;
-    {
-        const double t0 = GATHER_TERM(p0), t1 = GATHER_TERM(p1), t2 = GATHER_TERM(p2), t3 = GATHER_TERM(p3);
-        acc0 = t0 + t2; acc1 = t1 + t3;
-    }
-    int k = 4;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (K > 4) {
+        const unsigned long long a0 = __ldg(e), a1 = __ldg(e + 32), a2 = __ldg(e + 64), a3 = __ldg(e + 96);
+        unsigned long long b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        if (K > 8) { b0 = __ldg(e + 128); b1 = __ldg(e + 160); b2 = __ldg(e + 192); b3 = __ldg(e + 224); }
+        GATHER_BATCH(p0, p1, p2, p3, 0);
+        GATHER_BATCH(a0, a1, a2, a3, 4);
+        if (K > 8) {
+            GATHER_BATCH(b0, b1, b2, b3, 8);
+            e += 256;
 #pragma unroll 1
-    for (; k + 4 <= K; k += 4, e += 128) {
-        const unsigned long long e0 = __ldg(e), e1 = __ldg(e + 32), e2 = __ldg(e + 64), e3 = __ldg(e + 96);
-        const double t0 = GATHER_TERM(e0), t1 = GATHER_TERM(e1), t2 = GATHER_TERM(e2), t3 = GATHER_TERM(e3);
-        acc0 += t0; acc1 += t1; acc0 += t2; acc1 += t3;
-    }
-    if (k < K) {      // warp-uniform
-        const int rem = K - k;
-        unsigned long long e0 = __ldg(e), e1 = __ldg(e + 32), e2 = __ldg(e + 64);
-        e1 = rem > 1 ? e1 : pad; e2 = rem > 2 ? e2 : pad;
-        const double t0 = GATHER_TERM(e0), t1 = GATHER_TERM(e1), t2 = GATHER_TERM(e2);
-        acc0 += t0; acc1 += t1; acc0 += t2;
+            for (int k = 12; k < K; k += 4, e += 128) {
+                const unsigned long long c0 = __ldg(e), c1 = __ldg(e + 32), c2 = __ldg(e + 64), c3 = __ldg(e + 96);
+                GATHER_BATCH(c0, c1, c2, c3, k);
+            }
+        }
+    } else {
+        GATHER_BATCH(p0, p1, p2, p3, 0);
     }
     return group_sum_sh(acc0 + acc1, sh);
 }

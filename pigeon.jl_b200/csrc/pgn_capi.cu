@@ -248,7 +248,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
         if ((rc_ = dev_upload(h, pack(t.inv_task), &q.inv_task))) return bail(rc_);
         std::vector<unsigned long long> fe(t.fac_ent.begin(), t.fac_ent.end()), ie(t.inv_ent.begin(), t.inv_ent.end());
         const unsigned long long padent = (unsigned long long)t.zslot | ((unsigned long long)t.zslot << 16);
-        fe.resize(fe.size() + 128, padent); ie.resize(ie.size() + 128, padent);      // the partial last batch of a task reads up to 96 slots past it
+        fe.resize(fe.size() + 512, padent); ie.resize(ie.size() + 512, padent);      // masked batches read whole groups of four slot rows past a task's end
         if ((rc_ = dev_upload(h, fe, &q.fac_ent))) return bail(rc_);
         if ((rc_ = dev_upload(h, ie, &q.inv_ent))) return bail(rc_);
     }
