@@ -301,6 +301,24 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
 #undef FAC_PREFETCH
     // level ranges: replace the in-range block of W by the explicit inverse M of the unit lower block L[range, range], level by level:
     //   M_ij = -(W_ij / d_j + sum_{j<k<i} W_ik / d_k M_kj)     (targets of one level are computed into registers before any is written)
+    // (the first task of the next level is fetched before the barriers of the current one, as in the factor levels)
+    uint2 idn = make_uint2(0, 0);
+    unsigned long long ie0 = 0, ie1 = 0, ie2 = 0, ie3 = 0;
+    uint32_t itg = 0;
+    bool ihave = false;
+#define INV_PREFETCH(lvl)                                                                                   \
+    do {                                                                                                    \
+        const int t__ = s.inv_lvl[lvl] + warp;                                                              \
+        ihave = t__ < (int)s.inv_lvl[(lvl) + 1];                                                            \
+        if (ihave) {                                                                                        \
+            idn = s.inv_task[t__];                                                                          \
+            const unsigned long long* e__ = q.inv_ent + ((size_t)(idn.x & 0xffff) << 5) + lane;             \
+            ie0 = __ldg(e__); ie1 = __ldg(e__ + 32); ie2 = __ldg(e__ + 64); ie3 = __ldg(e__ + 96);          \
+            const int sh__ = (idn.y >> 16) & 0xff, rr__ = lane >> sh__;                                     \
+            itg = __ldg(q.inv_tgt + (idn.x >> 16) + min(rr__, (int)((idn.y >> 8) & 0xff) - 1));             \
+        }                                                                                                   \
+    } while (0)
+    if (q.n_inv_levels > 0) INV_PREFETCH(0);
     for (int l = 0; l < q.n_inv_levels; l++) {
         const int t0 = s.inv_lvl[l] + warp, t1 = s.inv_lvl[l + 1];
         double v[INV_MAX_TASKS_PER_WARP];
@@ -310,24 +328,26 @@ __device__ void factor(const QpDev& q, const Smem& s, double sigma, double rho, 
             const int t = t0 + k * NW;
             id[k] = -1;
             if (t < t1) {
-                const uint2 d = s.inv_task[t];
+                const uint2 d = k == 0 ? idn : s.inv_task[t];
                 const int sh = (d.y >> 16) & 0xff, rr = lane >> sh;
                 const bool writer = (lane & ((1 << sh) - 1)) == 0 && rr < (int)((d.y >> 8) & 0xff);
-                uint32_t tg = 0;
-                if (writer) tg = __ldg(q.inv_tgt + (d.x >> 16) + rr);
-                const double acc = gather_task(s, d, q.inv_ent, lane, pad);
+                uint32_t tg = itg;
+                if (k > 0 && writer) tg = __ldg(q.inv_tgt + (d.x >> 16) + rr);
+                const double acc = k == 0 ? gather_task_pre(s, d, q.inv_ent, lane, pad, ie0, ie1, ie2, ie3) : gather_task(s, d, q.inv_ent, lane, pad);
                 if (writer) {
                     id[k] = tg & 0xffff;
                     v[k] = -(s.Lval[id[k]] * s.Dinv[tg >> 16] + acc);
                 }
             }
         }
+        if (l + 1 < q.n_inv_levels) INV_PREFETCH(l + 1); else ihave = false;
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < INV_MAX_TASKS_PER_WARP; k++)
             if (id[k] >= 0) s.Lval[id[k]] = v[k];
         __syncthreads();
     }
+#undef INV_PREFETCH
     FAC_T(111);
     // dense tail: symmetric sweep of the packed lower Schur complement S over all pivots, in place:  S <- -S^-1.
     // Pivot p: S_ik -= S_ip S_kp / d,  S_ip <- S_ip / d,  S_pp <- -1 / d.  The pivot column (and 1/d) of step p+1 is staged into a small
