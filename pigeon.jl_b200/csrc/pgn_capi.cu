@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -200,7 +201,22 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->have_traj = false; h->have_assign = false; h->stage_bytes = 0; h->d_stage = nullptr;
     memset(&h->hji, 0, sizeof(h->hji)); memset(&h->traj, 0, sizeof(h->traj));
     char err[256];
-    if (!build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err))) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
+    // ADMM build variant: if the QP is small enough for TWO CTAs per SM (256 threads each, static tables read through L1) the warp
+    // programs are scheduled for 8 warps; otherwise one 512-thread CTA per SM with the tables in shared memory.  PGN_ADMM_VARIANT=512|256
+    // forces a variant (experiments).
+    {
+        const char* force = getenv("PGN_ADMM_VARIANT");
+        const int want = force ? atoi(force) : 0;
+        h->admm_threads = 512;
+        if (want != 512) {
+            if (!build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 8)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
+            const size_t sm = admm_smem_bytes(h->tab, 256, false);
+            if (2 * (sm + 1024) <= (size_t)227 * 1024) h->admm_threads = 256;
+            else if (want == 256) { delete h; return set_err(PGN_EINVAL, "PGN_ADMM_VARIANT=256: two CTAs of %zu bytes do not fit one SM", sm); }
+        }
+        if (h->admm_threads == 512 &&
+            !build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 16)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
+    }
     auto bail = [&](int rc) { pgn_destroy(h); return rc; };
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return set_err(PGN_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }

@@ -139,6 +139,6 @@ void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, dou
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
 void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n);
-size_t admm_smem_bytes(const QpTables& t);
+size_t admm_smem_bytes(const QpTables& t, int nthreads, bool tables_in_smem);
 int admm_configure(pgn_handle* h);   // sets the max dynamic shared memory attribute; returns cudaError
 }  // namespace pgn

@@ -117,7 +117,7 @@ void nd_classes(int lo, int hi, int depth, int leaf, std::vector<int>& sep_depth
 
 }  // namespace
 
-bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& Q, char* err, int errlen) {
+bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& Q, char* err, int errlen, int nwarps) {
     auto fail = [&](const char* msg) { snprintf(err, errlen, "%s", msg); return false; };
     if (N_short < 1 || N_long < 0) return fail("N_short must be >= 1 and N_long >= 0");
     Q = QpTables();
@@ -374,7 +374,8 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     }
 
     // ---- warp programs -----------------------------------------------------------------------------------------------------------
-    const int NWARP = ADMM_THREADS / 32;
+    const int NWARP = nwarps;
+    Q.nwarps = nwarps;
     std::vector<int> range_pa, range_pb;
     for (size_t k = 0; k + 1 < Q.range_lvl.size(); k += 2) { range_pa.push_back(Q.lvl_ptr[Q.range_lvl[k]]); range_pb.push_back(Q.lvl_ptr[Q.range_lvl[k + 1]]); }
     const int nr = (int)range_pa.size();

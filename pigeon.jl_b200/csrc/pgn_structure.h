@@ -86,6 +86,7 @@ struct QpTables {
     //
     // The factor is kept in the unscaled form W = L D (W_ij = L_ij d_j): W_ij = K_ij - sum_k W_ik W_jk / d_k needs no column scaling
     // phase, and the solves absorb 1/d (flags above).  L values live in the order the FORWARD solve consumes them (`nslots` slots).
+    int nwarps;                                        // warps the programs below were scheduled for
     int nslots, zslot;
     std::vector<uint32_t> sol_task;                    // solve tasks, 4 words each: forward phases then backward phases
     std::vector<uint16_t> sol_ph_ptr;                  // phase -> first task; n_fwd_ph forward phases, then n_bwd_ph backward phases
@@ -114,6 +115,7 @@ struct QpTables {
 };
 
 // ordering: 0 nested dissection over stages, 1 minimum degree
-bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& out, char* err, int errlen);
+// nwarps: warps of the ADMM CTA the warp programs are laid out for (ADMM_THREADS / 32 by default; 8 for the two-CTAs-per-SM variant)
+bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& out, char* err, int errlen, int nwarps = ADMM_THREADS / 32);
 
 }  // namespace pgn

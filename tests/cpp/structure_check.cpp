@@ -12,8 +12,9 @@ using namespace pgn;
 
 int main(int argc, char** argv) {
     int kind = argc > 1 ? atoi(argv[1]) : 0, Ns = argc > 2 ? atoi(argv[2]) : 10, Nl = argc > 3 ? atoi(argv[3]) : 20, ord = argc > 4 ? atoi(argv[4]) : 0;
+    const int nwarps = argc > 6 ? atoi(argv[6]) : ADMM_THREADS / 32;      // argv[5]: verbose flag, argv[6]: warps the programs are scheduled for
     QpTables Q; char err[256];
-    if (!build_qp_tables(kind, Ns, Nl, ord, Q, err, 256)) { printf("FAIL %s\n", err); return 1; }
+    if (!build_qp_tables(kind, Ns, Nl, ord, Q, err, 256, nwarps)) { printf("FAIL %s\n", err); return 1; }
     const int Nk = Q.Nk, n = Q.n, m = Q.m;
     std::mt19937_64 rng(7);
     std::uniform_real_distribution<double> U(-1, 1);
