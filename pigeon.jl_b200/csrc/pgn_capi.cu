@@ -289,7 +289,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se, 2 * B); AL(d_tskip, B);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se0, 2 * B); AL(d_se, 2 * B); AL(d_tskip, B);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));

@@ -106,6 +106,7 @@ struct pgn_handle {
     // and the CUDA graph of the whole call (H2D copy, unpack, the five step stages, pack, D2H copy), re-captured when a setter bumps `epoch`
     // plant rollout beside the ADMM launch (pgn_step_rollout_device / pgn_simulate): shadow state, side stream, fork / join events
     double* d_state_next; cudaStream_t side_stream; cudaEvent_t ev_fork, ev_join;
+    double* d_se0;                                       // decoupled node generation: (s0, e0) handed from the scan kernel to the rollout kernel
     double *h_io, *d_io, *d_se; uint8_t* d_tskip; int in_callback;
     cudaGraph_t cb_graph; cudaGraphExec_t cb_exec; long long epoch, cb_epoch, cb_launches; cudaStream_t cb_stream; int cb_has_exec;
     int32_t* d_order;                                    // ticket -> vehicle order of the ADMM launch

@@ -141,9 +141,78 @@ struct NodeArgs {
     const double *ts, *dt, *prev_ts, *sol_x;
     double *qs, *us, *ps;
     uint8_t* skip; double pause_below_speed;      // guard of src/ros_integration.jl:84-87
+    double* se0;                                  // decoupled: (s0, e0) of the closest-segment scan, [2][B]
     int window; int32_t* last_seg;                // optional windowed closest-segment search (pgn_set_path_search_window)
     const uint8_t* tskip;                         // callback entry point only: time outside the trajectory interval (src/ros_integration.jl:77-80)
 };
+
+// decoupled: always the steady-state rollout (decoupled_lat_long.jl:65-103).  A recurrence over the horizon nodes, one vehicle per
+// THREAD: run on lane 0 of the vehicle's warp it left 31 lanes idle (1.6 ms per 8192 vehicles); the closest-segment scan stays
+// warp-per-vehicle in k_nodes and hands (s0, e0) over through a small buffer.
+__device__ void decoupled_cold_rollout(const NodeArgs& a, int v, double s0, double e0) {
+    const int B = a.B, N = a.N, Ns = a.Ns;
+    const VehParams& P = a.P;
+    const CtrlParams& C = a.C;
+    const double E0 = a.state[0 * B + v], N0 = a.state[1 * B + v], psi0 = a.state[2 * B + v];
+    const double Ux0 = a.state[3 * B + v], Uy0 = a.state[4 * B + v], r0 = a.state[5 * B + v];
+    const double d0 = a.control[0 * B + v], Fxf0 = a.control[1 * B + v], Fxr0 = a.control[2 * B + v];
+    const double Fx0 = Fxf0 + Fxr0;
+    const bool path_mode = isnan(a.toff[v]);
+    const int base = a.traj_id[v] * a.tv.n_nodes;
+    const double* ts = a.ts + (size_t)v * N;
+    const double* dt = a.dt + (size_t)v * (N - 1);
+    double* qs = a.qs + (size_t)v * N * 4;
+    double* us = a.us + (size_t)v * N * 2;
+    double* ps = a.ps + (size_t)v * N * 4;
+        // decoupled: always the steady-state rollout (decoupled_lat_long.jl:65-103)
+        double s = s0;
+        double V = hypot(Ux0, Uy0);
+        const double beta0 = atan2(Uy0, Ux0);
+        double Fyf0, Fyr0;
+        {
+            double sd, cd;
+            sincos(d0, &sd, &cd);
+            lateral_tire_forces<double>(P, atan2(Uy0 + P.a * r0, Ux0) - d0, atan2(Uy0 - P.b * r0, Ux0), Fxf0, Fxr0, sd, cd, Fyf0, Fyr0);
+        }
+        double sb0, cb0;
+        sincos(beta0, &sb0, &cb0);
+        for (int i = 0; i < N; i++) {
+            const double tau = (i == N - 1) ? dt[i - 1] : dt[i];
+            TrajNode tj = traj_at_s(a.tv, base, s);
+            const double kappa = tj.kappa;
+            double A_des = tj.A + C.k_V * (tj.V - V) / tau + (path_mode ? 0.0 : C.k_s * (traj_at_time(a.tv, base, ts[i]).s - s) / tau / tau);
+            A_des = fmin(fmax(A_des, (C.V_min - V) / tau), (C.V_max - V) / tau);
+            double A;
+            if (i == 0) {
+                qs[0] = Uy0; qs[1] = r0; qs[2] = adiff(psi0, tj.psi); qs[3] = e0;
+                us[0] = d0; us[1] = Fx0;
+                ps[0] = Ux0; ps[1] = kappa; ps[2] = 0; ps[3] = 0;
+                double q6[6] = {E0, N0, psi0, Ux0, Uy0, r0}, qd[6];
+                vehicle_model<MODEL_BICYCLE, double>(P, q6, d0, Fx0, 0.0, 0.0, qd);
+                A = (qd[3] - r0 * Uy0) * cb0 + (qd[4] + r0 * Ux0) * sb0;
+            } else if (i <= Ns) {
+                SteadyState est = steady_state_estimates(P, V, A_des, kappa, 1, r0, beta0, d0, Fyf0);
+                qs[4 * i + 0] = Uy0; qs[4 * i + 1] = r0; qs[4 * i + 2] = adiff(psi0, tj.psi); qs[4 * i + 3] = e0;
+                us[2 * i + 0] = est.delta; us[2 * i + 1] = est.Fxf + est.Fxr;
+                ps[4 * i + 0] = est.Ux; ps[4 * i + 1] = kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
+                A = est.A;
+            } else {
+                SteadyState est = steady_state_estimates(P, V, A_des, kappa, 4, V * kappa, 0.0, 0.0, 0.0);
+                qs[4 * i + 0] = est.Uy; qs[4 * i + 1] = est.r; qs[4 * i + 2] = -est.beta; qs[4 * i + 3] = 0;
+                us[2 * i + 0] = est.delta; us[2 * i + 1] = est.Fxf + est.Fxr;
+                ps[4 * i + 0] = est.Ux; ps[4 * i + 1] = kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
+                A = est.A;
+            }
+            if (i == N - 1) break;
+            V = V + A * tau;
+            s = s + V * tau + A * tau * tau / 2;
+        }
+}
+__global__ void __launch_bounds__(128) k_nodes_decoupled_rollout(const NodeArgs a, const double* __restrict__ se0) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.B) return;
+    decoupled_cold_rollout(a, v, se0[v], se0[a.B + v]);
+}
 
 // One warp per vehicle: the lanes share the closest-segment scan and, on warm steps, take one horizon node each; the cold rollout
 // (a recurrence over the nodes) runs on lane 0.
@@ -254,49 +323,7 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
             }
         }
     } else if (lane == 0) {
-        // decoupled: always the steady-state rollout (decoupled_lat_long.jl:65-103)
-        double s = s0;
-        double V = hypot(Ux0, Uy0);
-        const double beta0 = atan2(Uy0, Ux0);
-        double Fyf0, Fyr0;
-        {
-            double sd, cd;
-            sincos(d0, &sd, &cd);
-            lateral_tire_forces<double>(P, atan2(Uy0 + P.a * r0, Ux0) - d0, atan2(Uy0 - P.b * r0, Ux0), Fxf0, Fxr0, sd, cd, Fyf0, Fyr0);
-        }
-        double sb0, cb0;
-        sincos(beta0, &sb0, &cb0);
-        for (int i = 0; i < N; i++) {
-            const double tau = (i == N - 1) ? dt[i - 1] : dt[i];
-            TrajNode tj = traj_at_s(a.tv, base, s);
-            const double kappa = tj.kappa;
-            double A_des = tj.A + C.k_V * (tj.V - V) / tau + (path_mode ? 0.0 : C.k_s * (traj_at_time(a.tv, base, ts[i]).s - s) / tau / tau);
-            A_des = fmin(fmax(A_des, (C.V_min - V) / tau), (C.V_max - V) / tau);
-            double A;
-            if (i == 0) {
-                qs[0] = Uy0; qs[1] = r0; qs[2] = adiff(psi0, tj.psi); qs[3] = e0;
-                us[0] = d0; us[1] = Fx0;
-                ps[0] = Ux0; ps[1] = kappa; ps[2] = 0; ps[3] = 0;
-                double q6[6] = {E0, N0, psi0, Ux0, Uy0, r0}, qd[6];
-                vehicle_model<MODEL_BICYCLE, double>(P, q6, d0, Fx0, 0.0, 0.0, qd);
-                A = (qd[3] - r0 * Uy0) * cb0 + (qd[4] + r0 * Ux0) * sb0;
-            } else if (i <= Ns) {
-                SteadyState est = steady_state_estimates(P, V, A_des, kappa, 1, r0, beta0, d0, Fyf0);
-                qs[4 * i + 0] = Uy0; qs[4 * i + 1] = r0; qs[4 * i + 2] = adiff(psi0, tj.psi); qs[4 * i + 3] = e0;
-                us[2 * i + 0] = est.delta; us[2 * i + 1] = est.Fxf + est.Fxr;
-                ps[4 * i + 0] = est.Ux; ps[4 * i + 1] = kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
-                A = est.A;
-            } else {
-                SteadyState est = steady_state_estimates(P, V, A_des, kappa, 4, V * kappa, 0.0, 0.0, 0.0);
-                qs[4 * i + 0] = est.Uy; qs[4 * i + 1] = est.r; qs[4 * i + 2] = -est.beta; qs[4 * i + 3] = 0;
-                us[2 * i + 0] = est.delta; us[2 * i + 1] = est.Fxf + est.Fxr;
-                ps[4 * i + 0] = est.Ux; ps[4 * i + 1] = kappa; ps[4 * i + 2] = 0; ps[4 * i + 3] = 0;
-                A = est.A;
-            }
-            if (i == N - 1) break;
-            V = V + A * tau;
-            s = s + V * tau + A * tau * tau / 2;
-        }
+        a.se0[v] = s0; a.se0[B + v] = e0;          // decoupled: the rollout runs one vehicle per thread in k_nodes_decoupled_rollout
     }
 }
 
@@ -424,9 +451,13 @@ void launch_nodes(pgn_handle* h) {
     a.ts = h->d_ts; a.dt = h->d_dt; a.prev_ts = h->d_prev_ts; a.sol_x = h->d_sol_x;
     a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps;
     a.skip = h->d_skip; a.pause_below_speed = h->guard_pause; a.tskip = h->in_callback ? h->d_tskip : nullptr;
-    a.window = h->path_window; a.last_seg = h->d_last_seg;
+    a.window = h->path_window; a.last_seg = h->d_last_seg; a.se0 = h->d_se0;
     k_nodes<<<(h->B + 3) / 4, 128, 0, h->stream>>>(a);
     h->launches++;
+    if (h->cfg.kind == PGN_DECOUPLED) {
+        k_nodes_decoupled_rollout<<<(h->B + 127) / 128, 128, 0, h->stream>>>(a, h->d_se0);
+        h->launches++;
+    }
 }
 void launch_callback_in(pgn_handle* h) {
     k_callback_in<<<(h->B + 3) / 4, 128, 0, h->stream>>>(h->B, h->traj, h->d_traj_id, h->d_io, h->d_toff, h->d_state, h->d_control, h->d_other, h->d_t0, h->d_tskip, h->d_se, h->path_window, h->d_last_seg);
