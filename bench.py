@@ -321,7 +321,9 @@ def run_gpu(args):
                 "peak_source": peak_src, "traffic": None, "launch_ms": admm_ms,
                 "share_of_step": admm_ms / max(1e-9, (stage["nodes"] + stage["linearize"] + stage["hji"] + stage["admm"] + stage["controls"] + stage["rollout"]) / nprof),
                 "fp64": {"achieved_tflops": B * flop_qp / (admm_ms * 1e-3) / 1e12, "nominal_peak_tflops": 37.0, "flop_per_qp": flop_qp},
-                "note": "one QP per CTA; the solve is a chain of dependent sparse triangular solves in shared memory: latency/occupancy-bound, neither HBM- nor tensor-bound (SURVEY.md 8d)"}
+                "note": "one QP per CTA; the solve is a chain of dependent sparse triangular solves in shared memory: latency/occupancy-bound, neither HBM- nor tensor-bound (SURVEY.md 8d)",
+                "limiter": {"what": "dependent-instruction latency of the slowest warp in each barrier interval (about 4.7 cycles per instruction of a lone warp), then shared-memory wavefronts (every 8-byte load of a warp is >= 2 wavefronts of one 128 B/clk pipe)",
+                            "evidence": "tools/ubench/*.cu (B200 latencies), DESIGN.md 4.1 (table of measurements, rejected variants), profiles/r1b_admm_ncu_full.md (0.42 IPC per scheduler, stalls: barrier >> wait ~ short scoreboard)"}}
         roof["frac"] = roof["achieved"] / roof["peak"]
         # DRAM traffic of one launch from the committed `ncu --set full` capture of the same workload (read + written bytes)
         try:
