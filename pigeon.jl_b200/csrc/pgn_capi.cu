@@ -243,7 +243,17 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
 #define UP(field) if ((rc = dev_upload(h, t.field, &q.field))) return bail(rc)
     UP(a_src); UP(a_slot); UP(l_type); UP(u_type); UP(l_idx); UP(u_idx); UP(P_mode); UP(q_mode); UP(P_w); UP(q_w); UP(P_t); UP(q_t);
     UP(q_hji_t); UP(pos_var); UP(pos_con); UP(pos2idx); UP(is_con); UP(kadj_ptr); UP(kadj_e); UP(kadj_nb);
-    UP(sol_orow); UP(fidx); UP(bent); UP(fac_lvl_ptr); UP(fac_tgt); UP(inv_lvl_ptr); UP(inv_tgt);
+    UP(fac_lvl_ptr); UP(fac_tgt); UP(inv_lvl_ptr); UP(inv_tgt);
+    {   // the solve tables are read in batches of four slot rows with the surplus masked AFTER the load: the device copies carry four slot
+        // rows of padding (zero entries) so that the variant that reads them from global memory never leaves its allocations
+        std::vector<uint16_t> orow(t.sol_orow), fidx(t.fidx);
+        std::vector<uint32_t> bent(t.bent);
+        orow.resize(orow.size() + 64, 0); fidx.resize(fidx.size() + 128, (uint16_t)t.Nk);
+        bent.resize(bent.size() + 128, (uint32_t)t.zslot | ((uint32_t)t.Nk << 16));
+        if ((rc = dev_upload(h, orow, &q.sol_orow))) return bail(rc);
+        if ((rc = dev_upload(h, fidx, &q.fidx))) return bail(rc);
+        if ((rc = dev_upload(h, bent, &q.bent))) return bail(rc);
+    }
     {
         std::vector<uint32_t> rc(t.nnzA);
         for (int e = 0; e < t.nnzA; e++) rc[e] = (uint32_t)t.a_rowpos[e] | ((uint32_t)t.a_colpos[e] << 16);
@@ -263,7 +273,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
         if ((rc_ = dev_upload(h, pack(t.fac_task), &q.fac_task))) return bail(rc_);
         if ((rc_ = dev_upload(h, pack(t.inv_task), &q.inv_task))) return bail(rc_);
         std::vector<unsigned long long> fe(t.fac_ent.begin(), t.fac_ent.end()), ie(t.inv_ent.begin(), t.inv_ent.end());
-        const unsigned long long padent = (unsigned long long)t.zslot | ((unsigned long long)t.zslot << 16);
+        const unsigned long long padent = (unsigned long long)t.zslot | ((unsigned long long)t.zslot << 16) | ((unsigned long long)t.Nk << 32);
         fe.resize(fe.size() + 512, padent); ie.resize(ie.size() + 512, padent);      // masked batches read whole groups of four slot rows past a task's end
         if ((rc_ = dev_upload(h, fe, &q.fac_ent))) return bail(rc_);
         if ((rc_ = dev_upload(h, ie, &q.inv_ent))) return bail(rc_);

@@ -471,7 +471,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     auto emit_level = [&](const std::vector<Tgt>& tg, std::vector<uint32_t>& tasks, std::vector<uint32_t>& lvl_ptr, std::vector<uint32_t>& tgts, std::vector<uint64_t>& ents) {
         std::vector<int> len(tg.size());
         for (size_t i = 0; i < tg.size(); i++) len[i] = (int)tg[i].ents.size();
-        const uint64_t padent = (uint64_t)Q.zslot | ((uint64_t)Q.zslot << 16);
+        const uint64_t padent = (uint64_t)Q.zslot | ((uint64_t)Q.zslot << 16) | ((uint64_t)Nk << 32);      // 0 * 0 / Dinv[Nk]: element Nk of Dinv is never written by the factorisation (kept at 0)
         for (const SchedTask& t : schedule_phase(len, NWARP)) {
             const int g = 1 << t.sh, ebase = (int)ents.size(), rbase = (int)tgts.size();
             ents.resize(ebase + 32 * t.K, padent);

@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
     // emulate the kernel factorisation (unscaled form W = L D, one gather pass per level, no scaling pass)
     const int NS = Q.nslots;
     const int ts = Q.tail_start, Dm = Q.tail_dim, npk = Dm * (Dm + 1) / 2;
-    std::vector<double> L(NS + npk, 0.0), Dinv(Nk);                      // L slots followed by the packed lower dense tail block
+    std::vector<double> L(NS + npk, 0.0), Dinv(Nk + 1, 0.0);                      // L slots followed by the packed lower dense tail block
     for (int e = 0; e < Q.nnzA; e++) L[Q.a_slot[e]] = Aval[e];
     for (int p = 0; p < Nk; p++) {
         const double kpp = Q.is_con[p] ? -rhoinv[Q.pos2idx[p]] : Pd[Q.pos2idx[p]];
