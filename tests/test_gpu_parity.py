@@ -166,6 +166,36 @@ def test_fixture_trajectory_single_vehicle_config1(p):
     g.close()
 
 
+@pytest.mark.parametrize("kind", ["coupled", "decoupled"])
+def test_msg_fixture_variable_speed_closed_loop(p, kind, tmp_path):
+    """The one reference fixture that only exists as a serialised path message (test/path/variable_speed.msg: 28 nodes, speed and
+    acceleration varying along the path): read through read_msg -> TrajectoryTube(p::path) (src/ros_integration.jl:13-16), closed loop."""
+    raw = np.load(os.path.join(ROOT, "tests", "golden", "msg_raw.npz"))["variable_speed"]
+    f = str(tmp_path / "variable_speed.msg")
+    raw.tofile(f)
+    w = p.read_msg(f)
+    tr = p.trajectory_from_msg(f)
+    ctor = p.BatchedCoupledTrajectoryTrackingMPC if kind == "coupled" else p.BatchedDecoupledTrajectoryTrackingMPC
+    g = ctor(p.X1(), tr, 1)
+    k0 = 2
+    q0 = np.array([[w["posE_m"][k0] + 0.2, w["posN_m"][k0] - 0.1, w["psi_rad"][k0] + 0.02, w["UxDes_mps"][k0] + 0.3, 0.0, 0.0]])
+    g.set_state(q0, np.zeros((1, 3)), FAR[None])
+    m = o.Mpc(o.MPC_COUPLED if kind == "coupled" else o.MPC_DECOUPLED)
+    m.set_trajectory(o.Trajectory(**{k: getattr(tr, k) for k in o.TRAJ_FIELDS}))
+    m.set_state(q0[0], [0, 0, 0], other4=FAR)
+    t0 = tr.t[k0]
+    for k in range(40):
+        ug = g.step(t0 + 0.01 * k)
+        g.rollout(0.01)
+        m.simulate_step(t0 + 0.01 * k)
+        qo, uo = m.get_state()
+        assert g.stats()["iters"][0] == m.stats()["iter"]
+        assert np.max(np.abs(ug[0] - uo) / U_RANGE) < 1e-4
+    qg, _ = g.get_state()
+    assert np.allclose(qg[0], qo, rtol=1e-8, atol=1e-7)
+    g.close()
+
+
 def test_simulate_on_device_matches_stepwise(p):
     B = 32
     trajs = p.synthetic.synthetic_trajectories(n_traj=4, n_nodes=300)

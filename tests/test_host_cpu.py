@@ -194,6 +194,45 @@ def test_world_reader_round_trip_and_fixtures(p, tmp_path):
         p.read_world(bad)
 
 
+def test_msg_reader_on_reference_bytes(p, tmp_path):
+    """Serialised `path` messages (reference test/path/*.msg): the reader decodes the reference's own bytes (two fixtures travel raw in
+    tests/golden/msg_raw.npz), agrees bit for bit with the .world twin, re-serialises to the identical bytes, loads the fixture that has no
+    .world twin (variable_speed.msg, 28 nodes, varying speed) into a TrajectoryTube, and rejects truncated files."""
+    golden = os.path.join(ROOT, "tests", "golden")
+    raw = np.load(os.path.join(golden, "msg_raw.npz"))
+    assert sorted(raw.files) == ["curvy", "variable_speed"]
+    for name in raw.files:
+        f = str(tmp_path / f"{name}.msg")
+        raw[name].tofile(f)
+        m = p.read_msg(f)
+        g = str(tmp_path / f"{name}_again.msg")
+        p.write_msg(g, m, is_open=m["isOpen"], frame_id=m["frame_id"], seq=m["seq"], stamp=m["stamp"], reserved=m["reserved"])
+        assert open(g, "rb").read() == raw[name].tobytes()
+    m = p.read_msg(str(tmp_path / "curvy.msg"))
+    w = np.load(os.path.join(golden, "world_curvy.npz"))
+    assert m["frame_id"] == "curvy" and m["isOpen"] == int(w["isOpen"])
+    for k in p.world.WORLD_KEYS:
+        assert np.array_equal(m[k], w[k]), k
+    v = p.read_msg(str(tmp_path / "variable_speed.msg"))
+    assert len(v["s_m"]) == 28 and v["frame_id"] == "world" and np.ptp(v["UxDes_mps"]) > 0.1
+    t = p.trajectory_from_msg(str(tmp_path / "variable_speed.msg"))
+    assert len(t) == 28 and t.t[0] == 0.0 and np.all(np.diff(t.t) > 0)
+    assert np.allclose(np.diff(t.t), 2 * np.diff(v["s_m"]) / (v["UxDes_mps"][:-1] + v["UxDes_mps"][1:]), rtol=1e-13)
+    bad = str(tmp_path / "bad.msg")
+    raw["variable_speed"][:-9].tofile(bad)
+    with pytest.raises(ValueError):
+        p.read_msg(bad)
+    np.concatenate([raw["variable_speed"], np.zeros(3, np.uint8)]).tofile(bad)
+    with pytest.raises(ValueError):
+        p.read_msg(bad)
+    ref = "/root/reference/test/path"
+    if os.path.isdir(ref):                                        # build container only: every .msg equals its .world twin
+        for f in sorted(os.listdir(ref)):
+            if f.endswith(".msg") and os.path.exists(os.path.join(ref, f[:-4] + ".world")):
+                mm, ww = p.read_msg(os.path.join(ref, f)), p.read_world(os.path.join(ref, f[:-4] + ".world"))
+                assert all(np.array_equal(mm[k], ww[k]) for k in p.world.WORLD_KEYS) and mm["isOpen"] == ww["isOpen"], f
+
+
 def test_hji_cache_file_round_trip(p, tmp_path):
     """The flat PGNHJI1 file (julia/export_hji_cache.jl writes it from the reference's JLD2 objects) round-trips an HJICache bit for bit, in the
     memory order pgn_set_hji_cache expects, and rejects truncated files."""
