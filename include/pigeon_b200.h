@@ -140,6 +140,16 @@ PGN_API int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d
 /* simulate (model_predictive_control.jl:80-100): n_steps closed-loop steps fully on the device:
  * step at t0 + k*dt, plant rollout propagate(dynamics, state, StepControl(dt, control)), apply the new control */
 PGN_API int pgn_simulate(pgn_handle* h, const double* t0 /*[B]*/, double dt, int32_t n_steps);
+/* the same loop with t0 a DEVICE pointer, enqueued on the handle's stream without a host synchronisation (results are stream-ordered) */
+PGN_API int pgn_simulate_device(pgn_handle* h, const double* d_t0 /*[B]*/, double dt, int32_t n_steps);
+/* Pipeline parts of the fused entry points (pgn_step, pgn_step_device, pgn_step_rollout_device, pgn_simulate, pgn_simulate_device): the batch is
+ * run as `parts` contiguous vehicle ranges, each on its own stream, so that the per-vehicle stages (nodes, linearisation, HJI, controls, plant
+ * step) of one range run while the ADMM kernel of another drains; inside pgn_simulate every range runs all its steps without waiting for the
+ * others (a vehicle's step k+1 depends only on its own step k: the `for` loop of model_predictive_control.jl:87-98 per vehicle).  Every vehicle's
+ * results are bit-identical for any part count.  parts = 1 (the default): one range on the caller's stream; 0: chosen from the batch size; <= 8.
+ * The five single-stage calls and pgn_from_autobox always run the whole batch on the caller's stream. */
+PGN_API int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts);
+PGN_API int pgn_get_pipeline_parts(pgn_handle* h, int32_t* parts);
 /* one plant rollout + control application (the tail of the simulate loop) */
 PGN_API int pgn_rollout(pgn_handle* h, double dt);
 

@@ -19,7 +19,7 @@ export X1, CoupledControlParams, DecoupledControlParams, TrajectoryTube, straigh
        BatchedTrajectoryTrackingMPC, BatchedCoupledTrajectoryTrackingMPC, BatchedDecoupledTrajectoryTrackingMPC,
        compute_time_steps!, compute_linearization_nodes!, update_QP!, solve!, get_next_control, step!, simulate,
        set_state!, set_HJI_cache!, reset_solved!, reset_solver!, solver_stats, set_guards!, from_autobox!, set_hji_policy!, hji_values,
-       optimal_control, set_path_search_window!, step_rollout_device!
+       optimal_control, set_path_search_window!, step_rollout_device!, set_pipeline_parts!, pipeline_parts, simulate_device!
 
 const libpigeon = get(ENV, "PGN_LIB_PATH", joinpath(@__DIR__, "..", "pigeon.jl_b200", "libpigeon_b200.so"))
 
@@ -225,6 +225,17 @@ end
 "one iteration of the simulate loop (src/model_predictive_control.jl:87-98) on device-resident data: d_t0 / d_out are device pointers (CuPtr); the plant step runs beside the QP solve"
 step_rollout_device!(mpc::BatchedTrajectoryTrackingMPC, d_t0::Ptr{Float64}, d_out::Ptr{Float64}, dt::Float64=0.01) =
     check(ccall((:pgn_step_rollout_device, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), mpc.handle, d_t0, d_out, dt))
+
+"pipeline parts of the fused calls (step!, step_rollout_device!, simulate): vehicle ranges on their own streams; 0 = automatic, 1 = off; results do not depend on it"
+set_pipeline_parts!(mpc::BatchedTrajectoryTrackingMPC, parts::Integer) = check(ccall((:pgn_set_pipeline_parts, libpigeon), Cint, (Ptr{Cvoid}, Int32), mpc.handle, Int32(parts)))
+function pipeline_parts(mpc::BatchedTrajectoryTrackingMPC)
+    n = Ref{Int32}(0)
+    check(ccall((:pgn_get_pipeline_parts, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Int32}), mpc.handle, n))
+    Int(n[])
+end
+"the simulate loop with t0 resident on the device (CuPtr), enqueued on the handle's stream without a host synchronisation"
+simulate_device!(mpc::BatchedTrajectoryTrackingMPC, d_t0::Ptr{Float64}, dt::Float64, n_steps::Integer) =
+    check(ccall((:pgn_simulate_device, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Int32), mpc.handle, d_t0, dt, Int32(n_steps)))
 
 "simulate(mpc, q0, u0, dt) (src/model_predictive_control.jl:80-100) for the whole batch, entirely on the device; returns the final (state, control)."
 function simulate(mpc::BatchedTrajectoryTrackingMPC, q0::Matrix{Float64}, u0::Matrix{Float64}; dt=0.01, t0=zeros(mpc.B), n_steps::Integer)

@@ -29,7 +29,8 @@ SYMBOLS = ["pgn_default_config", "pgn_x1_vehicle_params", "pgn_default_control_p
            "pgn_solve", "pgn_get_next_control", "pgn_step", "pgn_step_device", "pgn_simulate", "pgn_rollout", "pgn_qp_dims", "pgn_get_state",
            "pgn_get_time_steps", "pgn_get_nodes", "pgn_set_nodes", "pgn_get_qp_data", "pgn_get_solution", "pgn_get_stats", "pgn_hji_lookup",
            "pgn_hji_lookup_device", "pgn_device_controls", "pgn_device_stats", "pgn_set_profiling", "pgn_get_stage_ms", "pgn_get_admm_cycles",
-           "pgn_get_hji_values", "pgn_hji_optimal_control", "pgn_set_hji_policy", "pgn_from_autobox", "pgn_step_rollout_device", "pgn_set_path_search_window"]
+           "pgn_get_hji_values", "pgn_hji_optimal_control", "pgn_set_hji_policy", "pgn_from_autobox", "pgn_step_rollout_device", "pgn_set_path_search_window",
+           "pgn_simulate_device", "pgn_set_pipeline_parts", "pgn_get_pipeline_parts"]
 
 _lib = None
 
@@ -50,6 +51,9 @@ def load():
         getattr(lib, name)   # AttributeError if the library does not export a declared symbol
     lib.pgn_create.argtypes = [C.POINTER(PgnConfig), C.POINTER(C.c_void_p)]
     lib.pgn_simulate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int32]
+    lib.pgn_simulate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int32]
+    lib.pgn_set_pipeline_parts.argtypes = [C.c_void_p, C.c_int32]
+    lib.pgn_get_pipeline_parts.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     lib.pgn_rollout.argtypes = [C.c_void_p, C.c_double]
     lib.pgn_step_rollout_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
     lib.pgn_set_guards.argtypes = [C.c_void_p, C.c_int32, C.c_double]

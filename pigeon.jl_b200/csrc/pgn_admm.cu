@@ -97,7 +97,7 @@ namespace v256 {
 
 // Ticket order of the persistent CTAs: vehicles whose previous solve took the most iterations go first (longest-processing-time-first),
 // so that a slow QP starts at the beginning of the launch instead of becoming its tail.  Counting sort on iters / 25 in one CTA.
-__global__ void __launch_bounds__(1024) k_admm_order(const int32_t* __restrict__ iters, int32_t* __restrict__ order, int B) {
+__global__ void __launch_bounds__(1024) k_admm_order(const int32_t* __restrict__ iters, int32_t* __restrict__ order, int B, int v0) {
     __shared__ int hist[257];
     for (int i = threadIdx.x; i < 257; i += blockDim.x) hist[i] = 0;
     __syncthreads();
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(1024) k_admm_order(const int32_t* __restrict__
         for (int i = 0; i < 256; i++) { const int c = hist[i]; hist[i] = acc; acc += c; }
     }
     __syncthreads();
-    for (int v = threadIdx.x; v < B; v += blockDim.x) order[atomicAdd(&hist[255 - min(iters[v] / 25, 255)], 1)] = v;
+    for (int v = threadIdx.x; v < B; v += blockDim.x) order[atomicAdd(&hist[255 - min(iters[v] / 25, 255)], 1)] = v0 + v;
 }
 
 int admm_configure(pgn_handle* h) {
@@ -127,21 +127,21 @@ int admm_configure(pgn_handle* h) {
 
 void launch_admm(pgn_handle* h) {
     AdmmArgs a;
-    a.q = h->qd; a.st = h->st; a.B = h->B;
+    a.q = h->qd; a.st = h->st; a.B = h->nv;          // tickets of this launch; `order` holds global vehicle indices
     a.rec = h->d_rec; a.ws_xz = h->d_ws_xz; a.ws_y = h->d_ws_y; a.rho = h->d_rho;
     a.sol_x = h->d_sol_x; a.sol_y = h->d_sol_y;
     a.iters = h->d_iters; a.status = h->d_status; a.rho_updates = h->d_rho_updates; a.pri_res = h->d_pri_res; a.dua_res = h->d_dua_res;
-    a.solved = h->d_solved; a.counter = h->d_counter;
+    a.solved = h->d_solved; a.counter = h->d_counter + h->part;
     a.cycles = h->profiling >= 2 ? h->d_cycles : nullptr;      // 1: stage timers only, 2: + in-kernel cycle counters
-    cudaMemsetAsync(h->d_counter, 0, sizeof(int), h->stream);
-    k_admm_order<<<1, 1024, 0, h->stream>>>(h->d_iters, h->d_order, h->B);
+    cudaMemsetAsync(h->d_counter + h->part, 0, sizeof(int), h->stream);
+    k_admm_order<<<1, 1024, 0, h->stream>>>(h->d_iters + h->v0, h->d_order + h->v0, h->nv, h->v0);
     h->launches++;
-    a.order = h->d_order;
+    a.order = h->d_order + h->v0;
     a.skip = (h->guard_pause > 0.0 || h->in_callback) ? h->d_skip : nullptr; a.cold = h->d_cold;
     for (size_t i = 0; i < h->tab.sol_ph_ptr.size() && i <= ADMM_MAX_PHASES; i++) a.ph_ptr[i] = h->tab.sol_ph_ptr[i];
     const bool small = h->admm_threads == 256;
     int grid = h->num_sms * (small ? 2 : 1);
-    if (grid > h->B) grid = h->B;
+    if (grid > h->nv) grid = h->nv;
     if (small) {
         if (a.cycles) v256::k_admm<true><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
         else v256::k_admm<false><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);

@@ -158,6 +158,29 @@ int set_hji_internal(pgn_handle* h, const int32_t dims[7], const float* knots, c
     return PGN_OK;
 }
 
+// Runs `body` once per pipeline part: the part's vehicle range, stream, side stream and fork / join events are swapped into the handle
+// (the launchers read them from there), every part stream starts after what is already queued on the caller's stream, and the caller's
+// stream continues after all parts.  One part (or stage timers on): `body` runs as is on the caller's stream.
+template <class F>
+int for_each_part(pgn_handle* h, F body) {
+    if (h->parts <= 1 || h->profiling) return body();
+    cudaStream_t s0 = h->stream, side0 = h->side_stream;
+    cudaEvent_t f0 = h->ev_fork, j0 = h->ev_join;
+    int rc = PGN_OK;
+    cudaEventRecord(h->part_begin, s0);
+    for (int p = 0; p < h->parts && rc == PGN_OK; p++) {
+        cudaStreamWaitEvent(h->part_stream[p], h->part_begin, 0);
+        h->stream = h->part_stream[p]; h->side_stream = h->part_side[p]; h->ev_fork = h->part_evf[p]; h->ev_join = h->part_evj[p];
+        h->part = p; h->v0 = (int)((long long)h->B * p / h->parts); h->nv = (int)((long long)h->B * (p + 1) / h->parts) - h->v0;
+        rc = body();
+        cudaEventRecord(h->part_done[p], h->part_stream[p]);
+    }
+    h->stream = s0; h->side_stream = side0; h->ev_fork = f0; h->ev_join = j0;
+    h->part = 0; h->v0 = 0; h->nv = h->B;
+    for (int p = 0; p < h->parts; p++) cudaStreamWaitEvent(s0, h->part_done[p], 0);
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -223,6 +246,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->stream = h->own_stream;
     cudaEventCreate(&h->ev[0]); cudaEventCreate(&h->ev[1]);
     h->side_stream = nullptr;
+    h->parts = 1; h->parts_created = 0; h->v0 = 0; h->nv = h->B; h->part = 0;
     cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     double vp[PGN_VEHICLE_PARAMS_LEN], cp[PGN_CONTROL_PARAMS_LEN];
@@ -299,7 +323,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 4); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se0, 2 * B); AL(d_se, 2 * B); AL(d_tskip, B);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 2 * PGN_MAX_PARTS); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se0, 2 * B); AL(d_se, 2 * B); AL(d_tskip, B);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
@@ -360,6 +384,13 @@ int pgn_destroy(pgn_handle* h) {
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->parts_created) {
+        for (int p = 0; p < PGN_MAX_PARTS; p++) {
+            cudaStreamDestroy(h->part_stream[p]); cudaStreamDestroy(h->part_side[p]);
+            cudaEventDestroy(h->part_done[p]); cudaEventDestroy(h->part_evf[p]); cudaEventDestroy(h->part_evj[p]);
+        }
+        cudaEventDestroy(h->part_begin);
+    }
     cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
     cudaEventDestroy(h->ev[0]); cudaEventDestroy(h->ev[1]);
     delete h;
@@ -492,11 +523,15 @@ int pgn_get_next_control(pgn_handle* h, double* out) {
 }
 int pgn_step_device(pgn_handle* h, const double* d_t0, double* d_out) {
     REQUIRE(h && d_t0, "NULL argument");
-    step_time_steps_dev(h, d_t0);
-    step_nodes(h);
-    step_update(h);
-    step_solve(h);
-    step_controls(h, h->d_controls);
+    int rc = for_each_part(h, [&]() {
+        step_time_steps_dev(h, d_t0);
+        step_nodes(h);
+        step_update(h);
+        step_solve(h);
+        step_controls(h, h->d_controls);
+        return (int)PGN_OK;
+    });
+    if (rc) return rc;
     if (d_out) CK(cudaMemcpyAsync(d_out, h->d_controls, (size_t)h->B * 3 * 8, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaGetLastError());
     return PGN_OK;
@@ -564,14 +599,8 @@ int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const doub
     memcpy(out, io + 1 + 14 * B, 5 * B * 8);
     return PGN_OK;
 }
-// step + plant rollout of `simulate` (model_predictive_control.jl:87-98) with the plant step beside the QP solve
-int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d_out, double dt) {
-    REQUIRE(h && d_t0, "NULL argument");
-    if (h->profiling || !h->side_stream) {            // stage timers synchronise: serial order
-        int rc = pgn_step_device(h, d_t0, d_out);
-        if (rc) return rc;
-        return pgn_rollout(h, dt);
-    }
+// one closed-loop step of the current vehicle range on the current stream: the step stages, the plant step on the side stream
+static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt) {
     step_time_steps_dev(h, d_t0);
     step_nodes(h);
     step_update(h);
@@ -582,9 +611,21 @@ int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d_out, do
     CK(cudaEventRecord(h->ev_join, h->side_stream));
     step_solve(h);
     step_controls(h, h->d_controls);
-    if (d_out) CK(cudaMemcpyAsync(d_out, h->d_controls, (size_t)h->B * 3 * 8, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     launch_commit_rollout(h);
+    return PGN_OK;
+}
+// step + plant rollout of `simulate` (model_predictive_control.jl:87-98) with the plant step beside the QP solve
+int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d_out, double dt) {
+    REQUIRE(h && d_t0, "NULL argument");
+    if (h->profiling || !h->side_stream) {            // stage timers synchronise: serial order
+        int rc = pgn_step_device(h, d_t0, d_out);
+        if (rc) return rc;
+        return pgn_rollout(h, dt);
+    }
+    int rc = for_each_part(h, [&]() { return step_rollout_body(h, d_t0, dt); });
+    if (rc) return rc;
+    if (d_out) CK(cudaMemcpyAsync(d_out, h->d_controls, (size_t)h->B * 3 * 8, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaGetLastError());
     return PGN_OK;
 }
@@ -594,18 +635,68 @@ int pgn_rollout(pgn_handle* h, double dt) {
     CK(cudaGetLastError());
     return PGN_OK;
 }
+// the `simulate` loop on the device: every pipeline part runs ALL its steps on its own stream (a vehicle's step k+1 depends only on its own
+// step k), so the parts drift apart and the small per-vehicle kernels of one part fill the SMs the ADMM kernel of another leaves idle
+static int simulate_enqueue(pgn_handle* h, double dt, int n_steps) {
+    if (h->profiling || !h->side_stream) {
+        for (int k = 0; k < n_steps; k++) {
+            launch_time_axpy(h, h->d_t0_base, (double)k, dt, h->d_t0, h->B);
+            int rc = pgn_step_rollout_device(h, h->d_t0, nullptr, dt);
+            if (rc) return rc;
+        }
+        return PGN_OK;
+    }
+    return for_each_part(h, [&]() {
+        for (int k = 0; k < n_steps; k++) {
+            launch_time_axpy(h, h->d_t0_base + h->v0, (double)k, dt, h->d_t0 + h->v0, h->nv);
+            int rc = step_rollout_body(h, h->d_t0, dt);
+            if (rc) return rc;
+        }
+        return (int)PGN_OK;
+    });
+}
+// automatic part count: one part per two full waves of ADMM CTAs, at most 4 (measured on B = 1024: 1 part 2.91 ms, 2 parts 2.69, 4 parts 2.50 per step)
+static int auto_parts(pgn_handle* h) {
+    const int ctas = h->num_sms * (h->admm_threads == 256 ? 2 : 1);
+    int p = h->B / (2 * ctas);
+    return p < 1 ? 1 : (p > 4 ? 4 : p);
+}
 int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
     REQUIRE(h && t0 && n_steps >= 0, "bad argument");
     CK(cudaMemcpyAsync(h->d_t0_base, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
-    for (int k = 0; k < n_steps; k++) {
-        launch_time_axpy(h, h->d_t0_base, (double)k, dt, h->d_t0, h->B);
-        int rc = pgn_step_rollout_device(h, h->d_t0, nullptr, dt);
-        if (rc) return rc;
-    }
+    int rc = simulate_enqueue(h, dt, n_steps);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     return PGN_OK;
 }
+int pgn_simulate_device(pgn_handle* h, const double* d_t0, double dt, int32_t n_steps) {
+    REQUIRE(h && d_t0 && n_steps >= 0, "bad argument");
+    CK(cudaMemcpyAsync(h->d_t0_base, d_t0, (size_t)h->B * 8, cudaMemcpyDeviceToDevice, h->stream));
+    int rc = simulate_enqueue(h, dt, n_steps);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return PGN_OK;
+}
+int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts) {
+    REQUIRE(h, "NULL handle");
+    REQUIRE(parts >= 0 && parts <= PGN_MAX_PARTS, "parts must be 0 (automatic) or 1..8");
+    if (parts == 0) parts = auto_parts(h);
+    if (parts > h->B) parts = h->B;
+    if (parts > 1 && !h->parts_created) {
+        CK(cudaEventCreateWithFlags(&h->part_begin, cudaEventDisableTiming));
+        for (int p = 0; p < PGN_MAX_PARTS; p++) {
+            CK(cudaStreamCreateWithFlags(&h->part_stream[p], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->part_side[p], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->part_done[p], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->part_evf[p], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->part_evj[p], cudaEventDisableTiming));
+        }
+        h->parts_created = 1;
+    }
+    h->epoch++;
+    h->parts = parts;
+    return PGN_OK;
+}
+int pgn_get_pipeline_parts(pgn_handle* h, int32_t* parts) { REQUIRE(h && parts, "NULL argument"); *parts = h->parts; return PGN_OK; }
 
 // ---- introspection -----------------------------------------------------------------------------------------------------------
 int pgn_qp_dims(pgn_handle* h, int32_t* o) {

@@ -94,11 +94,12 @@ __global__ void __launch_bounds__(128) k_hji_lookup(HjiView H, int M, const doub
 }
 
 // reachability constraint M u + b >= -sigma for every vehicle; writes (M1*un1, M2*un2, b) into the record
-__global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, VehParams P, double eps, double un0, double un1, const double* __restrict__ state,
+__global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, int v0, int nv, VehParams P, double eps, double un0, double un1, const double* __restrict__ state,
                                                         const double* __restrict__ control, const double* __restrict__ other, double* __restrict__ rec,
                                                         int rec_len, int o_hji, double* __restrict__ hji_val /*[8][B]: gradV[0..6], V*/) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= B) return;
+    const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iv >= nv) return;
+    const int v = v0 + iv;
     const double E = state[0 * B + v], N = state[1 * B + v], psi = state[2 * B + v], Ux = state[3 * B + v], Uy = state[4 * B + v], r = state[5 * B + v];
     const double oE = other[0 * B + v], oN = other[1 * B + v], opsi = other[2 * B + v], oV = other[3 * B + v];
     // HJIRelativeState: `cψ, sψ = sincos(-ψ)` binds cψ <- sin(-ψ), sψ <- cos(-ψ) (HJI_computation.jl:21-22)
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, VehPar
 
 void launch_hji_constraint(pgn_handle* h) {
     const int B = h->B;
-    k_hji_constraint<<<(B + 127) / 128, 128, 0, h->stream>>>(h->hji, B, h->veh, h->cfg.hji_eps, h->un[0], h->un[1], h->d_state, h->d_control, h->d_other,
+    k_hji_constraint<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(h->hji, B, h->v0, h->nv, h->veh, h->cfg.hji_eps, h->un[0], h->un[1], h->d_state, h->d_control, h->d_other,
                                                              h->d_rec, h->tab.rec.rec_len, h->tab.rec.o_hji, h->d_hji_val);
     h->launches++;
 }

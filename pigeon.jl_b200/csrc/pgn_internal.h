@@ -20,6 +20,8 @@
 #include "pgn_device.cuh"
 #include "pgn_structure.h"
 
+#define PGN_MAX_PARTS 8
+
 namespace pgn {
 
 struct TrajView {
@@ -106,6 +108,12 @@ struct pgn_handle {
     // and the CUDA graph of the whole call (H2D copy, unpack, the five step stages, pack, D2H copy), re-captured when a setter bumps `epoch`
     // plant rollout beside the ADMM launch (pgn_step_rollout_device / pgn_simulate): shadow state, side stream, fork / join events
     double* d_state_next; cudaStream_t side_stream; cudaEvent_t ev_fork, ev_join;
+    // pipeline parts (pgn_set_pipeline_parts): the fused entry points run the batch as `parts` contiguous vehicle ranges, each on its own
+    // stream, so that the thread-per-vehicle stages of one range run while the ADMM kernel of another drains.  Launchers read the range
+    // of the current launch from (v0, nv, part); outside the fused entry points it is the whole batch (0, B, 0).
+    int parts, parts_created, v0, nv, part;
+    cudaStream_t part_stream[PGN_MAX_PARTS], part_side[PGN_MAX_PARTS];
+    cudaEvent_t part_begin, part_done[PGN_MAX_PARTS], part_evf[PGN_MAX_PARTS], part_evj[PGN_MAX_PARTS];
     double* d_se0;                                       // decoupled node generation: (s0, e0) handed from the scan kernel to the rollout kernel
     double *h_io, *d_io, *d_se; uint8_t* d_tskip; int in_callback;
     cudaGraph_t cb_graph; cudaGraphExec_t cb_exec; long long epoch, cb_epoch, cb_launches; cudaStream_t cb_stream; int cb_has_exec;

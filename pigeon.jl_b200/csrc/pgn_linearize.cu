@@ -247,11 +247,12 @@ __global__ void __launch_bounds__(128) k_linearize_decoupled(const LinArgs a) {
 
 void launch_linearize(pgn_handle* h) {
     LinArgs a;
-    a.B = h->B; a.N = h->N; a.T = h->T; a.Ns = h->cfg.N_short; a.nsub = h->cfg.rk4_substeps;
+    a.B = h->nv; a.N = h->N; a.T = h->T; a.Ns = h->cfg.N_short; a.nsub = h->cfg.rk4_substeps;     // per-vehicle rows only: a pipeline part is an offset
     a.P = h->veh; a.C = h->ctl; a.un0 = h->un[0]; a.un1 = h->un[1];
     a.R = h->tab.rec;
-    a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps; a.dt = h->d_dt; a.rec = h->d_rec;
-    const long long nodes = (long long)h->B * h->T;
+    const size_t o = (size_t)h->v0;
+    a.qs = h->d_qs + o * h->N * h->nx; a.us = h->d_us + o * h->N * 2; a.ps = h->d_ps + o * h->N * 4; a.dt = h->d_dt + o * h->T; a.rec = h->d_rec + o * h->tab.rec.rec_len;
+    const long long nodes = (long long)h->nv * h->T;
     if (h->cfg.kind == PGN_COUPLED) {
         const long long threads = nodes * 4;
         k_linearize_coupled<<<(unsigned)((threads + 127) / 128), 128, 0, h->stream>>>(a);

@@ -135,6 +135,7 @@ __global__ void k_time_steps(int B, int Ns, int Nl, double dt_short, double dt_l
 // ---- compute_linearization_nodes! ------------------------------------------------------------------------------------
 struct NodeArgs {
     int B, N, Ns, kind, n_sol;
+    int v0, nv;                                   // vehicle range of this launch (a pipeline part, pgn_set_pipeline_parts); B stays the SoA stride
     VehParams P; CtrlParams C; double un0, un1;
     TrajView tv;
     const double *state, *control, *toff; const uint8_t* solved; const int32_t* traj_id;
@@ -209,16 +210,18 @@ __device__ void decoupled_cold_rollout(const NodeArgs& a, int v, double s0, doub
         }
 }
 __global__ void __launch_bounds__(128) k_nodes_decoupled_rollout(const NodeArgs a, const double* __restrict__ se0) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= a.B) return;
+    const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iv >= a.nv) return;
+    const int v = a.v0 + iv;
     decoupled_cold_rollout(a, v, se0[v], se0[a.B + v]);
 }
 
 // One warp per vehicle: the lanes share the closest-segment scan and, on warm steps, take one horizon node each; the cold rollout
 // (a recurrence over the nodes) runs on lane 0.
 __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
-    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (v >= a.B) return;
+    const int iv = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (iv >= a.nv) return;
+    const int v = a.v0 + iv;
     const int B = a.B, N = a.N, Ns = a.Ns;
     const VehParams& P = a.P;
     const CtrlParams& C = a.C;
@@ -330,12 +333,13 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
 // ---- get_next_control ------------------------------------------------------------------------------------------------
 // With the guards of src/ros_integration.jl: a paused vehicle (Ux below the threshold, :84-87) and a vehicle whose QP returned NaN
 // (:134-147) keep their current control; the latter is also re-initialised (cold ADMM iterates, mpc.solved = false).
-__global__ void k_controls(int B, int kind, int n_sol, int iv_delta, int iv_fx, double un0, double un1, VehParams P,
+__global__ void k_controls(int B, int v0, int nv, int kind, int n_sol, int iv_delta, int iv_fx, double un0, double un1, VehParams P,
                            const double* __restrict__ sol_x, const double* __restrict__ us, int N, double* __restrict__ out,
                            const double* __restrict__ control, const uint8_t* __restrict__ skip, int guard_nan, uint8_t* __restrict__ cold,
                            uint8_t* __restrict__ solved, const double* __restrict__ hji_val, double hji_eps, const double* __restrict__ state) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= B) return;
+    const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iv >= nv) return;
+    const int v = v0 + iv;
     double d, Fx;
     if (hji_val && hji_val[(size_t)7 * B + v] <= hji_eps) {
         // use_HJI_policy && V <= HJI_eps (ros_integration.jl:115-118): optimal_control replaces the QP's control
@@ -437,14 +441,16 @@ __global__ void k_time_axpy(int n, const double* __restrict__ base, double k, do
 
 // ---- launchers -------------------------------------------------------------------------------------------------------
 void launch_time_steps(pgn_handle* h, const double* d_t0) {
-    const int B = h->B;
+    const int B = h->nv;          // per-vehicle rows only: a part is an offset into every array
+    const size_t o = (size_t)h->v0;
     k_time_steps<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.N_short, h->cfg.N_long, h->cfg.dt_short, h->cfg.dt_long, h->cfg.use_correction_step,
-                                                         d_t0, h->d_ts, h->d_dt, h->d_prev_ts);
+                                                         d_t0 + o, h->d_ts + o * h->N, h->d_dt + o * h->T, h->d_prev_ts + o * h->N);
     h->launches++;
 }
 void launch_nodes(pgn_handle* h) {
     NodeArgs a;
     a.B = h->B; a.N = h->N; a.Ns = h->cfg.N_short; a.kind = h->cfg.kind; a.n_sol = h->tab.n;
+    a.v0 = h->v0; a.nv = h->nv;
     a.P = h->veh; a.C = h->ctl; a.un0 = h->un[0]; a.un1 = h->un[1];
     a.tv = h->traj;
     a.state = h->d_state; a.control = h->d_control; a.toff = h->d_toff; a.solved = h->d_solved; a.traj_id = h->d_traj_id;
@@ -452,10 +458,10 @@ void launch_nodes(pgn_handle* h) {
     a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps;
     a.skip = h->d_skip; a.pause_below_speed = h->guard_pause; a.tskip = h->in_callback ? h->d_tskip : nullptr;
     a.window = h->path_window; a.last_seg = h->d_last_seg; a.se0 = h->d_se0;
-    k_nodes<<<(h->B + 3) / 4, 128, 0, h->stream>>>(a);
+    k_nodes<<<(h->nv + 3) / 4, 128, 0, h->stream>>>(a);
     h->launches++;
     if (h->cfg.kind == PGN_DECOUPLED) {
-        k_nodes_decoupled_rollout<<<(h->B + 127) / 128, 128, 0, h->stream>>>(a, h->d_se0);
+        k_nodes_decoupled_rollout<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(a, h->d_se0);
         h->launches++;
     }
 }
@@ -469,7 +475,7 @@ void launch_callback_out(pgn_handle* h) {
 }
 void launch_controls(pgn_handle* h, double* d_out) {
     const int B = h->B;
-    k_controls<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.kind, h->tab.n, h->tab.var_u1_delta, h->tab.var_u1_fx, h->un[0], h->un[1], h->veh,
+    k_controls<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(B, h->v0, h->nv, h->cfg.kind, h->tab.n, h->tab.var_u1_delta, h->tab.var_u1_fx, h->un[0], h->un[1], h->veh,
                                                        h->d_sol_x, h->d_us, h->N, d_out, h->d_control, (h->guard_pause > 0.0 || h->in_callback) ? h->d_skip : nullptr, h->guard_nan,
                                                        h->d_cold, h->d_solved, (h->hji_policy && h->cfg.kind == PGN_COUPLED) ? h->d_hji_val : nullptr, h->cfg.hji_eps, h->d_state);
     h->launches++;
@@ -482,10 +488,11 @@ void launch_rollout(pgn_handle* h, double dt) {
 // The plant step only needs the state and the control that was applied DURING the interval, both known before the QP is solved, so it
 // can run beside the ADMM launch: propagate into a shadow state on the side stream, commit (state <- shadow, control <- new control) on
 // the main stream once both are done.
-__global__ void __launch_bounds__(128) k_propagate_shadow(int B, VehParams P, double dt, int nsub, const double* __restrict__ state, const double* __restrict__ control,
+__global__ void __launch_bounds__(128) k_propagate_shadow(int B, int v0, int nv, VehParams P, double dt, int nsub, const double* __restrict__ state, const double* __restrict__ control,
                                                           double* __restrict__ state_next) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= B) return;
+    const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iv >= nv) return;
+    const int v = v0 + iv;
     double x[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) x[i] = state[i * B + v];
@@ -494,9 +501,10 @@ __global__ void __launch_bounds__(128) k_propagate_shadow(int B, VehParams P, do
 #pragma unroll
     for (int i = 0; i < 6; i++) state_next[i * B + v] = x[i];
 }
-__global__ void k_commit_rollout(int B, const double* __restrict__ state_next, const double* __restrict__ new_control, double* __restrict__ state, double* __restrict__ control) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= B) return;
+__global__ void k_commit_rollout(int B, int v0, int nv, const double* __restrict__ state_next, const double* __restrict__ new_control, double* __restrict__ state, double* __restrict__ control) {
+    const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iv >= nv) return;
+    const int v = v0 + iv;
 #pragma unroll
     for (int i = 0; i < 6; i++) state[i * B + v] = state_next[i * B + v];
 #pragma unroll
@@ -504,12 +512,12 @@ __global__ void k_commit_rollout(int B, const double* __restrict__ state_next, c
 }
 void launch_propagate_shadow(pgn_handle* h, double dt, cudaStream_t side) {
     const int B = h->B;
-    k_propagate_shadow<<<(B + 127) / 128, 128, 0, side>>>(B, h->veh, dt, h->cfg.rk4_substeps, h->d_state, h->d_control, h->d_state_next);
+    k_propagate_shadow<<<(h->nv + 127) / 128, 128, 0, side>>>(B, h->v0, h->nv, h->veh, dt, h->cfg.rk4_substeps, h->d_state, h->d_control, h->d_state_next);
     h->launches++;
 }
 void launch_commit_rollout(pgn_handle* h) {
     const int B = h->B;
-    k_commit_rollout<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->d_state_next, h->d_controls, h->d_state, h->d_control);
+    k_commit_rollout<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(B, h->v0, h->nv, h->d_state_next, h->d_controls, h->d_state, h->d_control);
     h->launches++;
 }
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k) {

@@ -272,6 +272,21 @@ class BatchedTrajectoryTrackingMPC:
     def simulate_device(self, t0, dt, n_steps):
         check(self._lib.pgn_simulate(self._h, dptr(self._t0(t0)), float(dt), int(n_steps)))
 
+    def simulate_device_async(self, d_t0_ptr, dt, n_steps):
+        """pgn_simulate with t0 resident on the device, enqueued on the handle's stream (no host synchronisation)."""
+        check(self._lib.pgn_simulate_device(self._h, C.c_void_p(d_t0_ptr), float(dt), int(n_steps)))
+
+    def set_pipeline_parts(self, parts):
+        """Run the fused entry points as `parts` vehicle ranges on their own streams (0: automatic, 1: off); results do not depend on it."""
+        check(self._lib.pgn_set_pipeline_parts(self._h, int(parts)))
+        return self.pipeline_parts
+
+    @property
+    def pipeline_parts(self):
+        n = C.c_int32(0)
+        check(self._lib.pgn_get_pipeline_parts(self._h, C.byref(n)))
+        return int(n.value)
+
     def synchronize(self):
         check(self._lib.pgn_synchronize(self._h))
 

@@ -214,6 +214,70 @@ def test_simulate_on_device_matches_stepwise(p):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("kind", ["coupled", "decoupled"])
+def test_pipeline_parts_are_bit_identical(p, kind):
+    """pgn_set_pipeline_parts: the fused entry points run the batch as vehicle ranges on their own streams.  Every vehicle's results must be
+    bit-identical for any part count (ragged ranges included), through the host step, the device step + rollout and the on-device
+    simulate loop, with the guards on and an HJI cache that is active for part of the batch."""
+    import torch
+    B = 203                                                       # not a multiple of any part count
+    trajs = p.synthetic.synthetic_trajectories(n_traj=4, n_nodes=300)
+    tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
+    other = np.tile(FAR, (B, 1))
+    rng = np.random.default_rng(5)
+    other[::3, 0] = state[::3, 0] + rng.uniform(2, 8, len(other[::3])); other[::3, 1] = state[::3, 1] + rng.uniform(-3, 3, len(other[::3]))
+    other[::3, 2] = state[::3, 2]
+    ctor = p.BatchedCoupledTrajectoryTrackingMPC if kind == "coupled" else p.BatchedDecoupledTrajectoryTrackingMPC
+    knots, V, gV = p.synthetic.analytic_hji_grid((7, 7, 5, 5, 4, 5, 4))
+
+    def run(parts):
+        g = ctor(p.X1(), trajs, B, trajectory_index=tid)
+        if kind == "coupled":
+            g.set_HJI_cache(p.HJICache(knots, V, gV))
+        g.set_guards(True, 1.0)
+        assert g.set_pipeline_parts(parts) == parts
+        g.set_state(state, control, other)
+        outs = [g.step(t0)]                                       # host step (joined parts)
+        g.rollout(0.01)
+        d_t0 = torch.tensor(t0 + 0.01, dtype=torch.float64, device="cuda")
+        d_out = torch.zeros(3 * B, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        for k in range(3):                                        # device step + rollout
+            g.step_rollout_device(d_t0.data_ptr(), d_out.data_ptr(), 0.01)
+            g.synchronize()
+            outs.append(d_out.cpu().numpy().copy())
+            d_t0 += 0.01
+            torch.cuda.synchronize()
+        g.simulate_device(t0 + 0.04, 0.01, 5)                     # free-running parts
+        g.simulate_device_async(d_t0.data_ptr(), 0.01, 2); g.synchronize()
+        q, u = g.get_state()
+        st = g.stats()
+        x, y = g.solution()
+        g.close()
+        return outs, q, u, st["iters"].copy(), st["status"].copy(), x, y
+
+    ref = run(1)
+    for parts in (2, 3, 8):
+        got = run(parts)
+        for a, b in zip(ref[0], got[0]):
+            assert np.array_equal(a, b, equal_nan=True), parts
+        for a, b in zip(ref[1:], got[1:]):
+            assert np.array_equal(a, b, equal_nan=True), parts
+
+
+def test_pipeline_parts_arguments(p):
+    trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, 5, trajectory_index=np.zeros(5, np.int32))
+    assert g.pipeline_parts == 1
+    assert g.set_pipeline_parts(8) == 5                           # never more parts than vehicles
+    assert g.set_pipeline_parts(0) == 1                           # automatic: a small batch stays in one part
+    with pytest.raises(p.PigeonError):
+        g.set_pipeline_parts(9)
+    with pytest.raises(p.PigeonError):
+        g.set_pipeline_parts(-1)
+    g.close()
+
+
 def test_decoupled_uses_feedforward_force(p):
     # decoupled_lat_long.jl:275-278: delta from the QP, Fx from the node generator (us[2].Fx)
     B = 8
