@@ -146,6 +146,7 @@ def run_gpu(args):
     stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: the library launches on it, the events are recorded on it
     torch.cuda.set_stream(stream)
     mpc.set_stream(stream.cuda_stream)
+    parts = mpc.set_pipeline_parts(args.parts)      # vehicle ranges on their own streams inside the fused calls (0 = automatic); results do not depend on it
     dt = 0.01
 
     def barrier():
@@ -156,16 +157,29 @@ def run_gpu(args):
 
     # ---------------- device-resident arm (`value`) ----------------
     mpc.set_state(state, control, other)
-    d_t0 = torch.tensor(t0, dtype=torch.float64, device=dev)
+    d_base = torch.tensor(t0, dtype=torch.float64, device=dev)
+    d_t0 = d_base.clone()
     d_out = torch.zeros(3 * B, dtype=torch.float64, device=dev)
     rec_states, rec_controls = [], []     # closed-loop replay for the e2e arm
+    kstep = [0]                           # step k runs at t0 + k*dt on every path (per-step calls, the simulate loop, the e2e replay)
 
     def dev_step(record):
         if record:
             q, u = mpc.get_state()
             rec_states.append(q); rec_controls.append(u)
+        torch.add(d_base, kstep[0] * dt, out=d_t0)
         mpc.step_rollout_device(d_t0.data_ptr(), d_out.data_ptr(), dt)      # step + plant rollout (launched beside the QP solve)
-        d_t0.add_(dt)
+        kstep[0] += 1
+
+    def dev_steps(n):
+        """n closed-loop steps with device-resident inputs: one call of the on-device `simulate` loop (model_predictive_control.jl:87-98;
+        the pipeline parts run their steps independently), or n per-step calls with --loop steps."""
+        if args.loop == "simulate":
+            mpc.simulate_device_async(d_base.data_ptr(), dt, n, k0=kstep[0])
+            kstep[0] += n
+        else:
+            for _ in range(n):
+                dev_step(False)
 
     # pass 1 (untimed): record the closed-loop states of all SETTLE+W+K steps for the e2e replay
     for _ in range(SETTLE + W + K):
@@ -173,7 +187,7 @@ def run_gpu(args):
     # pass 2 (timed): identical closed loop from the same initial condition (the path is deterministic)
     mpc.reset_solver(); mpc.reset_solved()
     mpc.set_state(state, control, other)
-    d_t0.copy_(torch.tensor(t0, dtype=torch.float64, device=dev))
+    kstep[0] = 0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()           # nvidia-smi needs ~0.2 s to deliver its first sample: started before the settling pass, read over the whole loaded region
@@ -181,26 +195,31 @@ def run_gpu(args):
     barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record(stream)
-    for _ in range(SETTLE):
-        dev_step(False)
+    dev_steps(SETTLE)
     c1.record(stream)
     barrier()
     cold_ms = c0.elapsed_time(c1)
-    for _ in range(W):
-        dev_step(False)
+    dev_steps(W)
     barrier()
     t_timed = time.perf_counter()      # clock samples from here on are the ones reported (the GPU is warm: settling + warm-up ran just before)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mpc.stage_ms(reset=True)
     ev0.record(stream)
-    for _ in range(K):
-        dev_step(False)
+    dev_steps(K)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = mpc.stage_ms(reset=True)["launches"]
-    clocks = sampler.stop(t_timed) if rank == 0 else None
     st = mpc.stats()
+    # the same K steps as K per-step calls (pgn_step_rollout_device: the parts are joined at the end of every call), reported beside `value`
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    for _ in range(K):
+        dev_step(False)
+    ev3.record(stream)
+    barrier()
+    ms_calls = ev2.elapsed_time(ev3)
+    clocks = sampler.stop(t_timed) if rank == 0 else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -345,7 +364,11 @@ def run_gpu(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "horizon_nodes": mpc.N, "qp": {"n": n, "m": m, "nnzA": nnzA, "nnzL": nnzL, "levels": mpc.n_levels, "program": prog},
                            "l2": "per-step working set (records + iterates, ~%.0f MB per GPU) is rewritten every step; B=1024 fits L2, the ADMM kernel is not HBM-bound" % (B * bytes_per_qp / 1e6),
-                           "parallelism": f"batch sharded over {world} GPU(s), no hot-path collective"},
+                           "parallelism": f"batch sharded over {world} GPU(s), no hot-path collective",
+                           "loop": ("one pgn_simulate_device call of K closed-loop steps (the reference's `simulate` loop on the device)" if args.loop == "simulate" else "K pgn_step_rollout_device calls"),
+                           "pipeline_parts": parts},
+                "per_step_calls": {"value": world * B * K / (ms_calls * 1e-3), "unit": UNIT + " (rank 0 time)", "ms_per_step": ms_calls / K,
+                                   "call": "pgn_step_rollout_device x K, device-resident; the pipeline parts are joined at the end of every call"},
                 "roofline": roof, "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (6 + 3 + 1) * 8, "d2h_bytes_per_step": B * 3 * 8},
                 "gpu_launches": int(launches), "clocks": clocks,
@@ -370,6 +393,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1024, help="vehicles per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--parts", type=int, default=0, help="pipeline parts of the fused calls (0 = automatic, 1 = off)")
+    ap.add_argument("--loop", default="simulate", choices=["simulate", "steps"], help="timed region of `value`: one on-device simulate call of K steps, or K per-step calls")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the per-call latency leg")
     args = ap.parse_args()

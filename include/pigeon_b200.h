@@ -140,8 +140,9 @@ PGN_API int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d
 /* simulate (model_predictive_control.jl:80-100): n_steps closed-loop steps fully on the device:
  * step at t0 + k*dt, plant rollout propagate(dynamics, state, StepControl(dt, control)), apply the new control */
 PGN_API int pgn_simulate(pgn_handle* h, const double* t0 /*[B]*/, double dt, int32_t n_steps);
-/* the same loop with t0 a DEVICE pointer, enqueued on the handle's stream without a host synchronisation (results are stream-ordered) */
-PGN_API int pgn_simulate_device(pgn_handle* h, const double* d_t0 /*[B]*/, double dt, int32_t n_steps);
+/* the same loop with t0 a DEVICE pointer, enqueued on the handle's stream without a host synchronisation (results are stream-ordered);
+ * runs the steps k = k0 .. k0 + n_steps - 1 at t0 + k*dt, so that a long loop can be issued in pieces on one time axis */
+PGN_API int pgn_simulate_device(pgn_handle* h, const double* d_t0 /*[B]*/, double dt, int32_t k0, int32_t n_steps);
 /* Pipeline parts of the fused entry points (pgn_step, pgn_step_device, pgn_step_rollout_device, pgn_simulate, pgn_simulate_device): the batch is
  * run as `parts` contiguous vehicle ranges, each on its own stream, so that the per-vehicle stages (nodes, linearisation, HJI, controls, plant
  * step) of one range run while the ADMM kernel of another drains; inside pgn_simulate every range runs all its steps without waiting for the

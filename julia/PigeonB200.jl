@@ -234,8 +234,8 @@ function pipeline_parts(mpc::BatchedTrajectoryTrackingMPC)
     Int(n[])
 end
 "the simulate loop with t0 resident on the device (CuPtr), enqueued on the handle's stream without a host synchronisation"
-simulate_device!(mpc::BatchedTrajectoryTrackingMPC, d_t0::Ptr{Float64}, dt::Float64, n_steps::Integer) =
-    check(ccall((:pgn_simulate_device, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Int32), mpc.handle, d_t0, dt, Int32(n_steps)))
+simulate_device!(mpc::BatchedTrajectoryTrackingMPC, d_t0::Ptr{Float64}, dt::Float64, n_steps::Integer; k0::Integer=0) =
+    check(ccall((:pgn_simulate_device, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Int32, Int32), mpc.handle, d_t0, dt, Int32(k0), Int32(n_steps)))
 
 "simulate(mpc, q0, u0, dt) (src/model_predictive_control.jl:80-100) for the whole batch, entirely on the device; returns the final (state, control)."
 function simulate(mpc::BatchedTrajectoryTrackingMPC, q0::Matrix{Float64}, u0::Matrix{Float64}; dt=0.01, t0=zeros(mpc.B), n_steps::Integer)

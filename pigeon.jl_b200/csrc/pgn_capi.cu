@@ -637,9 +637,9 @@ int pgn_rollout(pgn_handle* h, double dt) {
 }
 // the `simulate` loop on the device: every pipeline part runs ALL its steps on its own stream (a vehicle's step k+1 depends only on its own
 // step k), so the parts drift apart and the small per-vehicle kernels of one part fill the SMs the ADMM kernel of another leaves idle
-static int simulate_enqueue(pgn_handle* h, double dt, int n_steps) {
+static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
     if (h->profiling || !h->side_stream) {
-        for (int k = 0; k < n_steps; k++) {
+        for (int k = k0; k < k0 + n_steps; k++) {
             launch_time_axpy(h, h->d_t0_base, (double)k, dt, h->d_t0, h->B);
             int rc = pgn_step_rollout_device(h, h->d_t0, nullptr, dt);
             if (rc) return rc;
@@ -647,7 +647,7 @@ static int simulate_enqueue(pgn_handle* h, double dt, int n_steps) {
         return PGN_OK;
     }
     return for_each_part(h, [&]() {
-        for (int k = 0; k < n_steps; k++) {
+        for (int k = k0; k < k0 + n_steps; k++) {
             launch_time_axpy(h, h->d_t0_base + h->v0, (double)k, dt, h->d_t0 + h->v0, h->nv);
             int rc = step_rollout_body(h, h->d_t0, dt);
             if (rc) return rc;
@@ -664,16 +664,16 @@ static int auto_parts(pgn_handle* h) {
 int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
     REQUIRE(h && t0 && n_steps >= 0, "bad argument");
     CK(cudaMemcpyAsync(h->d_t0_base, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = simulate_enqueue(h, dt, n_steps);
+    int rc = simulate_enqueue(h, dt, 0, n_steps);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     return PGN_OK;
 }
-int pgn_simulate_device(pgn_handle* h, const double* d_t0, double dt, int32_t n_steps) {
-    REQUIRE(h && d_t0 && n_steps >= 0, "bad argument");
+int pgn_simulate_device(pgn_handle* h, const double* d_t0, double dt, int32_t k0, int32_t n_steps) {
+    REQUIRE(h && d_t0 && n_steps >= 0 && k0 >= 0, "bad argument");
     CK(cudaMemcpyAsync(h->d_t0_base, d_t0, (size_t)h->B * 8, cudaMemcpyDeviceToDevice, h->stream));
-    int rc = simulate_enqueue(h, dt, n_steps);
+    int rc = simulate_enqueue(h, dt, k0, n_steps);
     if (rc) return rc;
     CK(cudaGetLastError());
     return PGN_OK;

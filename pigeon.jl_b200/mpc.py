@@ -272,9 +272,9 @@ class BatchedTrajectoryTrackingMPC:
     def simulate_device(self, t0, dt, n_steps):
         check(self._lib.pgn_simulate(self._h, dptr(self._t0(t0)), float(dt), int(n_steps)))
 
-    def simulate_device_async(self, d_t0_ptr, dt, n_steps):
-        """pgn_simulate with t0 resident on the device, enqueued on the handle's stream (no host synchronisation)."""
-        check(self._lib.pgn_simulate_device(self._h, C.c_void_p(d_t0_ptr), float(dt), int(n_steps)))
+    def simulate_device_async(self, d_t0_ptr, dt, n_steps, k0=0):
+        """pgn_simulate with t0 resident on the device, enqueued on the handle's stream (no host synchronisation): steps k0 .. k0+n_steps-1 at t0 + k*dt."""
+        check(self._lib.pgn_simulate_device(self._h, C.c_void_p(d_t0_ptr), float(dt), int(k0), int(n_steps)))
 
     def set_pipeline_parts(self, parts):
         """Run the fused entry points as `parts` vehicle ranges on their own streams (0: automatic, 1: off); results do not depend on it."""

@@ -85,7 +85,7 @@ for P in [int(a) for a in os.environ.get("SPLIT_LIB", "").split()]:
         for _ in range(K):
             m.step_rollout_device(d_t0.data_ptr(), d_out.data_ptr(), 0.01); d_t0.add_(0.01)
         b.record(s)
-        m.simulate_device_async(d_t0.data_ptr(), 0.01, K)
+        m.simulate_device_async(d_t0.data_ptr(), 0.01, K, 0)
         c.record(s)
         torch.cuda.synchronize()
     print(json.dumps({"library_parts": m.pipeline_parts, "batch": B, "per_step_calls_ms": a.elapsed_time(b) / K, "per_step_calls_steps_per_s": B * K / (a.elapsed_time(b) * 1e-3),
