@@ -655,10 +655,11 @@ static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
         return (int)PGN_OK;
     });
 }
-// automatic part count: one part per two full waves of ADMM CTAs, at most 4 (measured on B = 1024: 1 part 2.91 ms, 2 parts 2.69, 4 parts 2.50 per step)
+// automatic part count: at least one and a half waves of ADMM CTAs per part, at most 4.  Measured on B = 1024 (148 CTAs), simulate loop, ms per
+// step: 1 part 2.87, 2 parts 2.67, 3 parts 2.56, 4 parts 2.49, 6 parts 2.98 (170 QPs = 1.15 waves per launch), 8 parts 2.68.
 static int auto_parts(pgn_handle* h) {
     const int ctas = h->num_sms * (h->admm_threads == 256 ? 2 : 1);
-    int p = h->B / (2 * ctas);
+    int p = (int)((long long)h->B * 2 / (3 * ctas));
     return p < 1 ? 1 : (p > 4 ? 4 : p);
 }
 int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
