@@ -370,6 +370,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     }
     int ce = admm_configure(h);
     if (ce != 0) return bail(set_err(PGN_ECUDA, "ADMM kernel needs %d bytes of shared memory per CTA: %s", h->admm_smem_bytes, cudaGetErrorString((cudaError_t)ce)));
+    if ((rc = pgn_set_pipeline_parts(h, 0))) return bail(rc);     // automatic part count (1 for batches below ~1.5 waves of ADMM CTAs)
     CK(cudaDeviceSynchronize());
     *out = h;
     return PGN_OK;
