@@ -40,7 +40,12 @@ __device__ __forceinline__ void write_envelope(const LinArgs& a, int kind, const
 }
 
 // ---- coupled: 4 lanes per (vehicle, interval) ------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_linearize_coupled(const LinArgs a) {
+// PGN_LIN_MINCTAS (build-time experiment): resident CTAs per SM the register allocation is capped for (2: 244 registers, no spills;
+// 3: 168 registers, 380 B of spill stores; 4: 128 registers, 724 B)
+#ifndef PGN_LIN_MINCTAS
+#define PGN_LIN_MINCTAS 2
+#endif
+__global__ void __launch_bounds__(128, PGN_LIN_MINCTAS) k_linearize_coupled(const LinArgs a) {
     typedef Dual<2> D;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = gid & 3;                  // tangent group of this lane
