@@ -25,5 +25,18 @@ for cls, kw in ((p.BatchedCoupledTrajectoryTrackingMPC, {}), (p.BatchedCoupledTr
     oth = other.copy(); oth[:, 0] = q[:, 0] + 1.0; oth[:, 1] = q[:, 1]; oth[:, 2] = q[:, 2]
     out = m.from_autobox(q, out[:, :3], 0.0, other_car=oth)
     print(cls.__name__, kw, np.isfinite(out).all(), m.stats()["iters"])
+    # pipeline parts: vehicle ranges on their own streams (ragged: 4 parts over 6 vehicles), joined per call and free-running in simulate
+    m.set_pipeline_parts(4)
+    m.set_state(state, control, other)
+    u = m.step(t0)
+    m.rollout(0.01)
+    m.simulate_device(t0 + 0.01, 0.01, 3)
+    import torch
+    d = torch.tensor(t0 + 0.04, dtype=torch.float64, device="cuda"); o3 = torch.zeros(3 * B, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    m.step_rollout_device(d.data_ptr(), o3.data_ptr(), 0.01)
+    m.simulate_device_async(d.data_ptr(), 0.01, 2, k0=1)
+    m.synchronize()
+    print("  parts", m.pipeline_parts, np.isfinite(m.get_state()[0]).all(), m.stats()["iters"])
     m.close()
 print("done")
