@@ -147,7 +147,7 @@ PGN_API int pgn_simulate_device(pgn_handle* h, const double* d_t0 /*[B]*/, doubl
  * run as `parts` contiguous vehicle ranges, each on its own stream, so that the per-vehicle stages (nodes, linearisation, HJI, controls, plant
  * step) of one range run while the ADMM kernel of another drains; inside pgn_simulate every range runs all its steps without waiting for the
  * others (a vehicle's step k+1 depends only on its own step k: the `for` loop of model_predictive_control.jl:87-98 per vehicle).  Every vehicle's
- * results are bit-identical for any part count.  parts = 0 (what pgn_create sets): chosen from the batch size (1 for small batches, at most 4);
+ * results are bit-identical for any part count.  parts = 0 (what pgn_create sets): chosen from the batch size (4 from 64 vehicles up, else 1);
  * 1: one range on the caller's stream; <= 8.
  * The five single-stage calls and pgn_from_autobox always run the whole batch on the caller's stream. */
 PGN_API int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts);

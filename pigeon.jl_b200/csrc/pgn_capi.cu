@@ -656,13 +656,10 @@ static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
         return (int)PGN_OK;
     });
 }
-// automatic part count: at least one and a half waves of ADMM CTAs per part, at most 4.  Measured on B = 1024 (148 CTAs), simulate loop, ms per
-// step: 1 part 2.87, 2 parts 2.67, 3 parts 2.56, 4 parts 2.49, 6 parts 2.98 (170 QPs = 1.15 waves per launch), 8 parts 2.68.
-static int auto_parts(pgn_handle* h) {
-    const int ctas = h->num_sms * (h->admm_threads == 256 ? 2 : 1);
-    int p = (int)((long long)h->B * 2 / (3 * ctas));
-    return p < 1 ? 1 : (p > 4 ? 4 : p);
-}
+// automatic part count: 4 parts from 64 vehicles up.  Measured (simulate loop, coupled N = 31, ms per step with 1 / 2 / 4 / 8 parts): B = 64: 0.75 / 0.69 /
+// 0.63 / 1.10; 128: 0.78 / 0.74 / 0.68 / 1.20; 256: 1.12 / 0.91 / 0.86 / 1.34; 512: 1.74 / 1.46 / 1.29 / 1.63; 1024: 2.87 / 2.67 / 2.49 / 2.68 (3: 2.56, 5: 3.28,
+// 6: 2.98, 7: 2.79); 2048: 5.40 / 4.97 / 4.91; 4096: 10.31 / 9.74 / 9.69.  Per-step calls (parts joined every call) are never slower with 4 parts.
+static int auto_parts(pgn_handle* h) { return h->B >= 64 ? 4 : 1; }
 int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
     REQUIRE(h && t0 && n_steps >= 0, "bad argument");
     CK(cudaMemcpyAsync(h->d_t0_base, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
