@@ -141,7 +141,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, K, W = args.batch, args.steps, args.warmup
-    trajs, tid, state, control, t0, other = make_workload(B, seed_shift=1000 * rank)
+    trajs, tid, state, control, t0, other = make_workload(B, seed_shift=1000 * rank + args.seed_shift)
     mpc = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid, device=local)
     stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: the library launches on it, the events are recorded on it
     torch.cuda.set_stream(stream)
@@ -395,6 +395,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--parts", type=int, default=0, help="pipeline parts of the fused calls (0 = automatic, 1 = off)")
     ap.add_argument("--loop", default="simulate", choices=["simulate", "steps"], help="timed region of `value`: one on-device simulate call of K steps, or K per-step calls")
+    ap.add_argument("--seed-shift", type=int, default=0, help="added to the workload seed (rank r uses 1000*r + this): reproduces another rank's batch at N = 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the per-call latency leg")
     args = ap.parse_args()
