@@ -32,6 +32,17 @@ static int set_err(int code, const char* fmt, ...) {
 
 namespace {
 
+// Every entry point runs on the handle's own device and leaves the caller's current device as it found it, so that ONE host thread can
+// drive handles on several GPUs (the Julia deployment: a single process, one handle per GPU).
+struct DeviceGuard {
+    int prev; bool changed;
+    explicit DeviceGuard(int dev) : prev(-1), changed(false) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+#define ENTER(h, msg)  REQUIRE(h, msg); DeviceGuard dev_guard__((h)->device)
+
 struct StageTimer {
     pgn_handle* h; int idx;
     StageTimer(pgn_handle* h_, int idx_) : h(h_), idx(idx_) { if (h->profiling) cudaEventRecord(h->ev[0], h->stream); }
@@ -146,6 +157,12 @@ int set_hji_internal(pgn_handle* h, const int32_t dims[7], const float* knots, c
         recs[i * 8 + 7] = V[i];
     }
     float *d_k = nullptr, *d_r = nullptr;
+    CK(cudaStreamSynchronize(h->stream));            // kernels in flight may still read the grid that is replaced below
+    if (h->hji.valid) {                              // release the previous grid (319 MB for the real cache)
+        for (const void* old : {(const void*)h->hji.knots, (const void*)h->hji.gV})
+            for (size_t i = 0; i < h->allocs.size(); i++) if (h->allocs[i] == old) { h->allocs.erase(h->allocs.begin() + i); cudaFree((void*)old); break; }
+        h->hji.valid = 0;
+    }
     int rc = dev_alloc(h, &d_k, nk + 8); if (rc) return rc;
     rc = dev_alloc(h, &d_r, nn * 8 + 8); if (rc) return rc;
     CK(cudaMemcpy(d_k, knots, nk * sizeof(float), cudaMemcpyHostToDevice));
@@ -211,7 +228,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     int dev = cfg->device;
     if (dev < 0) CK(cudaGetDevice(&dev));
     REQUIRE(dev < ndev, "device ordinal out of range");
-    CK(cudaSetDevice(dev));
+    DeviceGuard dev_guard__(dev);            // the caller's current device is restored on return
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) return set_err(PGN_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
@@ -323,7 +340,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 2 * PGN_MAX_PARTS); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se0, 2 * B); AL(d_se, 2 * B); AL(d_tskip, B);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 2 * PGN_MAX_PARTS); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se0, 2 * B); AL(d_se, 2 * B); AL(d_tskip, B); AL(d_in, 18 * B); AL(d_mask, B);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
@@ -333,8 +350,12 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->path_window = 0; CK(cudaMemset(h->d_last_seg, 0xff, B * 4));
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
+    h->h_in = nullptr; h->in_pending = 0; h->d_hist = nullptr; h->hist_cap = h->hist_stride = h->hist_n = 0;
+    h->comm = nullptr; h->comm_rank = 0; h->comm_size = 1; h->d_gath_c = nullptr; h->d_gath_i = nullptr;
+    cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
     {
         cudaError_t e = cudaMallocHost((void**)&h->h_io, (1 + 19 * B) * sizeof(double));
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_in, 18 * B * sizeof(double));
         if (e != cudaSuccess) return bail(set_err(PGN_ENOMEM, "cudaMallocHost failed: %s", cudaGetErrorString(e)));
     }
     {   // no step yet: cache[x] = (Inf, 0)
@@ -378,11 +399,14 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
 
 int pgn_destroy(pgn_handle* h) {
     if (!h) return PGN_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard__(h->device);
     cudaDeviceSynchronize();
+    pgn_comm_destroy(h);
     for (void* p : h->allocs) cudaFree(p);
     if (h->cb_has_exec) { cudaGraphExecDestroy(h->cb_exec); cudaGraphDestroy(h->cb_graph); }
     if (h->h_io) cudaFreeHost(h->h_io);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    cudaEventDestroy(h->ev_in);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->parts_created) {
@@ -398,30 +422,34 @@ int pgn_destroy(pgn_handle* h) {
     return PGN_OK;
 }
 
-int pgn_set_stream(pgn_handle* h, void* s) { REQUIRE(h, "NULL handle"); h->epoch++; h->stream = s ? (cudaStream_t)s : h->own_stream; return PGN_OK; }
-int pgn_synchronize(pgn_handle* h) { REQUIRE(h, "NULL handle"); CK(cudaStreamSynchronize(h->stream)); return PGN_OK; }
+int pgn_set_stream(pgn_handle* h, void* s) { ENTER(h, "NULL handle"); h->epoch++; h->stream = s ? (cudaStream_t)s : h->own_stream; return PGN_OK; }
+int pgn_synchronize(pgn_handle* h) { ENTER(h, "NULL handle"); CK(cudaStreamSynchronize(h->stream)); return PGN_OK; }
 
 int pgn_set_vehicle_params(pgn_handle* h, const double* vp) {
-    REQUIRE(h && vp, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(vp, "NULL argument");
+    CK(cudaStreamSynchronize(h->stream));
     h->epoch++;
     memcpy(&h->veh, vp, sizeof(double) * PGN_VEHICLE_PARAMS_LEN);
     return upload_constants(h);
 }
 int pgn_set_control_params(pgn_handle* h, const double* cp) {
-    REQUIRE(h && cp, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(cp, "NULL argument");
+    CtrlParams tmp;
+    memcpy(&tmp, cp, sizeof(double) * PGN_CONTROL_PARAMS_LEN);
+    REQUIRE(tmp.N_HJI >= 0 && tmp.N_HJI <= h->cfg.N_short, "N_HJI must be within [0, N_short]");      // nothing is committed on failure
+    CK(cudaStreamSynchronize(h->stream));
     h->epoch++;
-    memcpy(&h->ctl, cp, sizeof(double) * PGN_CONTROL_PARAMS_LEN);
-    REQUIRE(h->ctl.N_HJI >= 0 && h->ctl.N_HJI <= h->cfg.N_short, "N_HJI must be within [0, N_short]");
+    h->ctl = tmp;
     return upload_constants(h);
 }
 int pgn_set_trajectories(pgn_handle* h, int32_t n_traj, int32_t n_nodes, const double* const fields[12]) {
-    REQUIRE(h && fields, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(fields, "NULL argument");
     REQUIRE(n_traj >= 1 && n_nodes >= 2, "need n_traj >= 1 and n_nodes >= 2");
     const size_t cnt = (size_t)n_traj * n_nodes;
     double* base = nullptr;
     h->epoch++;
+    CK(cudaStreamSynchronize(h->stream));
     if (h->have_traj && h->traj.f[0]) {      // latest_trajectory[] is replaced at run time (ros_integration.jl:19,53): release the previous tables
-        CK(cudaStreamSynchronize(h->stream));
         void* old = (void*)h->traj.f[0];
         for (size_t i = 0; i < h->allocs.size(); i++) if (h->allocs[i] == old) { h->allocs.erase(h->allocs.begin() + i); cudaFree(old); break; }
         h->traj.f[0] = nullptr;
@@ -440,39 +468,58 @@ int pgn_set_trajectories(pgn_handle* h, int32_t n_traj, int32_t n_nodes, const d
     return PGN_OK;
 }
 int pgn_assign_trajectories(pgn_handle* h, const int32_t* traj_id) {
-    REQUIRE(h && traj_id, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(traj_id, "NULL argument");
     for (int v = 0; v < h->B; v++) REQUIRE(traj_id[v] >= 0 && traj_id[v] < h->traj.n_traj, "trajectory id out of range");
+    CK(cudaStreamSynchronize(h->stream));        // the blocking copies below run on the legacy stream: order them after the handle's in-flight work
     CK(cudaMemcpy(h->d_traj_id, traj_id, (size_t)h->B * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(h->d_last_seg, 0xff, (size_t)h->B * 4));
+    h->epoch++;
     return PGN_OK;
 }
 int pgn_set_hji_cache(pgn_handle* h, const int32_t dims[7], const float* knots, const float* V, const float* gradV) {
-    REQUIRE(h && dims && knots && V && gradV, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(dims && knots && V && gradV, "NULL argument");
     h->epoch++;
     return set_hji_internal(h, dims, knots, V, gradV);
 }
+// host arrays -> the packed pinned buffer; returns the unpack flags.  The pinned buffer is reused by every call: wait for the previous copy.
+static int stage_inputs(pgn_handle* h, const double* q, const double* u, const double* other, const double* toff, const double* t0, int* flags_out) {
+    if (h->in_pending) { CK(cudaEventSynchronize(h->ev_in)); h->in_pending = 0; }
+    const size_t B = h->B;
+    int flags = 0;
+    if (q) { memcpy(h->h_in, q, 6 * B * 8); flags |= 1; }
+    if (u) { memcpy(h->h_in + 6 * B, u, 3 * B * 8); flags |= 2; }
+    if (other) { memcpy(h->h_in + 9 * B, other, 4 * B * 8); flags |= 4; }
+    if (toff) { memcpy(h->h_in + 13 * B, toff, B * 8); flags |= 8; }
+    if (t0) { memcpy(h->h_in + 14 * B, t0, B * 8); flags |= 16; }
+    *flags_out = flags;
+    if (!flags) return PGN_OK;
+    // one copy of the span that holds the present fields
+    const size_t lo = (flags & 1) ? 0 : (flags & 2) ? 6 * B : (flags & 4) ? 9 * B : (flags & 8) ? 13 * B : 14 * B;
+    const size_t hi = (flags & 16) ? 15 * B : (flags & 8) ? 14 * B : (flags & 4) ? 13 * B : (flags & 2) ? 9 * B : 6 * B;
+    CK(cudaMemcpyAsync(h->d_in + lo, h->h_in + lo, (hi - lo) * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev_in, h->stream));
+    h->in_pending = 1;
+    launch_unpack_state(h, flags);
+    return PGN_OK;
+}
 int pgn_set_state(pgn_handle* h, const double* q, const double* u, const double* other, const double* toff) {
-    REQUIRE(h, "NULL handle");
-    int rc;
-    if (q) CK(cudaMemsetAsync(h->d_last_seg, 0xff, (size_t)h->B * 4, h->stream));      // a new measured state may be anywhere on the path
-    if (q && (rc = upload_aos(h, q, h->d_state, 6))) return rc;
-    if (u && (rc = upload_aos(h, u, h->d_control, 3))) return rc;
-    if (other && (rc = upload_aos(h, other, h->d_other, 4))) return rc;
-    if (toff) CK(cudaMemcpyAsync(h->d_toff, toff, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // host buffers may be reused by the caller
+    ENTER(h, "NULL handle");
+    int flags;
+    int rc = stage_inputs(h, q, u, other, toff, nullptr, &flags);      // the caller's arrays are copied before the call returns; the rest is stream-ordered
+    if (rc) return rc;
+    CK(cudaGetLastError());
     return PGN_OK;
 }
 int pgn_reset_solved(pgn_handle* h, const uint8_t* mask) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     if (!mask) { CK(cudaMemsetAsync(h->d_solved, 0, h->B, h->stream)); return PGN_OK; }
-    std::vector<uint8_t> cur(h->B);
-    CK(cudaMemcpy(cur.data(), h->d_solved, h->B, cudaMemcpyDeviceToHost));
-    for (int v = 0; v < h->B; v++) if (mask[v]) cur[v] = 0;
-    CK(cudaMemcpy(h->d_solved, cur.data(), h->B, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyAsync(h->d_mask, mask, h->B, cudaMemcpyHostToDevice, h->stream));      // pageable source: staged before the call returns
+    launch_masked_reset(h, h->d_mask, 1);
+    CK(cudaGetLastError());
     return PGN_OK;
 }
 int pgn_set_guards(pgn_handle* h, int32_t nan_fallback, double pause_below_speed) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     REQUIRE(pause_below_speed >= 0.0, "pause_below_speed must be >= 0");
     h->epoch++;
     h->guard_nan = nan_fallback != 0; h->guard_pause = pause_below_speed;
@@ -480,19 +527,10 @@ int pgn_set_guards(pgn_handle* h, int32_t nan_fallback, double pause_below_speed
     return PGN_OK;
 }
 int pgn_reset_solver(pgn_handle* h, const uint8_t* mask) {
-    REQUIRE(h, "NULL handle");
-    CK(cudaStreamSynchronize(h->stream));
-    const size_t Nk = h->tab.Nk;
-    if (!mask) {
-        CK(cudaMemset(h->d_ws_xz, 0, (size_t)h->B * Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, (size_t)h->B * Nk * 8));
-        std::vector<double> rho(h->B, h->cfg.rho);
-        CK(cudaMemcpy(h->d_rho, rho.data(), (size_t)h->B * 8, cudaMemcpyHostToDevice));
-        return PGN_OK;
-    }
-    for (int v = 0; v < h->B; v++) if (mask[v]) {
-        CK(cudaMemset(h->d_ws_xz + (size_t)v * Nk, 0, Nk * 8)); CK(cudaMemset(h->d_ws_y + (size_t)v * Nk, 0, Nk * 8));
-        CK(cudaMemcpy(h->d_rho + v, &h->cfg.rho, 8, cudaMemcpyHostToDevice));
-    }
+    ENTER(h, "NULL handle");
+    if (mask) CK(cudaMemcpyAsync(h->d_mask, mask, h->B, cudaMemcpyHostToDevice, h->stream));
+    launch_masked_reset(h, mask ? h->d_mask : nullptr, 2);       // one kernel on the handle's stream, ordered with the solves before and after it
+    CK(cudaGetLastError());
     return PGN_OK;
 }
 
@@ -508,22 +546,24 @@ static int step_solve(pgn_handle* h) { StageTimer T(h, 3); launch_admm(h); retur
 static int step_controls(pgn_handle* h, double* d_out) { StageTimer T(h, 4); launch_controls(h, d_out); return PGN_OK; }
 
 int pgn_compute_time_steps(pgn_handle* h, const double* t0) {
-    REQUIRE(h && t0, "NULL argument");
-    CK(cudaMemcpyAsync(h->d_t0, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    ENTER(h, "NULL handle"); REQUIRE(t0, "NULL argument");
+    int flags;
+    int rc = stage_inputs(h, nullptr, nullptr, nullptr, nullptr, t0, &flags);
+    if (rc) return rc;
     step_time_steps_dev(h, h->d_t0);
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
     return PGN_OK;
 }
-int pgn_compute_linearization_nodes(pgn_handle* h) { REQUIRE(h, "NULL handle"); step_nodes(h); CK(cudaGetLastError()); return PGN_OK; }
-int pgn_update_qp(pgn_handle* h) { REQUIRE(h, "NULL handle"); step_update(h); CK(cudaGetLastError()); return PGN_OK; }
-int pgn_solve(pgn_handle* h) { REQUIRE(h, "NULL handle"); step_solve(h); CK(cudaGetLastError()); return PGN_OK; }
+int pgn_compute_linearization_nodes(pgn_handle* h) { ENTER(h, "NULL handle"); step_nodes(h); CK(cudaGetLastError()); return PGN_OK; }
+int pgn_update_qp(pgn_handle* h) { ENTER(h, "NULL handle"); step_update(h); CK(cudaGetLastError()); return PGN_OK; }
+int pgn_solve(pgn_handle* h) { ENTER(h, "NULL handle"); step_solve(h); CK(cudaGetLastError()); return PGN_OK; }
 int pgn_get_next_control(pgn_handle* h, double* out) {
-    REQUIRE(h && out, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(out, "NULL argument");
     step_controls(h, h->d_controls);
     return download_aos(h, h->d_controls, out, 3);
 }
 int pgn_step_device(pgn_handle* h, const double* d_t0, double* d_out) {
-    REQUIRE(h && d_t0, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(d_t0, "NULL argument");
     int rc = for_each_part(h, [&]() {
         step_time_steps_dev(h, d_t0);
         step_nodes(h);
@@ -538,11 +578,20 @@ int pgn_step_device(pgn_handle* h, const double* d_t0, double* d_out) {
     return PGN_OK;
 }
 int pgn_step(pgn_handle* h, const double* t0, double* out) {
-    REQUIRE(h && t0, "NULL argument");
-    CK(cudaMemcpyAsync(h->d_t0, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = pgn_step_device(h, h->d_t0, nullptr);
+    ENTER(h, "NULL handle"); REQUIRE(t0, "NULL argument");
+    int flags;
+    int rc = stage_inputs(h, nullptr, nullptr, nullptr, nullptr, t0, &flags);
     if (rc) return rc;
-    if (out) return download_aos(h, h->d_controls, out, 3);
+    rc = pgn_step_device(h, h->d_t0, nullptr);
+    if (rc) return rc;
+    if (out) {      // [3][B] -> [B][3] on the device, one D2H copy into the pinned tail, one host copy into the caller's array
+        const size_t B = h->B;
+        launch_transpose_out(h, h->d_controls, h->d_in + 15 * B, 3);
+        CK(cudaMemcpyAsync(h->h_in + 15 * B, h->d_in + 15 * B, 3 * B * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        memcpy(out, h->h_in + 15 * B, 3 * B * 8);
+        return PGN_OK;
+    }
     CK(cudaStreamSynchronize(h->stream));
     return PGN_OK;
 }
@@ -564,7 +613,7 @@ static int callback_enqueue(pgn_handle* h) {
     return PGN_OK;
 }
 int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const double* other, const double* stamp, double* out) {
-    REQUIRE(h && q && u && stamp && out, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(q && u && stamp && out, "NULL argument");
     REQUIRE(h->have_traj, "no trajectory set");
     const size_t B = h->B;
     double* io = h->h_io;
@@ -618,7 +667,7 @@ static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt) {
 }
 // step + plant rollout of `simulate` (model_predictive_control.jl:87-98) with the plant step beside the QP solve
 int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d_out, double dt) {
-    REQUIRE(h && d_t0, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(d_t0, "NULL argument");
     if (h->profiling || !h->side_stream) {            // stage timers synchronise: serial order
         int rc = pgn_step_device(h, d_t0, d_out);
         if (rc) return rc;
@@ -631,7 +680,7 @@ int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d_out, do
     return PGN_OK;
 }
 int pgn_rollout(pgn_handle* h, double dt) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     { StageTimer T(h, 5); launch_rollout(h, dt); }
     CK(cudaGetLastError());
     return PGN_OK;
@@ -661,7 +710,7 @@ static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
 // 6: 2.98, 7: 2.79); 2048: 5.40 / 4.97 / 4.91; 4096: 10.31 / 9.74 / 9.69.  Per-step calls (parts joined every call) are never slower with 4 parts.
 static int auto_parts(pgn_handle* h) { return h->B >= 64 ? 4 : 1; }
 int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
-    REQUIRE(h && t0 && n_steps >= 0, "bad argument");
+    ENTER(h, "NULL handle"); REQUIRE(t0 && n_steps >= 0, "bad argument");
     CK(cudaMemcpyAsync(h->d_t0_base, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
     int rc = simulate_enqueue(h, dt, 0, n_steps);
     if (rc) return rc;
@@ -670,7 +719,7 @@ int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
     return PGN_OK;
 }
 int pgn_simulate_device(pgn_handle* h, const double* d_t0, double dt, int32_t k0, int32_t n_steps) {
-    REQUIRE(h && d_t0 && n_steps >= 0 && k0 >= 0, "bad argument");
+    ENTER(h, "NULL handle"); REQUIRE(d_t0 && n_steps >= 0 && k0 >= 0, "bad argument");
     CK(cudaMemcpyAsync(h->d_t0_base, d_t0, (size_t)h->B * 8, cudaMemcpyDeviceToDevice, h->stream));
     int rc = simulate_enqueue(h, dt, k0, n_steps);
     if (rc) return rc;
@@ -678,7 +727,7 @@ int pgn_simulate_device(pgn_handle* h, const double* d_t0, double dt, int32_t k0
     return PGN_OK;
 }
 int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     REQUIRE(parts >= 0 && parts <= PGN_MAX_PARTS, "parts must be 0 (automatic) or 1..8");
     if (parts == 0) parts = auto_parts(h);
     if (parts > h->B) parts = h->B;
@@ -695,18 +744,18 @@ int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts) {
     h->parts = parts;
     return PGN_OK;
 }
-int pgn_get_pipeline_parts(pgn_handle* h, int32_t* parts) { REQUIRE(h && parts, "NULL argument"); *parts = h->parts; return PGN_OK; }
+int pgn_get_pipeline_parts(pgn_handle* h, int32_t* parts) { ENTER(h, "NULL handle"); REQUIRE(parts, "NULL argument"); *parts = h->parts; return PGN_OK; }
 
 // ---- introspection -----------------------------------------------------------------------------------------------------------
 int pgn_qp_dims(pgn_handle* h, int32_t* o) {
-    REQUIRE(h && o, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(o, "NULL argument");
     o[0] = h->N; o[1] = h->nx; o[2] = h->nu; o[3] = h->tab.n; o[4] = h->tab.m; o[5] = h->tab.nnzA; o[6] = h->tab.nnzL; o[7] = h->tab.nlev;
     o[8] = h->tab.nslots; o[9] = h->tab.n_fwd_ph + h->tab.n_bwd_ph; o[10] = (int)h->tab.fac_ent.size(); o[11] = (int)h->tab.inv_ent.size(); o[12] = h->tab.tail_dim;
     o[13] = (int)h->tab.bent.size(); o[14] = h->admm_smem_bytes; o[15] = h->admm_threads;
     return PGN_OK;
 }
 int pgn_get_state(pgn_handle* h, double* q, double* u) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     int rc;
     if (q && (rc = download_aos(h, h->d_state, q, 6))) return rc;
     if (u && (rc = download_aos(h, h->d_control, u, 3))) return rc;
@@ -717,19 +766,19 @@ int pgn_get_state(pgn_handle* h, double* q, double* u) {
         if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(count) * sizeof(*(dst)), cudaMemcpyDeviceToHost, h->stream)); \
     } while (0)
 int pgn_get_time_steps(pgn_handle* h, double* ts, double* dt, double* prev_ts) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     D2H(ts, h->d_ts, (size_t)h->B * h->N); D2H(dt, h->d_dt, (size_t)h->B * h->T); D2H(prev_ts, h->d_prev_ts, (size_t)h->B * h->N);
     CK(cudaStreamSynchronize(h->stream));
     return PGN_OK;
 }
 int pgn_get_nodes(pgn_handle* h, double* qs, double* us, double* ps) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     D2H(qs, h->d_qs, (size_t)h->B * h->N * h->nx); D2H(us, h->d_us, (size_t)h->B * h->N * 2); D2H(ps, h->d_ps, (size_t)h->B * h->N * 4);
     CK(cudaStreamSynchronize(h->stream));
     return PGN_OK;
 }
 int pgn_set_nodes(pgn_handle* h, const double* qs, const double* us, const double* ps) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     if (qs) CK(cudaMemcpyAsync(h->d_qs, qs, (size_t)h->B * h->N * h->nx * 8, cudaMemcpyHostToDevice, h->stream));
     if (us) CK(cudaMemcpyAsync(h->d_us, us, (size_t)h->B * h->N * 2 * 8, cudaMemcpyHostToDevice, h->stream));
     if (ps) CK(cudaMemcpyAsync(h->d_ps, ps, (size_t)h->B * h->N * 4 * 8, cudaMemcpyHostToDevice, h->stream));
@@ -738,7 +787,7 @@ int pgn_set_nodes(pgn_handle* h, const double* qs, const double* us, const doubl
 }
 int pgn_get_qp_data(pgn_handle* h, double* A, double* B0, double* Bf, double* c, double* H, double* G, double* dmin, double* dmax, double* fxmax,
                     double* hji) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     const RecLayout& R = h->tab.rec;
     const size_t B = h->B, T = h->T, nx = h->nx, nu = h->nu;
     std::vector<double> rec(B * (size_t)R.rec_len);
@@ -763,27 +812,27 @@ int pgn_get_qp_data(pgn_handle* h, double* A, double* B0, double* Bf, double* c,
     return PGN_OK;
 }
 int pgn_get_solution(pgn_handle* h, double* x, double* y) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     D2H(x, h->d_sol_x, (size_t)h->B * h->tab.n); D2H(y, h->d_sol_y, (size_t)h->B * h->tab.m);
     CK(cudaStreamSynchronize(h->stream));
     return PGN_OK;
 }
 int pgn_get_stats(pgn_handle* h, int32_t* iters, int32_t* status, double* pri, double* dua, double* rho, int32_t* rho_updates) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     D2H(iters, h->d_iters, h->B); D2H(status, h->d_status, h->B); D2H(pri, h->d_pri_res, h->B); D2H(dua, h->d_dua_res, h->B); D2H(rho, h->d_rho, h->B);
     D2H(rho_updates, h->d_rho_updates, h->B);
     CK(cudaStreamSynchronize(h->stream));
     return PGN_OK;
 }
 int pgn_hji_lookup_device(pgn_handle* h, int32_t M, const double* d_x, double* d_V, double* d_gV) {
-    REQUIRE(h && d_x && d_V && d_gV && M >= 0, "bad argument");
+    ENTER(h, "NULL handle"); REQUIRE(d_x && d_V && d_gV && M >= 0, "bad argument");
     if (M == 0) return PGN_OK;
     { StageTimer T(h, 2); launch_hji_lookup(h, M, d_x, d_V, d_gV); }
     CK(cudaGetLastError());
     return PGN_OK;
 }
 int pgn_hji_lookup(pgn_handle* h, int32_t M, const double* x, double* V, double* gradV) {
-    REQUIRE(h && x && V && gradV && M >= 0, "bad argument");
+    ENTER(h, "NULL handle"); REQUIRE(x && V && gradV && M >= 0, "bad argument");
     if (M == 0) return PGN_OK;
     double *dx = nullptr, *dV = nullptr, *dg = nullptr;
     CK(cudaMalloc(&dx, (size_t)M * 7 * 8)); CK(cudaMalloc(&dV, (size_t)M * 8)); CK(cudaMalloc(&dg, (size_t)M * 7 * 8));
@@ -799,16 +848,16 @@ int pgn_hji_lookup(pgn_handle* h, int32_t M, const double* x, double* V, double*
     return PGN_OK;
 }
 int pgn_set_path_search_window(pgn_handle* h, int32_t half_width) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     REQUIRE(half_width >= 0, "half_width must be >= 0");
     h->epoch++;
     h->path_window = half_width;
     CK(cudaMemsetAsync(h->d_last_seg, 0xff, (size_t)h->B * 4, h->stream));
     return PGN_OK;
 }
-int pgn_set_hji_policy(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->epoch++; h->hji_policy = on != 0; return PGN_OK; }
+int pgn_set_hji_policy(pgn_handle* h, int32_t on) { ENTER(h, "NULL handle"); h->epoch++; h->hji_policy = on != 0; return PGN_OK; }
 int pgn_get_hji_values(pgn_handle* h, double* V, double* gradV) {
-    REQUIRE(h && V && gradV, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(V && gradV, "NULL argument");
     const size_t B = h->B;
     std::vector<double> hv(8 * B);
     CK(cudaStreamSynchronize(h->stream));
@@ -820,7 +869,7 @@ int pgn_get_hji_values(pgn_handle* h, double* V, double* gradV) {
     return PGN_OK;
 }
 int pgn_hji_optimal_control(pgn_handle* h, int32_t M, const double* x, const double* gradV, double* out) {
-    REQUIRE(h && x && gradV && out && M >= 0, "bad argument");
+    ENTER(h, "NULL handle"); REQUIRE(x && gradV && out && M >= 0, "bad argument");
     if (M == 0) return PGN_OK;
     double *dx = nullptr, *dg = nullptr, *dout = nullptr;
     CK(cudaMalloc(&dx, (size_t)M * 7 * 8)); CK(cudaMalloc(&dg, (size_t)M * 7 * 8)); CK(cudaMalloc(&dout, (size_t)M * 2 * 8));
@@ -832,16 +881,16 @@ int pgn_hji_optimal_control(pgn_handle* h, int32_t M, const double* x, const dou
     if (e != cudaSuccess) return set_err(PGN_ECUDA, "hji optimal control failed: %s", cudaGetErrorString(e));
     return PGN_OK;
 }
-int pgn_device_controls(pgn_handle* h, double** d_out) { REQUIRE(h && d_out, "NULL argument"); *d_out = h->d_controls; return PGN_OK; }
+int pgn_device_controls(pgn_handle* h, double** d_out) { ENTER(h, "NULL handle"); REQUIRE(d_out, "NULL argument"); *d_out = h->d_controls; return PGN_OK; }
 int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_status) {
-    REQUIRE(h, "NULL handle");
+    ENTER(h, "NULL handle");
     if (d_iters) *d_iters = h->d_iters;
     if (d_status) *d_status = h->d_status;
     return PGN_OK;
 }
-int pgn_set_profiling(pgn_handle* h, int32_t on) { REQUIRE(h, "NULL handle"); h->epoch++; h->profiling = on; return PGN_OK; }
+int pgn_set_profiling(pgn_handle* h, int32_t on) { ENTER(h, "NULL handle"); h->epoch++; h->profiling = on; return PGN_OK; }
 int pgn_get_admm_cycles(pgn_handle* h, double* out, int32_t reset) {
-    REQUIRE(h && out, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(out, "NULL argument");
     unsigned long long c[512];
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(c, h->d_cycles, 4096, cudaMemcpyDeviceToHost));
@@ -850,7 +899,7 @@ int pgn_get_admm_cycles(pgn_handle* h, double* out, int32_t reset) {
     return PGN_OK;
 }
 int pgn_get_stage_ms(pgn_handle* h, double* out, int32_t reset) {
-    REQUIRE(h && out, "NULL argument");
+    ENTER(h, "NULL handle"); REQUIRE(out, "NULL argument");
     for (int i = 0; i < 6; i++) out[i] = h->stage_ms[i];
     out[6] = (double)h->launches; out[7] = 0;
     if (reset) { memset(h->stage_ms, 0, sizeof(h->stage_ms)); h->launches = 0; }

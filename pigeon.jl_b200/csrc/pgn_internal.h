@@ -122,6 +122,15 @@ struct pgn_handle {
     unsigned long long* d_cycles;                        // [8] per-phase cycle counters of the ADMM kernel (profiling only)
     double* d_stage;                                     // AoS<->SoA staging
     size_t stage_bytes;
+    // host inputs of pgn_set_state / pgn_step: ONE packed pinned buffer [q 6B | u 3B | other 4B | toff B | t0 B] -> one H2D copy -> one unpack
+    // kernel; results [B][3] come back through the pinned tail.  ev_in fences the reuse of the pinned buffer.
+    double *h_in, *d_in; cudaEvent_t ev_in; int in_pending;
+    uint8_t* d_mask;                                     // [B] staging of the masks of pgn_reset_solved / pgn_reset_solver
+    // history recorder of simulate (model_predictive_control.jl:84-99 returns qs, xs, us, ps per step): [n_rec][6 + 3 + nx + 4][B], written on
+    // the device every `hist_stride` steps
+    double* d_hist; int hist_cap, hist_stride, hist_n;
+    // final gather (pgn_gather): NCCL communicator (ncclComm_t) of this handle, its rank / size, device staging of the gathered arrays
+    void* comm; int comm_rank, comm_size; double* d_gath_c; int32_t* d_gath_i;
     // trajectories / HJI
     pgn::TrajView traj; bool have_traj, have_assign;
     pgn::HjiView hji;
@@ -148,6 +157,10 @@ void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, dou
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
 void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n);
+void launch_unpack_state(pgn_handle* h, int flags);                 // d_in -> SoA state / control / other / toff / t0 (flags: 1 q, 2 u, 4 other, 8 toff, 16 t0)
+void launch_masked_reset(pgn_handle* h, const uint8_t* d_mask, int what);   // what: 1 solved = 0, 2 ADMM iterates = 0 and rho = setting (mask nullptr = all)
+void launch_record(pgn_handle* h, int slot);                        // history recorder: (state, control, node 1, params 1) of the current range -> slot
+void launch_pack_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);        // [k][B] -> [B][k] for the current vehicle range only
 size_t admm_smem_bytes(const QpTables& t, int nthreads, bool tables_in_smem);
 int admm_configure(pgn_handle* h);   // sets the max dynamic shared memory attribute; returns cudaError
 }  // namespace pgn

@@ -115,10 +115,19 @@ __device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int ba
 }
 
 // ---- compute_time_steps! ---------------------------------------------------------------------------------------------
+// The guards of the callback run BEFORE compute_time_steps! (src/ros_integration.jl:77-87 return early): a vehicle that is paused (Ux below
+// the threshold) or whose time lies outside the trajectory keeps ts, dt and prev_ts — prev_ts stays the knot vector of the last SOLVED QP,
+// which update_interpolations! needs when the vehicle resumes — and is flagged in `skip` for the stages that follow.
 __global__ void k_time_steps(int B, int Ns, int Nl, double dt_short, double dt_long, int corr, const double* __restrict__ t0v,
-                             double* __restrict__ ts, double* __restrict__ dtv, double* __restrict__ prev_ts) {
+                             double* __restrict__ ts, double* __restrict__ dtv, double* __restrict__ prev_ts,
+                             uint8_t* __restrict__ skip, const double* __restrict__ Ux, double pause_below_speed, const uint8_t* __restrict__ tskip) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= B) return;
+    if (skip) {
+        const bool sk = (pause_below_speed > 0.0 && Ux[v] < pause_below_speed) || (tskip && tskip[v]);
+        skip[v] = sk;
+        if (sk) return;
+    }
     const int N = 1 + Ns + Nl;
     double* tsv = ts + (size_t)v * N;
     double* pv = prev_ts + (size_t)v * N;
@@ -213,6 +222,7 @@ __global__ void __launch_bounds__(128) k_nodes_decoupled_rollout(const NodeArgs 
     const int iv = blockIdx.x * blockDim.x + threadIdx.x;
     if (iv >= a.nv) return;
     const int v = a.v0 + iv;
+    if ((a.pause_below_speed > 0.0 || a.tskip) && a.skip[v]) return;
     decoupled_cold_rollout(a, v, se0[v], se0[a.B + v]);
 }
 
@@ -230,7 +240,7 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
     const double d0 = a.control[0 * B + v], Fxf0 = a.control[1 * B + v], Fxr0 = a.control[2 * B + v];
     const double Fx0 = Fxf0 + Fxr0;
     const bool path_mode = isnan(a.toff[v]);
-    if ((a.pause_below_speed > 0.0 || a.tskip) && lane == 0) a.skip[v] = (a.pause_below_speed > 0.0 && Ux0 < a.pause_below_speed) || (a.tskip && a.tskip[v]);
+    if ((a.pause_below_speed > 0.0 || a.tskip) && a.skip[v]) return;      // flagged by k_time_steps: the callback returned early, nothing is touched
     const int base = a.traj_id[v] * a.tv.n_nodes;
     const double* ts = a.ts + (size_t)v * N;
     const double* dt = a.dt + (size_t)v * (N - 1);
@@ -439,12 +449,67 @@ __global__ void k_time_axpy(int n, const double* __restrict__ base, double k, do
     if (i < n) v[i] = __dadd_rn(base[i], __dmul_rn(k, dt));   // no FMA contraction: bitwise the host's t0 + k*dt
 }
 
+// ---- host inputs: one packed buffer [q [B][6] | u [B][3] | other [B][4] | toff [B] | t0 [B]] -> SoA ------------------------------------
+__global__ void k_unpack_state(int B, int flags, const double* __restrict__ in, double* __restrict__ state, double* __restrict__ control,
+                               double* __restrict__ other, double* __restrict__ toff, double* __restrict__ t0, int32_t* __restrict__ last_seg) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    const size_t Bs = (size_t)B;
+    if (flags & 1) {
+#pragma unroll
+        for (int f = 0; f < 6; f++) state[f * Bs + v] = in[(size_t)v * 6 + f];
+        last_seg[v] = -1;                 // a new measured state may be anywhere on the path: the next closest-segment search scans everything
+    }
+    if (flags & 2) {
+#pragma unroll
+        for (int f = 0; f < 3; f++) control[f * Bs + v] = in[6 * Bs + (size_t)v * 3 + f];
+    }
+    if (flags & 4) {
+#pragma unroll
+        for (int f = 0; f < 4; f++) other[f * Bs + v] = in[9 * Bs + (size_t)v * 4 + f];
+    }
+    if (flags & 8) toff[v] = in[13 * Bs + v];
+    if (flags & 16) t0[v] = in[14 * Bs + v];
+}
+// mpc.solved = false / Parametron.initialize! for the masked vehicles, on the handle's stream (no host round trip)
+__global__ void k_masked_reset(int B, const uint8_t* __restrict__ mask, int what, uint8_t* __restrict__ solved, double* __restrict__ ws_xz,
+                               double* __restrict__ ws_y, double* __restrict__ rho, int Nk, double rho0) {
+    const int v = blockIdx.x;
+    if (mask && !mask[v]) return;
+    if ((what & 1) && threadIdx.x == 0) solved[v] = 0;
+    if (what & 2) {
+        for (int p = threadIdx.x; p < Nk; p += blockDim.x) { ws_xz[(size_t)v * Nk + p] = 0.0; ws_y[(size_t)v * Nk + p] = 0.0; }
+        if (threadIdx.x == 0) rho[v] = rho0;
+    }
+}
+// history recorder of `simulate` (model_predictive_control.jl:84-99: qs / us before the step, xs = mpc.qs[1], ps = mpc.ps[1] after node generation)
+__global__ void k_record(int B, int v0, int nv, int nx, int N, const double* __restrict__ state, const double* __restrict__ control,
+                         const double* __restrict__ qs, const double* __restrict__ ps, double* __restrict__ slot) {
+    const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iv >= nv) return;
+    const int v = v0 + iv;
+    const size_t Bs = (size_t)B;
+    for (int f = 0; f < 6; f++) slot[f * Bs + v] = state[f * Bs + v];
+    for (int f = 0; f < 3; f++) slot[(6 + f) * Bs + v] = control[f * Bs + v];
+    for (int f = 0; f < nx; f++) slot[(9 + f) * Bs + v] = qs[(size_t)v * N * nx + f];
+    for (int f = 0; f < 4; f++) slot[(9 + nx + f) * Bs + v] = ps[(size_t)v * N * 4 + f];
+}
+__global__ void k_pack_out(int B, int v0, int nv, int k, const double* __restrict__ soa, double* __restrict__ aos) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nv * k) return;
+    const int iv = idx / k, f = idx - iv * k;
+    aos[(size_t)(v0 + iv) * k + f] = soa[(size_t)f * B + v0 + iv];
+}
+
 // ---- launchers -------------------------------------------------------------------------------------------------------
 void launch_time_steps(pgn_handle* h, const double* d_t0) {
     const int B = h->nv;          // per-vehicle rows only: a part is an offset into every array
     const size_t o = (size_t)h->v0;
+    const bool guarded = h->guard_pause > 0.0 || h->in_callback;
     k_time_steps<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.N_short, h->cfg.N_long, h->cfg.dt_short, h->cfg.dt_long, h->cfg.use_correction_step,
-                                                         d_t0 + o, h->d_ts + o * h->N, h->d_dt + o * h->T, h->d_prev_ts + o * h->N);
+                                                         d_t0 + o, h->d_ts + o * h->N, h->d_dt + o * h->T, h->d_prev_ts + o * h->N,
+                                                         guarded ? h->d_skip + o : nullptr, h->d_state + 3 * (size_t)h->B + o, h->guard_pause,
+                                                         h->in_callback ? h->d_tskip + o : nullptr);
     h->launches++;
 }
 void launch_nodes(pgn_handle* h) {
@@ -528,6 +593,24 @@ void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int 
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k) {
     const int n = h->B * k;
     k_transpose_out<<<(n + 255) / 256, 256, 0, h->stream>>>(h->B, k, d_soa, d_aos);
+    h->launches++;
+}
+void launch_unpack_state(pgn_handle* h, int flags) {
+    k_unpack_state<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, flags, h->d_in, h->d_state, h->d_control, h->d_other, h->d_toff, h->d_t0, h->d_last_seg);
+    h->launches++;
+}
+void launch_masked_reset(pgn_handle* h, const uint8_t* d_mask, int what) {
+    k_masked_reset<<<h->B, 128, 0, h->stream>>>(h->B, d_mask, what, h->d_solved, h->d_ws_xz, h->d_ws_y, h->d_rho, h->tab.Nk, h->cfg.rho);
+    h->launches++;
+}
+void launch_record(pgn_handle* h, int slot) {
+    const size_t rec = (size_t)(13 + h->nx) * h->B;
+    k_record<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(h->B, h->v0, h->nv, h->nx, h->N, h->d_state, h->d_control, h->d_qs, h->d_ps, h->d_hist + rec * slot);
+    h->launches++;
+}
+void launch_pack_out(pgn_handle* h, const double* d_soa, double* d_aos, int k) {
+    const int n = h->nv * k;
+    k_pack_out<<<(n + 255) / 256, 256, 0, h->stream>>>(h->B, h->v0, h->nv, k, d_soa, d_aos);
     h->launches++;
 }
 void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n) {
