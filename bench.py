@@ -1,16 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark: batched coupled lat-long MPC steps/s on B200 (BASELINE.json metric).
+"""bench.py — batched MPC steps/s on B200 for the workloads of BASELINE.json (metric: "MPC QP steps/sec, batched, whole box").
 
 A "step" is one pass of the hot path over the whole batch: compute_time_steps -> compute_linearization_nodes -> update_QP
 (linearisation + envelope + HJI constraint) -> solve (ADMM) -> get_next_control, followed by the plant rollout of `simulate`
 (reference src/model_predictive_control.jl:87-98) so that every step solves a new, warm-started QP.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1|2|3|4] [--batch B] [--impl reference] [--other-configs all|none|2,3,4]
 
-N > 1 is launched by torchrun (one process per GPU); the vehicle batch is sharded with no data-path collective (weak scaling,
-B vehicles per GPU) and the final controls/statistics are gathered once over NCCL after the timed region.
+--config selects the entry of BASELINE.json `configs` that the JSON line reports (default 1, the configuration the metric is quoted on):
+  1  1024 X1 vehicles per GPU, coupled lat-long MPC (N = 31)                      coupled_lat_long.jl:62-142,315-368
+  2  decoupled lat-long MPC, 8,192 vehicles per GPU (65,536 on 8 GPUs)            decoupled_lat_long.jl:52-104,228-273
+  3  coupled MPC with the HJI constraint ACTIVE for about half of 16,384 scenarios, 13x13x9^5 grid (319 MB) in HBM   coupled_lat_long.jl:341-346
+  4  closed-loop Monte-Carlo: 131,072 perturbed initial states per GPU (1,048,576 on 8) x 200 steps on the device    model_predictive_control.jl:80-100
+The default run (config 1) also measures configs 2-4 at their per-GPU size and appends them as `other_configs` to its ONE JSON line.
+
+N > 1 is launched by torchrun (one process per GPU); the vehicle batch is sharded with no data-path collective (weak scaling, the per-GPU
+batch above on every rank, a different seed per rank) and the final controls / statistics are gathered once over NCCL (pgn_gather) after the
+timed region.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -26,16 +35,75 @@ sys.path.insert(0, ROOT)
 METRIC = "mpc_qp_steps_per_sec"
 UNIT = "steps/s"
 SETTLE = 30     # closed-loop steps run before the warm-up: the perturbed cold start (a handful of QPs need thousands of ADMM iterations) is reported separately
-WORKLOAD = ("configs[1]: batch of 1024 X1 vehicles per GPU, coupled lat-long MPC (N_short=10, N_long=20, N=31), 64 synthetic 1000-node trajectories, "
-            "closed loop dt=0.01, timed after %d settling steps from the perturbed cold start" % SETTLE)
+DT = 0.01
+FAR = np.array([1e4, 1e4, 0.0, 5.0])      # other car far outside the HJI grid: constraint evaluated, inactive
+
+CONFIGS = {
+    1: dict(kind="coupled", batch=1024, seed=17, hji=False, guards=False,
+            label="configs[1]: batch of 1024 X1 vehicles per GPU, coupled lat-long MPC (N_short=10, N_long=20, N=31), 64 synthetic 1000-node trajectories, "
+                  "closed loop dt=0.01, timed after %d settling steps from the perturbed cold start" % SETTLE),
+    2: dict(kind="decoupled", batch=8192, seed=1, hji=False, guards=False,
+            label="configs[2]: decoupled lat-long MPC (lateral QP + longitudinal PD), 8,192 vehicles per GPU (65,536 on 8 GPUs), closed loop dt=0.01, "
+                  "timed after %d settling steps" % SETTLE),
+    3: dict(kind="coupled", batch=16384, seed=3, hji=True, guards=False,
+            label="configs[3]: coupled MPC with the HJI value/gradient safety constraint, 16,384 scenarios per GPU, analytic 13x13x9^5 grid (319 MB) resident in HBM, "
+                  "other car placed so that ~50 %% of the scenarios start with an active constraint and ~10 %% outside the grid; timed after %d settling steps" % SETTLE),
+    4: dict(kind="coupled", batch=131072, seed=2, hji=False, guards=True, mc_steps=200,
+            label="configs[4]: closed-loop Monte-Carlo, 131,072 perturbed initial states per GPU (1,048,576 on 8) x 200 timesteps, linearize -> QP -> rollout fully "
+                  "on the device (pgn_simulate), NaN guard of the callback on; timed from the cold start over all 200 steps"),
+}
 
 
-def make_workload(B, seed_shift=0):
+def trajectories():
     from pigeon.jl_b200 import synthetic
-    trajs = synthetic.synthetic_trajectories(seed=synthetic.SEED, n_traj=64, n_nodes=1000, ds=0.25)
-    tid, state, control, t0 = synthetic.synthetic_batch(trajs, B, seed=synthetic.SEED + 17 + seed_shift)
-    other = np.tile(np.array([1e4, 1e4, 0.0, 5.0]), (B, 1))   # other car far outside the HJI grid: constraint evaluated, inactive
+    return synthetic.synthetic_trajectories(seed=synthetic.SEED, n_traj=64, n_nodes=1000, ds=0.25)
+
+
+def make_workload(cfg_idx, B, seed_shift=0, trajs=None):
+    """Synthetic batch of BASELINE config `cfg_idx` (SURVEY.md 8d generator): trajectories, trajectory ids, states, controls, t0, other cars."""
+    from pigeon.jl_b200 import synthetic
+    c = CONFIGS[cfg_idx]
+    trajs = trajectories() if trajs is None else trajs
+    tid, state, control, t0 = synthetic.synthetic_batch(trajs, B, seed=synthetic.SEED + c["seed"] + seed_shift)
+    other = np.tile(FAR, (B, 1))
+    if c["hji"]:
+        # other car in the EGO BODY frame of the HJI relative state (HJI_computation.jl:20-24: x_rel = M (p_other - p_ego), M = [-sin psi, cos psi; -cos psi, -sin psi]):
+        # half of the scenarios inside the V <= eps ellipse of the analytic grid ((dE/4)^2 + (dN/2)^2 <= ~1), 40 % outside it but in the grid, 10 % out of the grid
+        rng = np.random.default_rng(synthetic.SEED + 4 + seed_shift)
+        cls = rng.random(B)
+        R = np.where(cls < 0.5, rng.uniform(0.25, 0.95, B), rng.uniform(1.3, 3.0, B))
+        ang = rng.uniform(-np.pi, np.pi, B)
+        r0, r1 = 4.0 * R * np.cos(ang), 2.0 * R * np.sin(ang)
+        psi = state[:, 2]
+        other[:, 0] = state[:, 0] + (-np.sin(psi) * r0 - np.cos(psi) * r1)
+        other[:, 1] = state[:, 1] + (np.cos(psi) * r0 - np.sin(psi) * r1)
+        other[:, 2] = psi + rng.normal(0, 0.3, B)
+        other[:, 3] = np.clip(state[:, 3] + rng.normal(0, 1.0, B), 1.5, 14.0)
+        far = cls >= 0.9
+        other[far, 0] += 500.0
     return trajs, tid, state, control, t0, other
+
+
+def make_mpc(p, cfg_idx, trajs, tid, B, device):
+    c = CONFIGS[cfg_idx]
+    ctor = p.BatchedCoupledTrajectoryTrackingMPC if c["kind"] == "coupled" else p.BatchedDecoupledTrajectoryTrackingMPC
+    mpc = ctor(p.X1(), trajs, B, trajectory_index=tid, device=device)
+    if c["guards"]:
+        # the callback's NaN guard (ros_integration.jl:134-147): ~0.7 % of the perturbed states of config 4 give a primal-infeasible QP on the second step
+        # (the CPU oracle reports the same status and iteration count); OSQP then returns NaN and, unguarded, the NaN control poisons the state for good
+        mpc.set_guards(nan_fallback=True, pause_below_speed=0.0)
+    return mpc
+
+
+_HJI = {}
+
+
+def hji_cache(p):
+    if "c" not in _HJI:
+        from pigeon.jl_b200 import synthetic
+        knots, V, gV = synthetic.analytic_hji_grid()
+        _HJI["c"] = p.HJICache(knots, V, gV)
+    return _HJI["c"]
 
 
 class ClockSampler:
@@ -83,71 +151,308 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(B_sample, steps, warmup, nthreads=0):
-    """Times the CPU oracle (oracle/, a restatement of the reference algorithm: kind "port") on the same workload."""
+def config_dict(cfg_idx, B, world, steps, warmup):
+    """The `config` object of the JSON line — the SAME for the B200 arm and the reference (CPU) arm of one command line."""
+    c = CONFIGS[cfg_idx]
+    return {"workload": c["label"], "baseline_config_index": cfg_idx, "controller": c["kind"], "batch_per_gpu": B, "global_batch": B * world,
+            "horizon_nodes": 31, "dt": DT, "settle_steps": 0 if cfg_idx == 4 else SETTLE, "timed_steps": c.get("mc_steps", steps), "warmup_steps": 0 if cfg_idx == 4 else warmup,
+            "seed": "0x5049474E + %d (+1000 per rank)" % c["seed"],
+            "l2": "inputs larger than L2 are not needed: the per-step working set (QP records + ADMM iterates, ~60 KB per vehicle) is rewritten by every step, nothing is re-read across timed iterations",
+            "parallelism": f"batch sharded over {world} GPU(s), no hot-path collective"}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------------------------------------------------
+def oracle_module():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as o
-    trajs, tid, state, control, t0, other = make_workload(B_sample)
-    cache = {}
-    ms = []
+    return o
+
+
+def cpu_closed_loop(cfg_idx, B_sample, steps, warmup, nthreads=0, native=True, settle=None, return_state=False, sel=None):
+    """Times the CPU oracle (oracle/, a restatement of the reference algorithm: kind "port") on the workload of config `cfg_idx`.
+    sel: indices of the vehicles of the full-size batch to run (default: the first B_sample of a B_sample batch)."""
+    o = oracle_module()
+    flags = o.use_native_build() if native else o.build_flags
+    c = CONFIGS[cfg_idx]
+    settle = (0 if cfg_idx == 4 else SETTLE) if settle is None else settle
+    if sel is None:
+        trajs, tid, state, control, t0, other = make_workload(cfg_idx, B_sample)
+    else:
+        trajs, tid, state, control, t0, other = sel
+        B_sample = len(tid)
+    cache, ms = {}, []
+    hc = None
+    if c["hji"]:
+        from pigeon.jl_b200 import synthetic
+        knots, V, gV = synthetic.analytic_hji_grid()
+        hc = o.HjiCache(knots, V, gV)
+    kind = o.MPC_COUPLED if c["kind"] == "coupled" else o.MPC_DECOUPLED
     for i in range(B_sample):
         j = int(tid[i])
         if j not in cache:
             cache[j] = o.Trajectory(**{k: trajs[k][j] for k in o.TRAJ_FIELDS})
-        m = o.Mpc(o.MPC_COUPLED)
+        m = o.Mpc(kind)
         m.set_trajectory(cache[j])
+        if hc is not None:
+            m.set_hji(hc)
         m.set_state(state[i], control[i], other4=other[i])
         ms.append(m)
     cores = o.max_threads() if nthreads <= 0 else nthreads
-    for k in range(SETTLE + warmup):
-        o.batch_step(ms, t0 + 0.01 * k, rollout=True, nthreads=cores)
+    for k in range(settle + warmup):
+        o.batch_step(ms, t0 + DT * k, rollout=True, nthreads=cores)
     t = time.perf_counter()
     for k in range(steps):
-        o.batch_step(ms, t0 + 0.01 * (SETTLE + warmup + k), rollout=True, nthreads=cores)
+        o.batch_step(ms, t0 + DT * (settle + warmup + k), rollout=True, nthreads=cores)
     el = time.perf_counter() - t
     iters = float(np.mean([m.stats()["iter"] for m in ms]))
-    return {"value": B_sample * steps / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{B_sample} vehicles x {steps} closed-loop steps after {SETTLE} settling + {warmup} warm-up steps, oracle/liboracle.so (C++ -O3, std::thread over vehicles), mean ADMM iters {iters:.1f}",
-            "ms_per_step": el / steps * 1e3}
+    r = {"value": B_sample * steps / el, "unit": UNIT, "cores": cores, "kind": "port", "build_flags": flags,
+         "sample": f"{B_sample} vehicles x {steps} closed-loop steps after {settle} settling + {warmup} warm-up steps, oracle (C++ restatement, std::thread over vehicles, {flags}), mean ADMM iters {iters:.1f}",
+         "ms_per_step": el / steps * 1e3}
+    if return_state:
+        r["final_state"] = np.array([m.get_state()[0] for m in ms])
+    return r
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.batch
-    r = cpu_baseline(B, args.steps, args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg_idx = args.config
+    B = args.batch or CONFIGS[cfg_idx]["batch"]
+    # bounded sample of the workload: at most 1024 vehicles per step (the CPU throughput does not depend on the batch size beyond the thread count)
+    Bs = min(B, 1024 if cfg_idx != 3 else 512)
+    steps, warm = (args.steps, args.warmup) if cfg_idx != 4 else (min(CONFIGS[4]["mc_steps"], 40), 0)
+    r = cpu_closed_loop(cfg_idx, Bs, steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_step": B, "note": "reference's Julia cannot run here (no julia in the image); CPU arm = oracle port on all host threads"},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": config_dict(cfg_idx, B, world, args.steps, args.warmup),
+            "note": "the reference's Julia cannot run here (no julia in the image, no network); CPU arm = the C++ port of its algorithm on all host threads, built on this box with " + r["build_flags"],
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "build_flags")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def iter_stats(st):
+    it = st["iters"]
+    return {"mean_iters": float(it.mean()), "p50_iters": float(np.median(it)), "p99_iters": float(np.percentile(it, 99)), "max_iters": int(it.max()),
+            "pct_not_solved": float((st["status"] != 1).mean() * 100)}
+
+
+def run_settled(cx, p, cfg_idx, B, K, W, seed_shift, want_stage=True, trajs=None):
+    """Closed loop of config 1 / 2 / 3 on the device: cold start, SETTLE steps (timed as `cold_start`), W warm-up steps, K timed steps as ONE
+    pgn_simulate_device call (max over ranks).  Returns the result dict and the live controller."""
+    import torch
+    trajs, tid, state, control, t0, other = make_workload(cfg_idx, B, seed_shift, trajs)
+    mpc = make_mpc(p, cfg_idx, trajs, tid, B, cx.local)
+    mpc.set_stream(cx.stream.cuda_stream)
+    parts = mpc.set_pipeline_parts(cx.args.parts)
+    extra = {}
+    if CONFIGS[cfg_idx]["hji"]:
+        mpc.set_HJI_cache(hji_cache(p))
+    mpc.set_state(state, control, other)
+    d_base = torch.tensor(t0, dtype=torch.float64, device=cx.dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    cx.barrier()
+    ev[0].record(cx.stream)
+    mpc.simulate_device_async(d_base.data_ptr(), DT, 1, k0=0)
+    if CONFIGS[cfg_idx]["hji"]:
+        cx.barrier()
+        Vv, _ = mpc.hji_values()
+        extra["hji_first_step"] = {"pct_active": float((Vv <= 0.05).mean() * 100), "pct_out_of_grid": float(np.isinf(Vv).mean() * 100)}
+    mpc.simulate_device_async(d_base.data_ptr(), DT, SETTLE - 1, k0=1)
+    ev[1].record(cx.stream)
+    cx.barrier()
+    cold_ms = ev[0].elapsed_time(ev[1])
+    mpc.simulate_device_async(d_base.data_ptr(), DT, W, k0=SETTLE)
+    cx.barrier()
+    mpc.stage_ms(reset=True)
+    ev[2].record(cx.stream)
+    mpc.simulate_device_async(d_base.data_ptr(), DT, K, k0=SETTLE + W)
+    ev[3].record(cx.stream)
+    cx.barrier()
+    ms = cx.max_over_ranks(ev[2].elapsed_time(ev[3]))
+    launches = mpc.stage_ms(reset=True)["launches"]
+    st = mpc.stats()
+    if CONFIGS[cfg_idx]["hji"]:
+        Vv, _ = mpc.hji_values()
+        extra["hji_last_step"] = {"pct_active": float((Vv <= 0.05).mean() * 100), "pct_out_of_grid": float(np.isinf(Vv).mean() * 100)}
+    res = {"workload": CONFIGS[cfg_idx]["label"], "batch_per_gpu": B, "n_gpus": cx.world, "value": cx.world * B * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+           "steps": K, "warmup": W, "settle_steps": SETTLE, "pipeline_parts": parts, "gpu_launches": int(launches),
+           "cold_start": {"steps": SETTLE, "value": B * SETTLE / (cold_ms * 1e-3), "unit": UNIT + " (this rank)", "ms_per_step": cold_ms / SETTLE},
+           "admm": iter_stats(st), "qp": {"n": mpc.n, "m": mpc.m, "nnzA": mpc.nnzA, "admm_threads": mpc.qp_program["admm_threads"], "admm_smem_bytes": mpc.qp_program["admm_smem_bytes"]}}
+    res.update(extra)
+    if want_stage:
+        d_t0 = d_base + DT * (SETTLE + W + K)
+        mpc.set_profiling(1)
+        for i in range(3):
+            mpc.step_rollout_device(d_t0.data_ptr(), None, DT); d_t0 += DT
+        stage = mpc.stage_ms(reset=True); mpc.set_profiling(0)
+        res["stage_ms_per_step"] = {k: stage[k] / 3 for k in ("nodes", "linearize", "hji", "admm", "controls", "rollout")}
+    return res, mpc, (trajs, tid, state, control, t0, other)
+
+
+def run_monte_carlo(cx, p, B, seed_shift, trajs=None, oracle_check=True):
+    """configs[4]: B perturbed initial states x 200 closed-loop steps as ONE pgn_simulate call from the cold start, history of the tracking error
+    recorded on the device every 20 steps; final-state check of a 1,024-vehicle subsample against the CPU oracle (rank 0)."""
+    import torch
+    c = CONFIGS[4]
+    NS = c["mc_steps"]
+    t_gen = time.perf_counter()
+    trajs, tid, state, control, t0, other = make_workload(4, B, seed_shift, trajs)
+    t_gen = time.perf_counter() - t_gen
+    mpc = make_mpc(p, 4, trajs, tid, B, cx.local)
+    mpc.set_stream(cx.stream.cuda_stream)
+    parts = mpc.set_pipeline_parts(cx.args.parts)
+    mpc.set_history(NS // 20, 20)
+    d_base = torch.tensor(t0, dtype=torch.float64, device=cx.dev)
+    pin_q = torch.from_numpy(state).pin_memory(); pin_u = torch.from_numpy(control).pin_memory(); pin_o = torch.from_numpy(other).pin_memory()
+    cx.barrier()
+    tw = time.perf_counter()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record(cx.stream)
+    mpc.set_state(pin_q.numpy(), pin_u.numpy(), pin_o.numpy())      # e2e: the job's inputs go in from pinned host memory ...
+    e[1].record(cx.stream)
+    mpc.simulate_device_async(d_base.data_ptr(), DT, NS, k0=0)
+    e[2].record(cx.stream)
+    cx.barrier()
+    q, u = mpc.get_state()                                          # ... and its result (final states and controls) comes back
+    wall_ms = (time.perf_counter() - tw) * 1e3
+    ms = cx.max_over_ranks(e[1].elapsed_time(e[2]))
+    e2e_ms = cx.max_over_ranks(max(wall_ms, e[0].elapsed_time(e[2])))
+    st = mpc.stats()
+    qs, xs, us, ps = mpc.history()
+    e_hist = np.abs(xs[:, :, 5])                                    # |e| (lateral error of node 1) every 20 steps
+    res = {"workload": c["label"], "batch_per_gpu": B, "n_gpus": cx.world, "value": cx.world * B * NS / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / NS, "steps": NS,
+           "seconds": ms * 1e-3, "pipeline_parts": parts, "host_workload_generation_s": t_gen,
+           "e2e": {"value": cx.world * B * NS / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 13 * 8 / NS, "d2h_bytes_per_step": B * 9 * 8 / NS,
+                   "call": "pgn_set_state (pinned host arrays) + pgn_simulate_device (200 steps) + pgn_get_state, wall clock"},
+           "pct_finite": float(np.isfinite(q).all(axis=1).mean() * 100), "admm_last_step": iter_stats(st),
+           "lateral_error_m_by_step": {str(20 * i): {"p50": float(np.nanmedian(e_hist[i])), "p99": float(np.nanpercentile(e_hist[i], 99)), "max": float(np.nanmax(e_hist[i]))} for i in range(e_hist.shape[0])}}
+    if oracle_check and cx.rank == 0:
+        # final tracking error of a 1,024-vehicle subsample on the GPU and on the CPU oracle, and the deviation between the two final states
+        sub = np.arange(0, B, max(1, B // 1024))[:1024]
+        sel = (trajs, tid[sub], state[sub], control[sub], t0[sub], other[sub])
+        t_or = time.perf_counter()
+        r = cpu_closed_loop(4, len(sub), NS, 0, settle=0, return_state=True, sel=sel, native=False)
+        t_or = time.perf_counter() - t_or
+        qo = r["final_state"]
+
+        def dist(qq):
+            return np.array([np.sqrt(np.min((trajs["E"][tid[i]] - qq[k, 0]) ** 2 + (trajs["N"][tid[i]] - qq[k, 1]) ** 2)) for k, i in enumerate(sub)])
+        ok = np.isfinite(qo).all(axis=1) & np.isfinite(q[sub]).all(axis=1)
+        dg, do = dist(q[sub]), dist(qo)
+        dev_pos = np.hypot(q[sub][ok, 0] - qo[ok, 0], q[sub][ok, 1] - qo[ok, 1])
+        pct = lambda a: {"p50": float(np.median(a)), "p99": float(np.percentile(a, 99)), "max": float(np.max(a))}
+        res["oracle_subsample"] = {"vehicles": int(len(sub)), "both_finite": int(ok.sum()), "oracle_seconds": t_or, "oracle_has_no_nan_guard": True,
+                                   "final_distance_to_path_m": {"gpu": pct(dg[ok]), "oracle": pct(do[ok])},
+                                   "final_position_deviation_gpu_vs_oracle_m": pct(dev_pos)}
+    mpc.set_history(0)
+    return res, mpc
+
+
+def hji_roofline(cx, p, mpc, M=1 << 24):
+    """Stand-alone HJI micro-benchmark: M uniformly random in-grid queries against the 319 MB grid (>> 126 MB L2)."""
+    import torch
+    from pigeon.jl_b200 import synthetic
+    g = torch.Generator(device=cx.dev); g.manual_seed(7)
+    lo = torch.tensor([r[0] for r in synthetic.HJI_RANGES], dtype=torch.float64, device=cx.dev)[:, None]
+    hi = torch.tensor([r[1] for r in synthetic.HJI_RANGES], dtype=torch.float64, device=cx.dev)[:, None]
+    x = (lo + (hi - lo) * (0.001 + 0.998 * torch.rand((7, M), dtype=torch.float64, device=cx.dev, generator=g))).contiguous()
+    V = torch.empty(M, dtype=torch.float64, device=cx.dev); gV = torch.empty((7, M), dtype=torch.float64, device=cx.dev)
+    for _ in range(2):
+        mpc.hji_lookup_device(M, x.data_ptr(), V.data_ptr(), gV.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e30
+    for _ in range(3):
+        e0.record(cx.stream)
+        mpc.hji_lookup_device(M, x.data_ptr(), V.data_ptr(), gV.data_ptr())
+        e1.record(cx.stream)
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    peak, src = cx.hbm_peak
+    ach = M * 4096.0 / (best * 1e-3) / 1e9
+    out = {"kernel": "k_hji_lookup", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src, "queries": M, "launch_ms": best,
+           "queries_per_s": M / (best * 1e-3), "algorithmic_bytes_per_query": 4096, "traffic": None,
+           "note": "128 corners x one 32-byte record {gradV[7], V} per query; inputs (the 319 MB grid) are larger than the 126 MB L2"}
+    tr = ncu_metric("r2_hji_lookup_ncu_full.md", "r1_hji_lookup_ncu_full.md")
+    if tr:
+        out["traffic"], out["traffic_source"] = tr["dram_bytes"], tr["source"] + " (DRAM bytes read + written by one launch of 2^22 queries, scaled to this launch's query count)"
+        if tr.get("queries"):
+            out["traffic"] = tr["dram_bytes"] * M / tr["queries"]
+    return out
+
+
+def ncu_metric(*names):
+    """dram__bytes_read.sum + dram__bytes_write.sum (and the shared-memory wavefront share) of the first committed `ncu --set full` summary that exists."""
+    import re
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for nm in names:
+        path = os.path.join(ROOT, "profiles", nm)
+        if not os.path.exists(path):
+            continue
+        txt = open(path).read()
+        rd = re.search(r"dram__bytes_read.sum`\) \| ([0-9.]+) \| (\w+)", txt); wr = re.search(r"dram__bytes_write.sum`\) \| ([0-9.]+) \| (\w+)", txt)
+        if not rd or not wr:
+            continue
+        out = {"dram_bytes": float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)], "source": "profiles/" + nm}
+        wf = re.search(r"l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed`\) \| ([0-9.]+)", txt)
+        if wf:
+            out["smem_pct"] = float(wf.group(1))
+        qn = re.search(r"queries per launch: (\d+)", txt)
+        if qn:
+            out["queries"] = int(qn.group(1))
+        return out
+    return None
+
+
+def measured_peaks():
+    """FP64-FMA and shared-memory peaks measured on this GPU by tools/ubench/peaks (run now when the binary is there, else the committed numbers)."""
+    exe = os.path.join(ROOT, "tools", "ubench", "peaks")
+    try:
+        if os.path.exists(exe):
+            o = json.loads(subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout.strip().splitlines()[-1])
+            o["source"] = "tools/ubench/peaks run on this GPU beside the benchmark"
+            return o
+    except Exception:
+        pass
+    try:
+        o = json.load(open(os.path.join(ROOT, "profiles", "peaks_r2.json")))
+        o["source"] = "profiles/peaks_r2.json (tools/ubench/peaks on a B200 of this pool)"
+        return o
+    except Exception:
+        return {"fp64_fma_tflops": 37.0, "source": "nominal (64 DFMA/clk/SM x 148 SMs x 1.965 GHz)"}
 
 
 def run_gpu(args):
     import torch
     import pigeon.jl_b200 as p
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cx = Ctx()
+    cx.args = args
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = int(os.environ.get("RANK", "0"))
+    cx.local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
-    if world > 1:
+    if cx.world > 1:
         import torch.distributed as dist_
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    B, K, W = args.batch, args.steps, args.warmup
-    trajs, tid, state, control, t0, other = make_workload(B, seed_shift=1000 * rank + args.seed_shift)
-    mpc = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid, device=local)
-    stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: the library launches on it, the events are recorded on it
-    torch.cuda.set_stream(stream)
-    mpc.set_stream(stream.cuda_stream)
-    parts = mpc.set_pipeline_parts(args.parts)      # vehicle ranges on their own streams inside the fused calls (0 = automatic); results do not depend on it
-    dt = 0.01
+        torch.cuda.set_device(cx.local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", cx.local))
+    torch.cuda.set_device(cx.local)
+    cx.dev = torch.device("cuda", cx.local)
+    cx.stream = torch.cuda.Stream(device=cx.dev)          # a real (non-NULL) stream: the library launches on it, the events are recorded on it
+    torch.cuda.set_stream(cx.stream)
+    world, rank, dev, stream = cx.world, cx.rank, cx.dev, cx.stream
 
     def barrier():
         torch.cuda.synchronize()
@@ -155,103 +460,112 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm (`value`) ----------------
-    mpc.set_state(state, control, other)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    cx.barrier, cx.max_over_ranks = barrier, max_over_ranks
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    cx.hbm_peak = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    cfg_idx = args.config
+    B, K, W = args.batch or CONFIGS[cfg_idx]["batch"], args.steps, args.warmup
+    seed_shift = 1000 * rank + args.seed_shift
+    trajs = trajectories()
+    sampler = ClockSampler(cx.local)
+    if rank == 0:
+        sampler.start()           # nvidia-smi needs ~0.2 s to deliver its first sample
+        time.sleep(0.3)
+    t_timed = time.perf_counter()
+
+    if cfg_idx == 4:
+        res, mpc = run_monte_carlo(cx, p, B, seed_shift, trajs)
+        clocks = sampler.stop(t_timed) if rank == 0 else None
+        gathered = final_gather(cx, p, mpc, dist)
+        if rank == 0:
+            line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": res["steps"], "warmup": 0, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(4, B, world, K, W), "e2e": res["e2e"],
+                    "gpu_launches": None, "clocks": clocks, "details": res, "gather": gathered}
+            print(json.dumps(line), flush=True)
+        mpc.close()
+        finish(dist)
+        return
+
+    res, mpc, wl = run_settled(cx, p, cfg_idx, B, K, W, seed_shift, trajs=trajs)
+    trajs, tid, state, control, t0, other = wl
+    ms_max = res["ms_per_step"] * K
+    value = res["value"]
+    st = mpc.stats()
     d_base = torch.tensor(t0, dtype=torch.float64, device=dev)
     d_t0 = d_base.clone()
     d_out = torch.zeros(3 * B, dtype=torch.float64, device=dev)
-    rec_states, rec_controls = [], []     # closed-loop replay for the e2e arm
-    kstep = [0]                           # step k runs at t0 + k*dt on every path (per-step calls, the simulate loop, the e2e replay)
+    kstep = [SETTLE + W + K + 3]
 
-    def dev_step(record):
-        if record:
+    def dev_step(record=None):
+        if record is not None:
             q, u = mpc.get_state()
-            rec_states.append(q); rec_controls.append(u)
-        torch.add(d_base, kstep[0] * dt, out=d_t0)
-        mpc.step_rollout_device(d_t0.data_ptr(), d_out.data_ptr(), dt)      # step + plant rollout (launched beside the QP solve)
+            record[0].append(q); record[1].append(u)
+        torch.add(d_base, kstep[0] * DT, out=d_t0)
+        mpc.step_rollout_device(d_t0.data_ptr(), d_out.data_ptr(), DT)      # step + plant rollout (launched beside the QP solve)
         kstep[0] += 1
 
-    def dev_steps(n):
-        """n closed-loop steps with device-resident inputs: one call of the on-device `simulate` loop (model_predictive_control.jl:87-98;
-        the pipeline parts run their steps independently), or n per-step calls with --loop steps."""
-        if args.loop == "simulate":
-            mpc.simulate_device_async(d_base.data_ptr(), dt, n, k0=kstep[0])
-            kstep[0] += n
-        else:
-            for _ in range(n):
-                dev_step(False)
-
-    # pass 1 (untimed): record the closed-loop states of all SETTLE+W+K steps for the e2e replay
-    for _ in range(SETTLE + W + K):
-        dev_step(True)
-    # pass 2 (timed): identical closed loop from the same initial condition (the path is deterministic)
-    mpc.reset_solver(); mpc.reset_solved()
-    mpc.set_state(state, control, other)
-    kstep[0] = 0
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()           # nvidia-smi needs ~0.2 s to deliver its first sample: started before the settling pass, read over the whole loaded region
-        time.sleep(0.3)
-    barrier()
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    c0.record(stream)
-    dev_steps(SETTLE)
-    c1.record(stream)
-    barrier()
-    cold_ms = c0.elapsed_time(c1)
-    dev_steps(W)
-    barrier()
-    t_timed = time.perf_counter()      # clock samples from here on are the ones reported (the GPU is warm: settling + warm-up ran just before)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    mpc.stage_ms(reset=True)
-    ev0.record(stream)
-    dev_steps(K)
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = mpc.stage_ms(reset=True)["launches"]
-    st = mpc.stats()
     # the same K steps as K per-step calls (pgn_step_rollout_device: the parts are joined at the end of every call), reported beside `value`
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     ev2.record(stream)
     for _ in range(K):
-        dev_step(False)
+        dev_step()
     ev3.record(stream)
     barrier()
     ms_calls = ev2.elapsed_time(ev3)
     clocks = sampler.stop(t_timed) if rank == 0 else None
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    value = world * B * K / (ms_max * 1e-3)
 
-    # per-stage device time of one profiled pass (CUDA events on the launch stream inside the library)
-    mpc.set_profiling(1)                       # CUDA events around every stage on the launch stream; the kernels are unchanged
-    for _ in range(min(K, 5)):
-        dev_step(False)
-    nprof = min(K, 5)
-    stage = mpc.stage_ms(reset=True)
-    mpc.set_profiling(2)                       # + in-kernel cycle counters of the ADMM phases (one extra step, not timed)
+    # in-kernel cycle shares of the ADMM phases (one extra step, not timed)
+    mpc.set_profiling(2)
     mpc.admm_cycles(reset=True)
-    dev_step(False)
+    dev_step()
     cyc = mpc.admm_cycles(reset=True)
     mpc.stage_ms(reset=True)
     mpc.set_profiling(0)
-    admm_ms = stage["admm"] / nprof
-    mean_iters = float(st["iters"].mean())
+    stage = res["stage_ms_per_step"]
+    admm_ms = stage["admm"]
+    mean_iters = res["admm"]["mean_iters"]
+
+    # ---------------- SURVEY.md 8(d) literal timing of config 2 (= BASELINE configs[1]): "1 cold step + 100 warm steps timed" ----------------
+    mpc.reset_solver(); mpc.reset_solved()
+    mpc.set_state(state, control, other)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    mpc.simulate_device_async(d_base.data_ptr(), DT, 101, k0=0)
+    c1.record(stream)
+    barrier()
+    ms101 = max_over_ranks(c0.elapsed_time(c1))
+    cold_literal = {"steps": 101, "value": world * B * 101 / (ms101 * 1e-3), "unit": UNIT, "ms_per_step": ms101 / 101,
+                    "note": "SURVEY.md 8(d) wording: 1 cold step + 100 warm steps from the perturbed cold start, one pgn_simulate_device call, nothing excluded; "
+                            "the settled `value` starts after %d of these steps" % SETTLE}
 
     # ---------------- end-to-end arm (`e2e`): host buffers through the C ABI, copies inside the timed region ----------------
-    nrec = len(rec_states)
+    # replay of the closed loop: pass 1 records the state before every step (device loop), pass 2 feeds them from pinned host memory
+    mpc.reset_solver(); mpc.reset_solved()
+    mpc.set_state(state, control, other)
+    rec = ([], [])
+    kstep[0] = 0
+    for _ in range(SETTLE + W + K):
+        dev_step(rec)
+    nrec = len(rec[0])
     pin_q = torch.empty((nrec, B, 6), dtype=torch.float64).pin_memory()
     pin_u = torch.empty((nrec, B, 3), dtype=torch.float64).pin_memory()
     pin_t = torch.empty((nrec, B), dtype=torch.float64).pin_memory()
     pin_o = torch.empty((nrec, B, 3), dtype=torch.float64).pin_memory()
-    pin_q.numpy()[:] = np.stack(rec_states); pin_u.numpy()[:] = np.stack(rec_controls)
-    pin_t.numpy()[:] = t0[None, :] + dt * np.arange(nrec)[:, None]
+    pin_q.numpy()[:] = np.stack(rec[0]); pin_u.numpy()[:] = np.stack(rec[1])
+    pin_t.numpy()[:] = t0[None, :] + DT * np.arange(nrec)[:, None]
     mpc.reset_solver(); mpc.reset_solved()
     qn, un_, tn, on = pin_q.numpy(), pin_u.numpy(), pin_t.numpy(), pin_o.numpy()
-    import ctypes as C
     lib, h = mpc._lib, mpc._h
 
     def e2e_step(k):
@@ -268,11 +582,8 @@ def run_gpu(args):
         e2e_step(k)
     e1.record(stream)
     barrier()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - tw) * 1e3)
-    t_e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / (float(t_e.item()) * 1e-3)
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - tw) * 1e3))
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
 
     # ---------------- per-call latency (BASELINE.json: "p50 per-step latency"): host wall clock around one C-ABI call, host buffers ----------------
     latency = None
@@ -284,103 +595,146 @@ def run_gpu(args):
             for i in range(n):
                 a_ = time.perf_counter(); fn(warm + i); ts_.append((time.perf_counter() - a_) * 1e3)
             return {"p50_ms": float(np.percentile(ts_, 50)), "p99_ms": float(np.percentile(ts_, 99)), "calls": n}
-        # (a) the batched step of this workload: pgn_set_state + pgn_step on the settled closed loop (states replayed cyclically)
         lo, hi = SETTLE + W, SETTLE + W + K
         latency = {"batched_step": dict(pct(lambda i: e2e_step(lo + i % (hi - lo))), batch=B, call="pgn_set_state + pgn_step (host buffers)")}
-        # (b) the reference's deployment point: ONE vehicle through the callback entry point (one packed copy in, one CUDA graph, one copy out)
-        one = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, 1, trajectory_index=tid[:1], device=local)
-        one.set_stream(stream.cuda_stream)
-        one.set_state(state[:1], control[:1], other[:1])
-        q1 = np.ascontiguousarray(np.stack(rec_states)[:, :1]); u1 = np.ascontiguousarray(np.stack(rec_controls)[:, :1])
-        o5 = np.zeros((1, 5)); st1 = np.zeros(1)
-        def cb(i):
-            k_ = min(i, nrec - 1)
-            lib.pgn_from_autobox(one._h, C.c_void_p(q1[k_].ctypes.data), C.c_void_p(u1[k_].ctypes.data), None, C.c_void_p(st1.ctypes.data), C.c_void_p(o5.ctypes.data))
-        latency["single_vehicle_callback"] = dict(pct(cb), batch=1, call="pgn_from_autobox (path-tracking mode; CUDA graph)")
-        def five(i):
-            k_ = min(i, nrec - 1)
-            lib.pgn_set_state(one._h, C.c_void_p(q1[k_].ctypes.data), C.c_void_p(u1[k_].ctypes.data), None, None)
-            lib.pgn_step(one._h, C.c_void_p(tn[k_][:1].copy().ctypes.data), C.c_void_p(o5.ctypes.data))
-        one.reset_solver(); one.reset_solved()
-        latency["single_vehicle_step"] = dict(pct(five), batch=1, call="pgn_set_state + pgn_step (stream launches)")
-        one.close()
+        if CONFIGS[cfg_idx]["kind"] == "coupled":
+            # the reference's deployment point: ONE vehicle through the callback entry point (one packed copy in, one CUDA graph, one copy out)
+            one = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, 1, trajectory_index=tid[:1], device=cx.local)
+            one.set_stream(stream.cuda_stream)
+            one.set_state(state[:1], control[:1], other[:1])
+            q1 = np.ascontiguousarray(np.stack(rec[0])[:, :1]); u1 = np.ascontiguousarray(np.stack(rec[1])[:, :1])
+            o5 = np.zeros((1, 5)); st1 = np.zeros(1)
 
-    # ---------------- final gather of controls + statistics (NCCL over NVLink, outside the timed region) ----------------
-    gathered = None
-    if dist is not None:
-        ctrl = d_out.clone()
-        iters_t = torch.tensor(st["iters"], dtype=torch.int32, device=dev)
-        gl = [torch.empty_like(ctrl) for _ in range(world)]
-        gi = [torch.empty_like(iters_t) for _ in range(world)]
-        dist.all_gather(gl, ctrl); dist.all_gather(gi, iters_t)
-        gathered = {"controls": int(sum(g.numel() for g in gl)), "mean_iters_all_ranks": float(torch.cat(gi).float().mean().item())}
+            def cb(i):
+                k_ = min(i, nrec - 1)
+                lib.pgn_from_autobox(one._h, C.c_void_p(q1[k_].ctypes.data), C.c_void_p(u1[k_].ctypes.data), None, C.c_void_p(st1.ctypes.data), C.c_void_p(o5.ctypes.data))
+            latency["single_vehicle_callback"] = dict(pct(cb), batch=1, call="pgn_from_autobox (path-tracking mode; CUDA graph)")
+
+            def five(i):
+                k_ = min(i, nrec - 1)
+                lib.pgn_set_state(one._h, C.c_void_p(q1[k_].ctypes.data), C.c_void_p(u1[k_].ctypes.data), None, None)
+                lib.pgn_step(one._h, C.c_void_p(tn[k_][:1].copy().ctypes.data), C.c_void_p(o5.ctypes.data))
+            one.reset_solver(); one.reset_solved()
+            latency["single_vehicle_step"] = dict(pct(five), batch=1, call="pgn_set_state + pgn_step (stream launches)")
+            one.close()
+
+    gathered = final_gather(cx, p, mpc, dist)
+
+    # ---------------- the other BASELINE configs at their per-GPU size (default run of config 1 only) ----------------
+    others, hji_roof = {}, None
+    want = [] if (cfg_idx != 1 or args.other_configs == "none") else ([2, 3, 4] if args.other_configs == "all" else [int(x) for x in args.other_configs.split(",")])
+    n, m, nnzA, nnzL, prog, Nh, nlev = mpc.n, mpc.m, mpc.nnzA, mpc.nnzL, mpc.qp_program, mpc.N, mpc.n_levels
+    if cfg_idx == 3 and rank == 0:
+        hji_roof = hji_roofline(cx, p, mpc)
+    mpc.close()
+    for oc in want:
+        t_oc = time.perf_counter()
+        try:
+            if oc == 4:
+                r, m4 = run_monte_carlo(cx, p, CONFIGS[4]["batch"], seed_shift, trajs)
+                m4.close()
+            else:
+                r, mo, _ = run_settled(cx, p, oc, CONFIGS[oc]["batch"], 30, 3, seed_shift, trajs=trajs)
+                if oc == 3 and rank == 0:
+                    hji_roof = hji_roofline(cx, p, mo)
+                mo.close()
+            r["bench_wall_s"] = time.perf_counter() - t_oc
+            others["configs[%d]" % oc] = r
+        except Exception as ex:      # an out-of-memory on a shared box must not lose the headline line
+            others["configs[%d]" % oc] = {"error": repr(ex)}
+    _HJI.clear()
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-        n, m, Nk = mpc.n, mpc.m, mpc.n + mpc.m
-        rec_len = 30 * 81 + 6 + 2 + 3 + 30
+        Nk = n + m
+        rec_len = 30 * 81 + 6 + 2 + 3 + 30 if CONFIGS[cfg_idx]["kind"] == "coupled" else 30 * 43 + 4 + 1 + 30
+        pk = measured_peaks()
+        fp64_peak = float(pk.get("fp64_fma_tflops", 37.0))
         # algorithmic HBM bytes of one ADMM launch: per QP the piece record in, warm iterates (x|z, y) in and out, solution x,y out, stats
         bytes_per_qp = 8 * (rec_len + 4 * Nk + n + m) + 40
         # algorithmic FP64 flops per QP, from the static programs of this QP: Ruiz (10 passes over A and diag P), factor
         # (3 flops per gather entry), range inverses, dense-tail sweep, then per iteration the forward/backward entries (2 flops each),
         # the dense tail mat-vec and ~15 flops per KKT row of vector updates; residual checks every 25 iterations
-        nnzL, nnzA = mpc.nnzL, mpc.nnzA
-        prog = mpc.qp_program
         Dm = prog["tail_dim"]
         flop_factor = 3 * prog["factor_entries"] + 3 * prog["inverse_entries"] + 3 * Dm * (Dm * (Dm + 1) // 2)
         flop_iter = 2 * (prog["l_slots"] + prog["backward_entries"]) + 2 * Dm * Dm + 15 * Nk
         flop_check = 4 * nnzA + 2 * n + 10 * Nk
         flop_qp = flop_factor + 10 * 2 * (nnzA + n) + mean_iters * flop_iter + (mean_iters / 25.0) * flop_check
+        hbm_peak, peak_src = cx.hbm_peak
         roof = {"kernel": "k_admm", "bound": "hbm", "achieved": B * bytes_per_qp / (admm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "peak_source": peak_src, "traffic": None, "launch_ms": admm_ms,
-                "share_of_step": admm_ms / max(1e-9, (stage["nodes"] + stage["linearize"] + stage["hji"] + stage["admm"] + stage["controls"] + stage["rollout"]) / nprof),
-                "fp64": {"achieved_tflops": B * flop_qp / (admm_ms * 1e-3) / 1e12, "nominal_peak_tflops": 37.0, "flop_per_qp": flop_qp},
-                "note": "one QP per CTA; the solve is a chain of dependent sparse triangular solves in shared memory: latency/occupancy-bound, neither HBM- nor tensor-bound (SURVEY.md 8d)",
-                "limiter": {"what": "dependent-instruction latency of the slowest warp in each barrier interval (about 4.7 cycles per instruction of a lone warp), then shared-memory wavefronts (every 8-byte load of a warp is >= 2 wavefronts of one 128 B/clk pipe)",
-                            "evidence": "tools/ubench/*.cu (B200 latencies), DESIGN.md 4.1 (table of measurements, rejected variants), profiles/r1b_admm_ncu_full.md (0.42 IPC per scheduler, stalls: barrier >> wait ~ short scoreboard)"}}
+                "share_of_step": admm_ms / max(1e-9, sum(stage[k] for k in ("nodes", "linearize", "hji", "admm", "controls", "rollout"))),
+                "fp64": {"achieved_tflops": B * flop_qp / (admm_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak, "peak_source": pk.get("source"), "flop_per_qp": flop_qp},
+                "note": "one QP per CTA; the solve is a chain of dependent sparse triangular solves on chip: latency/occupancy-bound, neither HBM- nor tensor-bound (SURVEY.md 8d)",
+                "limiter": {"what": "dependent-instruction latency of the slowest warp in each barrier interval (about 4.7 cycles per instruction of a lone warp), then shared-memory wavefronts",
+                            "evidence": "tools/ubench/*.cu (B200 latencies), DESIGN.md 4.1, profiles/r2_admm_ncu_full.md"}}
         roof["frac"] = roof["achieved"] / roof["peak"]
-        # DRAM traffic of one launch from the committed `ncu --set full` capture of the same workload (read + written bytes)
-        try:
-            import re
-            txt = open(os.path.join(ROOT, "profiles", "r1_admm_ncu_full.md")).read()
-            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            rd = re.search(r"dram__bytes_read.sum`\) \| ([0-9.]+) \| (\w+)", txt); wr = re.search(r"dram__bytes_write.sum`\) \| ([0-9.]+) \| (\w+)", txt)
-            wf = re.search(r"l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed`\) \| ([0-9.]+)", txt)
-            roof["traffic"] = float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)]
-            roof["traffic_source"] = "profiles/r1b_admm_ncu_full.md (B = 1024; below the algorithmic bytes because the records and iterates of 1024 vehicles stay in the 126 MB L2)"
-            if wf:
-                roof["smem"] = {"pct_of_peak_wavefronts": float(wf.group(1)), "source": "profiles/r1b_admm_ncu_full.md: the most loaded unit of the kernel is the shared-memory pipe"}
-        except Exception:
-            pass
-        roof["fp64"]["frac"] = roof["fp64"]["achieved_tflops"] / 37.0
+        roof["fp64"]["frac"] = roof["fp64"]["achieved_tflops"] / fp64_peak
+        tr = ncu_metric("r2_admm_ncu_full.md", "r1b_admm_ncu_full.md")
+        if tr:
+            roof["traffic"] = tr["dram_bytes"]
+            roof["traffic_source"] = tr["source"] + " (`ncu --set full` of one B = 1024 launch of this kernel; below the algorithmic bytes because the records and iterates of 1024 vehicles stay in the 126 MB L2)"
+            if "smem_pct" in tr:
+                roof["smem"] = {"pct_of_peak_wavefronts": tr["smem_pct"], "source": tr["source"], "measured_peak_bytes_per_clk_sm": pk.get("smem_lds64_bytes_per_clk_sm")}
         ncpu = min(B, 256)
-        cpu = cpu_baseline(ncpu, 3, 1) if not args.no_cpu else None
+        cpu = cpu_closed_loop(cfg_idx, ncpu, 3, 1) if not args.no_cpu else None
+        cfg = config_dict(cfg_idx, B, world, K, W)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "horizon_nodes": mpc.N, "qp": {"n": n, "m": m, "nnzA": nnzA, "nnzL": nnzL, "levels": mpc.n_levels, "program": prog},
-                           "l2": "per-step working set (records + iterates, ~%.0f MB per GPU) is rewritten every step; B=1024 fits L2, the ADMM kernel is not HBM-bound" % (B * bytes_per_qp / 1e6),
-                           "parallelism": f"batch sharded over {world} GPU(s), no hot-path collective",
-                           "loop": ("one pgn_simulate_device call of K closed-loop steps (the reference's `simulate` loop on the device)" if args.loop == "simulate" else "K pgn_step_rollout_device calls"),
-                           "pipeline_parts": parts},
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "details": {"horizon_nodes": Nh, "qp": {"n": n, "m": m, "nnzA": nnzA, "nnzL": nnzL, "levels": nlev, "program": prog},
+                            "loop": "one pgn_simulate_device call of K closed-loop steps (the reference's `simulate` loop on the device)", "pipeline_parts": res["pipeline_parts"]},
                 "per_step_calls": {"value": world * B * K / (ms_calls * 1e-3), "unit": UNIT + " (rank 0 time)", "ms_per_step": ms_calls / K,
                                    "call": "pgn_step_rollout_device x K, device-resident; the pipeline parts are joined at the end of every call"},
-                "roofline": roof, "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (6 + 3 + 1) * 8, "d2h_bytes_per_step": B * 3 * 8},
-                "gpu_launches": int(launches), "clocks": clocks,
-                "admm": {"mean_iters": mean_iters, "p50_iters": float(np.median(st["iters"])), "p99_iters": float(np.percentile(st["iters"], 99)), "max_iters": int(st["iters"].max()),
-                         "pct_not_solved": float((st["status"] != 1).mean() * 100)},
-                "stage_ms_per_step": {k: stage[k] / nprof for k in ("nodes", "linearize", "hji", "admm", "controls", "rollout")},
-                "admm_phase_share": {k: v / max(1.0, sum(cyc.values())) for k, v in cyc.items()},
+                "roofline": roof, "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "build_flags")} if cpu else None,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (6 + 3 + 1) * 8, "d2h_bytes_per_step": B * 3 * 8,
+                        "call": "pgn_set_state + pgn_step per step: one packed pinned H2D copy each, one D2H copy of the controls"},
+                "gpu_launches": res["gpu_launches"], "clocks": clocks, "admm": res["admm"],
+                "stage_ms_per_step": stage, "admm_phase_share": {k: v / max(1.0, sum(cyc.values())) for k, v in cyc.items()},
                 "latency": latency, "gather": gathered,
-                "cold_start": {"steps": SETTLE, "value": B * SETTLE / (cold_ms * 1e-3), "unit": UNIT + " (rank 0, device-resident)", "ms_per_step": cold_ms / SETTLE,
-                               "note": "first %d closed-loop steps from the perturbed cold start; a few QPs per step run to thousands of iterations (max_iter 4000) and one QP occupies one SM, so single stragglers set the launch time" % SETTLE}}
+                "cold_start": dict(res["cold_start"], note="first %d closed-loop steps from the perturbed cold start; a few QPs per step run to thousands of iterations (max_iter 4000)" % SETTLE),
+                "survey_8d_timing": cold_literal}
+        for k in ("hji_first_step", "hji_last_step"):
+            if k in res:
+                line[k] = res[k]
+        if hji_roof:
+            line["roofline_hji"] = hji_roof
+        if others:
+            line["other_configs"] = others
         print(json.dumps(line), flush=True)
-    mpc.close()
+    finish(dist)
+
+
+def final_gather(cx, p, mpc, dist):
+    """Final gather of controls + statistics through the library's own NCCL collective (pgn_gather), outside the timed region."""
+    if dist is None:
+        return None
+    import torch
+    lib = mpc._lib
+    idb = torch.zeros(128, dtype=torch.uint8)
+    if cx.rank == 0:
+        buf = (C.c_char * 128)()
+        rc = lib.pgn_comm_unique_id(buf)
+        if rc != 0:
+            return {"error": lib.pgn_last_error().decode()}
+        idb = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+    idb = idb.to(cx.dev)
+    dist.broadcast(idb, 0)                    # the launcher's job: ship the 128-byte id to every rank
+    raw = bytes(idb.cpu().numpy().tolist())
+    rc = lib.pgn_comm_init_rank(mpc._h, cx.world, cx.rank, raw)
+    if rc != 0:
+        return {"error": lib.pgn_last_error().decode()}
+    n = cx.world * mpc.B
+    ctrl, it, st = np.zeros((n, 3)), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    t = time.perf_counter()
+    rc = lib.pgn_gather(mpc._h, C.c_void_p(ctrl.ctypes.data), C.c_void_p(it.ctypes.data), C.c_void_p(st.ctypes.data))
+    el = time.perf_counter() - t
+    if rc != 0:
+        return {"error": lib.pgn_last_error().decode()}
+    lib.pgn_comm_destroy(mpc._h)
+    return {"call": "pgn_gather (ncclAllGather of controls [3][B] f64 + iters/status i32 per rank)", "ranks": cx.world, "controls": int(ctrl.shape[0]), "finite_controls_pct": float(np.isfinite(ctrl).all(axis=1).mean() * 100),
+            "mean_iters_all_ranks": float(it.mean()), "seconds_incl_host_copy": el}
+
+
+def finish(dist):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -391,10 +745,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=1024, help="vehicles per GPU")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="index into BASELINE.json `configs` (1 = the configuration the metric is quoted on)")
+    ap.add_argument("--batch", type=int, default=0, help="vehicles per GPU (default: the config's per-GPU size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--parts", type=int, default=0, help="pipeline parts of the fused calls (0 = automatic, 1 = off)")
-    ap.add_argument("--loop", default="simulate", choices=["simulate", "steps"], help="timed region of `value`: one on-device simulate call of K steps, or K per-step calls")
+    ap.add_argument("--other-configs", default="all", help="configs measured beside the default config-1 run and appended as `other_configs`: all | none | e.g. 2,3")
     ap.add_argument("--seed-shift", type=int, default=0, help="added to the workload seed (rank r uses 1000*r + this): reproduces another rank's batch at N = 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the per-call latency leg")

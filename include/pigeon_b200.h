@@ -11,7 +11,9 @@
  *  - every function returns 0 on success or a negative pgn_status; pgn_last_error() gives a thread-local message.
  *  - host arrays are caller-owned, vehicle-major ("[B][k]" = Julia Matrix{Float64}(k, B)), read/written only during the call.
  *  - all device memory, the CUDA stream and the static factorisation schedules are owned by the opaque handle.
- *  - a handle is bound to one CUDA device and must be driven by one host thread at a time.
+ *  - a handle is bound to one CUDA device and must be driven by one host thread at a time; every entry point switches to the handle's device
+ *    for the duration of the call and restores the caller's current device, so ONE host thread can drive handles on several GPUs.
+ *  - setters are ordered after the work already queued on the handle's stream (they synchronise it, or run on it).
  *  - there is NO CPU fallback: pgn_create fails with PGN_ECUDA when no sm_100 device is usable.
  */
 #ifndef PIGEON_B200_H
@@ -36,7 +38,8 @@ typedef enum pgn_status {
     PGN_EINVAL = -1,   /* bad argument / call order */
     PGN_ECUDA = -2,    /* CUDA runtime error (message in pgn_last_error) */
     PGN_ENOMEM = -3,
-    PGN_ESTATE = -4    /* required input (trajectories, state, ...) not set */
+    PGN_ESTATE = -4,   /* required input (trajectories, state, communicator, ...) not set */
+    PGN_ENCCL = -5     /* NCCL error or libnccl.so.2 not loadable (pgn_comm_*, pgn_gather only) */
 } pgn_status;
 
 enum { PGN_COUPLED = 0, PGN_DECOUPLED = 1 };
@@ -154,6 +157,25 @@ PGN_API int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts);
 PGN_API int pgn_get_pipeline_parts(pgn_handle* h, int32_t* parts);
 /* one plant rollout + control application (the tail of the simulate loop) */
 PGN_API int pgn_rollout(pgn_handle* h, double dt);
+/* The return values of simulate (model_predictive_control.jl:84-99: qs, xs, us, ps pushed once per step).  With capacity > 0 the loops of
+ * pgn_simulate / pgn_simulate_device record, on the device, every step k with k % stride == 0 (record k / stride, up to `capacity`):
+ * current_state and current_control BEFORE the step (qs, us), mpc.qs[1] and mpc.ps[1] of the step (xs, ps).  pgn_get_history copies the
+ * records out: qs [n][B][6], us [n][B][3], xs [n][B][nx], ps [n][B][4] (any may be NULL); n_records is always written.  0, 0 = off. */
+PGN_API int pgn_set_history(pgn_handle* h, int32_t capacity, int32_t stride);
+PGN_API int pgn_get_history(pgn_handle* h, int32_t* n_records, double* qs, double* us, double* xs, double* ps);
+
+/* --- multi-GPU: the batch is sharded over one handle per GPU with NO hot-path traffic; the only collective is this final gather ------------
+ * (the loop that is sharded: model_predictive_control.jl:87-98).  NCCL is loaded at run time (dlopen "libnccl.so.2").
+ *   one process, one handle per GPU (the Julia deployment):   pgn_comm_init_all(handles, n);  ...steps on every handle...;  pgn_gather_all(...)
+ *   one process per GPU:   rank 0: pgn_comm_unique_id(id), ship the 128 bytes to every rank;  each rank: pgn_comm_init_rank(h, n, rank, id);  pgn_gather(h, ...)
+ * Gathered arrays are rank-major: controls [n*B][3] = (delta, Fxf, Fxr) of the last step, iters / status [n*B] (any may be NULL).
+ * Every rank receives the full result (all-gather over NVLink). */
+PGN_API int pgn_comm_unique_id(char* id /*[128]*/);
+PGN_API int pgn_comm_init_rank(pgn_handle* h, int32_t nranks, int32_t rank, const char* id /*[128]*/);
+PGN_API int pgn_comm_init_all(pgn_handle* const* handles, int32_t n);
+PGN_API int pgn_comm_destroy(pgn_handle* h);
+PGN_API int pgn_gather(pgn_handle* h, double* controls, int32_t* iters, int32_t* status);            /* collective: every rank calls it */
+PGN_API int pgn_gather_all(pgn_handle* const* handles, int32_t n, double* controls, int32_t* iters, int32_t* status);
 
 /* --- outputs / introspection (used by the parity tests) ----------------------------------------------------------- */
 PGN_API int pgn_qp_dims(pgn_handle* h, int32_t* out /*[16] = N, nx, nu, n, m, nnz(A), nnz(L), n_levels, L slots, solve phases, factor entries, inverse entries, tail dim, backward entries, ADMM smem bytes, ADMM threads*/);

@@ -20,7 +20,31 @@ ip = C.POINTER(C.c_int)
 fp = C.POINTER(C.c_float)
 
 
+NATIVE_FLAGS = "-O3 -march=native -std=c++17 -pthread (FMA contraction on)"
+CHECKER_FLAGS = "-O3 -std=c++17 -pthread -ffp-contract=off (portable)"
+build_flags = CHECKER_FLAGS
+
+
+def use_native_build():
+    """bench.py's timed CPU arm only: build oracle/liboracle_native.so on THIS machine with -O3 -march=native (oracle/Makefile) and bind it.
+    Must be called before the first use of the library in the process.  Falls back to the portable checker build when make fails."""
+    global _LIB_PATH, build_flags
+    if _lib is not None:
+        return build_flags
+    native = os.path.join(_HERE, "liboracle_native.so")
+    try:
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle_native.so"], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        _LIB_PATH, build_flags = native, NATIVE_FLAGS
+    except Exception:
+        pass
+    return build_flags
+
+
 def build(force=False):
+    if _LIB_PATH.endswith("liboracle_native.so"):
+        return _LIB_PATH
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):

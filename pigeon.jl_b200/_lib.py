@@ -30,7 +30,8 @@ SYMBOLS = ["pgn_default_config", "pgn_x1_vehicle_params", "pgn_default_control_p
            "pgn_get_time_steps", "pgn_get_nodes", "pgn_set_nodes", "pgn_get_qp_data", "pgn_get_solution", "pgn_get_stats", "pgn_hji_lookup",
            "pgn_hji_lookup_device", "pgn_device_controls", "pgn_device_stats", "pgn_set_profiling", "pgn_get_stage_ms", "pgn_get_admm_cycles",
            "pgn_get_hji_values", "pgn_hji_optimal_control", "pgn_set_hji_policy", "pgn_from_autobox", "pgn_step_rollout_device", "pgn_set_path_search_window",
-           "pgn_simulate_device", "pgn_set_pipeline_parts", "pgn_get_pipeline_parts"]
+           "pgn_simulate_device", "pgn_set_pipeline_parts", "pgn_get_pipeline_parts", "pgn_set_history", "pgn_get_history", "pgn_comm_unique_id",
+           "pgn_comm_init_rank", "pgn_comm_init_all", "pgn_comm_destroy", "pgn_gather", "pgn_gather_all"]
 
 _lib = None
 
@@ -57,6 +58,14 @@ def load():
     lib.pgn_rollout.argtypes = [C.c_void_p, C.c_double]
     lib.pgn_step_rollout_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
     lib.pgn_set_guards.argtypes = [C.c_void_p, C.c_int32, C.c_double]
+    lib.pgn_set_history.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.pgn_get_history.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pgn_comm_unique_id.argtypes = [C.c_void_p]
+    lib.pgn_comm_init_rank.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.pgn_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+    lib.pgn_comm_destroy.argtypes = [C.c_void_p]
+    lib.pgn_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pgn_gather_all.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpigeon_b200.so")
-SOURCES = ["pgn_capi.cu", "pgn_nodes.cu", "pgn_linearize.cu", "pgn_hji.cu", "pgn_admm.cu", "pgn_structure.cpp"]
+SOURCES = ["pgn_capi.cu", "pgn_nodes.cu", "pgn_linearize.cu", "pgn_hji.cu", "pgn_admm.cu", "pgn_comm.cu", "pgn_structure.cpp"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-              "--expt-relaxed-constexpr", "-shared"]
+              "--expt-relaxed-constexpr", "-shared", "-ldl"]
 
 
 def needs_build():

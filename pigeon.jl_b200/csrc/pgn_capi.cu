@@ -20,6 +20,7 @@ static int set_err(int code, const char* fmt, ...) {
     va_end(ap);
     return code;
 }
+extern "C" void pgn_set_error_(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }      // for the other translation units
 #define CK(call)                                                                                                              \
     do {                                                                                                                      \
         cudaError_t e__ = (call);                                                                                             \
@@ -85,15 +86,6 @@ int ensure_stage(pgn_handle* h, size_t bytes) {
     return PGN_OK;
 }
 
-// host [B][k] -> device SoA [k][B]
-int upload_aos(pgn_handle* h, const double* host, double* d_soa, int k) {
-    size_t bytes = (size_t)h->B * k * sizeof(double);
-    int rc = ensure_stage(h, bytes);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h->d_stage, host, bytes, cudaMemcpyHostToDevice, h->stream));
-    launch_transpose_in(h, h->d_stage, d_soa, k);
-    return PGN_OK;
-}
 int download_aos(pgn_handle* h, const double* d_soa, double* host, int k) {
     size_t bytes = (size_t)h->B * k * sizeof(double);
     int rc = ensure_stage(h, bytes);
@@ -649,11 +641,19 @@ int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const doub
     memcpy(out, io + 1 + 14 * B, 5 * B * 8);
     return PGN_OK;
 }
-// one closed-loop step of the current vehicle range on the current stream: the step stages, the plant step on the side stream
-static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt) {
+// one closed-loop step of the current vehicle range on the current stream: the step stages, the plant step on the side stream.
+// rec_slot >= 0: the history recorder keeps (state, control, node 1, params 1) of this step (pgn_set_history).
+static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt, int rec_slot) {
     step_time_steps_dev(h, d_t0);
     step_nodes(h);
+    if (rec_slot >= 0) launch_record(h, rec_slot);
     step_update(h);
+    if (h->profiling || !h->side_stream) {            // stage timers synchronise: serial order
+        step_solve(h);
+        step_controls(h, h->d_controls);
+        { StageTimer T(h, 5); launch_rollout(h, dt); }
+        return PGN_OK;
+    }
     // fork: the propagation reads state / current control only (nothing on the main stream writes them before the commit)
     CK(cudaEventRecord(h->ev_fork, h->stream));
     CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
@@ -668,12 +668,7 @@ static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt) {
 // step + plant rollout of `simulate` (model_predictive_control.jl:87-98) with the plant step beside the QP solve
 int pgn_step_rollout_device(pgn_handle* h, const double* d_t0, double* d_out, double dt) {
     ENTER(h, "NULL handle"); REQUIRE(d_t0, "NULL argument");
-    if (h->profiling || !h->side_stream) {            // stage timers synchronise: serial order
-        int rc = pgn_step_device(h, d_t0, d_out);
-        if (rc) return rc;
-        return pgn_rollout(h, dt);
-    }
-    int rc = for_each_part(h, [&]() { return step_rollout_body(h, d_t0, dt); });
+    int rc = for_each_part(h, [&]() { return step_rollout_body(h, d_t0, dt, -1); });
     if (rc) return rc;
     if (d_out) CK(cudaMemcpyAsync(d_out, h->d_controls, (size_t)h->B * 3 * 8, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaGetLastError());
@@ -688,18 +683,12 @@ int pgn_rollout(pgn_handle* h, double dt) {
 // the `simulate` loop on the device: every pipeline part runs ALL its steps on its own stream (a vehicle's step k+1 depends only on its own
 // step k), so the parts drift apart and the small per-vehicle kernels of one part fill the SMs the ADMM kernel of another leaves idle
 static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
-    if (h->profiling || !h->side_stream) {
-        for (int k = k0; k < k0 + n_steps; k++) {
-            launch_time_axpy(h, h->d_t0_base, (double)k, dt, h->d_t0, h->B);
-            int rc = pgn_step_rollout_device(h, h->d_t0, nullptr, dt);
-            if (rc) return rc;
-        }
-        return PGN_OK;
-    }
+    auto slot_of = [&](int k) { return (h->hist_stride > 0 && k % h->hist_stride == 0 && k / h->hist_stride < h->hist_cap) ? k / h->hist_stride : -1; };
+    for (int k = k0; k < k0 + n_steps; k++) { const int sl = slot_of(k); if (sl + 1 > h->hist_n) h->hist_n = sl + 1; }
     return for_each_part(h, [&]() {
         for (int k = k0; k < k0 + n_steps; k++) {
             launch_time_axpy(h, h->d_t0_base + h->v0, (double)k, dt, h->d_t0 + h->v0, h->nv);
-            int rc = step_rollout_body(h, h->d_t0, dt);
+            int rc = step_rollout_body(h, h->d_t0, dt, slot_of(k));
             if (rc) return rc;
         }
         return (int)PGN_OK;
@@ -712,6 +701,7 @@ static int auto_parts(pgn_handle* h) { return h->B >= 64 ? 4 : 1; }
 int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
     ENTER(h, "NULL handle"); REQUIRE(t0 && n_steps >= 0, "bad argument");
     CK(cudaMemcpyAsync(h->d_t0_base, t0, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
+    h->hist_n = 0;
     int rc = simulate_enqueue(h, dt, 0, n_steps);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -721,6 +711,7 @@ int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
 int pgn_simulate_device(pgn_handle* h, const double* d_t0, double dt, int32_t k0, int32_t n_steps) {
     ENTER(h, "NULL handle"); REQUIRE(d_t0 && n_steps >= 0 && k0 >= 0, "bad argument");
     CK(cudaMemcpyAsync(h->d_t0_base, d_t0, (size_t)h->B * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if (k0 == 0) h->hist_n = 0;
     int rc = simulate_enqueue(h, dt, k0, n_steps);
     if (rc) return rc;
     CK(cudaGetLastError());
@@ -742,6 +733,41 @@ int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts) {
     }
     h->epoch++;
     h->parts = parts;
+    return PGN_OK;
+}
+// simulate's return values (model_predictive_control.jl:84-99): qs / us before every recorded step, xs = mpc.qs[1], ps = mpc.ps[1]
+int pgn_set_history(pgn_handle* h, int32_t capacity, int32_t stride) {
+    ENTER(h, "NULL handle");
+    REQUIRE(capacity >= 0 && stride >= 0 && (capacity == 0) == (stride == 0), "capacity and stride must both be positive, or both 0 (off)");
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->d_hist) {
+        for (size_t i = 0; i < h->allocs.size(); i++) if (h->allocs[i] == (void*)h->d_hist) { h->allocs.erase(h->allocs.begin() + i); cudaFree(h->d_hist); break; }
+        h->d_hist = nullptr;
+    }
+    h->hist_cap = h->hist_stride = h->hist_n = 0;
+    if (capacity == 0) return PGN_OK;
+    int rc = dev_alloc(h, &h->d_hist, (size_t)capacity * (13 + h->nx) * h->B);
+    if (rc) return rc;
+    h->hist_cap = capacity; h->hist_stride = stride;
+    return PGN_OK;
+}
+int pgn_get_history(pgn_handle* h, int32_t* n_records, double* qs, double* us, double* xs, double* ps) {
+    ENTER(h, "NULL handle"); REQUIRE(n_records, "NULL argument");
+    *n_records = h->hist_n;
+    if (h->hist_n == 0 || (!qs && !us && !xs && !ps)) return PGN_OK;
+    const size_t B = h->B, F = 13 + h->nx, nx = h->nx;
+    std::vector<double> rec((size_t)h->hist_n * F * B);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(rec.data(), h->d_hist, rec.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < (size_t)h->hist_n; r++) {
+        const double* s = rec.data() + r * F * B;
+        for (size_t v = 0; v < B; v++) {
+            if (qs) for (size_t f = 0; f < 6; f++) qs[(r * B + v) * 6 + f] = s[f * B + v];
+            if (us) for (size_t f = 0; f < 3; f++) us[(r * B + v) * 3 + f] = s[(6 + f) * B + v];
+            if (xs) for (size_t f = 0; f < nx; f++) xs[(r * B + v) * nx + f] = s[(9 + f) * B + v];
+            if (ps) for (size_t f = 0; f < 4; f++) ps[(r * B + v) * 4 + f] = s[(9 + nx + f) * B + v];
+        }
+    }
     return PGN_OK;
 }
 int pgn_get_pipeline_parts(pgn_handle* h, int32_t* parts) { ENTER(h, "NULL handle"); REQUIRE(parts, "NULL argument"); *parts = h->parts; return PGN_OK; }

@@ -173,6 +173,7 @@ class BatchedTrajectoryTrackingMPC:
                 raise ValueError("all trajectories of a batch must have the same number of nodes")
             fields = [np.ascontiguousarray(np.stack([getattr(t, k) for t in trajectories])) for k in TRAJ_FIELDS]
         n_traj, n_nodes = fields[0].shape
+        self.trajectory_end_time = float(fields[0][0, -1])         # mpc.trajectory.t[end] (of the first trajectory): simulate's default horizon
         arr = (C.c_void_p * 12)(*[f.ctypes.data for f in fields])
         check(self._lib.pgn_set_trajectories(self._h, n_traj, n_nodes, arr))
         self.n_traj = n_traj
@@ -275,6 +276,21 @@ class BatchedTrajectoryTrackingMPC:
     def simulate_device_async(self, d_t0_ptr, dt, n_steps, k0=0):
         """pgn_simulate with t0 resident on the device, enqueued on the handle's stream (no host synchronisation): steps k0 .. k0+n_steps-1 at t0 + k*dt."""
         check(self._lib.pgn_simulate_device(self._h, C.c_void_p(d_t0_ptr), float(dt), int(k0), int(n_steps)))
+
+    def set_history(self, capacity, stride=1):
+        """Record (on the device) every `stride`-th step of simulate_device / simulate_device_async: the reference's simulate returns
+        qs, xs, us, ps per step (model_predictive_control.jl:84-99).  capacity = 0 switches the recorder off."""
+        check(self._lib.pgn_set_history(self._h, int(capacity), int(stride) if capacity else 0))
+
+    def history(self):
+        """(qs, xs, us, ps) of the recorded steps: arrays of shape (n, B, 6), (n, B, nx), (n, B, 3), (n, B, 4)."""
+        n = C.c_int32(0)
+        check(self._lib.pgn_get_history(self._h, C.byref(n), None, None, None, None))
+        n = int(n.value)
+        qs, us, xs, ps = np.zeros((n, self.B, 6)), np.zeros((n, self.B, 3)), np.zeros((n, self.B, self.nx)), np.zeros((n, self.B, 4))
+        if n:
+            check(self._lib.pgn_get_history(self._h, C.byref(C.c_int32(0)), dptr(qs), dptr(us), dptr(xs), dptr(ps)))
+        return qs, xs, us, ps
 
     def set_pipeline_parts(self, parts):
         """Run the fused entry points as `parts` vehicle ranges on their own streams (0: automatic, 1: off); results do not depend on it."""
@@ -390,6 +406,21 @@ def BatchedDecoupledTrajectoryTrackingMPC(vehicle, trajectories, batch, control_
     return BatchedTrajectoryTrackingMPC(PGN_DECOUPLED, vehicle, trajectories, batch, control_params=control_params, **kw)
 
 
+def comm_init_all(mpcs):
+    """One process, one controller batch per GPU: form the NCCL communicator of the final gather (pgn_comm_init_all)."""
+    arr = (C.c_void_p * len(mpcs))(*[m._h.value for m in mpcs])
+    check(_lib.load().pgn_comm_init_all(arr, len(mpcs)))
+
+
+def gather_all(mpcs):
+    """Final gather over NCCL of the last step's controls and per-QP statistics of all batches (rank-major)."""
+    n, B = len(mpcs), mpcs[0].B
+    arr = (C.c_void_p * n)(*[m._h.value for m in mpcs])
+    c, it, st = np.zeros((n * B, 3)), np.zeros(n * B, np.int32), np.zeros(n * B, np.int32)
+    check(_lib.load().pgn_gather_all(arr, n, dptr(c), dptr(it), dptr(st)))
+    return c, it, st
+
+
 # the reference's generic functions (model_predictive_control.jl:70-78)
 def compute_time_steps(mpc, t0):
     mpc.compute_time_steps(t0)
@@ -411,15 +442,26 @@ def get_next_control(mpc):
     return mpc.get_next_control()
 
 
-def simulate(mpc, q0, u0, dt=0.01, t0=0.0, n_steps=None, T_end=None, record=True):
-    """simulate(mpc, q0, u0, dt) (model_predictive_control.jl:80-100) for the whole batch.  Returns the list of states and controls
-    before each step when record=True (host round trip per step); record=False runs the loop on the device (pgn_simulate)."""
+def simulate(mpc, q0, u0, dt=0.01, t0=0.0, n_steps=None, T_end=None, record=True, stride=1, on_device=True):
+    """simulate(mpc, q0, u0, dt) (model_predictive_control.jl:80-100) for the whole batch: `for t in 0:dt:mpc.trajectory.t[end]`.
+    T_end defaults to the end time of the (first) trajectory, as in the reference.  record=True returns the reference's
+    (qs, xs, us, ps) — states / controls before each step, mpc.qs[1], mpc.ps[1] — every `stride`-th step, recorded ON THE DEVICE
+    (pgn_set_history) while the loop runs as one pgn_simulate call; record=False returns only the final (state, control).
+    on_device=False drives the five step calls from the host (one round trip per step; qs, us only)."""
     mpc.set_state(current_state=q0, current_control=u0)
     if n_steps is None:
-        n_steps = int(math.floor((T_end - 0.0) / dt)) + 1
-    if not record:
+        if T_end is None:
+            T_end = mpc.trajectory_end_time
+        n_steps = int(math.floor((T_end - 0.0) / dt + 1e-9)) + 1
+    if on_device:
+        if record:
+            mpc.set_history((n_steps + stride - 1) // stride, stride)
         mpc.simulate_device(t0, dt, n_steps)
-        return mpc.get_state()
+        if not record:
+            return mpc.get_state()
+        out = mpc.history()
+        mpc.set_history(0)
+        return out
     qs, us = [], []
     t0 = np.broadcast_to(np.asarray(t0, float), (mpc.B,)).copy()
     for k in range(n_steps):

@@ -47,7 +47,38 @@ def synthetic_trajectories(seed=SEED, n_traj=64, n_nodes=1000, ds=0.25):
 
 def synthetic_batch(trajs, B, seed=SEED + 17, s_frac=0.5, L=2.87, Cd0=241.0, Cd1=25.1):
     """Perturbed initial states for B vehicles; vehicle i follows trajectory i mod n_traj.
-    Returns traj_id (B,) int32, state (B,6) [E,N,psi,Ux,Uy,r], control (B,3) [delta,Fxf,Fxr], t0 (B,)."""
+    Returns traj_id (B,) int32, state (B,6) [E,N,psi,Ux,Uy,r], control (B,3) [delta,Fxf,Fxr], t0 (B,).
+    Vectorised over the vehicles of one trajectory (a million-vehicle batch in seconds); draws the random numbers in the same order as the
+    per-vehicle loop it replaced, so every seed gives bit-identical batches (tests/test_host_cpu.py)."""
+    rng = np.random.default_rng(seed)
+    n_traj, n_nodes = trajs["s"].shape
+    tid = (np.arange(B) % n_traj).astype(np.int32)
+    s_end = trajs["s"][tid, -1]
+    s0 = rng.uniform(0.0, s_frac, size=B) * s_end
+    e = rng.normal(0, 0.3, B)
+    dpsi = rng.normal(0, 0.05, B)
+    z = rng.standard_normal((B, 3))          # per vehicle: Ux, Uy, r perturbations, in this order
+    f = {k: np.zeros(B) for k in ("psi", "kappa", "V", "E", "N", "t")}
+    for j in range(min(n_traj, B)):
+        sel = np.arange(j, B, n_traj)
+        for k in f:
+            f[k][sel] = np.interp(s0[sel], trajs["s"][j], trajs[k][j])
+    psi, kap, V = f["psi"], f["kappa"], f["V"]
+    state = np.zeros((B, 6))
+    control = np.zeros((B, 3))
+    state[:, 0] = f["E"] + e * (-np.cos(psi))      # left normal of heading-from-North: (-cos psi, -sin psi)
+    state[:, 1] = f["N"] + e * (-np.sin(psi))
+    state[:, 2] = psi + dpsi
+    state[:, 3] = np.maximum(V + (0.0 + 0.5 * z[:, 0]), 1.5)
+    state[:, 4] = 0.0 + 0.1 * z[:, 1]
+    state[:, 5] = kap * V + (0.0 + 0.02 * z[:, 2])
+    control[:, 0] = np.arctan(L * kap)
+    control[:, 2] = Cd0 + Cd1 * state[:, 3]        # drag equilibrium on the rear (driven) axle
+    return tid, state, control, f["t"].copy()
+
+
+def _synthetic_batch_loop(trajs, B, seed=SEED + 17, s_frac=0.5, L=2.87, Cd0=241.0, Cd1=25.1):
+    """The original per-vehicle formulation of synthetic_batch (kept as the reference of the vectorised one)."""
     rng = np.random.default_rng(seed)
     n_traj, n_nodes = trajs["s"].shape
     tid = (np.arange(B) % n_traj).astype(np.int32)
@@ -62,14 +93,14 @@ def synthetic_batch(trajs, B, seed=SEED + 17, s_frac=0.5, L=2.87, Cd0=241.0, Cd1
         j = tid[i]
         f = lambda k: np.interp(s0[i], trajs["s"][j], trajs[k][j])
         psi, kap, V = f("psi"), f("kappa"), f("V")
-        state[i, 0] = f("E") + e[i] * (-np.cos(psi))      # left normal of heading-from-North: (-cos psi, -sin psi)
+        state[i, 0] = f("E") + e[i] * (-np.cos(psi))
         state[i, 1] = f("N") + e[i] * (-np.sin(psi))
         state[i, 2] = psi + dpsi[i]
         state[i, 3] = max(V + rng.normal(0, 0.5), 1.5)
         state[i, 4] = rng.normal(0, 0.1)
         state[i, 5] = kap * V + rng.normal(0, 0.02)
         control[i, 0] = np.arctan(L * kap)
-        control[i, 2] = Cd0 + Cd1 * state[i, 3]           # drag equilibrium on the rear (driven) axle
+        control[i, 2] = Cd0 + Cd1 * state[i, 3]
         t0[i] = f("t")
     return tid, state, control, t0
 

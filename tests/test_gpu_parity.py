@@ -209,8 +209,10 @@ def test_simulate_on_device_matches_stepwise(p):
         b.step(t0 + 0.01 * k); b.rollout(0.01)
     qa, ua = a.get_state(); qb, ub = b.get_state()
     assert np.array_equal(qa, qb) and np.array_equal(ua, ub)      # bitwise: same kernels, same order
-    qs, us = p.simulate(b, state, control, 0.01, t0=t0, n_steps=3)
+    qs, us = p.simulate(b, state, control, 0.01, t0=t0, n_steps=3, on_device=False)
     assert qs.shape == (3, B, 6) and np.array_equal(qs[0], state)
+    qd, xd, ud, pd = p.simulate(a, state, control, 0.01, t0=t0, n_steps=3)          # the same loop on the device, histories recorded there
+    assert np.array_equal(qd, qs) and np.array_equal(ud, us) and xd.shape == (3, B, 6) and pd.shape == (3, B, 4)
     a.close(); b.close()
 
 
