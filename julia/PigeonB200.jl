@@ -15,11 +15,35 @@
 # Every array is vehicle-major: a Julia `Matrix{Float64}(k, B)` is the C `[B][k]` the ABI expects, so no transposes happen.
 module PigeonB200
 
-export X1, CoupledControlParams, DecoupledControlParams, TrajectoryTube, straight_trajectory, HJICache, placeholder_HJICache,
-       BatchedTrajectoryTrackingMPC, BatchedCoupledTrajectoryTrackingMPC, BatchedDecoupledTrajectoryTrackingMPC,
-       compute_time_steps!, compute_linearization_nodes!, update_QP!, solve!, get_next_control, step!, simulate,
+# Two ways to load this file:
+#   (a) EMBEDDED — `include("…/julia/PigeonB200.jl")` inside `module Pigeon`, after src/model_predictive_control.jl (INTEGRATION.md).  The
+#       shim then EXTENDS the reference's own generic functions (compute_time_steps!, compute_linearization_nodes!, update_QP!,
+#       get_next_control, simulate from the parent module, solve! from Parametron) with methods for BatchedTrajectoryTrackingMPC, takes the
+#       parent's TrajectoryTube / HJICache / control-parameter structs as they are, and exports only the batched names — nothing collides with
+#       Pigeon's exports (X1, TrajectoryTube, HJICache, straight_trajectory, …), so `using .PigeonB200` inside Pigeon is safe.
+#   (b) STANDALONE — `include` at top level (no Pigeon around): the shim defines its own generics and light-weight stand-ins of the reference's
+#       types, and exports them too.
+const EMBEDDED = parentmodule(@__MODULE__) !== @__MODULE__ && parentmodule(@__MODULE__) !== Main &&
+                 isdefined(parentmodule(@__MODULE__), :TrajectoryTrackingMPC)
+
+@static if EMBEDDED
+    import ..compute_time_steps!, ..compute_linearization_nodes!, ..update_QP!, ..get_next_control, ..simulate
+    import Parametron: solve!
+else
+    function compute_time_steps! end
+    function compute_linearization_nodes! end
+    function update_QP! end
+    function solve! end
+    function get_next_control end
+    function simulate end
+    export X1, CoupledControlParams, DecoupledControlParams, TrajectoryTube, straight_trajectory, HJICache, placeholder_HJICache,
+           compute_time_steps!, compute_linearization_nodes!, update_QP!, solve!, get_next_control, simulate
+end
+
+export BatchedTrajectoryTrackingMPC, BatchedCoupledTrajectoryTrackingMPC, BatchedDecoupledTrajectoryTrackingMPC, step!,
        set_state!, set_HJI_cache!, reset_solved!, reset_solver!, solver_stats, set_guards!, from_autobox!, set_hji_policy!, hji_values,
-       optimal_control, set_path_search_window!, step_rollout_device!, set_pipeline_parts!, pipeline_parts, simulate_device!
+       hji_optimal_control, set_path_search_window!, step_rollout_device!, set_pipeline_parts!, pipeline_parts, simulate_device!,
+       set_history!, history, comm_init_all!, gather_all
 
 const libpigeon = get(ENV, "PGN_LIB_PATH", joinpath(@__DIR__, "..", "pigeon.jl_b200", "libpigeon_b200.so"))
 
@@ -54,12 +78,7 @@ const VP_NAMES = (:L, :a, :b, :h, :G, :m, :Izz, :μ, :Cαf, :Cαr, :Cd0, :Cd1, :
                   :Fx_max, :Fx_min, :Px_max, :δ_max, :κ_max, :inv_fiala_corrected)
 const CP_NAMES = (:V_min, :V_max, :k_V, :k_s, :δ̇_max, :Q_Δs, :Q_Δψ, :Q_e, :W_β, :W_r, :W_HJI, :N_HJI, :R_δ, :R_Δδ, :R_Fx, :R_ΔFx)
 
-"X1(): the reference's parameter Dict (src/vehicles.jl:1-59), values served by the library so both sides agree bit for bit."
-function X1()
-    v = zeros(Float64, 23)
-    check(ccall((:pgn_x1_vehicle_params, libpigeon), Cint, (Ptr{Float64},), v))
-    Dict{Symbol,Float64}(zip(VP_NAMES, v))
-end
+const TRAJ_FIELDS = (:t, :s, :V, :A, :E, :N, :ψ, :κ, :θ, :ϕ, :edge_L, :edge_R)
 
 function _control_params(kind::Int32; kw...)
     c = zeros(Float64, 16)
@@ -71,6 +90,18 @@ function _control_params(kind::Int32; kw...)
     end
     d
 end
+# control parameters arrive as the reference's CoupledControlParams / DecoupledControlParams struct (embedded) or as a Dict (standalone): same field names
+_cp(cp::AbstractDict, k) = Float64(cp[k])
+_cp(cp, k) = Float64(getproperty(cp, k))
+
+@static if !EMBEDDED      # light-weight stand-ins of the reference's types; inside Pigeon the reference's own are used
+"X1(): the reference's parameter Dict (src/vehicles.jl:1-59), values served by the library so both sides agree bit for bit."
+function X1()
+    v = zeros(Float64, 23)
+    check(ccall((:pgn_x1_vehicle_params, libpigeon), Cint, (Ptr{Float64},), v))
+    Dict{Symbol,Float64}(zip(VP_NAMES, v))
+end
+
 CoupledControlParams(; kw...)   = _control_params(PGN_COUPLED; kw...)
 DecoupledControlParams(; kw...) = _control_params(PGN_DECOUPLED; kw...)
 
@@ -87,7 +118,6 @@ struct TrajectoryTube
     end
 end
 Base.length(tr::TrajectoryTube) = length(tr.t)
-const TRAJ_FIELDS = (:t, :s, :V, :A, :E, :N, :ψ, :κ, :θ, :ϕ, :edge_L, :edge_R)
 
 "straight_trajectory(len, vel) (src/trajectories.jl:96-105)"
 straight_trajectory(len, vel) = TrajectoryTube([0.0, len / vel], [0.0, len], [vel, vel], [0.0, 0.0], [0.0, 0.0], [0.0, len], [0.0, 0.0], [0.0, 0.0])
@@ -100,6 +130,8 @@ struct HJICache
 end
 placeholder_HJICache() = HJICache(ntuple(_ -> Float32[-1000, 1000], 7), zeros(Float32, ntuple(_ -> 2, 7)), zeros(Float32, 7, ntuple(_ -> 2, 7)...))
 
+end # !EMBEDDED
+
 "Batched TrajectoryTrackingMPC (src/model_predictive_control.jl:32-68): B independent controllers living on one B200."
 mutable struct BatchedTrajectoryTrackingMPC
     handle::Ptr{Cvoid}
@@ -107,12 +139,12 @@ mutable struct BatchedTrajectoryTrackingMPC
     B::Int
     N::Int; nx::Int; nu::Int; n::Int; m::Int
     vehicle::Dict{Symbol,Float64}
-    control_params::Dict{Symbol,Float64}
-    trajectories::Vector{TrajectoryTube}
-    HJI_cache::Union{Nothing,HJICache}
+    control_params                 # Dict, or the reference's Coupled/DecoupledControlParams struct
+    trajectories::Vector           # TrajectoryTubes (the reference's, or the stand-in above): anything with the 12 vector fields
+    HJI_cache                      # nothing | HJICache (the reference's interpolants, or the stand-in's raw arrays)
 end
 
-function BatchedTrajectoryTrackingMPC(kind::Int32, vehicle::Dict{Symbol,Float64}, trajectories::Vector{TrajectoryTube}, B::Integer;
+function BatchedTrajectoryTrackingMPC(kind::Int32, vehicle::Dict{Symbol,Float64}, trajectories::Vector, B::Integer;
                                       control_params=_control_params(kind), N_short=10, N_long=20, dt_short=0.01, dt_long=0.2,
                                       use_correction_step=true, device=-1, trajectory_index=nothing)
     cfg = PgnConfig()
@@ -126,7 +158,7 @@ function BatchedTrajectoryTrackingMPC(kind::Int32, vehicle::Dict{Symbol,Float64}
     mpc = BatchedTrajectoryTrackingMPC(h[], kind, B, d[1], d[2], d[3], d[4], d[5], vehicle, control_params, trajectories, nothing)
     finalizer(m -> (m.handle != C_NULL && ccall((:pgn_destroy, libpigeon), Cint, (Ptr{Cvoid},), m.handle); m.handle = C_NULL), mpc)
     vp = Float64[get(vehicle, k, 0.0) for k in VP_NAMES]
-    cp = Float64[control_params[k] for k in CP_NAMES]
+    cp = Float64[_cp(control_params, k) for k in CP_NAMES]
     check(ccall((:pgn_set_vehicle_params, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}), mpc.handle, vp))
     check(ccall((:pgn_set_control_params, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}), mpc.handle, cp))
     set_trajectories!(mpc, trajectories, trajectory_index === nothing ? Int32[(i - 1) % length(trajectories) for i in 1:B] : Int32.(trajectory_index))
@@ -136,7 +168,7 @@ BatchedCoupledTrajectoryTrackingMPC(vehicle, trajectories, B; kw...)   = Batched
 BatchedDecoupledTrajectoryTrackingMPC(vehicle, trajectories, B; kw...) = BatchedTrajectoryTrackingMPC(PGN_DECOUPLED, vehicle, trajectories, B; kw...)
 
 "mpc.trajectory = ... for the batch: `trajectory_index[i]` (0-based) selects the tube vehicle i tracks."
-function set_trajectories!(mpc::BatchedTrajectoryTrackingMPC, trajectories::Vector{TrajectoryTube}, trajectory_index::Vector{Int32})
+function set_trajectories!(mpc::BatchedTrajectoryTrackingMPC, trajectories::Vector, trajectory_index::Vector{Int32})
     n = length(trajectories[1])
     all(length(t) == n for t in trajectories) || throw(ArgumentError("all trajectories of a batch must have the same number of nodes"))
     # fields[k] is C [n_traj][n_nodes] == Julia Matrix(n_nodes, n_traj)
@@ -151,11 +183,14 @@ function set_trajectories!(mpc::BatchedTrajectoryTrackingMPC, trajectories::Vect
 end
 
 "mpc.HJI_cache = cache (Pigeon.jl:40)"
-function set_HJI_cache!(mpc::BatchedTrajectoryTrackingMPC, cache::HJICache)
+function set_HJI_cache!(mpc::BatchedTrajectoryTrackingMPC, cache)
     dims = Int32[length(k) for k in cache.grid_knots]
     knots = vcat(cache.grid_knots...)
-    check(ccall((:pgn_set_hji_cache, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
-                mpc.handle, dims, knots, cache.V, cache.∇V))
+    # the reference's HJICache holds gridded interpolants (coefs: Array{Float32,7} and Array{SVector{7,Float32},7}); the stand-in holds the raw arrays
+    V  = cache.V isa Array ? cache.V : cache.V.coefs
+    gV = cache.∇V isa Array{Float32} ? cache.∇V : Array(reinterpret(Float32, cache.∇V.coefs))      # 7 components fastest (save(), HJI_computation.jl:59-64)
+    GC.@preserve V gV check(ccall((:pgn_set_hji_cache, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+                                  mpc.handle, dims, knots, V, gV))
     mpc.HJI_cache = cache
     mpc
 end
@@ -197,7 +232,7 @@ function hji_values(mpc)
     V, g
 end
 "optimal_control(dynamics, relative_state, ∇V) (src/HJI_computation.jl:133-158) for 7×M relative states / gradients -> 2×M (δ, Fx)"
-function optimal_control(mpc, relative_state::Matrix{Float64}, gradV::Matrix{Float64})
+function hji_optimal_control(mpc, relative_state::Matrix{Float64}, gradV::Matrix{Float64})
     M = size(relative_state, 2); out = Matrix{Float64}(undef, 2, M)
     check(ccall((:pgn_hji_optimal_control, libpigeon), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), mpc.handle, Int32(M), relative_state, gradV, out))
     out
@@ -237,13 +272,46 @@ end
 simulate_device!(mpc::BatchedTrajectoryTrackingMPC, d_t0::Ptr{Float64}, dt::Float64, n_steps::Integer; k0::Integer=0) =
     check(ccall((:pgn_simulate_device, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Int32, Int32), mpc.handle, d_t0, dt, Int32(k0), Int32(n_steps)))
 
-"simulate(mpc, q0, u0, dt) (src/model_predictive_control.jl:80-100) for the whole batch, entirely on the device; returns the final (state, control)."
-function simulate(mpc::BatchedTrajectoryTrackingMPC, q0::Matrix{Float64}, u0::Matrix{Float64}; dt=0.01, t0=zeros(mpc.B), n_steps::Integer)
+"record every `stride`-th step of simulate on the device (capacity records); 0, 0 switches the recorder off"
+set_history!(mpc::BatchedTrajectoryTrackingMPC, capacity::Integer, stride::Integer=1) =
+    check(ccall((:pgn_set_history, libpigeon), Cint, (Ptr{Cvoid}, Int32, Int32), mpc.handle, Int32(capacity), Int32(capacity == 0 ? 0 : stride)))
+"(qs, xs, us, ps) of the recorded steps: 6×B×n, nx×B×n, 3×B×n, 4×B×n"
+function history(mpc::BatchedTrajectoryTrackingMPC)
+    n = Ref{Int32}(0)
+    check(ccall((:pgn_get_history, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), mpc.handle, n, C_NULL, C_NULL, C_NULL, C_NULL))
+    qs = Array{Float64}(undef, 6, mpc.B, n[]); us = Array{Float64}(undef, 3, mpc.B, n[]); xs = Array{Float64}(undef, mpc.nx, mpc.B, n[]); ps = Array{Float64}(undef, 4, mpc.B, n[])
+    n[] > 0 && check(ccall((:pgn_get_history, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), mpc.handle, n, qs, us, xs, ps))
+    qs, xs, us, ps
+end
+
+"""
+simulate(mpc, q0, u0, dt=0.01) (src/model_predictive_control.jl:80-100) for the whole batch: `for t in 0:dt:mpc.trajectory.t[end]`, entirely on
+the device (one pgn_simulate call); returns the reference's (qs, xs, us, ps), recorded on the device every `stride`-th step.
+q0 is 6×B, u0 3×B; t0 (B) shifts every vehicle's time axis.
+"""
+function simulate(mpc::BatchedTrajectoryTrackingMPC, q0::Matrix{Float64}, u0::Matrix{Float64}, dt=0.01; t0=zeros(mpc.B), stride::Integer=1,
+                  n_steps::Integer=length(0:dt:mpc.trajectories[1].t[end]))
     set_state!(mpc; current_state=q0, current_control=u0)
-    check(ccall((:pgn_simulate, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Int32), mpc.handle, t0, dt, n_steps))
-    q = Matrix{Float64}(undef, 6, mpc.B); u = Matrix{Float64}(undef, 3, mpc.B)
-    check(ccall((:pgn_get_state, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), mpc.handle, q, u))
-    q, u
+    set_history!(mpc, cld(n_steps, stride), stride)
+    check(ccall((:pgn_simulate, libpigeon), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Int32), mpc.handle, t0, Float64(dt), Int32(n_steps)))
+    out = history(mpc)
+    set_history!(mpc, 0, 0)
+    out
+end
+
+# ---- multi-GPU: one handle per GPU driven by this one Julia thread, final gather over NCCL (SURVEY.md 8e) ------------------------------------
+"form the NCCL communicator of the final gather over the handles' devices (one handle per GPU, equal batch sizes)"
+function comm_init_all!(mpcs::Vector{BatchedTrajectoryTrackingMPC})
+    hs = Ptr{Cvoid}[m.handle for m in mpcs]
+    check(ccall((:pgn_comm_init_all, libpigeon), Cint, (Ptr{Ptr{Cvoid}}, Int32), hs, Int32(length(hs))))
+end
+"controls (3 × n·B), iteration counts and statuses (n·B) of the last step of every handle, rank-major, gathered with ncclAllGather over NVLink"
+function gather_all(mpcs::Vector{BatchedTrajectoryTrackingMPC})
+    n, B = length(mpcs), mpcs[1].B
+    hs = Ptr{Cvoid}[m.handle for m in mpcs]
+    c = Matrix{Float64}(undef, 3, n * B); it = Vector{Int32}(undef, n * B); st = Vector{Int32}(undef, n * B)
+    check(ccall((:pgn_gather_all, libpigeon), Cint, (Ptr{Ptr{Cvoid}}, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}), hs, Int32(n), c, it, st))
+    c, it, st
 end
 
 "per-vehicle OSQP-style statistics of the last solve! (the reference never inspects them, ros_integration.jl:127)"

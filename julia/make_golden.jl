@@ -124,6 +124,10 @@ function four_calls!(mpc, t)
     P.compute_time_steps!(mpc, t); P.compute_linearization_nodes!(mpc); P.update_QP!(mpc); P.solve!(mpc)
 end
 
+# The default other_car_state is zeros(SimpleCarState): with the placeholder cache (V = 0 <= HJI_ϵ, ∇V = 0) the constraint counts as active and
+# optimal_disturbance divides by the other car's speed 0 (src/HJI_computation.jl:103): b_HJI becomes NaN.  The golden runs therefore park the
+# other car outside the placeholder grid (|x| > 1000): cache[x] = (Inf, 0), constraint inactive (M = 0, b = 1) — what the tests of this repo use.
+const FAR_CAR = P.SimpleCarState(1e4, 1e4, 0., 5.)
 pin_interval!(mpc, n) = MOI.set!(mpc.model.optimizer, P.OSQPSettings.AdaptiveRhoInterval(), n)
 
 # ---- (a) the dry run of src/Pigeon.jl:34-57 -----------------------------------------------------------------------------------------------
@@ -133,6 +137,7 @@ function dry_run(name, ctor, coupled; kw...)
         pin && pin_interval!(mpc, 25)
         mpc.current_state = P.BicycleState(0., 0., 0., 5., 0., 0.)
         mpc.current_control = P.BicycleControl(0., 0., 0.)
+        mpc.other_car_state = FAR_CAR
         Parametron.initialize!(mpc.model)
         four_calls!(mpc, 0.)
         put_step("$tag/$name", mpc, coupled)
@@ -164,6 +169,7 @@ function sim_run(tag, name, ctor, coupled, pin; nsteps = 200, dt = 0.01, kw...)
     Parametron.initialize!(mpc.model)
     mpc.current_state = P.BicycleState(traj.E[1], traj.N[1], traj.ψ[1], 6., 0., 0.)
     mpc.current_control = P.BicycleControl(0., 0., 0.)
+    mpc.other_car_state = FAR_CAR
     for k in 0:nsteps-1          # the body of simulate (model_predictive_control.jl:87-98), with the per-step dump added
         t = k * dt
         pre = "$tag/$name/step$(lpad(k, 3, '0'))"

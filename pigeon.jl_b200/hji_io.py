@@ -1,10 +1,11 @@
-"""On-disk form of the HJI cache for hosts without Julia.
+"""On-disk forms of the HJI cache.
 
 The reference keeps `grid_knots`, `V_raw` and `∇V_raw` in a JLD2 file (`HJICache(fname)` / `save`, src/HJI_computation.jl:39-64; the file is
-downloaded by deps/build.jl).  JLD2 is an HDF5 dialect with Julia type encodings; this image has neither Julia nor an HDF5 library, and no
-copy of the real file to validate a parser against, so the JLD2 container itself is not read here.  Instead `julia/export_hji_cache.jl` (run
-once where Julia + JLD2.jl are installed) dumps exactly those three objects, in Julia's memory order, into the flat little-endian file below,
-which this module reads and writes:
+downloaded by deps/build.jl).  `load_hji_cache` / `save_hji_cache` read and write
+  * that JLD2 container (an HDF5 dialect) through the minimal parser / writer of pigeon.jl_b200/jld2.py — any path ending in `.jld2`, or any
+    file that starts with JLD2's text header;
+  * the flat little-endian dump below, which `julia/export_hji_cache.jl` produces where Julia + JLD2.jl are installed (a fallback that does not
+    depend on the container format at all):
 
     bytes 0..7     magic  b"PGNHJI1\\0"
     7 x int32      grid dimensions n1..n7
@@ -21,6 +22,9 @@ MAGIC = b"PGNHJI1\x00"
 
 
 def save_hji_cache(path, cache):
+    if str(path).endswith(".jld2"):
+        from .jld2 import save_hji_jld2
+        return save_hji_jld2(path, cache.grid_knots, cache.V, cache.gradV)
     dims = np.array([len(k) for k in cache.grid_knots], dtype="<i4")
     with open(path, "wb") as f:
         f.write(MAGIC)
@@ -31,6 +35,11 @@ def save_hji_cache(path, cache):
 
 
 def load_hji_cache(path):
+    with open(path, "rb") as f:
+        head = f.read(16)
+    if str(path).endswith(".jld2") or head.startswith(b"Julia data file") or head.startswith(b"\x89HDF"):
+        from .jld2 import load_hji_jld2
+        return HJICache(*load_hji_jld2(path))
     with open(path, "rb") as f:
         if f.read(8) != MAGIC:
             raise ValueError(f"{path}: not a PGNHJI1 file")

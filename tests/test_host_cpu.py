@@ -253,3 +253,52 @@ def test_hji_cache_file_round_trip(p, tmp_path):
     open(f, "wb").write(raw[:-5])
     with pytest.raises(ValueError):
         p.load_hji_cache(f)
+
+
+def test_synthetic_batch_vectorised_equals_the_loop(p):
+    """The vectorised workload generator (a million vehicles in seconds) draws the same random numbers in the same order as the per-vehicle
+    loop it replaced: every seed gives bit-identical batches, so round-1 and round-2 numbers are measured on the same vehicles."""
+    tr = p.synthetic.synthetic_trajectories(n_traj=8, n_nodes=200)
+    for B, seed in ((257, p.synthetic.SEED + 17), (64, 5), (3, 1)):
+        a, b = p.synthetic.synthetic_batch(tr, B, seed=seed), p.synthetic._synthetic_batch_loop(tr, B, seed=seed)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_jld2_hji_cache_round_trip_and_structure(p, tmp_path):
+    """BicycleCAvoid.jld2 (src/HJI_computation.jl:39-64): the minimal JLD2 / HDF5 writer and reader agree with each other bit for bit, and the
+    file has the structure JLD2 0.1 writes: 512-byte text header, version-2 superblock at 512 with base address 512 and a valid lookup3
+    checksum, "OHDR" object headers, root links `grid_knots`, `V_raw`, `∇V_raw`, `_types`; ∇V_raw with the size Julia 1.0's reinterpret gives."""
+    import struct
+    from pigeon.jl_b200 import jld2
+    knots, V, gV = p.synthetic.analytic_hji_grid((5, 4, 5, 4, 3, 4, 3))
+    c = p.HJICache(knots, V, gV)
+    f = str(tmp_path / "BicycleCAvoid.jld2")
+    p.save_hji_cache(f, c)
+    r = p.load_hji_cache(f)
+    assert all(np.array_equal(a, b) for a, b in zip(r.grid_knots, c.grid_knots))
+    assert np.array_equal(r.V, c.V) and np.array_equal(r.gradV, c.gradV)
+    raw = open(f, "rb").read()
+    assert raw.startswith(b"Julia data file (HDF5)") and raw[512:520] == b"\x89HDF\r\n\x1a\n" and raw[520] == 2
+    base, ext, eof, root = struct.unpack_from("<QQQQ", raw, 524)
+    assert base == 512 and eof == len(raw) - 512 and raw[512 + root:512 + root + 4] == b"OHDR"
+    assert jld2.lookup3(raw[512:556]) == struct.unpack_from("<I", raw, 556)[0]
+    # lookup3 known answers (Bob Jenkins' lookup3.c self-test): hashlittle("", 0) = 0xdeadbeef, hashlittle("Four score and seven years ago", 0) = 0x17770551
+    assert jld2.lookup3(b"") == 0xDEADBEEF and jld2.lookup3(b"Four score and seven years ago") == 0x17770551 and jld2.lookup3(b"Four score and seven years ago", 1) == 0xCD628161
+    d = jld2.read_jld2(f)
+    assert set(d) == {"grid_knots", "V_raw", "∇V_raw"} and isinstance(d["grid_knots"], tuple) and len(d["grid_knots"]) == 7
+    assert d["∇V_raw"].shape == (7 * 5, 4, 5, 4, 3, 4, 3) and d["V_raw"].shape == (5, 4, 5, 4, 3, 4, 3)
+    # Julia memory order inside the file: V_raw with dimension 1 fastest
+    pos = raw.find(np.asfortranarray(V).tobytes(order="F")[:64])
+    assert pos > 512
+    # a flipped byte in an object header is caught by its checksum; a truncated file is rejected
+    bad = bytearray(raw); bad[512 + root + 12] ^= 0x40
+    open(f, "wb").write(bytes(bad))
+    with pytest.raises(ValueError):
+        p.load_hji_cache(f)
+    open(f, "wb").write(raw[:600])
+    with pytest.raises((ValueError, struct.error, IndexError)):
+        p.load_hji_cache(f)
+    # the later-Julia shape of ∇V_raw, (7, n1, ..., n7), is accepted as well (same memory)
+    jld2.write_jld2(f, {"grid_knots": tuple(knots), "V_raw": V, "∇V_raw": gV})
+    r2 = p.load_hji_cache(f)
+    assert np.array_equal(r2.gradV, c.gradV)
