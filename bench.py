@@ -582,8 +582,31 @@ def run_gpu(args):
         e2e_step(k)
     e1.record(stream)
     barrier()
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - tw) * 1e3))
+    e2e_joined_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - tw) * 1e3))
+    # the same replay through the pipelined calls: every step's inputs go in from pinned host memory and every step's controls come back,
+    # with up to DEPTH steps in flight (the callback is fed MEASURED states, so step k+1 does not wait for step k's output)
+    DEPTH = 3
+    mpc.reset_solver(); mpc.reset_solved()
+
+    def submit(k):
+        lib.pgn_step_submit(h, C.c_void_p(qn[k].ctypes.data), C.c_void_p(un_[k].ctypes.data), None, C.c_void_p(tn[k].ctypes.data))
+
+    def run_pipelined(k0, k1):
+        for k in range(k0, k1):
+            submit(k)
+            if k - k0 >= DEPTH - 1:
+                lib.pgn_step_collect(h, C.c_void_p(on[k - DEPTH + 1].ctypes.data))
+        for k in range(max(k0, k1 - DEPTH + 1), k1):
+            lib.pgn_step_collect(h, C.c_void_p(on[k].ctypes.data))
+    run_pipelined(0, SETTLE + W)
+    barrier()
+    tw = time.perf_counter()
+    run_pipelined(SETTLE + W, SETTLE + W + K)          # ends with every result of the K steps on the host
+    e2e_wall = (time.perf_counter() - tw) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(e2e_wall)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
+    e2e_joined = world * B * K / (e2e_joined_ms * 1e-3)
 
     # ---------------- per-call latency (BASELINE.json: "p50 per-step latency"): host wall clock around one C-ABI call, host buffers ----------------
     latency = None
@@ -686,7 +709,8 @@ def run_gpu(args):
                                    "call": "pgn_step_rollout_device x K, device-resident; the pipeline parts are joined at the end of every call"},
                 "roofline": roof, "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "build_flags")} if cpu else None,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * (6 + 3 + 1) * 8, "d2h_bytes_per_step": B * 3 * 8,
-                        "call": "pgn_set_state + pgn_step per step: one packed pinned H2D copy each, one D2H copy of the controls"},
+                        "call": "pgn_step_submit + pgn_step_collect per step (host buffers in and out every step, %d steps in flight, host wall clock incl. the final drain)" % DEPTH,
+                        "joined": {"value": e2e_joined, "unit": UNIT, "call": "pgn_set_state + pgn_step per step: the caller waits for every step's controls before it sends the next state"}},
                 "gpu_launches": res["gpu_launches"], "clocks": clocks, "admm": res["admm"],
                 "stage_ms_per_step": stage, "admm_phase_share": {k: v / max(1.0, sum(cyc.values())) for k, v in cyc.items()},
                 "latency": latency, "gather": gathered,

@@ -126,6 +126,15 @@ PGN_API int pgn_solve(pgn_handle* h);                                           
 PGN_API int pgn_get_next_control(pgn_handle* h, double* out /*[B][3] = (delta, Fxf, Fxr)*/);  /* get_next_control(mpc) */
 /* the five calls fused (host buffers; copies inside) */
 PGN_API int pgn_step(pgn_handle* h, const double* t0 /*[B]*/, double* out /*[B][3]*/);
+/* Pipelined host-buffer stepping.  The callback is fed MEASURED states (ros_integration.jl:50-53): step k+1's inputs do not wait for step k's
+ * output, so a host that serves many vehicles may keep up to 4 steps in flight.  pgn_step_submit = pgn_set_state(q, u, other, keep time_offset)
+ * + pgn_step(t0) without the wait (q / u / other may be NULL = keep); the inputs are copied before it returns.  pgn_step_collect blocks until the
+ * OLDEST step in flight is done and copies its controls [B][3] out.  The pipeline parts are not joined between steps (as inside pgn_simulate),
+ * which hides the per-vehicle stages behind the ADMM kernels; per vehicle the results are bit-identical to pgn_set_state + pgn_step.  Any other
+ * entry point first waits for the steps in flight. */
+PGN_API int pgn_step_submit(pgn_handle* h, const double* q, const double* u, const double* other_car, const double* t0 /*[B]*/);
+PGN_API int pgn_step_collect(pgn_handle* h, double* out /*[B][3]*/);
+PGN_API int pgn_steps_in_flight(pgn_handle* h, int32_t* n);
 /* from_autobox_callback (ros_integration.jl:48-151) for the whole batch in ONE call — the low-latency entry point (B = 1 is the
  * reference's deployment).  Writes current_state q [B][6] and current_control u [B][3] (and other_car_state [B][4] unless NULL), picks
  * the MPC time per vehicle: stamp[v] - time_offset[v], or the path_coordinates time when time_offset is NaN (path-tracking mode,

@@ -31,6 +31,11 @@ extern "C" void pgn_set_error_(const char* msg) { snprintf(g_err, sizeof(g_err),
         if (!(cond)) return set_err(PGN_EINVAL, "%s", msg);  \
     } while (0)
 
+static void drain_ring(pgn_handle* h) {
+    for (int i = 0, sl = h->ring_tail; i < h->ring_count; i++, sl = (sl + 1) % PGN_RING)
+        for (int p = 0; p < h->ring_parts[sl]; p++) cudaEventSynchronize(h->ring_done[sl][p]);
+}
+
 namespace {
 
 // Every entry point runs on the handle's own device and leaves the caller's current device as it found it, so that ONE host thread can
@@ -42,7 +47,9 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
 };
-#define ENTER(h, msg)  REQUIRE(h, msg); DeviceGuard dev_guard__((h)->device)
+// steps submitted with pgn_step_submit run on the part streams: every other entry point first waits for them (their results stay collectable)
+#define ENTER_NODRAIN(h, msg)  REQUIRE(h, msg); DeviceGuard dev_guard__((h)->device)
+#define ENTER(h, msg)  ENTER_NODRAIN(h, msg); if ((h)->ring_count) drain_ring(h)
 
 struct StageTimer {
     pgn_handle* h; int idx;
@@ -57,6 +64,7 @@ struct StageTimer {
         }
     }
 };
+
 
 template <class T>
 int dev_alloc(pgn_handle* h, T** p, size_t count) {
@@ -342,6 +350,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->path_window = 0; CK(cudaMemset(h->d_last_seg, 0xff, B * 4));
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
+    h->h_ring = nullptr; h->d_ring = nullptr; h->ring_head = h->ring_tail = h->ring_count = h->ring_created = 0;
     h->h_in = nullptr; h->in_pending = 0; h->d_hist = nullptr; h->hist_cap = h->hist_stride = h->hist_n = 0;
     h->comm = nullptr; h->comm_rank = 0; h->comm_size = 1; h->d_gath_c = nullptr; h->d_gath_i = nullptr;
     cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
@@ -398,6 +407,9 @@ int pgn_destroy(pgn_handle* h) {
     if (h->cb_has_exec) { cudaGraphExecDestroy(h->cb_exec); cudaGraphDestroy(h->cb_graph); }
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_ring) cudaFreeHost(h->h_ring);
+    if (h->ring_created)
+        for (int sl = 0; sl < PGN_RING; sl++) { cudaEventDestroy(h->ring_h2d[sl]); for (int p = 0; p < PGN_MAX_PARTS; p++) cudaEventDestroy(h->ring_done[sl][p]); }
     cudaEventDestroy(h->ev_in);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -587,6 +599,85 @@ int pgn_step(pgn_handle* h, const double* t0, double* out) {
     CK(cudaStreamSynchronize(h->stream));
     return PGN_OK;
 }
+// ---- pipelined host-buffer stepping ---------------------------------------------------------------------------------------------------------
+// The callback feeds MEASURED states (src/ros_integration.jl:50-53): step k+1's inputs do not depend on step k's output, so a host that serves
+// many vehicles can keep several steps in flight.  pgn_step_submit copies the inputs into the slot's pinned block and enqueues, per pipeline
+// part and on the part's own stream, [unpack -> the five stages -> pack -> D2H of the part's controls]; nothing joins the parts, so — as in the
+// simulate loop — the per-vehicle stages of one part run while the ADMM kernel of another drains.  pgn_step_collect waits for the OLDEST
+// submitted step and hands its controls over.  Per vehicle the sequence of operations is exactly that of pgn_set_state + pgn_step.
+static int ring_create(pgn_handle* h) {
+    if (h->ring_created) return PGN_OK;
+    const size_t B = h->B;
+    cudaError_t e = cudaMallocHost((void**)&h->h_ring, (size_t)PGN_RING * 18 * B * sizeof(double));
+    if (e != cudaSuccess) return set_err(PGN_ENOMEM, "cudaMallocHost failed: %s", cudaGetErrorString(e));
+    int rc = dev_alloc(h, &h->d_ring, (size_t)PGN_RING * 18 * B);
+    if (rc) return rc;
+    for (int sl = 0; sl < PGN_RING; sl++) {
+        CK(cudaEventCreateWithFlags(&h->ring_h2d[sl], cudaEventDisableTiming));
+        for (int p = 0; p < PGN_MAX_PARTS; p++) CK(cudaEventCreateWithFlags(&h->ring_done[sl][p], cudaEventDisableTiming));
+    }
+    h->ring_created = 1;
+    return PGN_OK;
+}
+int pgn_step_submit(pgn_handle* h, const double* q, const double* u, const double* other, const double* t0) {
+    ENTER_NODRAIN(h, "NULL handle"); REQUIRE(t0, "t0 is NULL");
+    REQUIRE(h->ring_count < PGN_RING, "too many steps in flight: call pgn_step_collect first");
+    int rc = ring_create(h);
+    if (rc) return rc;
+    const size_t B = h->B;
+    const int sl = h->ring_head;
+    double* hin = h->h_ring + (size_t)sl * 18 * B;
+    double* din = h->d_ring + (size_t)sl * 18 * B;
+    int flags = 16;
+    if (q) { memcpy(hin, q, 6 * B * 8); flags |= 1; }
+    if (u) { memcpy(hin + 6 * B, u, 3 * B * 8); flags |= 2; }
+    if (other) { memcpy(hin + 9 * B, other, 4 * B * 8); flags |= 4; }
+    memcpy(hin + 14 * B, t0, B * 8);      // slot layout = k_unpack_state's: q [0, 6B) | u | other | (time_offset, not sent) | t0 [14B, 15B) | out [15B, 18B)
+    cudaStream_t s0 = h->stream;
+    const size_t lo = (flags & 1) ? 0 : (flags & 2) ? 6 * B : (flags & 4) ? 9 * B : 14 * B;
+    CK(cudaMemcpyAsync(din + lo, hin + lo, (15 * B - lo) * 8, cudaMemcpyHostToDevice, s0));      // ONE copy of the span that holds the present fields
+    CK(cudaEventRecord(h->ring_h2d[sl], s0));
+    const int P = (h->parts <= 1 || h->profiling) ? 1 : h->parts;
+    cudaStream_t side0 = h->side_stream;
+    cudaEvent_t f0 = h->ev_fork, j0 = h->ev_join;
+    for (int p = 0; p < P; p++) {
+        if (P > 1) {
+            CK(cudaStreamWaitEvent(h->part_stream[p], h->ring_h2d[sl], 0));
+            h->stream = h->part_stream[p]; h->side_stream = h->part_side[p]; h->ev_fork = h->part_evf[p]; h->ev_join = h->part_evj[p];
+            h->part = p; h->v0 = (int)((long long)h->B * p / P); h->nv = (int)((long long)h->B * (p + 1) / P) - h->v0;
+        }
+        launch_unpack_range(h, din, flags & ~8);
+        step_time_steps_dev(h, h->d_t0);
+        step_nodes(h);
+        step_update(h);
+        step_solve(h);
+        step_controls(h, h->d_controls);
+        launch_pack_out(h, h->d_controls, din + 15 * B, 3);            // [3][B] -> rows v0 .. v0+nv of [B][3] in the slot's output block
+        CK(cudaMemcpyAsync(hin + 15 * B + (size_t)h->v0 * 3, din + 15 * B + (size_t)h->v0 * 3, (size_t)h->nv * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ring_done[sl][p], h->stream));
+    }
+    h->stream = s0; h->side_stream = side0; h->ev_fork = f0; h->ev_join = j0;
+    h->part = 0; h->v0 = 0; h->nv = h->B;
+    h->ring_parts[sl] = P; h->ring_flags[sl] = flags;
+    h->ring_head = (sl + 1) % PGN_RING; h->ring_count++;
+    CK(cudaGetLastError());
+    return PGN_OK;
+}
+int pgn_step_collect(pgn_handle* h, double* out) {
+    ENTER_NODRAIN(h, "NULL handle");
+    REQUIRE(h->ring_count > 0, "no step in flight: call pgn_step_submit first");
+    const size_t B = h->B;
+    const int sl = h->ring_tail;
+    for (int p = 0; p < h->ring_parts[sl]; p++) CK(cudaEventSynchronize(h->ring_done[sl][p]));
+    if (out) memcpy(out, h->h_ring + (size_t)sl * 18 * B + 15 * B, 3 * B * 8);
+    h->ring_tail = (sl + 1) % PGN_RING; h->ring_count--;
+    if (h->ring_count == 0 && h->ring_parts[sl] > 1) {      // the caller's stream continues after everything the parts did
+        for (int p = 0; p < h->ring_parts[sl]; p++) CK(cudaStreamWaitEvent(h->stream, h->ring_done[sl][p], 0));
+    }
+    return PGN_OK;
+}
+int pgn_steps_in_flight(pgn_handle* h, int32_t* n) { ENTER_NODRAIN(h, "NULL handle"); REQUIRE(n, "NULL argument"); *n = h->ring_count; return PGN_OK; }
+
 // from_autobox_callback (ros_integration.jl:48-151): the whole callback for B vehicles as one packed H2D copy, one graph launch
 // (unpack + time selection + the five step stages + pack) and one D2H copy.
 static int callback_enqueue(pgn_handle* h) {

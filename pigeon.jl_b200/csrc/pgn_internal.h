@@ -21,6 +21,7 @@
 #include "pgn_structure.h"
 
 #define PGN_MAX_PARTS 8
+#define PGN_RING 4          // steps in flight of the pipelined host-buffer API (pgn_step_submit / pgn_step_collect)
 
 namespace pgn {
 
@@ -125,6 +126,11 @@ struct pgn_handle {
     // host inputs of pgn_set_state / pgn_step: ONE packed pinned buffer [q 6B | u 3B | other 4B | toff B | t0 B] -> one H2D copy -> one unpack
     // kernel; results [B][3] come back through the pinned tail.  ev_in fences the reuse of the pinned buffer.
     double *h_in, *d_in; cudaEvent_t ev_in; int in_pending;
+    // pipelined host-buffer stepping (pgn_step_submit / pgn_step_collect): a ring of PGN_RING steps in flight.  Slot s owns a pinned input block
+    // [q 6B | u 3B | other 4B | t0 B] + a pinned output block [B][3], their device twins, the event of its H2D copy and one completion event
+    // per pipeline part (kernels + the part's D2H copy).  ring_head = next slot to submit, ring_tail = oldest slot not yet collected.
+    double *h_ring, *d_ring; cudaEvent_t ring_h2d[PGN_RING], ring_done[PGN_RING][PGN_MAX_PARTS]; int ring_flags[PGN_RING], ring_parts[PGN_RING];
+    int ring_head, ring_tail, ring_count, ring_created;
     uint8_t* d_mask;                                     // [B] staging of the masks of pgn_reset_solved / pgn_reset_solver
     // history recorder of simulate (model_predictive_control.jl:84-99 returns qs, xs, us, ps per step): [n_rec][6 + 3 + nx + 4][B], written on
     // the device every `hist_stride` steps
@@ -157,6 +163,7 @@ void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, dou
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
 void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n);
+void launch_unpack_range(pgn_handle* h, const double* d_in, int flags);   // the same for the current vehicle range, from a ring slot
 void launch_unpack_state(pgn_handle* h, int flags);                 // d_in -> SoA state / control / other / toff / t0 (flags: 1 q, 2 u, 4 other, 8 toff, 16 t0)
 void launch_masked_reset(pgn_handle* h, const uint8_t* d_mask, int what);   // what: 1 solved = 0, 2 ADMM iterates = 0 and rho = setting (mask nullptr = all)
 void launch_record(pgn_handle* h, int slot);                        // history recorder: (state, control, node 1, params 1) of the current range -> slot

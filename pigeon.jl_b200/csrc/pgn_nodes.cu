@@ -450,10 +450,11 @@ __global__ void k_time_axpy(int n, const double* __restrict__ base, double k, do
 }
 
 // ---- host inputs: one packed buffer [q [B][6] | u [B][3] | other [B][4] | toff [B] | t0 [B]] -> SoA ------------------------------------
-__global__ void k_unpack_state(int B, int flags, const double* __restrict__ in, double* __restrict__ state, double* __restrict__ control,
+__global__ void k_unpack_state(int B, int v0, int nv, int flags, const double* __restrict__ in, double* __restrict__ state, double* __restrict__ control,
                                double* __restrict__ other, double* __restrict__ toff, double* __restrict__ t0, int32_t* __restrict__ last_seg) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= B) return;
+    const int iv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iv >= nv) return;
+    const int v = v0 + iv;
     const size_t Bs = (size_t)B;
     if (flags & 1) {
 #pragma unroll
@@ -596,7 +597,11 @@ void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int
     h->launches++;
 }
 void launch_unpack_state(pgn_handle* h, int flags) {
-    k_unpack_state<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, flags, h->d_in, h->d_state, h->d_control, h->d_other, h->d_toff, h->d_t0, h->d_last_seg);
+    k_unpack_state<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->B, 0, h->B, flags, h->d_in, h->d_state, h->d_control, h->d_other, h->d_toff, h->d_t0, h->d_last_seg);
+    h->launches++;
+}
+void launch_unpack_range(pgn_handle* h, const double* d_in, int flags) {
+    k_unpack_state<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(h->B, h->v0, h->nv, flags, d_in, h->d_state, h->d_control, h->d_other, h->d_toff, h->d_t0, h->d_last_seg);
     h->launches++;
 }
 void launch_masked_reset(pgn_handle* h, const uint8_t* d_mask, int what) {

@@ -260,6 +260,19 @@ class BatchedTrajectoryTrackingMPC:
         check(self._lib.pgn_step(self._h, dptr(self._t0(t0)), dptr(out)))
         return out
 
+    def step_submit(self, t0, current_state=None, current_control=None, other_car_state=None):
+        """Pipelined stepping: set_state + step without the wait (up to 4 steps in flight); results come from step_collect, oldest first."""
+        B = self.B
+        q = None if current_state is None else f64(current_state, (B, 6))
+        u = None if current_control is None else f64(current_control, (B, 3))
+        o = None if other_car_state is None else f64(other_car_state, (B, 4))
+        check(self._lib.pgn_step_submit(self._h, dptr(q), dptr(u), dptr(o), dptr(self._t0(t0))))
+
+    def step_collect(self):
+        out = np.zeros((self.B, 3))
+        check(self._lib.pgn_step_collect(self._h, dptr(out)))
+        return out
+
     def step_device(self, d_t0_ptr, d_out_ptr=None):
         check(self._lib.pgn_step_device(self._h, C.c_void_p(d_t0_ptr), C.c_void_p(d_out_ptr) if d_out_ptr else None))
 
