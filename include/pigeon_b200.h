@@ -187,7 +187,7 @@ PGN_API int pgn_gather(pgn_handle* h, double* controls, int32_t* iters, int32_t*
 PGN_API int pgn_gather_all(pgn_handle* const* handles, int32_t n, double* controls, int32_t* iters, int32_t* status);
 
 /* --- outputs / introspection (used by the parity tests) ----------------------------------------------------------- */
-PGN_API int pgn_qp_dims(pgn_handle* h, int32_t* out /*[16] = N, nx, nu, n, m, nnz(A), nnz(L), n_levels, L slots, solve phases, factor entries, inverse entries, tail dim, backward entries, ADMM smem bytes, ADMM threads*/);
+PGN_API int pgn_qp_dims(pgn_handle* h, int32_t* out /*[16] = N, nx, nu, n, m, nnz(A), nnz(L), n_levels, L slots, solve phases, factor entries, inverse entries, tail dim, backward entries, ADMM smem bytes, ADMM threads | tensor-memory variant << 16 | resident CTAs per SM << 20*/);
 PGN_API int pgn_get_state(pgn_handle* h, double* q /*[B][6]*/, double* u /*[B][3]*/);
 PGN_API int pgn_get_time_steps(pgn_handle* h, double* ts /*[B][N]*/, double* dt /*[B][N-1]*/, double* prev_ts /*[B][N]*/);
 PGN_API int pgn_get_nodes(pgn_handle* h, double* qs /*[B][N][nx]*/, double* us /*[B][N][2]*/, double* ps /*[B][N][4]*/);

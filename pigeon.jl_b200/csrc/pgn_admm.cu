@@ -19,6 +19,7 @@
 namespace pgn {
 
 #define ADMM_NCYC 256
+#define ADMM_TMEM_COLS 256      // tensor-memory columns per CTA of the vtm variant (half an SM)
 
 static const double OSQP_INFTY = 1e20;
 
@@ -37,6 +38,7 @@ struct AdmmArgs {
     const uint8_t* skip;           // guard: paused vehicles are not solved (nullptr = guard off)
     uint8_t* cold;                 // guard: vehicles whose iterates / rho start from scratch (Parametron.initialize! after a NaN)
     uint16_t ph_ptr[ADMM_MAX_PHASES + 1];   // first task of every solve phase (forward phases, then backward phases): uniform constant-bank reads
+    double* scratch;              // tensor-memory variant: per-CTA global scratch (scaled A, scalings, spilled vectors), tm_scratch_doubles each
     unsigned long long* cycles;   // optional per-phase cycle counters (profiling builds of the host call): gather, ruiz, factor, solve, update, check, store
 };
 
@@ -49,6 +51,15 @@ struct Smem {
     // aliases inside the Lval region, valid between the gather and the first factorisation of a QP (Ruiz equilibration)
     uint16_t *kptr, *ke;
     uint32_t* arc;
+    // views used while a QP is gathered / equilibrated (identical to Aval, lo, hi, sc, yq except in the tensor-memory variant, where the big
+    // shared-memory region is time-shared)
+    double *rz_Aval, *rz_lo, *rz_hi, *rz_sc, *rz_yq;
+    // tensor-memory variant: spilled copies in the CTA's global scratch, writable index tables of the iteration views, this warp's TMEM base
+    // address (lane field = first lane of its quadrant), per-task TMEM column and backward source positions
+    double *g_lo, *g_hi, *g_yq;
+    uint16_t *fidx_w, *bsrc_w;
+    const uint16_t *bsrc, *tcol;
+    uint32_t tm_base;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -57,6 +68,30 @@ __host__ __device__ inline size_t lval_region_doubles(int nslots, int tail_dim, 
     const size_t alias = align_up((size_t)(Nk + 1) * 2 + (size_t)nnzA * 4, 4) + (size_t)nnzA * 4;      // kptr, ke (u16) + arc (u32)
     const size_t a = (alias + 7) / 8, l = (size_t)nslots + (size_t)tail_dim * (tail_dim + 1) / 2;
     return a > l ? a : l;
+}
+
+// tensor-memory variant: the time-shared region must hold (a) the factor + dense tail during a factorisation, (b) scaled A | lo | hi | sc |
+// adjacency aliases while a QP is equilibrated, (c) y | lo | hi | fidx | bsrc in front of the dense tail during the iterations
+__host__ __device__ inline size_t tm_region_doubles(int nslots, int tail_dim, int Nk, int nnzA, int n_bent) {
+    const size_t V = vec_len(Nk), A2 = (nnzA + 1) & ~1;
+    const size_t fac = (size_t)nslots + (size_t)tail_dim * (tail_dim + 1) / 2;
+    const size_t alias = align_up((size_t)(Nk + 1) * 2 + (size_t)nnzA * 4, 4) + (size_t)nnzA * 4;
+    const size_t ruiz = A2 + 3 * V + (alias + 7) / 8;
+    return fac > ruiz ? fac : ruiz;
+}
+__host__ __device__ inline size_t tm_iter_view_doubles(int nslots, int Nk, int n_bent) {
+    return 3 * (size_t)vec_len(Nk) + ((size_t)(nslots + 128) * 2 + (size_t)(n_bent + 128) * 2 + 7) / 8;
+}
+__host__ __device__ inline size_t tm_scratch_doubles(int Nk, int nnzA) { return (size_t)((nnzA + 1) & ~1) + 4 * (size_t)vec_len(Nk); }
+size_t admm_smem_bytes_tmem(const QpTables& t, int nthreads) {
+    const size_t V = vec_len(t.Nk);
+    const size_t d = tm_region_doubles(t.nslots, t.tail_dim, t.Nk, t.nnzA, (int)t.bent.size()) + 4 * V + 16 * (nthreads / 32) + 8;
+    return d * 8 + align_up((size_t)t.Nk, 8) + 64;
+}
+// whether the tensor-memory variant can run this QP: iteration views in front of the dense tail, TMEM columns within one CTA's half of an SM
+bool admm_tmem_fits(const QpTables& t) {
+    return t.tmem_layout && t.tmem_cols <= 256 && tm_iter_view_doubles(t.nslots, t.Nk, (int)t.bent.size()) <= (size_t)t.nslots &&
+           2 * (admm_smem_bytes_tmem(t, 256) + 1024) <= (size_t)227 * 1024;
 }
 
 // nthreads: threads of the CTA (the reduction scratch holds 16 doubles per warp); tables_in_smem: whether the static warp programs of the
@@ -76,6 +111,9 @@ size_t admm_smem_bytes(const QpTables& t, int nthreads, bool tables_in_smem) {
 // v256: half the threads and the static tables left in global memory (L1-resident), for QPs small enough that TWO CTAs fit an SM
 //       (deployed horizon N = 16, decoupled controller): at 128 registers a 512-thread CTA owns the whole register file, so the small
 //       QPs gained nothing from their smaller shared-memory footprint before.
+// vtm:  256 threads, two CTAs per SM, L values of the solves in TENSOR MEMORY (tcgen05.ld / tcgen05.st, 256 columns per CTA): the coupled
+//       N = 31 QP, whose 60 KB factor cannot sit in shared memory twice.
+#define ADMM_TMEM 0
 #define ADMM_NT 512
 #define ADMM_MINCTAS 1
 #define ADMM_TABSMEM 1
@@ -94,6 +132,18 @@ namespace v256 {
 #undef ADMM_NT
 #undef ADMM_MINCTAS
 #undef ADMM_TABSMEM
+#undef ADMM_TMEM
+#define ADMM_TMEM 1
+#define ADMM_NT 256
+#define ADMM_MINCTAS 2
+#define ADMM_TABSMEM 0
+namespace vtm {
+#include "pgn_admm_kernel.inc"
+}
+#undef ADMM_NT
+#undef ADMM_MINCTAS
+#undef ADMM_TABSMEM
+#undef ADMM_TMEM
 
 // Ticket order of the persistent CTAs: vehicles whose previous solve took the most iterations go first (longest-processing-time-first),
 // so that a slow QP starts at the beginning of the launch instead of becoming its tail.  Counting sort on iters / 25 in one CTA.
@@ -113,8 +163,22 @@ __global__ void __launch_bounds__(1024) k_admm_order(const int32_t* __restrict__
 
 int admm_configure(pgn_handle* h) {
     const bool small = h->admm_threads == 256;
-    h->admm_smem_bytes = (int)admm_smem_bytes(h->tab, h->admm_threads, !small);
     cudaError_t e;
+    if (h->admm_tmem) {
+        h->admm_smem_bytes = (int)admm_smem_bytes_tmem(h->tab, 256);
+        e = cudaFuncSetAttribute(vtm::k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(vtm::k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
+        // two CTAs per SM need the whole shared-memory carve-out (2 x 111 KB)
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(vtm::k_admm<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(vtm::k_admm<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that contains tcgen05.alloc (it cannot know the column
+        // count), but two CTAs that allocate 256 of the 512 columns each do share an SM: measured with a per-SM counter, tools/ubench/occ_tmem.cu.
+        // Resident CTAs follow from shared memory (2 x (bytes + 1 KB) <= 228 KB) and registers (<= 128 x 256 x 2), both checked at build / create time.
+        h->admm_ctas_per_sm = 2;
+        return (int)e;
+    }
+    h->admm_smem_bytes = (int)admm_smem_bytes(h->tab, h->admm_threads, !small);
+    h->admm_ctas_per_sm = small ? 2 : 1;
     if (small) {
         e = cudaFuncSetAttribute(v256::k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(v256::k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
@@ -140,9 +204,15 @@ void launch_admm(pgn_handle* h) {
     a.skip = (h->guard_pause > 0.0 || h->in_callback) ? h->d_skip : nullptr; a.cold = h->d_cold;
     for (size_t i = 0; i < h->tab.sol_ph_ptr.size() && i <= ADMM_MAX_PHASES; i++) a.ph_ptr[i] = h->tab.sol_ph_ptr[i];
     const bool small = h->admm_threads == 256;
-    int grid = h->num_sms * (small ? 2 : 1);
+    const int full = h->num_sms * (small ? 2 : 1);
+    int grid = full;
     if (grid > h->nv) grid = h->nv;
-    if (small) {
+    // launches of different pipeline parts may overlap: every part owns a slice of the scratch
+    a.scratch = h->admm_tmem ? h->d_admm_scratch + (size_t)h->part * full * tm_scratch_doubles(h->tab.Nk, h->tab.nnzA) : nullptr;
+    if (h->admm_tmem) {
+        if (a.cycles) vtm::k_admm<true><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
+        else vtm::k_admm<false><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
+    } else if (small) {
         if (a.cycles) v256::k_admm<true><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
         else v256::k_admm<false><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
     } else {
@@ -150,6 +220,10 @@ void launch_admm(pgn_handle* h) {
         else v512::k_admm<false><<<grid, 512, h->admm_smem_bytes, h->stream>>>(a);
     }
     h->launches++;
+}
+
+size_t admm_scratch_doubles(const pgn_handle* h) {
+    return h->admm_tmem ? (size_t)PGN_MAX_PARTS * h->num_sms * 2 * tm_scratch_doubles(h->tab.Nk, h->tab.nnzA) : 0;
 }
 
 }  // namespace pgn

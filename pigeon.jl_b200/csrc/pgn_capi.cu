@@ -241,18 +241,23 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->have_traj = false; h->have_assign = false; h->stage_bytes = 0; h->d_stage = nullptr;
     memset(&h->hji, 0, sizeof(h->hji)); memset(&h->traj, 0, sizeof(h->traj));
     char err[256];
-    // ADMM build variant: if the QP is small enough for TWO CTAs per SM (256 threads each, static tables read through L1) the warp
-    // programs are scheduled for 8 warps; otherwise one 512-thread CTA per SM with the tables in shared memory.  PGN_ADMM_VARIANT=512|256
-    // forces a variant (experiments).
+    // ADMM build variant.  QP small enough for TWO 256-thread CTAs per SM with everything in shared memory (static tables read through
+    // L1): v256.  Otherwise, if the factor fits one CTA's half of TENSOR MEMORY and the rest fits shared memory twice: vtm (the coupled
+    // N = 31 QP).  Otherwise one 512-thread CTA per SM with the tables in shared memory: v512.  PGN_ADMM_VARIANT=512|256|tmem forces one.
     {
         const char* force = getenv("PGN_ADMM_VARIANT");
-        const int want = force ? atoi(force) : 0;
-        h->admm_threads = 512;
+        const int want = !force ? 0 : (!strcmp(force, "tmem") ? 3 : atoi(force));
+        h->admm_threads = 512; h->admm_tmem = 0; h->d_admm_scratch = nullptr;
         if (want != 512) {
-            if (!build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 8)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
+            if (!build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 8, want == 3 ? 1 : 0)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
             const size_t sm = admm_smem_bytes(h->tab, 256, false);
-            if (2 * (sm + 1024) <= (size_t)227 * 1024) h->admm_threads = 256;
+            if (want != 3 && 2 * (sm + 1024) <= (size_t)227 * 1024) h->admm_threads = 256;
             else if (want == 256) { delete h; return set_err(PGN_EINVAL, "PGN_ADMM_VARIANT=256: two CTAs of %zu bytes do not fit one SM", sm); }
+            else {
+                if (!h->tab.tmem_layout && !build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 8, 1)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
+                if (admm_tmem_fits(h->tab)) { h->admm_threads = 256; h->admm_tmem = 1; }
+                else if (want == 3) { delete h; return set_err(PGN_EINVAL, "PGN_ADMM_VARIANT=tmem: this QP does not fit (TMEM columns %d, shared memory %zu bytes per CTA)", h->tab.tmem_cols, admm_smem_bytes_tmem(h->tab, 256)); }
+            }
         }
         if (h->admm_threads == 512 &&
             !build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 16)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
@@ -290,6 +295,12 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
         std::vector<uint16_t> orow(t.sol_orow), fidx(t.fidx);
         std::vector<uint32_t> bent(t.bent);
         orow.resize(orow.size() + 64, 0); fidx.resize(fidx.size() + 128, (uint16_t)t.Nk);
+        {   // tensor-memory variant: per-task TMEM column and the backward source positions (padded like the other solve tables)
+            std::vector<uint16_t> tcol(t.sol_tcol), bsrc(t.bsrc);
+            tcol.resize(tcol.size() + 8, 0); bsrc.resize(bsrc.size() + 128, (uint16_t)t.Nk);
+            if ((rc = dev_upload(h, tcol, &q.sol_tcol))) return bail(rc);
+            if ((rc = dev_upload(h, bsrc, &q.bsrc))) return bail(rc);
+        }
         bent.resize(bent.size() + 128, (uint32_t)t.zslot | ((uint32_t)t.Nk << 16));
         if ((rc = dev_upload(h, orow, &q.sol_orow))) return bail(rc);
         if ((rc = dev_upload(h, fidx, &q.fidx))) return bail(rc);
@@ -390,6 +401,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
         for (int k = 0; k < 12; k++) fp[k] = f[k];
         if ((rc = pgn_set_trajectories(h, 1, 2, fp))) return bail(rc);
     }
+    if (h->admm_tmem && (rc = dev_alloc(h, &h->d_admm_scratch, admm_scratch_doubles(h)))) return bail(rc);
     int ce = admm_configure(h);
     if (ce != 0) return bail(set_err(PGN_ECUDA, "ADMM kernel needs %d bytes of shared memory per CTA: %s", h->admm_smem_bytes, cudaGetErrorString((cudaError_t)ce)));
     if ((rc = pgn_set_pipeline_parts(h, 0))) return bail(rc);     // automatic part count (1 for batches below ~1.5 waves of ADMM CTAs)
@@ -868,7 +880,7 @@ int pgn_qp_dims(pgn_handle* h, int32_t* o) {
     ENTER(h, "NULL handle"); REQUIRE(o, "NULL argument");
     o[0] = h->N; o[1] = h->nx; o[2] = h->nu; o[3] = h->tab.n; o[4] = h->tab.m; o[5] = h->tab.nnzA; o[6] = h->tab.nnzL; o[7] = h->tab.nlev;
     o[8] = h->tab.nslots; o[9] = h->tab.n_fwd_ph + h->tab.n_bwd_ph; o[10] = (int)h->tab.fac_ent.size(); o[11] = (int)h->tab.inv_ent.size(); o[12] = h->tab.tail_dim;
-    o[13] = (int)h->tab.bent.size(); o[14] = h->admm_smem_bytes; o[15] = h->admm_threads;
+    o[13] = (int)h->tab.bent.size(); o[14] = h->admm_smem_bytes; o[15] = h->admm_threads | (h->admm_tmem << 16) | (h->admm_ctas_per_sm << 20);      // threads | tensor-memory variant << 16 | resident CTAs per SM << 20
     return PGN_OK;
 }
 int pgn_get_state(pgn_handle* h, double* q, double* u) {

@@ -56,7 +56,7 @@ struct QpDev {
     const uint16_t* a_slot;                     // per A entry: L slot
     // warp programs (pgn_structure.h): packed task descriptors {ebase/32 | rbase << 16, K | nrows << 8 | sh << 16 | flags << 24}
     const uint2 *sol_task, *fac_task, *inv_task;
-    const uint16_t *sol_orow, *fidx;
+    const uint16_t *sol_orow, *fidx, *sol_tcol, *bsrc;
     const uint32_t* bent;
     const uint32_t *fac_lvl_ptr, *fac_tgt, *inv_lvl_ptr, *inv_tgt;
     const unsigned long long *fac_ent, *inv_ent;
@@ -143,6 +143,8 @@ struct pgn_handle {
     // profiling
     int profiling; cudaEvent_t ev[2]; double stage_ms[8]; long long launches;
     int admm_smem_bytes, admm_threads, num_sms;
+    int admm_tmem, admm_ctas_per_sm;                     // tensor-memory variant of the ADMM kernel (two coupled N = 31 QPs per SM); resident CTAs per SM
+    double* d_admm_scratch;                              // its per-CTA global scratch
 };
 
 namespace pgn {
@@ -169,5 +171,8 @@ void launch_masked_reset(pgn_handle* h, const uint8_t* d_mask, int what);   // w
 void launch_record(pgn_handle* h, int slot);                        // history recorder: (state, control, node 1, params 1) of the current range -> slot
 void launch_pack_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);        // [k][B] -> [B][k] for the current vehicle range only
 size_t admm_smem_bytes(const QpTables& t, int nthreads, bool tables_in_smem);
+size_t admm_smem_bytes_tmem(const QpTables& t, int nthreads);
+bool admm_tmem_fits(const QpTables& t);
+size_t admm_scratch_doubles(const pgn_handle* h);
 int admm_configure(pgn_handle* h);   // sets the max dynamic shared memory attribute; returns cudaError
 }  // namespace pgn

@@ -117,7 +117,7 @@ void nd_classes(int lo, int hi, int depth, int leaf, std::vector<int>& sep_depth
 
 }  // namespace
 
-bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& Q, char* err, int errlen, int nwarps) {
+bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& Q, char* err, int errlen, int nwarps, int tmem_layout) {
     auto fail = [&](const char* msg) { snprintf(err, errlen, "%s", msg); return false; };
     if (N_short < 1 || N_long < 0) return fail("N_short must be >= 1 and N_long >= 0");
     Q = QpTables();
@@ -376,6 +376,38 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     // ---- warp programs -----------------------------------------------------------------------------------------------------------
     const int NWARP = nwarps;
     Q.nwarps = nwarps;
+    Q.tmem_layout = tmem_layout; Q.tmem_cols = 0;
+    // TMEM layout: columns used so far per quadrant; a phase's task list is permuted inside every round of NWARP tasks (one task per warp and
+    // round either way, so the time balance of the schedule is unchanged) such that the biggest task of the round goes to the emptiest quadrant
+    int quad_cols[4] = {0, 0, 0, 0};
+    auto place_tasks = [&](std::vector<SchedTask> t) {
+        if (!tmem_layout) return t;
+        std::vector<SchedTask> out(t.size());
+        for (size_t r0 = 0; r0 < t.size(); r0 += NWARP) {
+            const size_t n = std::min((size_t)NWARP, t.size() - r0);
+            std::vector<int> by_k(n), warps(n);
+            for (size_t i = 0; i < n; i++) { by_k[i] = (int)(r0 + i); warps[i] = (int)i; }
+            std::stable_sort(by_k.begin(), by_k.end(), [&](int a, int b) { return t[a].K > t[b].K; });
+            int q_add[4] = {0, 0, 0, 0};
+            std::vector<char> used(n, 0);
+            for (size_t i = 0; i < n; i++) {          // biggest first -> the free warp whose quadrant is emptiest
+                int best = -1;
+                for (size_t w = 0; w < n; w++) if (!used[w] && (best < 0 || quad_cols[w & 3] + q_add[w & 3] < quad_cols[best & 3] + q_add[best & 3])) best = (int)w;
+                used[best] = 1;
+                q_add[best & 3] += 2 * t[by_k[i]].K;
+                out[r0 + best] = t[by_k[i]];
+            }
+            for (int q = 0; q < 4; q++) quad_cols[q] += q_add[q];
+        }
+        return out;
+    };
+    int quad_next[4] = {0, 0, 0, 0};
+    auto tmem_place = [&](size_t task_in_phase, int K) {      // called once per task in program order
+        if (!tmem_layout) return;
+        const int q = (int)(task_in_phase % NWARP) & 3;
+        Q.sol_tcol.push_back((uint16_t)quad_next[q]);
+        quad_next[q] += 2 * K;
+    };
     std::vector<int> range_pa, range_pb;
     for (size_t k = 0; k + 1 < Q.range_lvl.size(); k += 2) { range_pa.push_back(Q.lvl_ptr[Q.range_lvl[k]]); range_pb.push_back(Q.lvl_ptr[Q.range_lvl[k + 1]]); }
     const int nr = (int)range_pa.size();
@@ -400,7 +432,9 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
             for (int x = Q.lrow_ptr[r]; x < Q.lrow_ptr[r + 1]; x++) if (Q.lrow_col[x] >= c_lo && Q.lrow_col[x] < c_hi) ents[r - pa].push_back(x);
             len[r - pa] = (int)ents[r - pa].size();
         }
-        for (const SchedTask& t : schedule_phase(len, NWARP)) {
+        size_t tip = 0;
+        for (const SchedTask& t : place_tasks(schedule_phase(len, NWARP))) {
+            tmem_place(tip++, t.K);
             const int g = 1 << t.sh, ebase = nslots, rbase = (int)Q.sol_orow.size();
             Q.fidx.resize(ebase + 32 * t.K, (uint16_t)Nk);
             for (size_t rr = 0; rr < t.rows.size(); rr++) {
@@ -436,7 +470,9 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
             for (int x = Q.lcol_ptr[c]; x < Q.lcol_ptr[c + 1]; x++) if (Q.lcol_row[x] >= r_lo && Q.lcol_row[x] < r_hi) ents[c - pa].push_back(x);
             len[c - pa] = (int)ents[c - pa].size();
         }
-        for (const SchedTask& t : schedule_phase(len, NWARP)) {
+        size_t tip = 0;
+        for (const SchedTask& t : place_tasks(schedule_phase(len, NWARP))) {
+            tmem_place(tip++, t.K);
             const int g = 1 << t.sh, ebase = (int)Q.bent.size(), rbase = (int)Q.sol_orow.size();
             Q.bent.resize(ebase + 32 * t.K, (uint32_t)Q.zslot | ((uint32_t)Nk << 16));
             for (size_t rr = 0; rr < t.rows.size(); rr++) {
@@ -456,6 +492,12 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         bwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD);                    // x = v + M' v               (tmp -> sol)
     }
     Q.n_bwd_ph = (int)Q.sol_ph_ptr.size() - 1 - Q.n_fwd_ph;
+    if (tmem_layout) {
+        Q.bsrc.resize(Q.bent.size());
+        for (size_t e = 0; e < Q.bent.size(); e++) Q.bsrc[e] = (uint16_t)(Q.bent[e] >> 16);
+        // a partial batch reads a whole group of four slot rows (8 columns): 6 columns of slack behind the last task of every quadrant
+        Q.tmem_cols = *std::max_element(quad_next, quad_next + 4) + 6;
+    }
 
     // A entries -> L slot, or (both ends in the tail) nslots + packed lower index i (i + 1) / 2 + j of the dense Schur complement
     Q.a_slot.resize(Q.nnzA);

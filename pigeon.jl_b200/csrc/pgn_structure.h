@@ -95,6 +95,14 @@ struct QpTables {
     std::vector<uint16_t> fidx;                        // forward: source position per L slot (size nslots)
     std::vector<uint32_t> bent;                        // backward entries in program order: L slot | source position << 16
     int rhs_tmp_end;                                   // positions [0, rhs_tmp_end) = first range: their right-hand side goes to the scratch vector
+    // Tensor-memory layout of the L values (tmem_layout = 1, the two-QPs-per-SM variant for QPs whose factor does not fit shared memory twice):
+    // task t of a phase runs on warp (t - first task of the phase) % nwarps, and a warp reaches only the 32 TMEM lanes of quadrant warp % 4; the
+    // K slot rows of task t occupy the 2 K 32-bit columns [sol_tcol[t], sol_tcol[t] + 2 K) of that quadrant — lane l, slot k of the task is the
+    // double at (lane 32 q + l, column sol_tcol[t] + 2 k): the slot-major program layout IS the TMEM layout.  Backward tasks get their own
+    // copy in program order (bsrc[e] = source position of backward entry e; the L slot it copies from stays in `bent`).  Tasks are permuted
+    // inside every round of `nwarps` so that the four quadrants fill evenly; tmem_cols = columns the fullest quadrant needs (+ read slack).
+    int tmem_layout, tmem_cols;
+    std::vector<uint16_t> sol_tcol, bsrc;
     // numeric factorisation: per level a list of tasks; target: FAC_TGT_PIVOT | position, or a slot (an L slot, or nslots + packed lower
     // index of the dense tail Schur complement, gathered by the last pass); entry: a | b << 16 | k << 32  (product W[a] * W[b] / d_k)
     std::vector<uint32_t> fac_task, fac_lvl_ptr, fac_tgt;
@@ -116,6 +124,7 @@ struct QpTables {
 
 // ordering: 0 nested dissection over stages, 1 minimum degree
 // nwarps: warps of the ADMM CTA the warp programs are laid out for (ADMM_THREADS / 32 by default; 8 for the two-CTAs-per-SM variant)
-bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& out, char* err, int errlen, int nwarps = ADMM_THREADS / 32);
+// tmem_layout: 1 = balance the solve tasks over the TMEM quadrants and emit sol_tcol / bsrc (see QpTables)
+bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& out, char* err, int errlen, int nwarps = ADMM_THREADS / 32, int tmem_layout = 0);
 
 }  // namespace pgn

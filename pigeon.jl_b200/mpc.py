@@ -125,7 +125,8 @@ class BatchedTrajectoryTrackingMPC:
         check(lib.pgn_qp_dims(self._h, dptr(d)))
         self.N, self.nx, self.nu, self.n, self.m, self.nnzA, self.nnzL, self.n_levels = (int(x) for x in d[:8])
         self.qp_program = dict(l_slots=int(d[8]), solve_phases=int(d[9]), factor_entries=int(d[10]), inverse_entries=int(d[11]), tail_dim=int(d[12]),
-                               backward_entries=int(d[13]), admm_smem_bytes=int(d[14]), admm_threads=int(d[15]))
+                               backward_entries=int(d[13]), admm_smem_bytes=int(d[14]), admm_threads=int(d[15]) & 0xffff,
+                               admm_variant="tmem" if (int(d[15]) >> 16) & 1 else "smem", admm_ctas_per_sm=(int(d[15]) >> 20) & 0xf)
         self.T = self.N - 1
         self.vehicle = dict(vehicle)
         self.control_params = dict(control_params) if control_params is not None else _control_params(kind, {})

@@ -735,35 +735,41 @@ def test_windowed_path_search_equals_full_scan(p):
     ga.close(); gb.close()
 
 
-@pytest.mark.parametrize("kind,Ns,Nl", [(0, 5, 10), (1, 10, 20)])
+@pytest.mark.parametrize("kind,Ns,Nl", [(0, 5, 10), (1, 10, 20), (0, 10, 20)])
 def test_admm_build_variants_agree(p, kind, Ns, Nl, monkeypatch):
-    """Small QPs (deployed horizon N = 16, decoupled controller) run the 256-thread / two-CTAs-per-SM build of the ADMM kernel; forcing the
-    512-thread build gives the same iteration counts and controls (different warp programs: the sums are ordered differently), and
-    both match the oracle; the coupled N = 31 QP keeps the 512-thread build."""
+    """Small QPs (deployed horizon N = 16, decoupled controller) run the 256-thread / two-CTAs-per-SM build of the ADMM kernel with everything
+    in shared memory; the coupled N = 31 QP runs the TENSOR-MEMORY build (256 threads, two CTAs per SM, the L values of the solves in TMEM,
+    shared memory time-shared between equilibration / factorisation / iteration views).  Forcing the 512-thread build gives the same
+    iteration counts and controls (different warp programs: the sums are ordered differently), and both match the oracle — over several
+    closed-loop steps, with cold starts whose rho adaptations refactor (and re-fill tensor memory) in mid-solve."""
     B = 48
     trajs = p.synthetic.synthetic_trajectories(n_traj=2, n_nodes=300)
     tid, state, control, t0 = p.synthetic.synthetic_batch(trajs, B)
     other = np.tile(FAR, (B, 1))
     cls = p.BatchedCoupledTrajectoryTrackingMPC if kind == 0 else p.BatchedDecoupledTrajectoryTrackingMPC
-    big = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, 2, trajectory_index=tid[:2])
-    assert big.qp_program["admm_threads"] == 512
-    big.close()
     g256 = cls(p.X1(), trajs, B, trajectory_index=tid, N_short=Ns, N_long=Nl)
     monkeypatch.setenv("PGN_ADMM_VARIANT", "512")
     g512 = cls(p.X1(), trajs, B, trajectory_index=tid, N_short=Ns, N_long=Nl)
     monkeypatch.delenv("PGN_ADMM_VARIANT")
+    big = (kind, Ns, Nl) == (0, 10, 20)
     assert g256.qp_program["admm_threads"] == 256 and g512.qp_program["admm_threads"] == 512
+    assert g256.qp_program["admm_variant"] == ("tmem" if big else "smem") and g512.qp_program["admm_variant"] == "smem"
+    assert g256.qp_program["admm_ctas_per_sm"] == 2 and 2 * (g256.qp_program["admm_smem_bytes"] + 1024) <= 227 * 1024
     ms = oracles_for(kind, trajs, tid, state, control, other, N_short=Ns, N_long=Nl)
     for g in (g256, g512):
         g.set_state(state, control, other)
+    n_rho = 0
     for k in range(4):
         ua, ub = g256.step(t0 + 0.01 * k), g512.step(t0 + 0.01 * k)
         g256.rollout(0.01); g512.rollout(0.01)
         assert np.array_equal(g256.stats()["iters"], g512.stats()["iters"])
+        assert np.array_equal(g256.stats()["rho_updates"], g512.stats()["rho_updates"])
+        n_rho += int(g256.stats()["rho_updates"].sum())
         fin = np.isfinite(ua).all(axis=1)
         assert np.array_equal(fin, np.isfinite(ub).all(axis=1))
         assert np.max(np.abs(ua[fin] - ub[fin]) / U_RANGE) < 1e-7
         for i, m in enumerate(ms):
             m.simulate_step(t0[i] + 0.01 * k)
             assert g256.stats()["iters"][i] == m.stats()["iter"]
+    assert n_rho > 0                     # mid-solve refactorisations happened (the tensor-memory build spills, refactors, refills)
     g256.close(); g512.close()
