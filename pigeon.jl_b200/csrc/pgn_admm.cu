@@ -57,8 +57,9 @@ struct Smem {
     // tensor-memory variant: spilled copies in the CTA's global scratch, writable index tables of the iteration views, this warp's TMEM base
     // address (lane field = first lane of its quadrant), per-task TMEM column and backward source positions
     double *g_lo, *g_hi, *g_yq;
-    uint16_t *fidx_w, *bsrc_w;
-    const uint16_t *bsrc, *tcol;
+    uint16_t *fidx_w, *bsrc_w, *orow_bw, *orow_fw, *tcol_w;
+    uint2* task_w;
+    const uint16_t *bsrc, *tcol, *orow_f, *orow_b;
     uint32_t tm_base;
 };
 
@@ -79,18 +80,25 @@ __host__ __device__ inline size_t tm_region_doubles(int nslots, int tail_dim, in
     const size_t ruiz = A2 + 3 * V + (alias + 7) / 8;
     return fac > ruiz ? fac : ruiz;
 }
-__host__ __device__ inline size_t tm_iter_view_doubles(int nslots, int Nk, int n_bent) {
-    return 3 * (size_t)vec_len(Nk) + ((size_t)(nslots + 128) * 2 + (size_t)(n_bent + 128) * 2 + 7) / 8;
+__host__ __device__ inline size_t tm_iter_view_doubles(int nslots, int Nk, int n_bent, int n_orow_bwd) {
+    return 3 * (size_t)vec_len(Nk) + ((size_t)(nslots + 128) * 2 + (size_t)(n_bent + 128) * 2 + (size_t)n_orow_bwd * 2 + 7) / 8;
+}
+static int orow_fwd_count(const QpTables& t) {       // output rows of the forward phases = row base of the first backward task
+    const size_t first_bwd = t.sol_ph_ptr[t.n_fwd_ph];
+    return first_bwd * 4 + 1 < t.sol_task.size() ? (int)(t.sol_task[4 * first_bwd + 1] & 0xffff) : (int)t.sol_orow.size();
 }
 __host__ __device__ inline size_t tm_scratch_doubles(int Nk, int nnzA) { return (size_t)((nnzA + 1) & ~1) + 4 * (size_t)vec_len(Nk); }
 size_t admm_smem_bytes_tmem(const QpTables& t, int nthreads) {
     const size_t V = vec_len(t.Nk);
-    const size_t d = tm_region_doubles(t.nslots, t.tail_dim, t.Nk, t.nnzA, (int)t.bent.size()) + 4 * V + 16 * (nthreads / 32) + 8;
+    const size_t ntask = t.sol_task.size() / 4;
+    const size_t d = tm_region_doubles(t.nslots, t.tail_dim, t.Nk, t.nnzA, (int)t.bent.size()) + 4 * V + 16 * (nthreads / 32) + 8 + ntask +
+                     (((ntask + 3) & ~(size_t)3) + orow_fwd_count(t) + 3) / 4;
     return d * 8 + align_up((size_t)t.Nk, 8) + 64;
 }
 // whether the tensor-memory variant can run this QP: iteration views in front of the dense tail, TMEM columns within one CTA's half of an SM
 bool admm_tmem_fits(const QpTables& t) {
-    return t.tmem_layout && t.tmem_cols <= 256 && tm_iter_view_doubles(t.nslots, t.Nk, (int)t.bent.size()) <= (size_t)t.nslots &&
+    return t.tmem_layout && t.tmem_cols <= 256 &&
+           tm_iter_view_doubles(t.nslots, t.Nk, (int)t.bent.size(), (int)t.sol_orow.size() - orow_fwd_count(t)) <= (size_t)t.nslots &&
            2 * (admm_smem_bytes_tmem(t, 256) + 1024) <= (size_t)227 * 1024;
 }
 
@@ -222,6 +230,7 @@ void launch_admm(pgn_handle* h) {
     h->launches++;
 }
 
+int admm_orow_fwd(const QpTables& t) { return orow_fwd_count(t); }
 size_t admm_scratch_doubles(const pgn_handle* h) {
     return h->admm_tmem ? (size_t)PGN_MAX_PARTS * h->num_sms * 2 * tm_scratch_doubles(h->tab.Nk, h->tab.nnzA) : 0;
 }

@@ -332,7 +332,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     }
     q.nslots = t.nslots; q.zslot = t.zslot; q.rhs_tmp_end = t.rhs_tmp_end; q.n_fwd_ph = t.n_fwd_ph; q.n_bwd_ph = t.n_bwd_ph;
     q.n_sol_task = (int)t.sol_task.size() / 4; q.n_fac_task = (int)t.fac_task.size() / 4; q.n_inv_task = (int)t.inv_task.size() / 4;
-    q.n_bent = (int)t.bent.size(); q.n_orow = (int)t.sol_orow.size(); q.n_fac_lvl = (int)t.fac_lvl_ptr.size() - 1; q.n_inv_levels = (int)t.inv_lvl_ptr.size() - 1;
+    q.n_bent = (int)t.bent.size(); q.n_orow = (int)t.sol_orow.size(); q.n_orow_fwd = admm_orow_fwd(t); q.n_fac_lvl = (int)t.fac_lvl_ptr.size() - 1; q.n_inv_levels = (int)t.inv_lvl_ptr.size() - 1;
     q.tail_level = t.tail_level; q.tail_start = t.tail_start; q.tail_dim = t.tail_dim;
     if (t.n_fwd_ph + t.n_bwd_ph > ADMM_MAX_PHASES) return bail(set_err(PGN_EINVAL, "too many solve phases for this KKT ordering"));
 #undef UP

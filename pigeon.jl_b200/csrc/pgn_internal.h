@@ -60,7 +60,7 @@ struct QpDev {
     const uint32_t* bent;
     const uint32_t *fac_lvl_ptr, *fac_tgt, *inv_lvl_ptr, *inv_tgt;
     const unsigned long long *fac_ent, *inv_ent;
-    int nslots, zslot, rhs_tmp_end, n_fwd_ph, n_bwd_ph, n_sol_task, n_fac_task, n_inv_task, n_bent, n_orow, n_fac_lvl, n_inv_levels;
+    int nslots, zslot, rhs_tmp_end, n_fwd_ph, n_bwd_ph, n_sol_task, n_fac_task, n_inv_task, n_bent, n_orow, n_orow_fwd, n_fac_lvl, n_inv_levels;
     int tail_level, tail_start, tail_dim;
     const double* ctab;      // [CT_LEN]
     const double* wtab;      // [W_LEN] cost weights
@@ -174,5 +174,6 @@ size_t admm_smem_bytes(const QpTables& t, int nthreads, bool tables_in_smem);
 size_t admm_smem_bytes_tmem(const QpTables& t, int nthreads);
 bool admm_tmem_fits(const QpTables& t);
 size_t admm_scratch_doubles(const pgn_handle* h);
+int admm_orow_fwd(const QpTables& t);
 int admm_configure(pgn_handle* h);   // sets the max dynamic shared memory attribute; returns cudaError
 }  // namespace pgn
