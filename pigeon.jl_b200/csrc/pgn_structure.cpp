@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -88,6 +89,10 @@ std::vector<SchedTask> schedule_rows(const std::vector<int>& len, int kmax) {
 // the longest warp's latency chain against the issue slots of the whole CTA.
 std::vector<SchedTask> schedule_phase(const std::vector<int>& len, int nw) {
     static const int ladder[] = {2, 3, 4, 6, 8, 12, 16, 24, 32, 64, 255};
+    // experiments: PGN_SCHED="a,b,c" overrides the latency model lat = a + b K + c sh
+    static double ca = 120.0, cb = 22.0, cc = 30.0;
+    static bool init = false;
+    if (!init) { init = true; if (const char* e = getenv("PGN_SCHED")) sscanf(e, "%lf,%lf,%lf", &ca, &cb, &cc); }
     std::vector<SchedTask> best;
     double best_cost = 1e300;
     for (int kmax : ladder) {
@@ -97,7 +102,7 @@ std::vector<SchedTask> schedule_phase(const std::vector<int>& len, int nw) {
         double issue = 0.0;
         for (size_t i = 0; i < t.size(); i++) {
             if (t[i].K > 255) ok = false;
-            lat[i % nw] += 120.0 + 22.0 * t[i].K + 30.0 * t[i].sh;      // measured: ~90 cycles per batch of 4 entries, ~30 per shuffle stage
+            lat[i % nw] += ca + cb * t[i].K + cc * t[i].sh;      // measured: ~90 cycles per batch of 4 entries, ~30 per shuffle stage
             issue += 40.0 + 6.0 * t[i].K + 8.0 * t[i].sh;
         }
         if (!ok) continue;
