@@ -270,14 +270,17 @@ def run_settled(cx, p, cfg_idx, B, K, W, seed_shift, want_stage=True, trajs=None
         Vv, _ = mpc.hji_values()
         extra["hji_first_step"] = {"pct_active": float((Vv <= 0.05).mean() * 100), "pct_out_of_grid": float(np.isinf(Vv).mean() * 100)}
     mpc.simulate_device_async(d_base.data_ptr(), DT, SETTLE - 1, k0=1)
+    mpc.synchronize()              # deferred solves: the vehicles that fell behind are caught up INSIDE the region that caused them
     ev[1].record(cx.stream)
     cx.barrier()
     cold_ms = ev[0].elapsed_time(ev[1])
     mpc.simulate_device_async(d_base.data_ptr(), DT, W, k0=SETTLE)
+    mpc.synchronize()
     cx.barrier()
     mpc.stage_ms(reset=True)
     ev[2].record(cx.stream)
     mpc.simulate_device_async(d_base.data_ptr(), DT, K, k0=SETTLE + W)
+    mpc.synchronize()
     ev[3].record(cx.stream)
     cx.barrier()
     ms = cx.max_over_ranks(ev[2].elapsed_time(ev[3]))
@@ -323,6 +326,7 @@ def run_monte_carlo(cx, p, B, seed_shift, trajs=None, oracle_check=True):
     mpc.set_state(pin_q.numpy(), pin_u.numpy(), pin_o.numpy())      # e2e: the job's inputs go in from pinned host memory ...
     e[1].record(cx.stream)
     mpc.simulate_device_async(d_base.data_ptr(), DT, NS, k0=0)
+    mpc.synchronize()              # includes the catch-up rounds of the vehicles whose solves were deferred
     e[2].record(cx.stream)
     cx.barrier()
     q, u = mpc.get_state()                                          # ... and its result (final states and controls) comes back
@@ -542,6 +546,7 @@ def run_gpu(args):
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record(stream)
     mpc.simulate_device_async(d_base.data_ptr(), DT, 101, k0=0)
+    mpc.synchronize()
     c1.record(stream)
     barrier()
     ms101 = max_over_ranks(c0.elapsed_time(c1))

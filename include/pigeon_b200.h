@@ -47,7 +47,8 @@ enum { PGN_COUPLED = 0, PGN_DECOUPLED = 1 };
 /* per-QP solver status, same codes as libosqp */
 enum {
     PGN_QP_SOLVED = 1, PGN_QP_SOLVED_INACCURATE = 2, PGN_QP_PRIMAL_INFEASIBLE_INACCURATE = 3, PGN_QP_DUAL_INFEASIBLE_INACCURATE = 4,
-    PGN_QP_MAX_ITER_REACHED = -2, PGN_QP_PRIMAL_INFEASIBLE = -3, PGN_QP_DUAL_INFEASIBLE = -4, PGN_QP_UNSOLVED = -10
+    PGN_QP_MAX_ITER_REACHED = -2, PGN_QP_PRIMAL_INFEASIBLE = -3, PGN_QP_DUAL_INFEASIBLE = -4, PGN_QP_UNSOLVED = -10,
+    PGN_QP_PENDING = -11      /* inside a simulate loop only: the solve continues in the next round (pgn_set_solve_cap) */
 };
 
 /* Mirrors the keyword arguments of CoupledTrajectoryTrackingMPC / DecoupledTrajectoryTrackingMPC
@@ -163,6 +164,14 @@ PGN_API int pgn_simulate_device(pgn_handle* h, const double* d_t0 /*[B]*/, doubl
  * 1: one range on the caller's stream; <= 8.
  * The five single-stage calls and pgn_from_autobox always run the whole batch on the caller's stream. */
 PGN_API int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts);
+/* Deferred solves inside pgn_simulate / pgn_simulate_device.  Iteration counts of the batch spread from 25 to max_iter = 4000, and one QP is
+ * one CTA: a single 4000-iteration QP used to hold every vehicle of its range for the whole solve.  With a cap, a QP that has not terminated
+ * after `iters` ADMM iterations of one launch saves its iterates (the warm-start buffers) and continues in the NEXT round's launch while only
+ * ITS vehicle waits; every vehicle counts its own steps, and the vehicles that fell behind are caught up at the end of pgn_simulate (or, for
+ * pgn_simulate_device, at the next entry point that needs results, pgn_synchronize included).  The continued solve recomputes scaling and
+ * factor from the unchanged QP data and resumes at iteration k + 1: every vehicle's results are bit-identical with and without the cap.
+ * iters must be a multiple of check_termination and adaptive_rho_interval; 0 = off; default 200.  The step entry points are never capped. */
+PGN_API int pgn_set_solve_cap(pgn_handle* h, int32_t iters);
 PGN_API int pgn_get_pipeline_parts(pgn_handle* h, int32_t* parts);
 /* one plant rollout + control application (the tail of the simulate loop) */
 PGN_API int pgn_rollout(pgn_handle* h, double dt);

@@ -37,6 +37,9 @@ struct AdmmArgs {
     const int32_t* order;          // ticket -> vehicle (longest previous solve first)
     const uint8_t* skip;           // guard: paused vehicles are not solved (nullptr = guard off)
     uint8_t* cold;                 // guard: vehicles whose iterates / rho start from scratch (Parametron.initialize! after a NaN)
+    uint8_t* hold;                 // deferred solves (nullptr = off): 1 = this QP continues an earlier launch, 2 = vehicle finished; written 0 / 1 here
+    int32_t* iters_acc;            // iterations a continued QP has behind it
+    int iter_cap;                  // iterations of one QP per launch (0 = unlimited); a multiple of check_termination and adaptive_rho_interval
     uint16_t ph_ptr[ADMM_MAX_PHASES + 1];   // first task of every solve phase (forward phases, then backward phases): uniform constant-bank reads
     double* scratch;              // tensor-memory variant: per-CTA global scratch (scaled A, scalings, spilled vectors), tm_scratch_doubles each
     unsigned long long* cycles;   // optional per-phase cycle counters (profiling builds of the host call): gather, ruiz, factor, solve, update, check, store
@@ -210,6 +213,7 @@ void launch_admm(pgn_handle* h) {
     h->launches++;
     a.order = h->d_order + h->v0;
     a.skip = (h->guard_pause > 0.0 || h->in_callback) ? h->d_skip : nullptr; a.cold = h->d_cold;
+    a.hold = h->hold_on ? h->d_hold : nullptr; a.iters_acc = h->d_iters_acc; a.iter_cap = h->hold_on ? h->round_cap : 0;
     for (size_t i = 0; i < h->tab.sol_ph_ptr.size() && i <= ADMM_MAX_PHASES; i++) a.ph_ptr[i] = h->tab.sol_ph_ptr[i];
     const bool small = h->admm_threads == 256;
     const int full = h->num_sms * (small ? 2 : 1);

@@ -31,6 +31,7 @@ extern "C" void pgn_set_error_(const char* msg) { snprintf(g_err, sizeof(g_err),
         if (!(cond)) return set_err(PGN_EINVAL, "%s", msg);  \
     } while (0)
 
+extern "C" { static int finish_sim(pgn_handle* h); }      // defined beside the simulate loop, inside the extern "C" block
 static void drain_ring(pgn_handle* h) {
     for (int i = 0, sl = h->ring_tail; i < h->ring_count; i++, sl = (sl + 1) % PGN_RING)
         for (int p = 0; p < h->ring_parts[sl]; p++) cudaEventSynchronize(h->ring_done[sl][p]);
@@ -48,8 +49,9 @@ struct DeviceGuard {
     ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
 };
 // steps submitted with pgn_step_submit run on the part streams: every other entry point first waits for them (their results stay collectable)
+// ... and for the vehicles that a simulate loop with deferred solves left behind (finish_sim: catch-up rounds until every vehicle has its steps)
 #define ENTER_NODRAIN(h, msg)  REQUIRE(h, msg); DeviceGuard dev_guard__((h)->device)
-#define ENTER(h, msg)  ENTER_NODRAIN(h, msg); if ((h)->ring_count) drain_ring(h)
+#define ENTER(h, msg)  ENTER_NODRAIN(h, msg); if ((h)->ring_count) drain_ring(h); if ((h)->sim_open) { int rc__ = finish_sim(h); if (rc__) return rc__; }
 
 struct StageTimer {
     pgn_handle* h; int idx;
@@ -351,7 +353,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     AL(d_ws_xz, B * (size_t)t.Nk); AL(d_ws_y, B * (size_t)t.Nk); AL(d_rho, B);
     AL(d_sol_x, B * (size_t)t.n); AL(d_sol_y, B * (size_t)t.m);
     AL(d_iters, B); AL(d_status, B); AL(d_rho_updates, B); AL(d_pri_res, B); AL(d_dua_res, B);
-    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 2 * PGN_MAX_PARTS); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se0, 2 * B); AL(d_se, 2 * B); AL(d_tskip, B); AL(d_in, 18 * B); AL(d_mask, B);
+    AL(d_controls, 3 * B); AL(d_t0, B); AL(d_t0_base, B); AL(d_counter, 2 * PGN_MAX_PARTS); AL(d_order, B); AL(d_skip, B); AL(d_cold, B); AL(d_cycles, 512); AL(d_hji_val, 8 * B); AL(d_io, 1 + 19 * B); AL(d_state_next, 6 * B); AL(d_last_seg, B); AL(d_se0, 2 * B); AL(d_se, 2 * B); AL(d_tskip, B); AL(d_in, 18 * B); AL(d_mask, B); AL(d_hold, B); AL(d_kstep, B); AL(d_iters_acc, B); AL(d_lag, 4);
 #undef AL
     CK(cudaMemset(h->d_state, 0, 6 * B * 8)); CK(cudaMemset(h->d_control, 0, 3 * B * 8)); CK(cudaMemset(h->d_solved, 0, B)); CK(cudaMemset(h->d_traj_id, 0, B * 4));
     CK(cudaMemset(h->d_ws_xz, 0, B * t.Nk * 8)); CK(cudaMemset(h->d_ws_y, 0, B * t.Nk * 8));
@@ -361,6 +363,14 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->path_window = 0; CK(cudaMemset(h->d_last_seg, 0xff, B * 4));
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
+    h->hold_on = 0; h->sim_open = 0; h->sim_target = 0; h->sim_dt = 0.0; h->round_cap = 0; h->h_lag = nullptr;
+    {   // deferred solves inside the simulate loops: on by default with 200 iterations per launch when the check / adaptation intervals divide it
+        const int c = h->st.check_termination, a = (h->st.adaptive_rho && h->st.adaptive_rho_interval > 0) ? h->st.adaptive_rho_interval : 1;
+        h->solve_cap = (c > 0 && 200 % c == 0 && 200 % a == 0) ? 200 : 0;
+        if (getenv("PGN_SOLVE_CAP")) h->solve_cap = atoi(getenv("PGN_SOLVE_CAP"));
+    }
+    CK(cudaMemset(h->d_hold, 0, B)); CK(cudaMemset(h->d_kstep, 0, B * 4)); CK(cudaMemset(h->d_iters_acc, 0, B * 4));
+    if (cudaMallocHost((void**)&h->h_lag, 16) != cudaSuccess) return bail(set_err(PGN_ENOMEM, "cudaMallocHost failed"));
     h->h_ring = nullptr; h->d_ring = nullptr; h->ring_head = h->ring_tail = h->ring_count = h->ring_created = 0;
     h->h_in = nullptr; h->in_pending = 0; h->d_hist = nullptr; h->hist_cap = h->hist_stride = h->hist_n = 0;
     h->comm = nullptr; h->comm_rank = 0; h->comm_size = 1; h->d_gath_c = nullptr; h->d_gath_i = nullptr;
@@ -419,6 +429,7 @@ int pgn_destroy(pgn_handle* h) {
     if (h->cb_has_exec) { cudaGraphExecDestroy(h->cb_exec); cudaGraphDestroy(h->cb_graph); }
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_lag) cudaFreeHost(h->h_lag);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->ring_created)
         for (int sl = 0; sl < PGN_RING; sl++) { cudaEventDestroy(h->ring_h2d[sl]); for (int p = 0; p < PGN_MAX_PARTS; p++) cudaEventDestroy(h->ring_done[sl][p]); }
@@ -786,6 +797,29 @@ int pgn_rollout(pgn_handle* h, double dt) {
 // the `simulate` loop on the device: every pipeline part runs ALL its steps on its own stream (a vehicle's step k+1 depends only on its own
 // step k), so the parts drift apart and the small per-vehicle kernels of one part fill the SMs the ADMM kernel of another leaves idle
 static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
+    if (h->solve_cap > 0 && !h->profiling) {
+        // Deferred solves: every vehicle counts its own steps.  A round = one step attempt of every vehicle of the range that is not held; a QP
+        // that uses up its share of ADMM iterations keeps its vehicle on hold and continues in the next round's launch, so a 4000-iteration
+        // straggler costs its own vehicle a few rounds instead of costing every vehicle of the range the whole solve.  n_steps rounds are
+        // enqueued here; the vehicles that fell behind are finished by finish_sim at the next point that needs results.
+        if (k0 == 0) {
+            CK(cudaMemsetAsync(h->d_kstep, 0, (size_t)h->B * 4, h->stream));
+            CK(cudaMemsetAsync(h->d_hold, 0, h->B, h->stream));
+        }
+        h->sim_target = k0 + n_steps; h->sim_dt = dt; h->sim_open = 1;
+        if (h->hist_stride > 0) { const int nrec = std::min(h->hist_cap, (h->sim_target + h->hist_stride - 1) / h->hist_stride); if (nrec > h->hist_n) h->hist_n = nrec; }
+        h->hold_on = 1; h->round_cap = h->solve_cap;
+        int rc = for_each_part(h, [&]() {
+            for (int k = 0; k < n_steps; k++) {
+                launch_round_begin(h, dt, h->sim_target);
+                int rc2 = step_rollout_body(h, h->d_t0, dt, h->hist_stride > 0 ? 0 : -1);
+                if (rc2) return rc2;
+            }
+            return (int)PGN_OK;
+        });
+        h->hold_on = 0;
+        return rc;
+    }
     auto slot_of = [&](int k) { return (h->hist_stride > 0 && k % h->hist_stride == 0 && k / h->hist_stride < h->hist_cap) ? k / h->hist_stride : -1; };
     for (int k = k0; k < k0 + n_steps; k++) { const int sl = slot_of(k); if (sl + 1 > h->hist_n) h->hist_n = sl + 1; }
     return for_each_part(h, [&]() {
@@ -797,6 +831,28 @@ static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
         return (int)PGN_OK;
     });
 }
+// catch-up rounds of a simulate loop with deferred solves: until every vehicle has completed its steps.  The remaining solves get a larger
+// share of iterations per launch (nothing else is waiting for the SMs any more).
+static int finish_sim(pgn_handle* h) {
+    if (!h->sim_open) return PGN_OK;
+    h->sim_open = 0;
+    for (int round = 0;; round++) {
+        launch_count_lag(h, h->sim_target);
+        CK(cudaMemcpyAsync(h->h_lag, h->d_lag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (*h->h_lag == 0) break;
+        if (round > 100000) return set_err(PGN_ECUDA, "simulate: %d vehicles do not reach step %d", *h->h_lag, h->sim_target);
+        h->hold_on = 1; h->round_cap = 5 * h->solve_cap;
+        int rc = for_each_part(h, [&]() {
+            launch_round_begin(h, h->sim_dt, h->sim_target);
+            return step_rollout_body(h, h->d_t0, h->sim_dt, h->hist_stride > 0 ? 0 : -1);
+        });
+        h->hold_on = 0;
+        if (rc) return rc;
+    }
+    CK(cudaGetLastError());
+    return PGN_OK;
+}
 // automatic part count: 4 parts from 64 vehicles up.  Measured (simulate loop, coupled N = 31, ms per step with 1 / 2 / 4 / 8 parts): B = 64: 0.75 / 0.69 /
 // 0.63 / 1.10; 128: 0.78 / 0.74 / 0.68 / 1.20; 256: 1.12 / 0.91 / 0.86 / 1.34; 512: 1.74 / 1.46 / 1.29 / 1.63; 1024: 2.87 / 2.67 / 2.49 / 2.68 (3: 2.56, 5: 3.28,
 // 6: 2.98, 7: 2.79); 2048: 5.40 / 4.97 / 4.91; 4096: 10.31 / 9.74 / 9.69.  Per-step calls (parts joined every call) are never slower with 4 parts.
@@ -807,12 +863,16 @@ int pgn_simulate(pgn_handle* h, const double* t0, double dt, int32_t n_steps) {
     h->hist_n = 0;
     int rc = simulate_enqueue(h, dt, 0, n_steps);
     if (rc) return rc;
+    if ((rc = finish_sim(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     return PGN_OK;
 }
 int pgn_simulate_device(pgn_handle* h, const double* d_t0, double dt, int32_t k0, int32_t n_steps) {
-    ENTER(h, "NULL handle"); REQUIRE(d_t0 && n_steps >= 0 && k0 >= 0, "bad argument");
+    ENTER_NODRAIN(h, "NULL handle"); REQUIRE(d_t0 && n_steps >= 0 && k0 >= 0, "bad argument");
+    if (h->ring_count) drain_ring(h);
+    // a call that continues the time axis of the previous one (k0 = its end) leaves the vehicles that are behind where they are: they go on here
+    if (h->sim_open && !(k0 == h->sim_target && dt == h->sim_dt && h->solve_cap > 0)) { int rc0 = finish_sim(h); if (rc0) return rc0; }
     CK(cudaMemcpyAsync(h->d_t0_base, d_t0, (size_t)h->B * 8, cudaMemcpyDeviceToDevice, h->stream));
     if (k0 == 0) h->hist_n = 0;
     int rc = simulate_enqueue(h, dt, k0, n_steps);
@@ -871,6 +931,17 @@ int pgn_get_history(pgn_handle* h, int32_t* n_records, double* qs, double* us, d
             if (ps) for (size_t f = 0; f < 4; f++) ps[(r * B + v) * 4 + f] = s[(9 + nx + f) * B + v];
         }
     }
+    return PGN_OK;
+}
+int pgn_set_solve_cap(pgn_handle* h, int32_t iters) {
+    ENTER(h, "NULL handle");
+    REQUIRE(iters >= 0, "iters must be >= 0");
+    if (iters > 0) {
+        const int c = h->st.check_termination, a = (h->st.adaptive_rho && h->st.adaptive_rho_interval > 0) ? h->st.adaptive_rho_interval : 1;
+        REQUIRE(c > 0 && iters % c == 0 && iters % a == 0, "the cap must be a multiple of check_termination and of adaptive_rho_interval");
+    }
+    h->epoch++;
+    h->solve_cap = iters;
     return PGN_OK;
 }
 int pgn_get_pipeline_parts(pgn_handle* h, int32_t* parts) { ENTER(h, "NULL handle"); REQUIRE(parts, "NULL argument"); *parts = h->parts; return PGN_OK; }

@@ -96,10 +96,11 @@ __global__ void __launch_bounds__(128) k_hji_lookup(HjiView H, int M, const doub
 // reachability constraint M u + b >= -sigma for every vehicle; writes (M1*un1, M2*un2, b) into the record
 __global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, int v0, int nv, VehParams P, double eps, double un0, double un1, const double* __restrict__ state,
                                                         const double* __restrict__ control, const double* __restrict__ other, double* __restrict__ rec,
-                                                        int rec_len, int o_hji, double* __restrict__ hji_val /*[8][B]: gradV[0..6], V*/) {
+                                                        int rec_len, int o_hji, double* __restrict__ hji_val /*[8][B]: gradV[0..6], V*/, const uint8_t* __restrict__ hold) {
     const int iv = blockIdx.x * blockDim.x + threadIdx.x;
     if (iv >= nv) return;
     const int v = v0 + iv;
+    if (hold && hold[v]) return;          // deferred solve in progress: the record keeps the constraint of the step being solved
     const double E = state[0 * B + v], N = state[1 * B + v], psi = state[2 * B + v], Ux = state[3 * B + v], Uy = state[4 * B + v], r = state[5 * B + v];
     const double oE = other[0 * B + v], oN = other[1 * B + v], opsi = other[2 * B + v], oV = other[3 * B + v];
     // HJIRelativeState: `cψ, sψ = sincos(-ψ)` binds cψ <- sin(-ψ), sψ <- cos(-ψ) (HJI_computation.jl:21-22)
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(128) k_hji_constraint(HjiView H, int B, int v0
 void launch_hji_constraint(pgn_handle* h) {
     const int B = h->B;
     k_hji_constraint<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(h->hji, B, h->v0, h->nv, h->veh, h->cfg.hji_eps, h->un[0], h->un[1], h->d_state, h->d_control, h->d_other,
-                                                             h->d_rec, h->tab.rec.rec_len, h->tab.rec.o_hji, h->d_hji_val);
+                                                             h->d_rec, h->tab.rec.rec_len, h->tab.rec.o_hji, h->d_hji_val, h->hold_on ? h->d_hold : nullptr);
     h->launches++;
 }
 void launch_hji_optimal_control(pgn_handle* h, int M, const double* d_x, const double* d_gV, double* d_out) {

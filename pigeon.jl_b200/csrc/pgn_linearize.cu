@@ -18,6 +18,7 @@ struct LinArgs {
     RecLayout R;
     const double *qs, *us, *ps, *dt;
     double* rec;
+    const uint8_t* hold;      // simulate loops with deferred solves: the record of a held vehicle belongs to a QP that is still being solved
 };
 
 // envelope + limits of node t+1 and the per-vehicle global part of the record
@@ -51,9 +52,9 @@ __global__ void __launch_bounds__(128, PGN_LIN_MINCTAS) k_linearize_coupled(cons
     const int g = gid & 3;                  // tangent group of this lane
     const int node = gid >> 2;
     const int total = a.B * a.T;
-    const bool active = node < total;
-    const int nd = active ? node : total - 1;
+    const int nd = node < total ? node : total - 1;
     const int v = nd / a.T, t = nd - v * a.T;
+    const bool active = node < total && !(a.hold && a.hold[v]);
     const bool ramp = t >= a.Ns;
     const double* q = a.qs + ((size_t)v * a.N + t) * 6;
     const double* u0p = a.us + ((size_t)v * a.N + t) * 2;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(128) k_linearize_decoupled(const LinArgs a) {
     const int node = blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= a.B * a.T) return;
     const int v = node / a.T, t = node - v * a.T;
+    if (a.hold && a.hold[v]) return;
     const bool ramp = t >= a.Ns;
     const double* q = a.qs + ((size_t)v * a.N + t) * 4;
     const double* u0p = a.us + ((size_t)v * a.N + t) * 2;
@@ -257,6 +259,7 @@ void launch_linearize(pgn_handle* h) {
     a.R = h->tab.rec;
     const size_t o = (size_t)h->v0;
     a.qs = h->d_qs + o * h->N * h->nx; a.us = h->d_us + o * h->N * 2; a.ps = h->d_ps + o * h->N * 4; a.dt = h->d_dt + o * h->T; a.rec = h->d_rec + o * h->tab.rec.rec_len;
+    a.hold = h->hold_on ? h->d_hold + o : nullptr;
     const long long nodes = (long long)h->nv * h->T;
     if (h->cfg.kind == PGN_COUPLED) {
         const long long threads = nodes * 4;

@@ -5,6 +5,8 @@
 //   trajectory lookups             src/trajectories.jl:47-94, src/math.jl:4-9
 //   get_next_control               src/coupled_lat_long.jl:370-374, src/decoupled_lat_long.jl:275-278
 //   simulate's plant step          src/model_predictive_control.jl:94-95
+#include <algorithm>
+
 #include "pgn_internal.h"
 
 namespace pgn {
@@ -120,9 +122,11 @@ __device__ __forceinline__ void path_coordinates_warp(const TrajView& tv, int ba
 // which update_interpolations! needs when the vehicle resumes — and is flagged in `skip` for the stages that follow.
 __global__ void k_time_steps(int B, int Ns, int Nl, double dt_short, double dt_long, int corr, const double* __restrict__ t0v,
                              double* __restrict__ ts, double* __restrict__ dtv, double* __restrict__ prev_ts,
-                             uint8_t* __restrict__ skip, const double* __restrict__ Ux, double pause_below_speed, const uint8_t* __restrict__ tskip) {
+                             uint8_t* __restrict__ skip, const double* __restrict__ Ux, double pause_below_speed, const uint8_t* __restrict__ tskip,
+                             const uint8_t* __restrict__ hold) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= B) return;
+    if (hold && hold[v]) return;          // deferred solve in progress / vehicle already at the end of the loop: nothing of the step is touched
     if (skip) {
         const bool sk = (pause_below_speed > 0.0 && Ux[v] < pause_below_speed) || (tskip && tskip[v]);
         skip[v] = sk;
@@ -154,6 +158,7 @@ struct NodeArgs {
     double* se0;                                  // decoupled: (s0, e0) of the closest-segment scan, [2][B]
     int window; int32_t* last_seg;                // optional windowed closest-segment search (pgn_set_path_search_window)
     const uint8_t* tskip;                         // callback entry point only: time outside the trajectory interval (src/ros_integration.jl:77-80)
+    const uint8_t* hold;                          // simulate loops with deferred solves: vehicles that do not start a new step in this round
 };
 
 // decoupled: always the steady-state rollout (decoupled_lat_long.jl:65-103).  A recurrence over the horizon nodes, one vehicle per
@@ -222,6 +227,7 @@ __global__ void __launch_bounds__(128) k_nodes_decoupled_rollout(const NodeArgs 
     const int iv = blockIdx.x * blockDim.x + threadIdx.x;
     if (iv >= a.nv) return;
     const int v = a.v0 + iv;
+    if (a.hold && a.hold[v]) return;
     if ((a.pause_below_speed > 0.0 || a.tskip) && a.skip[v]) return;
     decoupled_cold_rollout(a, v, se0[v], se0[a.B + v]);
 }
@@ -232,6 +238,7 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
     const int iv = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (iv >= a.nv) return;
     const int v = a.v0 + iv;
+    if (a.hold && a.hold[v]) return;
     const int B = a.B, N = a.N, Ns = a.Ns;
     const VehParams& P = a.P;
     const CtrlParams& C = a.C;
@@ -346,10 +353,12 @@ __global__ void __launch_bounds__(128) k_nodes(const NodeArgs a) {
 __global__ void k_controls(int B, int v0, int nv, int kind, int n_sol, int iv_delta, int iv_fx, double un0, double un1, VehParams P,
                            const double* __restrict__ sol_x, const double* __restrict__ us, int N, double* __restrict__ out,
                            const double* __restrict__ control, const uint8_t* __restrict__ skip, int guard_nan, uint8_t* __restrict__ cold,
-                           uint8_t* __restrict__ solved, const double* __restrict__ hji_val, double hji_eps, const double* __restrict__ state) {
+                           uint8_t* __restrict__ solved, const double* __restrict__ hji_val, double hji_eps, const double* __restrict__ state,
+                           const uint8_t* __restrict__ hold) {
     const int iv = blockIdx.x * blockDim.x + threadIdx.x;
     if (iv >= nv) return;
     const int v = v0 + iv;
+    if (hold && hold[v]) return;          // QP still pending (or vehicle finished): no new control in this round
     double d, Fx;
     if (hji_val && hji_val[(size_t)7 * B + v] <= hji_eps) {
         // use_HJI_policy && V <= HJI_eps (ros_integration.jl:115-118): optimal_control replaces the QP's control
@@ -485,11 +494,18 @@ __global__ void k_masked_reset(int B, const uint8_t* __restrict__ mask, int what
 }
 // history recorder of `simulate` (model_predictive_control.jl:84-99: qs / us before the step, xs = mpc.qs[1], ps = mpc.ps[1] after node generation)
 __global__ void k_record(int B, int v0, int nv, int nx, int N, const double* __restrict__ state, const double* __restrict__ control,
-                         const double* __restrict__ qs, const double* __restrict__ ps, double* __restrict__ slot) {
+                         const double* __restrict__ qs, const double* __restrict__ ps, double* __restrict__ slot,
+                         const uint8_t* __restrict__ hold, const int32_t* __restrict__ kstep, int stride, int cap) {
     const int iv = blockIdx.x * blockDim.x + threadIdx.x;
     if (iv >= nv) return;
     const int v = v0 + iv;
     const size_t Bs = (size_t)B;
+    if (hold) {      // deferred solves: every vehicle is at its own step; `slot` is the base of the history buffer
+        if (hold[v]) return;
+        const int k = kstep[v];
+        if (k % stride != 0 || k / stride >= cap) return;
+        slot += (size_t)(k / stride) * (13 + nx) * Bs;
+    }
     for (int f = 0; f < 6; f++) slot[f * Bs + v] = state[f * Bs + v];
     for (int f = 0; f < 3; f++) slot[(6 + f) * Bs + v] = control[f * Bs + v];
     for (int f = 0; f < nx; f++) slot[(9 + f) * Bs + v] = qs[(size_t)v * N * nx + f];
@@ -510,7 +526,7 @@ void launch_time_steps(pgn_handle* h, const double* d_t0) {
     k_time_steps<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.N_short, h->cfg.N_long, h->cfg.dt_short, h->cfg.dt_long, h->cfg.use_correction_step,
                                                          d_t0 + o, h->d_ts + o * h->N, h->d_dt + o * h->T, h->d_prev_ts + o * h->N,
                                                          guarded ? h->d_skip + o : nullptr, h->d_state + 3 * (size_t)h->B + o, h->guard_pause,
-                                                         h->in_callback ? h->d_tskip + o : nullptr);
+                                                         h->in_callback ? h->d_tskip + o : nullptr, h->hold_on ? h->d_hold + o : nullptr);
     h->launches++;
 }
 void launch_nodes(pgn_handle* h) {
@@ -524,6 +540,7 @@ void launch_nodes(pgn_handle* h) {
     a.qs = h->d_qs; a.us = h->d_us; a.ps = h->d_ps;
     a.skip = h->d_skip; a.pause_below_speed = h->guard_pause; a.tskip = h->in_callback ? h->d_tskip : nullptr;
     a.window = h->path_window; a.last_seg = h->d_last_seg; a.se0 = h->d_se0;
+    a.hold = h->hold_on ? h->d_hold : nullptr;
     k_nodes<<<(h->nv + 3) / 4, 128, 0, h->stream>>>(a);
     h->launches++;
     if (h->cfg.kind == PGN_DECOUPLED) {
@@ -543,7 +560,8 @@ void launch_controls(pgn_handle* h, double* d_out) {
     const int B = h->B;
     k_controls<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(B, h->v0, h->nv, h->cfg.kind, h->tab.n, h->tab.var_u1_delta, h->tab.var_u1_fx, h->un[0], h->un[1], h->veh,
                                                        h->d_sol_x, h->d_us, h->N, d_out, h->d_control, (h->guard_pause > 0.0 || h->in_callback) ? h->d_skip : nullptr, h->guard_nan,
-                                                       h->d_cold, h->d_solved, (h->hji_policy && h->cfg.kind == PGN_COUPLED) ? h->d_hji_val : nullptr, h->cfg.hji_eps, h->d_state);
+                                                       h->d_cold, h->d_solved, (h->hji_policy && h->cfg.kind == PGN_COUPLED) ? h->d_hji_val : nullptr, h->cfg.hji_eps, h->d_state,
+                                                       h->hold_on ? h->d_hold : nullptr);
     h->launches++;
 }
 void launch_rollout(pgn_handle* h, double dt) {
@@ -555,10 +573,13 @@ void launch_rollout(pgn_handle* h, double dt) {
 // can run beside the ADMM launch: propagate into a shadow state on the side stream, commit (state <- shadow, control <- new control) on
 // the main stream once both are done.
 __global__ void __launch_bounds__(128) k_propagate_shadow(int B, int v0, int nv, VehParams P, double dt, int nsub, const double* __restrict__ state, const double* __restrict__ control,
-                                                          double* __restrict__ state_next) {
+                                                          double* __restrict__ state_next, const uint8_t* hold) {
     const int iv = blockIdx.x * blockDim.x + threadIdx.x;
     if (iv >= nv) return;
     const int v = v0 + iv;
+    // runs beside the ADMM kernel, which moves hold[v] between 0 and 1 only: 2 (vehicle finished, set before the fork) is stable.  A vehicle
+    // whose QP stays pending is propagated again in a later round from the same state and control: same result.
+    if (hold && hold[v] == 2) return;
     double x[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) x[i] = state[i * B + v];
@@ -567,10 +588,15 @@ __global__ void __launch_bounds__(128) k_propagate_shadow(int B, int v0, int nv,
 #pragma unroll
     for (int i = 0; i < 6; i++) state_next[i * B + v] = x[i];
 }
-__global__ void k_commit_rollout(int B, int v0, int nv, const double* __restrict__ state_next, const double* __restrict__ new_control, double* __restrict__ state, double* __restrict__ control) {
+__global__ void k_commit_rollout(int B, int v0, int nv, const double* __restrict__ state_next, const double* __restrict__ new_control, double* __restrict__ state, double* __restrict__ control,
+                                 const uint8_t* __restrict__ hold, int32_t* __restrict__ kstep) {
     const int iv = blockIdx.x * blockDim.x + threadIdx.x;
     if (iv >= nv) return;
     const int v = v0 + iv;
+    if (hold) {
+        if (hold[v]) return;              // the vehicle's step is not complete (QP pending) or it has none left
+        kstep[v]++;
+    }
 #pragma unroll
     for (int i = 0; i < 6; i++) state[i * B + v] = state_next[i * B + v];
 #pragma unroll
@@ -578,12 +604,14 @@ __global__ void k_commit_rollout(int B, int v0, int nv, const double* __restrict
 }
 void launch_propagate_shadow(pgn_handle* h, double dt, cudaStream_t side) {
     const int B = h->B;
-    k_propagate_shadow<<<(h->nv + 127) / 128, 128, 0, side>>>(B, h->v0, h->nv, h->veh, dt, h->cfg.rk4_substeps, h->d_state, h->d_control, h->d_state_next);
+    k_propagate_shadow<<<(h->nv + 127) / 128, 128, 0, side>>>(B, h->v0, h->nv, h->veh, dt, h->cfg.rk4_substeps, h->d_state, h->d_control, h->d_state_next,
+                                                              h->hold_on ? h->d_hold : nullptr);
     h->launches++;
 }
 void launch_commit_rollout(pgn_handle* h) {
     const int B = h->B;
-    k_commit_rollout<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(B, h->v0, h->nv, h->d_state_next, h->d_controls, h->d_state, h->d_control);
+    k_commit_rollout<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(B, h->v0, h->nv, h->d_state_next, h->d_controls, h->d_state, h->d_control,
+                                                                 h->hold_on ? h->d_hold : nullptr, h->d_kstep);
     h->launches++;
 }
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k) {
@@ -610,7 +638,37 @@ void launch_masked_reset(pgn_handle* h, const uint8_t* d_mask, int what) {
 }
 void launch_record(pgn_handle* h, int slot) {
     const size_t rec = (size_t)(13 + h->nx) * h->B;
-    k_record<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(h->B, h->v0, h->nv, h->nx, h->N, h->d_state, h->d_control, h->d_qs, h->d_ps, h->d_hist + rec * slot);
+    if (h->hold_on) k_record<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(h->B, h->v0, h->nv, h->nx, h->N, h->d_state, h->d_control, h->d_qs, h->d_ps, h->d_hist, h->d_hold, h->d_kstep, h->hist_stride, h->hist_cap);
+    else k_record<<<(h->nv + 127) / 128, 128, 0, h->stream>>>(h->B, h->v0, h->nv, h->nx, h->N, h->d_state, h->d_control, h->d_qs, h->d_ps, h->d_hist + rec * slot, nullptr, nullptr, 1, 0);
+    h->launches++;
+}
+// simulate loops with deferred solves: per vehicle, the time of its own next step and whether it takes part in this round
+__global__ void k_round_begin(int n, const double* __restrict__ base, double dt, int target, const int32_t* __restrict__ kstep, uint8_t* __restrict__ hold, double* __restrict__ t0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = kstep[i];
+    if (hold[i] != 1) hold[i] = k >= target ? 2 : 0;         // 1 = a solve continues: untouched
+    t0[i] = __dadd_rn(base[i], __dmul_rn((double)k, dt));    // t_k = t0 + k*dt as the host computes it (no FMA contraction)
+}
+void launch_round_begin(pgn_handle* h, double dt, int target) {
+    const size_t o = (size_t)h->v0;
+    k_round_begin<<<(h->nv + 255) / 256, 256, 0, h->stream>>>(h->nv, h->d_t0_base + o, dt, target, h->d_kstep + o, h->d_hold + o, h->d_t0 + o);
+    h->launches++;
+}
+// vehicles that have not reached `target` steps yet (the catch-up rounds of a simulate loop with deferred solves run until this is 0)
+__global__ void k_count_lag(int B, const int32_t* __restrict__ kstep, int target, int* __restrict__ out) {
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    int c = 0;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < B; v += gridDim.x * blockDim.x) c += kstep[v] < target;
+    if (c) atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && s) atomicAdd(out, s);
+}
+void launch_count_lag(pgn_handle* h, int target) {
+    cudaMemsetAsync(h->d_lag, 0, sizeof(int), h->stream);
+    k_count_lag<<<std::min(64, (h->B + 255) / 256), 256, 0, h->stream>>>(h->B, h->d_kstep, target, h->d_lag);
     h->launches++;
 }
 void launch_pack_out(pgn_handle* h, const double* d_soa, double* d_aos, int k) {

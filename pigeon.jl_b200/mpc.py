@@ -306,6 +306,11 @@ class BatchedTrajectoryTrackingMPC:
             check(self._lib.pgn_get_history(self._h, C.byref(C.c_int32(0)), dptr(qs), dptr(us), dptr(xs), dptr(ps)))
         return qs, xs, us, ps
 
+    def set_solve_cap(self, iters):
+        """ADMM iterations of one QP per launch inside the simulate loops (0 = unlimited): a straggler QP then delays only its own vehicle;
+        results do not depend on it."""
+        check(self._lib.pgn_set_solve_cap(self._h, int(iters)))
+
     def set_pipeline_parts(self, parts):
         """Run the fused entry points as `parts` vehicle ranges on their own streams (0: automatic, 1: off); results do not depend on it."""
         check(self._lib.pgn_set_pipeline_parts(self._h, int(parts)))

@@ -266,3 +266,48 @@ def test_pipelined_submit_collect_is_bit_identical(p, kind):
         assert np.all(np.isfinite(last[-1])) and it.shape == (B,)
         g.close()
     ref.close()
+
+
+@pytest.mark.parametrize("kind,parts", [("coupled", 1), ("coupled", 4), ("decoupled", 3)])
+def test_deferred_solves_are_bit_identical(p, kind, parts):
+    """pgn_set_solve_cap: inside the simulate loops a QP that has not terminated after `cap` iterations of one launch continues in the next
+    round while only its vehicle waits.  With a cap of 25 or 50 almost every cold-start solve is cut several times; final states, controls,
+    solver statistics (total iteration counts included), warm-start state (checked through one more step) and the recorded histories must
+    be bit-identical to the uncapped loop — also when the loop is issued in pieces on one time axis, and with the NaN guard on."""
+    import torch
+    B = 101
+    trajs, tid, state, control, t0, other = batch(p, B, n_traj=4)
+    state = state.copy(); state[5, 4] = np.nan                      # one vehicle whose QP returns NaN: guard path (cold re-initialisation)
+    ctor = p.BatchedCoupledTrajectoryTrackingMPC if kind == "coupled" else p.BatchedDecoupledTrajectoryTrackingMPC
+    n = 12
+
+    def run(cap, pieces):
+        g = ctor(p.X1(), trajs, B, trajectory_index=tid)
+        g.set_pipeline_parts(parts)
+        g.set_guards(nan_fallback=True, pause_below_speed=0.0)
+        g.set_solve_cap(cap)
+        g.set_state(state, control, other)
+        g.set_history(n, 1)
+        d = torch.tensor(t0, dtype=torch.float64, device="cuda")
+        k = 0
+        for m in pieces:
+            g.simulate_device_async(d.data_ptr(), 0.01, m, k0=k); k += m
+        q, u = g.get_state()                                            # a getter: waits for the vehicles that are behind
+        st = g.stats()
+        hist = g.history()
+        nxt = g.step(t0 + 0.01 * n)                                     # warm-start state carried over correctly
+        out = (q, u, st["iters"], st["status"], st["rho"], st["rho_updates"], nxt) + hist
+        g.close()
+        return out
+    ref = run(0, [n])
+    assert np.isfinite(ref[0][np.arange(B) != 5]).all() and ref[2].max() > 50          # real closed loop, some long solves
+    for cap, pieces in ((25, [n]), (50, [5, 7]), (200, [1] * n)):
+        got = run(cap, pieces)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b, equal_nan=True), (cap, pieces)
+    with pytest.raises(p.PigeonError):
+        g = ctor(p.X1(), trajs, 4, trajectory_index=tid[:4])
+        try:
+            g.set_solve_cap(30)                                         # not a multiple of check_termination = 25
+        finally:
+            g.close()
