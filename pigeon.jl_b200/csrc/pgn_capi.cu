@@ -364,11 +364,8 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
     h->hold_on = 0; h->sim_open = 0; h->sim_target = 0; h->sim_dt = 0.0; h->round_cap = 0; h->h_lag = nullptr;
-    {   // deferred solves inside the simulate loops: on by default with 200 iterations per launch when the check / adaptation intervals divide it
-        const int c = h->st.check_termination, a = (h->st.adaptive_rho && h->st.adaptive_rho_interval > 0) ? h->st.adaptive_rho_interval : 1;
-        h->solve_cap = (c > 0 && 200 % c == 0 && 200 % a == 0) ? 200 : 0;
-        if (getenv("PGN_SOLVE_CAP")) h->solve_cap = atoi(getenv("PGN_SOLVE_CAP"));
-    }
+    h->solve_cap = -1; h->sim_cap = 0;      // deferred solves inside the simulate loops: automatic (effective_cap)
+    if (getenv("PGN_SOLVE_CAP")) h->solve_cap = atoi(getenv("PGN_SOLVE_CAP"));
     CK(cudaMemset(h->d_hold, 0, B)); CK(cudaMemset(h->d_kstep, 0, B * 4)); CK(cudaMemset(h->d_iters_acc, 0, B * 4));
     if (cudaMallocHost((void**)&h->h_lag, 16) != cudaSuccess) return bail(set_err(PGN_ENOMEM, "cudaMallocHost failed"));
     h->h_ring = nullptr; h->d_ring = nullptr; h->ring_head = h->ring_tail = h->ring_count = h->ring_created = 0;
@@ -796,8 +793,19 @@ int pgn_rollout(pgn_handle* h, double dt) {
 }
 // the `simulate` loop on the device: every pipeline part runs ALL its steps on its own stream (a vehicle's step k+1 depends only on its own
 // step k), so the parts drift apart and the small per-vehicle kernels of one part fill the SMs the ADMM kernel of another leaves idle
+// effective cap of this handle: the explicit setting, or (automatic, solve_cap < 0) 200 iterations when a range's ADMM launch is at most two
+// waves of CTAs — there one long solve IS the launch time — and none for large ranges, whose launches absorb a few-hundred-iteration straggler
+// in their many waves while a deferred one would surface in the catch-up rounds (measured: tools/gpu_cap_sweep.sh)
+static int effective_cap(const pgn_handle* h) {
+    if (h->solve_cap >= 0) return h->solve_cap;
+    const int c = h->st.check_termination, a = (h->st.adaptive_rho && h->st.adaptive_rho_interval > 0) ? h->st.adaptive_rho_interval : 1;
+    if (!(c > 0 && 200 % c == 0 && 200 % a == 0)) return 0;
+    const int per_range = h->B / (h->parts > 0 ? h->parts : 1), resident = h->num_sms * h->admm_ctas_per_sm;
+    return per_range <= 2 * resident ? 200 : 0;
+}
 static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
-    if (h->solve_cap > 0 && !h->profiling) {
+    const int cap = effective_cap(h);
+    if (cap > 0 && !h->profiling) {
         // Deferred solves: every vehicle counts its own steps.  A round = one step attempt of every vehicle of the range that is not held; a QP
         // that uses up its share of ADMM iterations keeps its vehicle on hold and continues in the next round's launch, so a 4000-iteration
         // straggler costs its own vehicle a few rounds instead of costing every vehicle of the range the whole solve.  n_steps rounds are
@@ -808,7 +816,7 @@ static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
         }
         h->sim_target = k0 + n_steps; h->sim_dt = dt; h->sim_open = 1;
         if (h->hist_stride > 0) { const int nrec = std::min(h->hist_cap, (h->sim_target + h->hist_stride - 1) / h->hist_stride); if (nrec > h->hist_n) h->hist_n = nrec; }
-        h->hold_on = 1; h->round_cap = h->solve_cap;
+        h->hold_on = 1; h->round_cap = cap; h->sim_cap = cap;
         int rc = for_each_part(h, [&]() {
             for (int k = 0; k < n_steps; k++) {
                 launch_round_begin(h, dt, h->sim_target);
@@ -842,7 +850,7 @@ static int finish_sim(pgn_handle* h) {
         CK(cudaStreamSynchronize(h->stream));
         if (*h->h_lag == 0) break;
         if (round > 100000) return set_err(PGN_ECUDA, "simulate: %d vehicles do not reach step %d", *h->h_lag, h->sim_target);
-        h->hold_on = 1; h->round_cap = 5 * h->solve_cap;
+        h->hold_on = 1; h->round_cap = 5 * h->sim_cap;
         int rc = for_each_part(h, [&]() {
             launch_round_begin(h, h->sim_dt, h->sim_target);
             return step_rollout_body(h, h->d_t0, h->sim_dt, h->hist_stride > 0 ? 0 : -1);
@@ -872,7 +880,7 @@ int pgn_simulate_device(pgn_handle* h, const double* d_t0, double dt, int32_t k0
     ENTER_NODRAIN(h, "NULL handle"); REQUIRE(d_t0 && n_steps >= 0 && k0 >= 0, "bad argument");
     if (h->ring_count) drain_ring(h);
     // a call that continues the time axis of the previous one (k0 = its end) leaves the vehicles that are behind where they are: they go on here
-    if (h->sim_open && !(k0 == h->sim_target && dt == h->sim_dt && h->solve_cap > 0)) { int rc0 = finish_sim(h); if (rc0) return rc0; }
+    if (h->sim_open && !(k0 == h->sim_target && dt == h->sim_dt && effective_cap(h) > 0)) { int rc0 = finish_sim(h); if (rc0) return rc0; }
     CK(cudaMemcpyAsync(h->d_t0_base, d_t0, (size_t)h->B * 8, cudaMemcpyDeviceToDevice, h->stream));
     if (k0 == 0) h->hist_n = 0;
     int rc = simulate_enqueue(h, dt, k0, n_steps);
@@ -935,7 +943,7 @@ int pgn_get_history(pgn_handle* h, int32_t* n_records, double* qs, double* us, d
 }
 int pgn_set_solve_cap(pgn_handle* h, int32_t iters) {
     ENTER(h, "NULL handle");
-    REQUIRE(iters >= 0, "iters must be >= 0");
+    REQUIRE(iters >= -1, "iters must be >= 0, or -1 (automatic)");
     if (iters > 0) {
         const int c = h->st.check_termination, a = (h->st.adaptive_rho && h->st.adaptive_rho_interval > 0) ? h->st.adaptive_rho_interval : 1;
         REQUIRE(c > 0 && iters % c == 0 && iters % a == 0, "the cap must be a multiple of check_termination and of adaptive_rho_interval");

@@ -146,7 +146,7 @@ struct pgn_handle {
     // Deferred solves inside the simulate loops (pgn_set_solve_cap): a QP that has not terminated after `solve_cap` iterations of one ADMM
     // launch saves its iterates and continues in the launch of the NEXT round, while its vehicle holds (no new step) and all others go on; every
     // vehicle therefore counts its own steps.  d_hold: 0 steps normally, 1 solve continues, 2 reached the target step count.
-    int solve_cap, round_cap, hold_on, sim_target, sim_open; double sim_dt;
+    int solve_cap, sim_cap, round_cap, hold_on, sim_target, sim_open; double sim_dt;
     uint8_t* d_hold; int32_t *d_kstep, *d_iters_acc; int *d_lag, *h_lag;
     int admm_tmem, admm_ctas_per_sm;                     // tensor-memory variant of the ADMM kernel (two coupled N = 31 QPs per SM); resident CTAs per SM
     double* d_admm_scratch;                              // its per-CTA global scratch
