@@ -99,10 +99,10 @@ size_t admm_smem_bytes_tmem(const QpTables& t, int nthreads) {
     return d * 8 + align_up((size_t)t.Nk, 8) + 64;
 }
 // whether the tensor-memory variant can run this QP: iteration views in front of the dense tail, TMEM columns within one CTA's half of an SM
-bool admm_tmem_fits(const QpTables& t) {
-    return t.tmem_layout && t.tmem_cols <= 256 &&
+bool admm_tmem_fits(const QpTables& t, int nthreads) {
+    return t.tmem_layout && t.tmem_cols <= 256 && t.nwarps * 32 == nthreads &&
            tm_iter_view_doubles(t.nslots, t.Nk, (int)t.bent.size(), (int)t.sol_orow.size() - orow_fwd_count(t)) <= (size_t)t.nslots &&
-           2 * (admm_smem_bytes_tmem(t, 256) + 1024) <= (size_t)227 * 1024;
+           2 * (admm_smem_bytes_tmem(t, nthreads) + 1024) <= (size_t)228 * 1024;
 }
 
 // nthreads: threads of the CTA (the reduction scratch holds 16 doubles per warp); tables_in_smem: whether the static warp programs of the
@@ -145,13 +145,16 @@ namespace v256 {
 #undef ADMM_TABSMEM
 #undef ADMM_TMEM
 #define ADMM_TMEM 1
-#define ADMM_NT 256
 #define ADMM_MINCTAS 2
 #define ADMM_TABSMEM 0
+#define ADMM_NT 256
 namespace vtm {
 #include "pgn_admm_kernel.inc"
 }
 #undef ADMM_NT
+// Measured with 12 and 16 warps per QP (384 / 512 threads, 80 / 64 registers per thread with 72 / 230 bytes of spills, still two CTAs per SM):
+// 487 k / 456 k steps/s against 519 k with 8 warps — more warps shorten a lone QP (cold start 255 k against 216 k) but two QPs of 8 warps
+// fill the issue slots better than they do (tools/gpu_tmem_threads.sh).  Only the 256-thread build is kept.
 #undef ADMM_MINCTAS
 #undef ADMM_TABSMEM
 #undef ADMM_TMEM
@@ -173,15 +176,19 @@ __global__ void __launch_bounds__(1024) k_admm_order(const int32_t* __restrict__
 }
 
 int admm_configure(pgn_handle* h) {
-    const bool small = h->admm_threads == 256;
+    const bool small = h->admm_threads == 256 && !h->admm_tmem;
     cudaError_t e;
     if (h->admm_tmem) {
-        h->admm_smem_bytes = (int)admm_smem_bytes_tmem(h->tab, 256);
-        e = cudaFuncSetAttribute(vtm::k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(vtm::k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);
-        // two CTAs per SM need the whole shared-memory carve-out (2 x 111 KB)
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(vtm::k_admm<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(vtm::k_admm<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        h->admm_smem_bytes = (int)admm_smem_bytes_tmem(h->tab, h->admm_threads);
+        e = cudaSuccess;
+        // two CTAs per SM need the whole shared-memory carve-out (2 x 112 KB)
+#define TM_ATTR(ns)                                                                                                                                   \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ns::k_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);          \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ns::k_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->admm_smem_bytes);           \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ns::k_admm<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ns::k_admm<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        TM_ATTR(vtm)
+#undef TM_ATTR
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for every kernel that contains tcgen05.alloc (it cannot know the column
         // count), but two CTAs that allocate 256 of the 512 columns each do share an SM: measured with a per-SM counter, tools/ubench/occ_tmem.cu.
         // Resident CTAs follow from shared memory (2 x (bytes + 1 KB) <= 228 KB) and registers (<= 128 x 256 x 2), both checked at build / create time.
@@ -215,15 +222,18 @@ void launch_admm(pgn_handle* h) {
     a.skip = (h->guard_pause > 0.0 || h->in_callback) ? h->d_skip : nullptr; a.cold = h->d_cold;
     a.hold = h->hold_on ? h->d_hold : nullptr; a.iters_acc = h->d_iters_acc; a.iter_cap = h->hold_on ? h->round_cap : 0;
     for (size_t i = 0; i < h->tab.sol_ph_ptr.size() && i <= ADMM_MAX_PHASES; i++) a.ph_ptr[i] = h->tab.sol_ph_ptr[i];
-    const bool small = h->admm_threads == 256;
-    const int full = h->num_sms * (small ? 2 : 1);
+    const bool small = h->admm_threads == 256 && !h->admm_tmem;
+    const int full = h->num_sms * h->admm_ctas_per_sm;
     int grid = full;
     if (grid > h->nv) grid = h->nv;
     // launches of different pipeline parts may overlap: every part owns a slice of the scratch
     a.scratch = h->admm_tmem ? h->d_admm_scratch + (size_t)h->part * full * tm_scratch_doubles(h->tab.Nk, h->tab.nnzA) : nullptr;
     if (h->admm_tmem) {
-        if (a.cycles) vtm::k_admm<true><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
-        else vtm::k_admm<false><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
+#define TM_LAUNCH(ns, nt)                                                                      \
+        if (a.cycles) ns::k_admm<true><<<grid, nt, h->admm_smem_bytes, h->stream>>>(a);       \
+        else ns::k_admm<false><<<grid, nt, h->admm_smem_bytes, h->stream>>>(a);
+        TM_LAUNCH(vtm, 256)
+#undef TM_LAUNCH
     } else if (small) {
         if (a.cycles) v256::k_admm<true><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
         else v256::k_admm<false><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);

@@ -256,12 +256,13 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
             if (want != 3 && 2 * (sm + 1024) <= (size_t)227 * 1024) h->admm_threads = 256;
             else if (want == 256) { delete h; return set_err(PGN_EINVAL, "PGN_ADMM_VARIANT=256: two CTAs of %zu bytes do not fit one SM", sm); }
             else {
-                if (!h->tab.tmem_layout && !build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 8, 1)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
-                if (admm_tmem_fits(h->tab)) { h->admm_threads = 256; h->admm_tmem = 1; }
+                const int tm_threads = 256;      // 384 / 512 threads per QP were measured and lose (pgn_admm.cu)
+                if ((!h->tab.tmem_layout || tm_threads != 256) && !build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), tm_threads / 32, 1)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
+                if (admm_tmem_fits(h->tab, tm_threads)) { h->admm_threads = tm_threads; h->admm_tmem = 1; }
                 else if (want == 3) { delete h; return set_err(PGN_EINVAL, "PGN_ADMM_VARIANT=tmem: this QP does not fit (TMEM columns %d, shared memory %zu bytes per CTA)", h->tab.tmem_cols, admm_smem_bytes_tmem(h->tab, 256)); }
             }
         }
-        if (h->admm_threads == 512 &&
+        if (h->admm_threads == 512 && !h->admm_tmem &&
             !build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 16)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
     }
     auto bail = [&](int rc) { pgn_destroy(h); return rc; };

@@ -179,7 +179,7 @@ void launch_record(pgn_handle* h, int slot);                        // history r
 void launch_pack_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);        // [k][B] -> [B][k] for the current vehicle range only
 size_t admm_smem_bytes(const QpTables& t, int nthreads, bool tables_in_smem);
 size_t admm_smem_bytes_tmem(const QpTables& t, int nthreads);
-bool admm_tmem_fits(const QpTables& t);
+bool admm_tmem_fits(const QpTables& t, int nthreads);
 size_t admm_scratch_doubles(const pgn_handle* h);
 int admm_orow_fwd(const QpTables& t);
 int admm_configure(pgn_handle* h);   // sets the max dynamic shared memory attribute; returns cudaError

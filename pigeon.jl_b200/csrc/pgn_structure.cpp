@@ -382,6 +382,9 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     const int NWARP = nwarps;
     Q.nwarps = nwarps;
     Q.tmem_layout = tmem_layout; Q.tmem_cols = 0;
+    // the tensor-memory build has no shared memory to spare: its solve tasks are always cut by the 8-warp cost model (the most compact slot
+    // layout), whatever the number of warps that run them
+    const int SCHED_NW = tmem_layout ? 8 : NWARP;
     // TMEM layout: columns used so far per quadrant; a phase's task list is permuted inside every round of NWARP tasks (one task per warp and
     // round either way, so the time balance of the schedule is unchanged) such that the biggest task of the round goes to the emptiest quadrant
     int quad_cols[4] = {0, 0, 0, 0};
@@ -438,7 +441,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
             len[r - pa] = (int)ents[r - pa].size();
         }
         size_t tip = 0;
-        for (const SchedTask& t : place_tasks(schedule_phase(len, NWARP))) {
+        for (const SchedTask& t : place_tasks(schedule_phase(len, SCHED_NW))) {
             tmem_place(tip++, t.K);
             const int g = 1 << t.sh, ebase = nslots, rbase = (int)Q.sol_orow.size();
             Q.fidx.resize(ebase + 32 * t.K, (uint16_t)Nk);
@@ -476,7 +479,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
             len[c - pa] = (int)ents[c - pa].size();
         }
         size_t tip = 0;
-        for (const SchedTask& t : place_tasks(schedule_phase(len, NWARP))) {
+        for (const SchedTask& t : place_tasks(schedule_phase(len, SCHED_NW))) {
             tmem_place(tip++, t.K);
             const int g = 1 << t.sh, ebase = (int)Q.bent.size(), rbase = (int)Q.sol_orow.size();
             Q.bent.resize(ebase + 32 * t.K, (uint32_t)Q.zslot | ((uint32_t)Nk << 16));
