@@ -373,26 +373,40 @@ def hji_roofline(cx, p, mpc, M=1 << 24):
     hi = torch.tensor([r[1] for r in synthetic.HJI_RANGES], dtype=torch.float64, device=cx.dev)[:, None]
     x = (lo + (hi - lo) * (0.001 + 0.998 * torch.rand((7, M), dtype=torch.float64, device=cx.dev, generator=g))).contiguous()
     V = torch.empty(M, dtype=torch.float64, device=cx.dev); gV = torch.empty((7, M), dtype=torch.float64, device=cx.dev)
-    for _ in range(2):
-        mpc.hji_lookup_device(M, x.data_ptr(), V.data_ptr(), gV.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    best = 1e30
-    for _ in range(3):
-        e0.record(cx.stream)
-        mpc.hji_lookup_device(M, x.data_ptr(), V.data_ptr(), gV.data_ptr())
-        e1.record(cx.stream)
-        torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
+
+    def timed(mode):
+        mpc.set_hji_lookup_order(mode)
+        for _ in range(2):
+            mpc.hji_lookup_device(M, x.data_ptr(), V.data_ptr(), gV.data_ptr())
+        best = 1e30
+        for _ in range(3):
+            e0.record(cx.stream)
+            mpc.hji_lookup_device(M, x.data_ptr(), V.data_ptr(), gV.data_ptr())
+            e1.record(cx.stream)
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+    ms_input = timed(0)          # the queries in the order they were given: a random 4 KB gather per query
+    Vi = V.clone()
+    best = timed(-1)             # default: counting sort by grid cell + the same gather in cell order (sort time included)
+    same = bool(torch.equal(Vi, V))
+    mpc.set_hji_lookup_order(-1)
     peak, src = cx.hbm_peak
     ach = M * 4096.0 / (best * 1e-3) / 1e9
-    out = {"kernel": "k_hji_lookup", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src, "queries": M, "launch_ms": best,
-           "queries_per_s": M / (best * 1e-3), "algorithmic_bytes_per_query": 4096, "traffic": None,
-           "note": "128 corners x one 32-byte record {gradV[7], V} per query; inputs (the 319 MB grid) are larger than the 126 MB L2"}
-    tr = ncu_metric("r2_hji_lookup_ncu_full.md", "r1_hji_lookup_ncu_full.md")
+    out = {"kernel": "k_hji_keys + scan + k_hji_scatter + k_hji_lookup_perm (cell-ordered lookup)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": src, "queries": M, "launch_ms": best,
+           "queries_per_s": M / (best * 1e-3), "algorithmic_bytes_per_query": 4096, "traffic": None, "bit_identical_to_input_order": same,
+           "input_order": {"kernel": "k_hji_lookup", "launch_ms": ms_input, "achieved": M * 4096.0 / (ms_input * 1e-3) / 1e9, "frac": M * 4096.0 / (ms_input * 1e-3) / 1e9 / peak,
+                           "note": "random gather: every 64-byte corner pair costs ~100 bytes of DRAM traffic (tools/ubench/hji_fetch.cu), 6.6 KB per query, DRAM pipe at 96 % of the measured copy bandwidth"},
+           "note": "128 corners x one 32-byte record {gradV[7], V} per query; the 319 MB grid is larger than the 126 MB L2; frac > 1 is possible in cell order because neighbouring queries share corners through L2 (algorithmic bytes count every query's 4 KB)"}
+    tr = ncu_metric("r2_hji_lookup_ncu.md")
     if tr:
-        out["traffic"], out["traffic_source"] = tr["dram_bytes"], tr["source"] + " (DRAM bytes read + written by one launch of 2^22 queries, scaled to this launch's query count)"
-        if tr.get("queries"):
-            out["traffic"] = tr["dram_bytes"] * M / tr["queries"]
+        out["traffic"] = tr["dram_bytes"] * (M / tr["queries"] if tr.get("queries") else 1.0)
+        out["traffic_source"] = tr["source"] + " (DRAM bytes read + written by the kernels of one cell-ordered lookup, scaled to this launch's query count)"
+    tr0 = ncu_metric("r1_hji_lookup_ncu_full.md")
+    if tr0:
+        out["input_order"]["traffic"] = tr0["dram_bytes"] * M / (1 << 22)
+        out["input_order"]["traffic_source"] = tr0["source"] + " (one launch of 2^22 queries, scaled)"
     return out
 
 

@@ -221,6 +221,10 @@ PGN_API int pgn_hji_optimal_control(pgn_handle* h, int32_t M, const double* x, c
  * gets BicycleControl(longitudinal_params, optimal_control(...)) from get_next_control / step instead of the QP's node-2 control
  * (the QP is still solved, as in the callback).  Off by default. */
 PGN_API int pgn_set_hji_policy(pgn_handle* h, int32_t on);
+/* Visiting order of the stand-alone lookups: 1 = the queries are counting-sorted by grid cell first, so that queries of the same and of
+ * neighbouring cells find their corners in L2 (a random query moves 6.6 KB through DRAM for its 4 KB of corners; in cell order the whole set
+ * reads about the table size); 0 = input order; -1 (default) = cell order from 2^19 queries up.  Results are bit-identical. */
+PGN_API int pgn_set_hji_lookup_order(pgn_handle* h, int32_t mode);
 /* device variant for the HBM roofline micro-benchmark: d_x [7][M] field-major, d_V [M], d_gradV [7][M] */
 PGN_API int pgn_hji_lookup_device(pgn_handle* h, int32_t M, const double* d_x, double* d_V, double* d_gradV);
 /* device pointers of library-owned buffers (for zero-copy gathers through torch.distributed / NCCL) */

@@ -31,7 +31,7 @@ SYMBOLS = ["pgn_default_config", "pgn_x1_vehicle_params", "pgn_default_control_p
            "pgn_hji_lookup_device", "pgn_device_controls", "pgn_device_stats", "pgn_set_profiling", "pgn_get_stage_ms", "pgn_get_admm_cycles",
            "pgn_get_hji_values", "pgn_hji_optimal_control", "pgn_set_hji_policy", "pgn_from_autobox", "pgn_step_rollout_device", "pgn_set_path_search_window",
            "pgn_simulate_device", "pgn_set_pipeline_parts", "pgn_get_pipeline_parts", "pgn_set_history", "pgn_get_history", "pgn_comm_unique_id",
-           "pgn_set_solve_cap", "pgn_step_submit", "pgn_step_collect", "pgn_steps_in_flight", "pgn_comm_init_rank", "pgn_comm_init_all", "pgn_comm_destroy", "pgn_gather", "pgn_gather_all"]
+           "pgn_set_solve_cap", "pgn_set_hji_lookup_order", "pgn_step_submit", "pgn_step_collect", "pgn_steps_in_flight", "pgn_comm_init_rank", "pgn_comm_init_all", "pgn_comm_destroy", "pgn_gather", "pgn_gather_all"]
 
 _lib = None
 
@@ -62,6 +62,7 @@ def load():
     lib.pgn_step_collect.argtypes = [C.c_void_p, C.c_void_p]
     lib.pgn_steps_in_flight.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     lib.pgn_set_solve_cap.argtypes = [C.c_void_p, C.c_int32]
+    lib.pgn_set_hji_lookup_order.argtypes = [C.c_void_p, C.c_int32]
     lib.pgn_set_history.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.pgn_get_history.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pgn_comm_unique_id.argtypes = [C.c_void_p]

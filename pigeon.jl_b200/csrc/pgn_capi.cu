@@ -364,6 +364,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->path_window = 0; CK(cudaMemset(h->d_last_seg, 0xff, B * 4));
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
+    h->hji_sort = getenv("PGN_HJI_SORT") ? atoi(getenv("PGN_HJI_SORT")) : -1; h->d_hji_ws = nullptr; h->hji_ws_bytes = 0;
     h->hold_on = 0; h->sim_open = 0; h->sim_target = 0; h->sim_dt = 0.0; h->round_cap = 0; h->h_lag = nullptr;
     h->solve_cap = -1; h->sim_cap = 0;      // deferred solves inside the simulate loops: automatic (effective_cap)
     if (getenv("PGN_SOLVE_CAP")) h->solve_cap = atoi(getenv("PGN_SOLVE_CAP"));
@@ -428,6 +429,7 @@ int pgn_destroy(pgn_handle* h) {
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_lag) cudaFreeHost(h->h_lag);
+    if (h->d_hji_ws) cudaFree(h->d_hji_ws);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->ring_created)
         for (int sl = 0; sl < PGN_RING; sl++) { cudaEventDestroy(h->ring_h2d[sl]); for (int p = 0; p < PGN_MAX_PARTS; p++) cudaEventDestroy(h->ring_done[sl][p]); }
@@ -1062,6 +1064,12 @@ int pgn_set_path_search_window(pgn_handle* h, int32_t half_width) {
     h->epoch++;
     h->path_window = half_width;
     CK(cudaMemsetAsync(h->d_last_seg, 0xff, (size_t)h->B * 4, h->stream));
+    return PGN_OK;
+}
+int pgn_set_hji_lookup_order(pgn_handle* h, int32_t mode) {
+    ENTER(h, "NULL handle");
+    REQUIRE(mode >= -1 && mode <= 1, "mode must be -1 (automatic), 0 (input order) or 1 (cell order)");
+    h->hji_sort = mode;
     return PGN_OK;
 }
 int pgn_set_hji_policy(pgn_handle* h, int32_t on) { ENTER(h, "NULL handle"); h->epoch++; h->hji_policy = on != 0; return PGN_OK; }

@@ -140,6 +140,8 @@ struct pgn_handle {
     // trajectories / HJI
     pgn::TrajView traj; bool have_traj, have_assign;
     pgn::HjiView hji;
+    int hji_sort;                                        // stand-alone lookups: -1 automatic (queries visited in cell order from 2^19 queries up), 0 never, 1 always
+    void* d_hji_ws; size_t hji_ws_bytes;                 // work space of the cell-ordered lookup
     // profiling
     int profiling; cudaEvent_t ev[2]; double stage_ms[8]; long long launches;
     int admm_smem_bytes, admm_threads, num_sms;

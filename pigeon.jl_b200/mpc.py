@@ -388,6 +388,10 @@ class BatchedTrajectoryTrackingMPC:
         """use_HJI_policy[] of the callback (src/ros_integration.jl:47,115-118): V <= HJI_eps => the "hammer" control."""
         check(self._lib.pgn_set_hji_policy(self._h, int(bool(on))))
 
+    def set_hji_lookup_order(self, mode):
+        """Stand-alone lookups: 1 visit the queries in grid-cell order (counting sort; corners shared through L2), 0 input order, -1 automatic."""
+        check(self._lib.pgn_set_hji_lookup_order(self._h, int(mode)))
+
     def hji_lookup_device(self, M, d_x, d_V, d_g):
         check(self._lib.pgn_hji_lookup_device(self._h, int(M), C.c_void_p(d_x), C.c_void_p(d_V), C.c_void_p(d_g)))
 

@@ -311,3 +311,39 @@ def test_deferred_solves_are_bit_identical(p, kind, parts):
             g.set_solve_cap(30)                                         # not a multiple of check_termination = 25
         finally:
             g.close()
+
+
+def test_cell_ordered_hji_lookup_is_bit_identical(p):
+    """pgn_set_hji_lookup_order: large stand-alone lookups visit the queries in grid-cell order (counting sort by cell, then the same
+    interpolation) so that neighbouring queries share their corners through L2.  Values and gradients must equal the input-order kernel bit
+    for bit — in-grid, on faces / knots, and outside the grid — and agree with the oracle."""
+    dims = (7, 6, 5, 5, 4, 5, 4)
+    knots, V, gV = p.synthetic.analytic_hji_grid(dims)
+    g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), [p.straight_trajectory(30.0, 5.0)], 1)
+    g.set_HJI_cache(p.HJICache(knots, V, gV))
+    rng = np.random.default_rng(11)
+    M = 70001                                   # not a multiple of anything (the automatic switch to cell order is at 2^19 queries)
+    lo = np.array([r[0] for r in p.synthetic.HJI_RANGES]); hi = np.array([r[1] for r in p.synthetic.HJI_RANGES])
+    x = lo + (hi - lo) * rng.uniform(-0.05, 1.05, (M, 7))         # ~30 % of the queries leave the grid in some dimension
+    x[:500, 0] = knots[0][rng.integers(0, dims[0], 500)]          # exactly on knots and faces
+    x[500:900, 3] = hi[3]; x[900:1200, 6] = lo[6]
+    g.set_hji_lookup_order(0)
+    V0, g0 = g.hji_lookup(x)
+    g.set_hji_lookup_order(1)
+    V1, g1 = g.hji_lookup(x)
+    g.set_hji_lookup_order(-1)
+    V2, g2 = g.hji_lookup(x)
+    assert np.array_equal(V0, V1) and np.array_equal(g0, g1) and np.array_equal(V0, V2) and np.array_equal(g0, g2)
+    inside = np.isfinite(V0)
+    assert 0.3 < inside.mean() < 0.9 and np.all(g0[~inside] == 0)
+    cache = o.HjiCache(knots, V, gV)
+    for j in rng.integers(0, M, 300):
+        v, gr = cache.lookup(x[j])
+        if np.isinf(v):
+            assert np.isinf(V1[j])
+        else:
+            assert abs(v - V1[j]) < 1e-6 and np.max(np.abs(gr - g1[j])) < 1e-6
+    g.set_hji_lookup_order(1)
+    Vs, gs = g.hji_lookup(x[:33])               # tiny sets work in cell order too
+    assert np.array_equal(Vs, V0[:33]) and np.array_equal(gs, g0[:33])
+    g.close()
