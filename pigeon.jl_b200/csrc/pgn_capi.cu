@@ -31,7 +31,7 @@ extern "C" void pgn_set_error_(const char* msg) { snprintf(g_err, sizeof(g_err),
         if (!(cond)) return set_err(PGN_EINVAL, "%s", msg);  \
     } while (0)
 
-extern "C" { static int finish_sim(pgn_handle* h); }      // defined beside the simulate loop, inside the extern "C" block
+extern "C" { static int finish_sim(pgn_handle* h); static void drop_round_graph(pgn_handle* h, int p); }      // defined beside the simulate loop, inside the extern "C" block
 static void drain_ring(pgn_handle* h) {
     for (int i = 0, sl = h->ring_tail; i < h->ring_count; i++, sl = (sl + 1) % PGN_RING)
         for (int p = 0; p < h->ring_parts[sl]; p++) cudaEventSynchronize(h->ring_done[sl][p]);
@@ -365,6 +365,8 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
     h->hji_sort = getenv("PGN_HJI_SORT") ? atoi(getenv("PGN_HJI_SORT")) : -1; h->d_hji_ws = nullptr; h->hji_ws_bytes = 0;
+    for (int p = 0; p < PGN_MAX_PARTS; p++) h->rg_exec[p] = nullptr;
+    h->sim_axis_valid = 0;
     h->hold_on = 0; h->sim_open = 0; h->sim_target = 0; h->sim_dt = 0.0; h->round_cap = 0; h->h_lag = nullptr;
     h->solve_cap = -1; h->sim_cap = 0;      // deferred solves inside the simulate loops: automatic (effective_cap)
     if (getenv("PGN_SOLVE_CAP")) h->solve_cap = atoi(getenv("PGN_SOLVE_CAP"));
@@ -426,6 +428,7 @@ int pgn_destroy(pgn_handle* h) {
     pgn_comm_destroy(h);
     for (void* p : h->allocs) cudaFree(p);
     if (h->cb_has_exec) { cudaGraphExecDestroy(h->cb_exec); cudaGraphDestroy(h->cb_graph); }
+    for (int p = 0; p < PGN_MAX_PARTS; p++) drop_round_graph(h, p);
     if (h->h_io) cudaFreeHost(h->h_io);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_lag) cudaFreeHost(h->h_lag);
@@ -531,6 +534,7 @@ static int stage_inputs(pgn_handle* h, const double* q, const double* u, const d
 }
 int pgn_set_state(pgn_handle* h, const double* q, const double* u, const double* other, const double* toff) {
     ENTER(h, "NULL handle");
+    h->sim_axis_valid = 0;
     int flags;
     int rc = stage_inputs(h, q, u, other, toff, nullptr, &flags);      // the caller's arrays are copied before the call returns; the rest is stream-ordered
     if (rc) return rc;
@@ -806,41 +810,66 @@ static int effective_cap(const pgn_handle* h) {
     const int per_range = h->B / (h->parts > 0 ? h->parts : 1), resident = h->num_sms * h->admm_ctas_per_sm;
     return per_range <= 2 * resident ? 200 : 0;
 }
+// One round of one pipeline part as a CUDA graph.  Nothing in a round depends on the host: the step time comes from the per-vehicle step
+// counters, the target step count sits in device memory, the recorder files by the counters — so the graph is captured once per part (and
+// again only when a setter bumps the epoch, or dt / cap / recorder change) and every further round is ONE graph launch instead of 13 kernel
+// launches and 4 event operations.  The loop was host-bound from 4 parts up (tools/gpu_parts_sweep.sh: 5 parts 401 k steps/s against 514 k with 4).
+static void drop_round_graph(pgn_handle* h, int p) {
+    if (h->rg_exec[p]) { cudaGraphExecDestroy(h->rg_exec[p]); cudaGraphDestroy(h->rg_graph[p]); h->rg_exec[p] = nullptr; }
+}
+static int ensure_round_graph(pgn_handle* h, int p, double dt, int cap, int rec) {      // called with the part's streams / range swapped into the handle
+    if (h->rg_exec[p] && h->rg_epoch[p] == h->epoch && h->rg_dt[p] == dt && h->rg_cap[p] == cap && h->rg_rec[p] == rec && h->rg_v0[p] == h->v0 && h->rg_nv[p] == h->nv) return PGN_OK;
+    drop_round_graph(h, p);
+    const long long l0 = h->launches;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    launch_round_begin(h, dt);
+    int rc = step_rollout_body(h, h->d_t0, dt, rec ? 0 : -1);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    h->rg_launches[p] = h->launches - l0; h->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return set_err(PGN_ECUDA, "graph capture of a simulate round failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->rg_exec[p], g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); h->rg_exec[p] = nullptr; return set_err(PGN_ECUDA, "graph instantiation failed: %s", cudaGetErrorString(e)); }
+    h->rg_graph[p] = g; h->rg_epoch[p] = h->epoch; h->rg_dt[p] = dt; h->rg_cap[p] = cap; h->rg_rec[p] = rec; h->rg_v0[p] = h->v0; h->rg_nv[p] = h->nv;
+    return PGN_OK;
+}
+// The simulate loop in ROUNDS: a round = one step attempt of every vehicle of the range that is not held.  Every vehicle counts its own steps
+// (d_kstep); with deferred solves (cap > 0) a QP that uses up its share of ADMM iterations keeps its vehicle on hold and continues in the next
+// round's launch, so a 4000-iteration straggler costs its own vehicle a few rounds instead of costing every vehicle of the range the whole
+// solve; the vehicles that fell behind are finished by finish_sim at the next point that needs results.  n_steps rounds are enqueued here.
 static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
     const int cap = effective_cap(h);
-    if (cap > 0 && !h->profiling) {
-        // Deferred solves: every vehicle counts its own steps.  A round = one step attempt of every vehicle of the range that is not held; a QP
-        // that uses up its share of ADMM iterations keeps its vehicle on hold and continues in the next round's launch, so a 4000-iteration
-        // straggler costs its own vehicle a few rounds instead of costing every vehicle of the range the whole solve.  n_steps rounds are
-        // enqueued here; the vehicles that fell behind are finished by finish_sim at the next point that needs results.
-        if (k0 == 0) {
-            CK(cudaMemsetAsync(h->d_kstep, 0, (size_t)h->B * 4, h->stream));
-            CK(cudaMemsetAsync(h->d_hold, 0, h->B, h->stream));
-        }
-        h->sim_target = k0 + n_steps; h->sim_dt = dt; h->sim_open = 1;
-        if (h->hist_stride > 0) { const int nrec = std::min(h->hist_cap, (h->sim_target + h->hist_stride - 1) / h->hist_stride); if (nrec > h->hist_n) h->hist_n = nrec; }
-        h->hold_on = 1; h->round_cap = cap; h->sim_cap = cap;
-        int rc = for_each_part(h, [&]() {
-            for (int k = 0; k < n_steps; k++) {
-                launch_round_begin(h, dt, h->sim_target);
-                int rc2 = step_rollout_body(h, h->d_t0, dt, h->hist_stride > 0 ? 0 : -1);
-                if (rc2) return rc2;
-            }
-            return (int)PGN_OK;
-        });
-        h->hold_on = 0;
-        return rc;
+    if (k0 == 0) {
+        CK(cudaMemsetAsync(h->d_kstep, 0, (size_t)h->B * 4, h->stream));
+        CK(cudaMemsetAsync(h->d_hold, 0, h->B, h->stream));
+    } else if (!(h->sim_axis_valid && k0 == h->sim_target)) {       // not the continuation of the previous call: every vehicle stands at step k0
+        launch_fill_i32(h, h->d_kstep, k0, h->B);
+        CK(cudaMemsetAsync(h->d_hold, 0, h->B, h->stream));
     }
-    auto slot_of = [&](int k) { return (h->hist_stride > 0 && k % h->hist_stride == 0 && k / h->hist_stride < h->hist_cap) ? k / h->hist_stride : -1; };
-    for (int k = k0; k < k0 + n_steps; k++) { const int sl = slot_of(k); if (sl + 1 > h->hist_n) h->hist_n = sl + 1; }
-    return for_each_part(h, [&]() {
-        for (int k = k0; k < k0 + n_steps; k++) {
-            launch_time_axpy(h, h->d_t0_base + h->v0, (double)k, dt, h->d_t0 + h->v0, h->nv);
-            int rc = step_rollout_body(h, h->d_t0, dt, slot_of(k));
-            if (rc) return rc;
+    h->sim_target = k0 + n_steps; h->sim_dt = dt; h->sim_open = cap > 0; h->sim_axis_valid = 1;
+    launch_fill_i32(h, h->d_lag + 1, h->sim_target, 1);           // the target step count the rounds read
+    const int rec = h->hist_stride > 0;
+    if (rec) { const int nrec = std::min(h->hist_cap, (h->sim_target + h->hist_stride - 1) / h->hist_stride); if (nrec > h->hist_n) h->hist_n = nrec; }
+    h->hold_on = 1; h->round_cap = cap; h->sim_cap = cap;
+    const bool graphs = h->parts > 1 && !h->profiling && !getenv("PGN_NO_GRAPHS");
+    int rc = for_each_part(h, [&]() {
+        if (graphs) {
+            int rc2 = ensure_round_graph(h, h->part, dt, cap, rec);
+            if (rc2) return rc2;
+            for (int k = 0; k < n_steps; k++) CK(cudaGraphLaunch(h->rg_exec[h->part], h->stream));
+            h->launches += (long long)n_steps * h->rg_launches[h->part];
+            return (int)PGN_OK;
+        }
+        for (int k = 0; k < n_steps; k++) {
+            launch_round_begin(h, dt);
+            int rc2 = step_rollout_body(h, h->d_t0, dt, rec ? 0 : -1);
+            if (rc2) return rc2;
         }
         return (int)PGN_OK;
     });
+    h->hold_on = 0;
+    return rc;
 }
 // catch-up rounds of a simulate loop with deferred solves: until every vehicle has completed its steps.  The remaining solves get a larger
 // share of iterations per launch (nothing else is waiting for the SMs any more).
@@ -855,7 +884,7 @@ static int finish_sim(pgn_handle* h) {
         if (round > 100000) return set_err(PGN_ECUDA, "simulate: %d vehicles do not reach step %d", *h->h_lag, h->sim_target);
         h->hold_on = 1; h->round_cap = 5 * h->sim_cap;
         int rc = for_each_part(h, [&]() {
-            launch_round_begin(h, h->sim_dt, h->sim_target);
+            launch_round_begin(h, h->sim_dt);
             return step_rollout_body(h, h->d_t0, h->sim_dt, h->hist_stride > 0 ? 0 : -1);
         });
         h->hold_on = 0;
@@ -919,6 +948,7 @@ int pgn_set_history(pgn_handle* h, int32_t capacity, int32_t stride) {
         h->d_hist = nullptr;
     }
     h->hist_cap = h->hist_stride = h->hist_n = 0;
+    h->epoch++;                                     // the recorder's arguments are baked into the round graphs
     if (capacity == 0) return PGN_OK;
     int rc = dev_alloc(h, &h->d_hist, (size_t)capacity * (13 + h->nx) * h->B);
     if (rc) return rc;

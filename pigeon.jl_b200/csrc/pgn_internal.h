@@ -148,7 +148,10 @@ struct pgn_handle {
     // Deferred solves inside the simulate loops (pgn_set_solve_cap): a QP that has not terminated after `solve_cap` iterations of one ADMM
     // launch saves its iterates and continues in the launch of the NEXT round, while its vehicle holds (no new step) and all others go on; every
     // vehicle therefore counts its own steps.  d_hold: 0 steps normally, 1 solve continues, 2 reached the target step count.
-    int solve_cap, sim_cap, round_cap, hold_on, sim_target, sim_open; double sim_dt;
+    int solve_cap, sim_cap, round_cap, hold_on, sim_target, sim_open, sim_axis_valid; double sim_dt;
+    // one simulate round per pipeline part as a CUDA graph (captured once, replayed every round)
+    cudaGraph_t rg_graph[PGN_MAX_PARTS]; cudaGraphExec_t rg_exec[PGN_MAX_PARTS]; long long rg_epoch[PGN_MAX_PARTS], rg_launches[PGN_MAX_PARTS];
+    double rg_dt[PGN_MAX_PARTS]; int rg_cap[PGN_MAX_PARTS], rg_rec[PGN_MAX_PARTS], rg_v0[PGN_MAX_PARTS], rg_nv[PGN_MAX_PARTS];
     uint8_t* d_hold; int32_t *d_kstep, *d_iters_acc; int *d_lag, *h_lag;
     int admm_tmem, admm_ctas_per_sm;                     // tensor-memory variant of the ADMM kernel (two coupled N = 31 QPs per SM); resident CTAs per SM
     double* d_admm_scratch;                              // its per-CTA global scratch
@@ -172,7 +175,8 @@ void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, dou
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
 void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n);
-void launch_round_begin(pgn_handle* h, double dt, int target);      // deferred solves: per-vehicle step time and hold flags of the current range
+void launch_round_begin(pgn_handle* h, double dt);      // target step count: d_lag[1]
+void launch_fill_i32(pgn_handle* h, int32_t* d, int value, int n);      // deferred solves: per-vehicle step time and hold flags of the current range
 void launch_count_lag(pgn_handle* h, int target);                   // vehicles with fewer than `target` completed steps -> d_lag
 void launch_unpack_range(pgn_handle* h, const double* d_in, int flags);   // the same for the current vehicle range, from a ring slot
 void launch_unpack_state(pgn_handle* h, int flags);                 // d_in -> SoA state / control / other / toff / t0 (flags: 1 q, 2 u, 4 other, 8 toff, 16 t0)

@@ -643,16 +643,24 @@ void launch_record(pgn_handle* h, int slot) {
     h->launches++;
 }
 // simulate loops with deferred solves: per vehicle, the time of its own next step and whether it takes part in this round
-__global__ void k_round_begin(int n, const double* __restrict__ base, double dt, int target, const int32_t* __restrict__ kstep, uint8_t* __restrict__ hold, double* __restrict__ t0) {
+__global__ void k_round_begin(int n, const double* __restrict__ base, double dt, const int* __restrict__ target_p, const int32_t* __restrict__ kstep, uint8_t* __restrict__ hold, double* __restrict__ t0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int k = kstep[i];
+    const int k = kstep[i], target = *target_p;              // the target lives in device memory: the round's graph does not change from call to call
     if (hold[i] != 1) hold[i] = k >= target ? 2 : 0;         // 1 = a solve continues: untouched
     t0[i] = __dadd_rn(base[i], __dmul_rn((double)k, dt));    // t_k = t0 + k*dt as the host computes it (no FMA contraction)
 }
-void launch_round_begin(pgn_handle* h, double dt, int target) {
+void launch_round_begin(pgn_handle* h, double dt) {
     const size_t o = (size_t)h->v0;
-    k_round_begin<<<(h->nv + 255) / 256, 256, 0, h->stream>>>(h->nv, h->d_t0_base + o, dt, target, h->d_kstep + o, h->d_hold + o, h->d_t0 + o);
+    k_round_begin<<<(h->nv + 255) / 256, 256, 0, h->stream>>>(h->nv, h->d_t0_base + o, dt, h->d_lag + 1, h->d_kstep + o, h->d_hold + o, h->d_t0 + o);
+    h->launches++;
+}
+__global__ void k_fill_i32(int32_t* __restrict__ d, int value, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = value;
+}
+void launch_fill_i32(pgn_handle* h, int32_t* d, int value, int n) {
+    k_fill_i32<<<(n + 255) / 256, 256, 0, h->stream>>>(d, value, n);
     h->launches++;
 }
 // vehicles that have not reached `target` steps yet (the catch-up rounds of a simulate loop with deferred solves run until this is 0)
