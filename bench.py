@@ -215,6 +215,30 @@ def cpu_closed_loop(cfg_idx, B_sample, steps, warmup, nthreads=0, native=True, s
     return r
 
 
+def cpu_single_vehicle(steps=400):
+    """BASELINE configs[0] — the reference's own operating point: ONE X1 vehicle, coupled MPC (N = 31) tracking test/path/skidpadoval.world
+    (converted as TrajectoryTube(p::path) does), closed loop on ONE host thread; per-step wall time of the four calls + propagate."""
+    o = oracle_module()
+    w = np.load(os.path.join(ROOT, "tests", "golden", "world_skidpadoval.npz"))
+    s_, V = w["s_m"], w["UxDes_mps"]
+    t = np.concatenate([[0.0], np.cumsum(2 * np.diff(s_) / (V[:-1] + V[1:]))])
+    traj = o.Trajectory(t=t, s=s_, V=V, A=w["AxDes_mps2"], E=w["posE_m"], N=w["posN_m"], psi=w["psi_rad"], kappa=w["k_1pm"], theta=w["grade_rad"],
+                        phi=np.zeros(len(s_)), edge_L=w["edgeL_m"], edge_R=w["edgeR_m"])
+    m = o.Mpc(o.MPC_COUPLED)
+    m.set_trajectory(traj)
+    m.set_state(np.array([w["posE_m"][0], w["posN_m"][0], w["psi_rad"][0], 6.0, 0.0, 0.0]), np.zeros(3), other4=FAR)
+    ts_, its = [], []
+    for k in range(steps):
+        a = time.perf_counter()
+        m.simulate_step(DT * k)
+        ts_.append((time.perf_counter() - a) * 1e3)
+        its.append(m.stats()["iter"])
+    ts_ = np.array(ts_[5:])
+    return {"workload": "configs[0]: single X1 vehicle, coupled lat-long MPC (N = 31) on test/path/skidpadoval.world, closed loop, 1 host thread", "steps": steps,
+            "ms_per_step": {"mean": float(ts_.mean()), "p50": float(np.percentile(ts_, 50)), "p99": float(np.percentile(ts_, 99))}, "steps_per_s": float(1e3 / ts_.mean()),
+            "mean_iters": float(np.mean(its)), "reference_budget_ms": 10.0}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -232,6 +256,10 @@ def run_reference(args):
             "note": "the reference's Julia cannot run here (no julia in the image, no network); CPU arm = the C++ port of its algorithm on all host threads, built on this box with " + r["build_flags"],
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "build_flags")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    try:
+        line["single_vehicle"] = cpu_single_vehicle()
+    except Exception as ex:
+        line["single_vehicle"] = {"error": repr(ex)}
     print(json.dumps(line), flush=True)
 
 
