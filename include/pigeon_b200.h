@@ -231,7 +231,8 @@ PGN_API int pgn_hji_lookup_device(pgn_handle* h, int32_t M, const double* d_x, d
 PGN_API int pgn_device_controls(pgn_handle* h, double** d_out /* [3][B] */);
 PGN_API int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_status);
 /* per-stage device time accumulated with CUDA events since the last reset, milliseconds:
- * [0] time steps + nodes, [1] linearisation + envelope, [2] HJI, [3] ADMM, [4] controls, [5] rollout, [6] launches counted */
+ * [0] time steps + nodes, [1] linearisation + envelope, [2] HJI, [3] ADMM, [4] controls, [5] rollout, [6] launches counted,
+ * [7] catch-up rounds run for vehicles whose solves were deferred (pgn_set_solve_cap) */
 PGN_API int pgn_set_profiling(pgn_handle* h, int32_t on);
 PGN_API int pgn_get_stage_ms(pgn_handle* h, double* out /*[8]*/, int32_t reset);
 /* SM cycles spent by the ADMM CTAs per phase while profiling is on (summed over CTAs):

@@ -148,7 +148,7 @@ struct pgn_handle {
     // Deferred solves inside the simulate loops (pgn_set_solve_cap): a QP that has not terminated after `solve_cap` iterations of one ADMM
     // launch saves its iterates and continues in the launch of the NEXT round, while its vehicle holds (no new step) and all others go on; every
     // vehicle therefore counts its own steps.  d_hold: 0 steps normally, 1 solve continues, 2 reached the target step count.
-    int solve_cap, sim_cap, round_cap, hold_on, sim_target, sim_open, sim_axis_valid; double sim_dt;
+    int solve_cap, sim_cap, round_cap, hold_on, sim_target, sim_open, sim_axis_valid; double sim_dt; long long catchup_rounds;
     // one simulate round per pipeline part as a CUDA graph (captured once, replayed every round)
     cudaGraph_t rg_graph[PGN_MAX_PARTS]; cudaGraphExec_t rg_exec[PGN_MAX_PARTS]; long long rg_epoch[PGN_MAX_PARTS], rg_launches[PGN_MAX_PARTS];
     double rg_dt[PGN_MAX_PARTS]; int rg_cap[PGN_MAX_PARTS], rg_rec[PGN_MAX_PARTS], rg_v0[PGN_MAX_PARTS], rg_nv[PGN_MAX_PARTS];

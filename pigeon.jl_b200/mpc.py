@@ -411,7 +411,7 @@ class BatchedTrajectoryTrackingMPC:
     def stage_ms(self, reset=True):
         out = np.zeros(8)
         check(self._lib.pgn_get_stage_ms(self._h, dptr(out), int(reset)))
-        return dict(nodes=out[0], linearize=out[1], hji=out[2], admm=out[3], controls=out[4], rollout=out[5], launches=int(out[6]))
+        return dict(nodes=out[0], linearize=out[1], hji=out[2], admm=out[3], controls=out[4], rollout=out[5], launches=int(out[6]), catchup_rounds=int(out[7]))
 
 
     def admm_cycles(self, reset=True):
