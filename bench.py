@@ -311,9 +311,13 @@ def run_settled(cx, p, cfg_idx, B, K, W, seed_shift, want_stage=True, trajs=None
     mpc.synchronize()
     ev[3].record(cx.stream)
     cx.barrier()
-    ms = cx.max_over_ranks(ev[2].elapsed_time(ev[3]))
-    launches = mpc.stage_ms(reset=True)["launches"]
+    ms_own = ev[2].elapsed_time(ev[3])
+    ms = cx.max_over_ranks(ms_own)
+    sm_ = mpc.stage_ms(reset=True)
+    launches = sm_["launches"]
     st = mpc.stats()
+    extra["by_rank"] = cx.gather_ranks([ms_own / K, float(st["iters"].max()), float(st["iters"].mean()), float(sm_["catchup_rounds"])],
+                                       ["ms_per_step", "max_iters_last_step", "mean_iters_last_step", "catchup_rounds"])
     if CONFIGS[cfg_idx]["hji"]:
         Vv, _ = mpc.hji_values()
         extra["hji_last_step"] = {"pct_active": float((Vv <= 0.05).mean() * 100), "pct_out_of_grid": float(np.isinf(Vv).mean() * 100)}
@@ -511,7 +515,15 @@ def run_gpu(args):
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-    cx.barrier, cx.max_over_ranks = barrier, max_over_ranks
+    def gather_ranks(vals, names):
+        """Per-rank values (the throughput is the max over ranks of the timed region: this shows which rank's batch set it)."""
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if dist is None:
+            return {n: [float(v)] for n, v in zip(names, vals)}
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return {n: [float(o[i].item()) for o in out] for i, n in enumerate(names)}
+    cx.barrier, cx.max_over_ranks, cx.gather_ranks = barrier, max_over_ranks, gather_ranks
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -763,7 +775,7 @@ def run_gpu(args):
                 "latency": latency, "gather": gathered,
                 "cold_start": dict(res["cold_start"], note="first %d closed-loop steps from the perturbed cold start; a few QPs per step run to thousands of iterations (max_iter 4000)" % SETTLE),
                 "survey_8d_timing": cold_literal}
-        for k in ("hji_first_step", "hji_last_step"):
+        for k in ("hji_first_step", "hji_last_step", "by_rank"):
             if k in res:
                 line[k] = res[k]
         if hji_roof:
