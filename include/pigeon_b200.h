@@ -170,7 +170,7 @@ PGN_API int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts);
  * ITS vehicle waits; every vehicle counts its own steps, and the vehicles that fell behind are caught up at the end of pgn_simulate (or, for
  * pgn_simulate_device, at the next entry point that needs results, pgn_synchronize included).  The continued solve recomputes scaling and
  * factor from the unchanged QP data and resumes at iteration k + 1: every vehicle's results are bit-identical with and without the cap.
- * iters must be a multiple of check_termination and adaptive_rho_interval; 0 = off; -1 (default) = automatic: 200 when a range's ADMM launch is at
+ * iters must be a multiple of check_termination and adaptive_rho_interval; 0 = off; -1 (default) = automatic: 400 when a range's ADMM launch is at
  * most two waves of CTAs (there one long solve is the launch time), off for large ranges (their launches absorb such a solve in their many waves,
  * and a deferred one would surface in the catch-up rounds).  The step entry points are never capped. */
 PGN_API int pgn_set_solve_cap(pgn_handle* h, int32_t iters);

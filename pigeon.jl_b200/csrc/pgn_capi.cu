@@ -800,15 +800,17 @@ int pgn_rollout(pgn_handle* h, double dt) {
 }
 // the `simulate` loop on the device: every pipeline part runs ALL its steps on its own stream (a vehicle's step k+1 depends only on its own
 // step k), so the parts drift apart and the small per-vehicle kernels of one part fill the SMs the ADMM kernel of another leaves idle
-// effective cap of this handle: the explicit setting, or (automatic, solve_cap < 0) 200 iterations when a range's ADMM launch is at most two
+// effective cap of this handle: the explicit setting, or (automatic, solve_cap < 0) 400 iterations when a range's ADMM launch is at most two
 // waves of CTAs — there one long solve IS the launch time — and none for large ranges, whose launches absorb a few-hundred-iteration straggler
-// in their many waves while a deferred one would surface in the catch-up rounds (measured: tools/gpu_cap_sweep.sh)
+// in their many waves while a deferred one would surface in the catch-up rounds (measured: tools/gpu_cap_sweep.sh).  400 and not
+// 200: a vehicle whose QP needs 200-400 iterations at EVERY step would fall one round behind per step (tools/gpu_rank2_cap.sh: the batch of rank 2
+// runs 442 k steps/s with 200, 472 k with 400, 480 k uncapped; the cold start of rank 0's batch 188 k uncapped, 217 k with 200, ~208 k with 400)
 static int effective_cap(const pgn_handle* h) {
     if (h->solve_cap >= 0) return h->solve_cap;
     const int c = h->st.check_termination, a = (h->st.adaptive_rho && h->st.adaptive_rho_interval > 0) ? h->st.adaptive_rho_interval : 1;
-    if (!(c > 0 && 200 % c == 0 && 200 % a == 0)) return 0;
+    if (!(c > 0 && 400 % c == 0 && 400 % a == 0)) return 0;
     const int per_range = h->B / (h->parts > 0 ? h->parts : 1), resident = h->num_sms * h->admm_ctas_per_sm;
-    return per_range <= 2 * resident ? 200 : 0;
+    return per_range <= 2 * resident ? 400 : 0;
 }
 // One round of one pipeline part as a CUDA graph.  Nothing in a round depends on the host: the step time comes from the per-vehicle step
 // counters, the target step count sits in device memory, the recorder files by the counters — so the graph is captured once per part (and
