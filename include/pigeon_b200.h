@@ -223,7 +223,9 @@ PGN_API int pgn_hji_optimal_control(pgn_handle* h, int32_t M, const double* x, c
 PGN_API int pgn_set_hji_policy(pgn_handle* h, int32_t on);
 /* Visiting order of the stand-alone lookups: 1 = the queries are counting-sorted by grid cell first, so that queries of the same and of
  * neighbouring cells find their corners in L2 (a random query moves 6.6 KB through DRAM for its 4 KB of corners; in cell order the whole set
- * reads about the table size); 0 = input order; -1 (default) = cell order from 2^19 queries up.  Results are bit-identical. */
+ * reads about the table size); 2 = cell order, and every block of cells stages ONE tile of corners in shared memory with TMA box loads
+ * (cp.async.bulk.tensor.5d over a 5-D view of the table; built and parity-tested, but measured slower than mode 1: DESIGN.md 4.4);
+ * 0 = input order; -1 (default) = mode 1 from 2^19 queries up.  Results are bit-identical in every mode. */
 PGN_API int pgn_set_hji_lookup_order(pgn_handle* h, int32_t mode);
 /* device variant for the HBM roofline micro-benchmark: d_x [7][M] field-major, d_V [M], d_gradV [7][M] */
 PGN_API int pgn_hji_lookup_device(pgn_handle* h, int32_t M, const double* d_x, double* d_V, double* d_gradV);

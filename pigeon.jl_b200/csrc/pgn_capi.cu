@@ -174,6 +174,7 @@ int set_hji_internal(pgn_handle* h, const int32_t dims[7], const float* knots, c
     long long st = 1;
     for (int d = 0; d < 7; d++) { H.dims[d] = dims[d]; H.kofs[d] = off; off += dims[d]; H.stride[d] = st; st *= dims[d]; }
     H.knots = d_k; H.V = nullptr; H.gV = d_r; H.valid = 1;
+    hji_make_tensor_map(h);               // optional: without it the large lookups stay on the plain cell-ordered gather
     return PGN_OK;
 }
 
@@ -364,7 +365,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->path_window = 0; CK(cudaMemset(h->d_last_seg, 0xff, B * 4));
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
-    h->hji_sort = getenv("PGN_HJI_SORT") ? atoi(getenv("PGN_HJI_SORT")) : -1; h->d_hji_ws = nullptr; h->hji_ws_bytes = 0;
+    h->hji_sort = getenv("PGN_HJI_SORT") ? atoi(getenv("PGN_HJI_SORT")) : -1; h->d_hji_ws = nullptr; h->hji_ws_bytes = 0; h->hji_tma_valid = 0;
     for (int p = 0; p < PGN_MAX_PARTS; p++) h->rg_exec[p] = nullptr;
     h->sim_axis_valid = 0; h->catchup_rounds = 0;
     h->hold_on = 0; h->sim_open = 0; h->sim_target = 0; h->sim_dt = 0.0; h->round_cap = 0; h->h_lag = nullptr;
@@ -1114,7 +1115,8 @@ int pgn_set_path_search_window(pgn_handle* h, int32_t half_width) {
 }
 int pgn_set_hji_lookup_order(pgn_handle* h, int32_t mode) {
     ENTER(h, "NULL handle");
-    REQUIRE(mode >= -1 && mode <= 1, "mode must be -1 (automatic), 0 (input order) or 1 (cell order)");
+    REQUIRE(mode >= -1 && mode <= 2, "mode must be -1 (automatic), 0 (input order), 1 (cell order) or 2 (cell order with TMA-staged tiles)");
+    REQUIRE(mode != 2 || h->hji_tma_valid, "no tensor map for this grid: the TMA-staged lookup is not available");
     h->hji_sort = mode;
     return PGN_OK;
 }

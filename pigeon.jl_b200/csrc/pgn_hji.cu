@@ -8,6 +8,8 @@
 // 32-byte record {gradV[0..6], V} (the 7->8 padding slot carries V), dimension 1 fastest.  A query touches the 2^7 corners of
 // its cell = 128 records = 128 sectors of 32 B = exactly the algorithmic 4096 B, fetched as 256 x LDG.128 with all of a
 // thread's loads for one dim-1 pair issued back to back (64 B contiguous).
+#include <cuda.h>
+
 #include "pgn_internal.h"
 
 namespace pgn {
@@ -265,6 +267,127 @@ __global__ void __launch_bounds__(128) k_hji_lookup_perm(HjiView H, int M, const
     for (int k = 0; k < 7; k++) gV[(size_t)k * M + i] = out[k];
 }
 
+// ---- very large query sets: one TMA-staged tile of corners per block of cells -----------------------------------------------------------------
+// In cell order the gather is bound by L2 -> SM traffic: every query still pulls its own 4 KB of corners.  The queries of a BLOCK of cells —
+// all cells along dimension 1, TMA_G consecutive cells along dimension 2, one cell in dimensions 3..7 — are one contiguous range of the
+// sorted order and share one set of corner records: (TMA_G + 1) x 2^5 dimension-1 rows of the table.  The table is described to the TMA unit
+// as a 5-D tensor (8 n1 floats | n2 | n3 | n4 | n5 n6 n7 — the three slow dimensions nest contiguously), one CTA stages the block's tile with
+// four box loads of (8 n1) x (TMA_G + 1) x 2 x 2 x 2 floats (cp.async.bulk.tensor.5d, completion on an mbarrier; rows past the grid are
+// zero-filled and never addressed), and its threads interpolate their queries out of shared memory with the arithmetic of hji_interp in the
+// same order: bit-identical results.  For the 13 x 13 x 9^5 grid: 98 304 blocks, 66.6 KB per tile, ~170 queries per block at 2^24 queries.
+// Measured slower than the plain cell-ordered gather (see launch_hji_lookup): selected only on request.
+#define TMA_G 4
+__global__ void __launch_bounds__(128) k_hji_lookup_tma(const __grid_constant__ CUtensorMap tmap, HjiView H, int M, const uint32_t* __restrict__ offs, const uint32_t* __restrict__ perm,
+                                                        const double* __restrict__ x, double* __restrict__ V, double* __restrict__ gV) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    // block -> (group along dim 2, cell coordinates of dims 3..7)
+    const int nc1 = H.dims[0] - 1, nc2 = H.dims[1] - 1;
+    const int ng = (nc2 + TMA_G - 1) / TMA_G;
+    int b = blockIdx.x;
+    const int g2 = b % ng; b /= ng;
+    int c[7];
+    c[1] = g2 * TMA_G;
+#pragma unroll
+    for (int d = 2; d < 7; d++) { c[d] = b % (H.dims[d] - 1); b /= (H.dims[d] - 1); }
+    long long cell_lo = 0, cs = 1;
+#pragma unroll
+    for (int d = 1; d < 7; d++) { cs *= H.dims[d - 1] - 1; cell_lo += (long long)c[d] * cs; }        // c1 = 0
+    const int rows = min(TMA_G, nc2 - c[1]);
+    const long long cell_hi = cell_lo + (long long)rows * nc1;
+    const uint32_t q0 = cell_lo ? offs[cell_lo - 1] : 0u, q1 = offs[cell_hi - 1];       // after the scatter offs[c] is the END of cell c's queries
+    if (q0 == q1) return;                                                                 // no query in this block (uniform)
+    const int row_floats = 8 * H.dims[0], box_floats = row_floats * (TMA_G + 1) * 8;
+    const uint32_t sm = (uint32_t)__cvta_generic_to_shared(tma_smem), mb = (uint32_t)__cvta_generic_to_shared(&mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((uint32_t)(4 * box_floats * 4)) : "memory");
+#pragma unroll
+        for (int bb = 0; bb < 4; bb++) {
+            const int c4 = c[4] + H.dims[4] * ((c[5] + (bb & 1)) + H.dims[5] * (c[6] + (bb >> 1)));
+            asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(sm + (uint32_t)(bb * box_floats * 4)),
+                         "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(0), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c4), "r"(mb)
+                         : "memory");
+        }
+    }
+    __syncthreads();                       // the barrier is initialised for everyone
+    {
+        uint32_t done = 0;
+        while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb), "r"(0) : "memory");
+    }
+    const float4* tile = reinterpret_cast<const float4*>(tma_smem);
+    for (uint32_t j = q0 + threadIdx.x; j < q1; j += blockDim.x) {
+        const int i = (int)perm[j];
+        double xq[7];
+#pragma unroll
+        for (int d = 0; d < 7; d++) xq[d] = x[(size_t)d * M + i];
+        const HjiCell cl = hji_locate(H, xq);
+        double acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0.0;
+        const int r2 = cl.idx[1] - c[1];                              // row of the query's cell inside the tile
+        for (int cnr = 0; cnr < 64; cnr++) {                           // the loop of hji_interp, corners read from the tile
+            double wgt = 1.0;
+#pragma unroll
+            for (int d = 1; d < 7; d++) {
+                const int bit = (cnr >> (d - 1)) & 1;
+                wgt *= bit ? cl.w[d] : (1.0 - cl.w[d]);
+            }
+            const int b2 = cnr & 1, b3 = (cnr >> 1) & 1, b4 = (cnr >> 2) & 1, b5 = (cnr >> 3) & 1, bb = (cnr >> 4) & 3;
+            const int frow = ((((bb * 2 + b5) * 2 + b4) * 2 + b3) * (TMA_G + 1) + r2 + b2);        // tile row: [box][i5][i4][i3][i2]
+            const float4* rec = tile + (size_t)frow * (row_floats / 4) + 2 * cl.idx[0];
+            const float4 a0 = rec[0], a1 = rec[1], b0 = rec[2], b1 = rec[3];
+            const double w0 = wgt * (1.0 - cl.w[0]), w1 = wgt * cl.w[0];
+            acc[0] += w0 * a0.x + w1 * b0.x; acc[1] += w0 * a0.y + w1 * b0.y; acc[2] += w0 * a0.z + w1 * b0.z; acc[3] += w0 * a0.w + w1 * b0.w;
+            acc[4] += w0 * a1.x + w1 * b1.x; acc[5] += w0 * a1.y + w1 * b1.y; acc[6] += w0 * a1.z + w1 * b1.z; acc[7] += w0 * a1.w + w1 * b1.w;
+        }
+        V[i] = acc[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) gV[(size_t)k * M + i] = acc[k];
+    }
+}
+// the queries outside the grid (the bucket behind the last cell): cache[x] = (Inf, 0)
+__global__ void __launch_bounds__(256) k_hji_outside(int M, const uint32_t* __restrict__ offs, long long ncell, const uint32_t* __restrict__ perm, double* __restrict__ V, double* __restrict__ gV) {
+    const uint32_t j = offs[ncell - 1] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (uint32_t)M) return;
+    const int i = (int)perm[j];
+    V[i] = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 7; k++) gV[(size_t)k * M + i] = 0.0;
+}
+
+// the table as a 5-D tensor for the TMA unit; returns false when the grid does not fit the scheme (then the lookups never take the TMA path)
+bool hji_make_tensor_map(pgn_handle* h) {
+    h->hji_tma_valid = 0;
+    const HjiView& H = h->hji;
+    if (!H.valid || 8 * H.dims[0] > 256 || H.dims[1] < 2) return false;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return false; }
+    const cuuint64_t n1 = H.dims[0], n2 = H.dims[1], n3 = H.dims[2], n4 = H.dims[3], n567 = (cuuint64_t)H.dims[4] * H.dims[5] * H.dims[6];
+    const cuuint64_t gdim[5] = {8 * n1, n2, n3, n4, n567};
+    const cuuint64_t gstr[4] = {32 * n1, 32 * n1 * n2, 32 * n1 * n2 * n3, 32 * n1 * n2 * n3 * n4};      // bytes, dimensions 1..4
+    const cuuint32_t box[5] = {(cuuint32_t)(8 * n1), TMA_G + 1, 2, 2, 2};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    static_assert(sizeof(CUtensorMap) <= sizeof(((pgn_handle*)0)->hji_tmap), "tensor map storage too small");
+    CUresult r = ((EncodeFn)fn)(reinterpret_cast<CUtensorMap*>(h->hji_tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)H.gV, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    const int tile_bytes = (int)(4 * 8 * n1 * (TMA_G + 1) * 8 * 4);
+    if (tile_bytes > 200 * 1024) return false;
+    if (cudaFuncSetAttribute(k_hji_lookup_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    h->hji_tma_tile_bytes = tile_bytes;
+    long long nb = ((long long)(n2 - 1) + TMA_G - 1) / TMA_G;
+    for (int d = 2; d < 7; d++) nb *= H.dims[d] - 1;
+    if (nb >= (1ll << 31)) return false;
+    h->hji_tma_blocks = nb;
+    h->hji_tma_valid = 1;
+    return true;
+}
+
 void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV) {
     long long ncell = 1;
     for (int d = 0; d < 7; d++) ncell *= h->hji.dims[d] - 1;
@@ -286,8 +409,19 @@ void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, dou
             k_scan_totals<<<1, 1024, 0, h->stream>>>(totals, nb);
             k_scan_add<<<nb, 256, 0, h->stream>>>(cnt, nc, totals);
             k_hji_scatter<<<(M + 255) / 256, 256, 0, h->stream>>>(M, keys, cnt, perm);
-            k_hji_lookup_perm<<<(M + 127) / 128, 128, 0, h->stream>>>(h->hji, M, perm, d_x, d_V, d_gV);
-            h->launches += 6;
+            // The TMA-staged tiles are built, parity-green and MEASURED, and they lose: 2^24 queries 13.4 ms against 9.3 ms for the plain
+            // cell-ordered gather (2^22: 4.6 / 2.2 ms; 2^20: 3.8 / 0.77 ms).  66.6 KB of tile per CTA leave 3 CTAs = 12 warps per SM, and a query
+            // is a chain of 64 dependent FP64 accumulations: too few warps to hide it, while the L2 gather runs 48+ warps per SM; the tile loads
+            // themselves (98 304 x 66.6 KB, not overlapped with the interpolation) cost 3.5 ms.  Kept behind pgn_set_hji_lookup_order(2).
+            const bool tma = h->hji_tma_valid && h->hji_sort == 2;
+            if (tma) {
+                k_hji_lookup_tma<<<(unsigned)h->hji_tma_blocks, 128, h->hji_tma_tile_bytes, h->stream>>>(*reinterpret_cast<const CUtensorMap*>(h->hji_tmap), h->hji, M, cnt, perm, d_x, d_V, d_gV);
+                k_hji_outside<<<(M + 255) / 256, 256, 0, h->stream>>>(M, cnt, nc, perm, d_V, d_gV);
+                h->launches += 7;
+            } else {
+                k_hji_lookup_perm<<<(M + 127) / 128, 128, 0, h->stream>>>(h->hji, M, perm, d_x, d_V, d_gV);
+                h->launches += 6;
+            }
             return;
         }
     }

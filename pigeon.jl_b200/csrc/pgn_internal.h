@@ -140,8 +140,10 @@ struct pgn_handle {
     // trajectories / HJI
     pgn::TrajView traj; bool have_traj, have_assign;
     pgn::HjiView hji;
-    int hji_sort;                                        // stand-alone lookups: -1 automatic (queries visited in cell order from 2^19 queries up), 0 never, 1 always
+    int hji_sort;                                        // stand-alone lookups: -1 automatic (cell order from 2^19 queries up, TMA-staged tiles when the blocks are well filled), 0 input order, 1 cell order, 2 cell order + TMA tiles
     void* d_hji_ws; size_t hji_ws_bytes;                 // work space of the cell-ordered lookup
+    alignas(64) unsigned char hji_tmap[128];             // CUtensorMap of the record table (5-D view) for the TMA-staged lookup
+    int hji_tma_valid, hji_tma_tile_bytes; long long hji_tma_blocks;
     // profiling
     int profiling; cudaEvent_t ev[2]; double stage_ms[8]; long long launches;
     int admm_smem_bytes, admm_threads, num_sms;
@@ -172,6 +174,7 @@ void launch_propagate_shadow(pgn_handle* h, double dt, cudaStream_t side);
 void launch_commit_rollout(pgn_handle* h);
 void launch_hji_optimal_control(pgn_handle* h, int M, const double* d_x, const double* d_gV, double* d_out);   // [M][7], [M][7] -> [M][2]
 void launch_hji_lookup(pgn_handle* h, int M, const double* d_x, double* d_V, double* d_gV);
+bool hji_make_tensor_map(pgn_handle* h);
 void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int k);    // [B][k] -> [k][B]
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
 void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n);

@@ -389,7 +389,8 @@ class BatchedTrajectoryTrackingMPC:
         check(self._lib.pgn_set_hji_policy(self._h, int(bool(on))))
 
     def set_hji_lookup_order(self, mode):
-        """Stand-alone lookups: 1 visit the queries in grid-cell order (counting sort; corners shared through L2), 0 input order, -1 automatic."""
+        """Stand-alone lookups: 1 visit the queries in grid-cell order (counting sort; corners shared through L2), 2 the same with one TMA-staged
+        tile of corners per block of cells, 0 input order, -1 automatic."""
         check(self._lib.pgn_set_hji_lookup_order(self._h, int(mode)))
 
     def hji_lookup_device(self, M, d_x, d_V, d_g):

@@ -333,7 +333,10 @@ def test_cell_ordered_hji_lookup_is_bit_identical(p):
     V1, g1 = g.hji_lookup(x)
     g.set_hji_lookup_order(-1)
     V2, g2 = g.hji_lookup(x)
+    g.set_hji_lookup_order(2)                   # cell order + one TMA-staged tile of corners per block of cells (cp.async.bulk.tensor.5d)
+    V3, g3 = g.hji_lookup(x)
     assert np.array_equal(V0, V1) and np.array_equal(g0, g1) and np.array_equal(V0, V2) and np.array_equal(g0, g2)
+    assert np.array_equal(V0, V3) and np.array_equal(g0, g3)
     inside = np.isfinite(V0)
     assert 0.3 < inside.mean() < 0.9 and np.all(g0[~inside] == 0)
     cache = o.HjiCache(knots, V, gV)
@@ -343,7 +346,8 @@ def test_cell_ordered_hji_lookup_is_bit_identical(p):
             assert np.isinf(V1[j])
         else:
             assert abs(v - V1[j]) < 1e-6 and np.max(np.abs(gr - g1[j])) < 1e-6
-    g.set_hji_lookup_order(1)
-    Vs, gs = g.hji_lookup(x[:33])               # tiny sets work in cell order too
-    assert np.array_equal(Vs, V0[:33]) and np.array_equal(gs, g0[:33])
+    for mode in (1, 2):
+        g.set_hji_lookup_order(mode)
+        Vs, gs = g.hji_lookup(x[:33])           # tiny sets work in cell order too
+        assert np.array_equal(Vs, V0[:33]) and np.array_equal(gs, g0[:33])
     g.close()
