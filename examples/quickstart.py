@@ -34,10 +34,23 @@ print("ADMM iterations:", mpc.stats()["iters"], "status:", mpc.stats()["status"]
 mpc.set_guards(nan_fallback=True, pause_below_speed=1.0)
 print("from_autobox:\n", mpc.from_autobox(state, u, stamp=0.0))
 
-# simulate (src/model_predictive_control.jl:80-100): 100 closed-loop steps on the device
+# simulate (src/model_predictive_control.jl:80-100): 100 closed-loop steps on the device; returns the reference's (qs, xs, us, ps) histories,
+# recorded on the device every 10th step
 mpc.reset_solver(); mpc.reset_solved()
-mpc.set_state(state, control)
-mpc.simulate_device(0.0, 0.01, 100)
+qs, xs, us, ps = p.simulate(mpc, state, control, 0.01, n_steps=100, stride=10)
 q, u = mpc.get_state()
+print("lateral error e of node 1 every 0.1 s (vehicle 3):", np.round(xs[:, 3, 5], 4))
 print("after 1 s: lateral position E =", q[:, 0], " Fx =", u[:, 1] + u[:, 2], "(drag equilibrium 366.5 N)")
+
+# pipelined host-buffer stepping: measured states go in, controls come out, three steps in flight (src/ros_integration.jl:50-53,96-99)
+for k in range(6):
+    mpc.step_submit(1.0 + 0.01 * k, q, u)
+    if k >= 2:
+        out = mpc.step_collect()
+while True:
+    try:
+        out = mpc.step_collect()
+    except p.PigeonError:
+        break
+print("last pipelined control:\n", out)
 mpc.close()
