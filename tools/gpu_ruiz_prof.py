@@ -20,3 +20,19 @@ names = ["norms + sqrt/rcp", "barrier after norms", "scale A", "vector updates",
 rz = out[8:14]
 print("inside Ruiz (share of the kernel):", {n: round(v / tot, 4) for n, v in zip(names, rz)}, "sum", round(rz.sum() / tot, 4), "cycles per pass and QP:", np.round(rz / 1024 / 10))
 m.close()
+# factorisation breakdown (CTA 0 only: cycles of its thread 0 over the QPs it solved in this launch)
+m2 = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, 1024, trajectory_index=tid)
+m2.set_state(state, control, other)
+for k in range(35):
+    m2.step(t0 + 0.01 * k); m2.rollout(0.01)
+m2.set_profiling(2); m2.admm_cycles(reset=True)
+m2.step(t0 + 0.35)
+out = np.zeros(512); m2._lib.pgn_get_admm_cycles(m2._h, out.ctypes.data_as(__import__("ctypes").c_void_p), 1)
+init, inv, tail = out[126], out[127], out[128]
+lv = out[136:186]
+tot_f = init + inv + tail + lv.sum()
+print("factor (CTA 0): init+scatter %.0f  levels %.0f  range inverses %.0f  dense tail sweep %.0f  (shares %.2f %.2f %.2f %.2f)" % (init, lv.sum(), inv, tail, init / tot_f, lv.sum() / tot_f, inv / tot_f, tail / tot_f))
+print("levels:", np.round(lv / max(1.0, lv.sum()), 3))
+sol = out[16:16 + 8]; tl = out[116]
+print("solve phases (CTA 0):", np.round(sol / (sol.sum() + tl), 3), "dense tail matvec", round(tl / (sol.sum() + tl), 3))
+m2.close()
