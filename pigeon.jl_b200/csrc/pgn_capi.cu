@@ -266,6 +266,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
         if (h->admm_threads == 512 && !h->admm_tmem &&
             !build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 16)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
     }
+    if (pgn::tail_segments(h->tab.tail_dim) > h->admm_threads) { delete h; return set_err(PGN_EINVAL, "dense tail of dimension %d needs more than %d ADMM threads", h->tab.tail_dim, h->admm_threads); }
     if (h->tab.Nk > (h->admm_threads >= 512 ? 3 : 5) * h->admm_threads) { delete h; return set_err(PGN_EINVAL, "QP too large: %d KKT rows for %d ADMM threads", h->tab.Nk, h->admm_threads); }
     auto bail = [&](int rc) { pgn_destroy(h); return rc; };
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);

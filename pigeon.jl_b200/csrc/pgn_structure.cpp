@@ -278,7 +278,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         while (Lt > 1) {
             int w = Q.lvl_ptr[Lt] - Q.lvl_ptr[Lt - 1];
             int D = Nk - Q.lvl_ptr[Lt - 1];
-            if (w > 4 || D > 64) break;
+            if (w > 4 || D > 64 || tail_segments(D) > 32 * nwarps) break;      // the sweep gives every eight-element row segment its own thread
             Lt--;
         }
         if (nlev - Lt < 4) Lt = nlev;      // not worth it

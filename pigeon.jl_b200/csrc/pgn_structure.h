@@ -28,6 +28,9 @@
 
 namespace pgn {
 
+// dense tail sweep of the ADMM kernel: eight-element row segments of the packed lower triangle of dimension D (one thread each)
+inline int tail_segments(int D) { int n = 0; for (int i = 0; i < D; i++) n += i / 8 + 1; return n; }
+
 // layout of the per-vehicle "QP piece record" written by the linearisation / HJI kernels and gathered by the ADMM kernel
 struct RecLayout {
     int nx, nu, T;
