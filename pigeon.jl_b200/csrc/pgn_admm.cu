@@ -68,6 +68,7 @@ struct Smem {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline int vec_len(int Nk) { return (Nk + 2) & ~1; }                 // Nk values + the always-zero element Nk
+__host__ __device__ inline int a_pad_len(int nnzA) { return (nnzA + 2) & ~1; }           // A values + at least one always-zero double (padding slots of the Ruiz norm program)
 __host__ __device__ inline size_t lval_region_doubles(int nslots, int tail_dim, int Nk, int nnzA) {
     const size_t alias = align_up((size_t)(Nk + 1) * 2 + (size_t)nnzA * 4, 4) + (size_t)nnzA * 4;      // kptr, ke (u16) + arc (u32)
     const size_t a = (alias + 7) / 8, l = (size_t)nslots + (size_t)tail_dim * (tail_dim + 1) / 2;
@@ -77,7 +78,7 @@ __host__ __device__ inline size_t lval_region_doubles(int nslots, int tail_dim, 
 // tensor-memory variant: the time-shared region must hold (a) the factor + dense tail during a factorisation, (b) scaled A | lo | hi | sc |
 // adjacency aliases while a QP is equilibrated, (c) y | lo | hi | fidx | bsrc in front of the dense tail during the iterations
 __host__ __device__ inline size_t tm_region_doubles(int nslots, int tail_dim, int Nk, int nnzA, int n_bent) {
-    const size_t V = vec_len(Nk), A2 = (nnzA + 1) & ~1;
+    const size_t V = vec_len(Nk), A2 = a_pad_len(nnzA);
     const size_t fac = (size_t)nslots + (size_t)tail_dim * (tail_dim + 1) / 2;
     const size_t alias = align_up((size_t)(Nk + 1) * 2 + (size_t)nnzA * 4, 4) + (size_t)nnzA * 4;
     const size_t ruiz = A2 + 3 * V + (alias + 7) / 8;
@@ -90,7 +91,7 @@ static int orow_fwd_count(const QpTables& t) {       // output rows of the forwa
     const size_t first_bwd = t.sol_ph_ptr[t.n_fwd_ph];
     return first_bwd * 4 + 1 < t.sol_task.size() ? (int)(t.sol_task[4 * first_bwd + 1] & 0xffff) : (int)t.sol_orow.size();
 }
-__host__ __device__ inline size_t tm_scratch_doubles(int Nk, int nnzA) { return (size_t)((nnzA + 1) & ~1) + 4 * (size_t)vec_len(Nk); }
+__host__ __device__ inline size_t tm_scratch_doubles(int Nk, int nnzA) { return (size_t)a_pad_len(nnzA) + 4 * (size_t)vec_len(Nk); }
 size_t admm_smem_bytes_tmem(const QpTables& t, int nthreads) {
     const size_t V = vec_len(t.Nk);
     const size_t ntask = t.sol_task.size() / 4;
@@ -109,7 +110,7 @@ bool admm_tmem_fits(const QpTables& t, int nthreads) {
 // solves / factor are copied into shared memory (large QPs, one CTA per SM) or read through L1 (small QPs, two CTAs per SM)
 size_t admm_smem_bytes(const QpTables& t, int nthreads, bool tables_in_smem) {
     const size_t V = vec_len(t.Nk);
-    size_t d = lval_region_doubles(t.nslots, t.tail_dim, t.Nk, t.nnzA) + V + align_up(t.nnzA, 2) + 7 * V + 16 * (nthreads / 32) + 8;
+    size_t d = lval_region_doubles(t.nslots, t.tail_dim, t.Nk, t.nnzA) + V + a_pad_len(t.nnzA) + 7 * V + 16 * (nthreads / 32) + 8;
     size_t u64 = (t.sol_task.size() + t.fac_task.size() + t.inv_task.size()) / 4;
     size_t u32 = t.bent.size() + t.fac_lvl_ptr.size() + t.inv_lvl_ptr.size() + 4;
     size_t u16 = (size_t)t.nslots + t.sol_orow.size() + 8;

@@ -296,6 +296,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     UP(a_src); UP(a_slot); UP(l_type); UP(u_type); UP(l_idx); UP(u_idx); UP(P_mode); UP(q_mode); UP(P_w); UP(q_w); UP(P_t); UP(q_t);
     UP(q_hji_t); UP(pos_var); UP(pos_con); UP(pos2idx); UP(is_con); UP(kadj_ptr); UP(kadj_e); UP(kadj_nb);
     UP(fac_lvl_ptr); UP(fac_tgt); UP(inv_lvl_ptr); UP(inv_tgt);
+    UP(rz_pos); UP(rz_idx); q.rz_prog = (t.rz_prog && h->admm_threads == RZP_NT) ? 1 : 0;
     {   // the solve tables are read in batches of four slot rows with the surplus masked AFTER the load: the device copies carry four slot
         // rows of padding (zero entries) so that the variant that reads them from global memory never leaves its allocations
         std::vector<uint16_t> orow(t.sol_orow), fidx(t.fidx);

@@ -52,6 +52,9 @@ struct QpDev {
     const uint16_t *pos_var, *pos_con, *pos2idx;
     const uint8_t* is_con;
     const uint16_t *kadj_ptr, *kadj_e, *kadj_nb;
+    const uint16_t* rz_pos;                     // Ruiz norm program (pgn_structure.h, RZP_*)
+    const uint32_t* rz_idx;
+    int rz_prog;
     const uint32_t* a_rc;                       // per A entry: row position | column position << 16
     const uint16_t* a_slot;                     // per A entry: L slot
     // warp programs (pgn_structure.h): packed task descriptors {ebase/32 | rbase << 16, K | nrows << 8 | sh << 16 | flags << 24}

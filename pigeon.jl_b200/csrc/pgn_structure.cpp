@@ -377,6 +377,52 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         Q.kadj_e[Q.kadj_ptr[p] + x] = (uint16_t)kadj[p][x].first;
         Q.kadj_nb[Q.kadj_ptr[p] + x] = (uint16_t)kadj[p][x].second;
     }
+    // Ruiz norm program (256-thread kernels): positions by decreasing adjacency length, class u = rank / 256
+    {
+        Q.rz_prog = 0;
+        Q.rz_pos.assign(RZP_U * RZP_NT, 0xFFFF);
+        Q.rz_idx.assign((RZP_SLOTS / 2) * RZP_NT, 0);
+        std::vector<int> byDeg(Nk);
+        for (int p = 0; p < Nk; p++) byDeg[p] = p;
+        std::stable_sort(byDeg.begin(), byDeg.end(), [&](int a, int c) { return kadj[a].size() > kadj[c].size(); });
+        bool fits = Nk <= RZP_U * RZP_NT;
+        const uint32_t pad = (uint32_t)Q.nnzA;      // the always-zero double behind the A values (a_pad_len): one address for every lane, no wavefront of its own
+        for (int r = 0; r < Nk && fits; r++) {
+            const int u = r / RZP_NT, deg = (int)kadj[byDeg[r]].size();
+            if (deg < 1 || deg > rzp_k(u)) fits = false;
+        }
+        // slot order inside a list: the 16 lanes of a half warp read slot k together (one 8-byte shared-memory bank each, 16 banks) — every lane
+        // picks, slot by slot, the remaining entry whose bank the lanes before it use least
+        long wavefronts = 0;
+        for (int u = 0, s0 = 0; u < RZP_U && fits; s0 += rzp_k(u), u++)
+            for (int h0 = 0; h0 < RZP_NT; h0 += 16) {
+                std::vector<std::vector<int>> left(16);
+                for (int l = 0; l < 16; l++) {
+                    const int r = u * RZP_NT + h0 + l;
+                    if (r >= Nk) continue;
+                    Q.rz_pos[u * RZP_NT + h0 + l] = (uint16_t)byDeg[r];
+                    for (auto& en : kadj[byDeg[r]]) left[l].push_back(en.first);
+                }
+                for (int k = 0; k < rzp_k(u); k++) {
+                    int use[16] = {0}, worst = 1;
+                    for (int l = 0; l < 16; l++) {
+                        uint32_t e = pad;
+                        if (!left[l].empty()) {
+                            size_t best = 0;
+                            for (size_t x = 1; x < left[l].size(); x++) if (use[left[l][x] & 15] < use[left[l][best] & 15]) best = x;
+                            e = (uint32_t)left[l][best];
+                            left[l].erase(left[l].begin() + best);
+                            worst = std::max(worst, ++use[e & 15]);
+                        }
+                        const int sl = s0 + k;
+                        Q.rz_idx[(sl >> 1) * RZP_NT + h0 + l] |= e << (16 * (sl & 1));
+                    }
+                    wavefronts += worst;
+                }
+            }
+        if (getenv("PGN_STRUCT_VERBOSE")) fprintf(stderr, "[pgn] Ruiz norm program: %ld shared-memory wavefronts per pass (%d slots x %d half warps)\n", wavefronts, RZP_SLOTS, RZP_NT / 16);
+        Q.rz_prog = fits ? 1 : 0;
+    }
 
     // ---- warp programs -----------------------------------------------------------------------------------------------------------
     const int NWARP = nwarps;

@@ -31,6 +31,14 @@ namespace pgn {
 // dense tail sweep of the ADMM kernel: eight-element row segments of the packed lower triangle of dimension D (one thread each)
 inline int tail_segments(int D) { int n = 0; for (int i = 0; i < D; i++) n += i / 8 + 1; return n; }
 
+// Ruiz norm program of the 256-thread ADMM kernels: thread t owns the positions rz_pos[u * 256 + t], u < RZP_U, handed out in order of
+// decreasing adjacency length, so class u needs at most RZP_K[u] entry slots; the A value indices of a thread's RZP_SLOTS slots (lists padded
+// by repeating their first entry: a maximum does not mind) sit in registers over the ten equilibration passes
+#define RZP_U 5
+#define RZP_NT 256
+#define RZP_SLOTS 38
+PGN_HOSTDEV constexpr int rzp_k(int u) { return u == 0 ? 16 : u == 1 ? 12 : u == 4 ? 2 : 4; }
+
 // layout of the per-vehicle "QP piece record" written by the linearisation / HJI kernels and gathered by the ADMM kernel
 struct RecLayout {
     int nx, nu, T;
@@ -78,6 +86,10 @@ struct QpTables {
     std::vector<uint16_t> a_rowpos, a_colpos, a_lpos;
     // off-diagonal KKT adjacency in position space: for position p, entries (A value index, neighbour position)
     std::vector<uint16_t> kadj_ptr, kadj_e, kadj_nb;
+    // Ruiz norm program (see RZP_*): rz_prog = 1 if the adjacency lengths fit its slot classes; rz_idx[k * 256 + t] = slots 2k | 2k+1 << 16 of thread t
+    int rz_prog;
+    std::vector<uint16_t> rz_pos;
+    std::vector<uint32_t> rz_idx;
     // level ranges [la, lb) of the sparse part whose in-range block of L is replaced by its explicit inverse after factorisation
     std::vector<int> range_lvl;
     // ---- warp programs -----------------------------------------------------------------------------------------------------------

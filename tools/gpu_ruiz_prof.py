@@ -18,6 +18,7 @@ tot = out[:8].sum()
 print("phases (gather, ruiz, factor, solve, update, check, store, ticket):", np.round(out[:8] / tot, 3), "cycles per QP:", tot / 1024)
 names = ["norms + sqrt/rcp", "barrier after norms", "scale A", "vector updates", "block reduce", "cost scaling"]
 rz = out[8:14]
+print("norm gathers (cycles per pass and QP): %.0f  sqrt / reciprocal / publish: %.0f" % (out[14] / 1024 / 10, out[8] / 1024 / 10))
 print("inside Ruiz (share of the kernel):", {n: round(v / tot, 4) for n, v in zip(names, rz)}, "sum", round(rz.sum() / tot, 4), "cycles per pass and QP:", np.round(rz / 1024 / 10))
 m.close()
 # factorisation breakdown (CTA 0 only: cycles of its thread 0 over the QPs it solved in this launch)
