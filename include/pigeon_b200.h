@@ -234,8 +234,12 @@ PGN_API int pgn_device_controls(pgn_handle* h, double** d_out /* [3][B] */);
 PGN_API int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_status);
 /* per-stage device time accumulated with CUDA events since the last reset, milliseconds:
  * [0] time steps + nodes, [1] linearisation + envelope, [2] HJI, [3] ADMM, [4] controls, [5] rollout, [6] launches counted,
- * [7] catch-up rounds run for vehicles whose solves were deferred (pgn_set_solve_cap) */
+ * [7] catch-up rounds run for vehicles whose solves were deferred (pgn_set_solve_cap).
+ * on: 0 off; 1 stage timers (stages serial, one pipeline part); 2 = 1 + cycle counters inside the ADMM kernel (pgn_get_admm_cycles);
+ * 3 = the cycle counters alone, pipeline parts and graphs untouched (counters of the free-running loop) */
 PGN_API int pgn_set_profiling(pgn_handle* h, int32_t on);
+/* profiling 3: one record (start ns, end ns, part | QPs solved << 8 | SM << 32; %globaltimer) per ADMM CTA launched since the last reset */
+PGN_API int pgn_get_admm_trace(pgn_handle* h, unsigned long long* out /* [3 * max_entries] */, int32_t max_entries, int32_t* n, int32_t reset);
 PGN_API int pgn_get_stage_ms(pgn_handle* h, double* out /*[8]*/, int32_t reset);
 /* SM cycles spent by the ADMM CTAs per phase while profiling is on (summed over CTAs):
  * [0] gather, [1] Ruiz scaling, [2] LDL' factorisation, [3] triangular solves, [4] x/z/y update, [5] residuals/termination/rho, [6] store, [7] ticket */

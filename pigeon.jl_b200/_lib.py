@@ -28,7 +28,7 @@ SYMBOLS = ["pgn_default_config", "pgn_x1_vehicle_params", "pgn_default_control_p
            "pgn_set_state", "pgn_reset_solved", "pgn_reset_solver", "pgn_set_guards", "pgn_compute_time_steps", "pgn_compute_linearization_nodes", "pgn_update_qp",
            "pgn_solve", "pgn_get_next_control", "pgn_step", "pgn_step_device", "pgn_simulate", "pgn_rollout", "pgn_qp_dims", "pgn_get_state",
            "pgn_get_time_steps", "pgn_get_nodes", "pgn_set_nodes", "pgn_get_qp_data", "pgn_get_solution", "pgn_get_stats", "pgn_hji_lookup",
-           "pgn_hji_lookup_device", "pgn_device_controls", "pgn_device_stats", "pgn_set_profiling", "pgn_get_stage_ms", "pgn_get_admm_cycles",
+           "pgn_hji_lookup_device", "pgn_device_controls", "pgn_device_stats", "pgn_set_profiling", "pgn_get_stage_ms", "pgn_get_admm_cycles", "pgn_get_admm_trace",
            "pgn_get_hji_values", "pgn_hji_optimal_control", "pgn_set_hji_policy", "pgn_from_autobox", "pgn_step_rollout_device", "pgn_set_path_search_window",
            "pgn_simulate_device", "pgn_set_pipeline_parts", "pgn_get_pipeline_parts", "pgn_set_history", "pgn_get_history", "pgn_comm_unique_id",
            "pgn_set_solve_cap", "pgn_set_hji_lookup_order", "pgn_step_submit", "pgn_step_collect", "pgn_steps_in_flight", "pgn_comm_init_rank", "pgn_comm_init_all", "pgn_comm_destroy", "pgn_gather", "pgn_gather_all"]

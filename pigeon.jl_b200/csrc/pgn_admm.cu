@@ -42,6 +42,7 @@ struct AdmmArgs {
     int iter_cap;                  // iterations of one QP per launch (0 = unlimited); a multiple of check_termination and adaptive_rho_interval
     uint16_t ph_ptr[ADMM_MAX_PHASES + 1];   // first task of every solve phase (forward phases, then backward phases): uniform constant-bank reads
     double* scratch;              // tensor-memory variant: per-CTA global scratch (scaled A, scalings, spilled vectors), tm_scratch_doubles each
+    unsigned long long* trace; int* trace_n; int trace_cap, part;      // optional CTA trace (profiling 3)
     unsigned long long* cycles;   // optional per-phase cycle counters (profiling builds of the host call): gather, ruiz, factor, solve, update, check, store
 };
 
@@ -215,6 +216,7 @@ void launch_admm(pgn_handle* h) {
     a.sol_x = h->d_sol_x; a.sol_y = h->d_sol_y;
     a.iters = h->d_iters; a.status = h->d_status; a.rho_updates = h->d_rho_updates; a.pri_res = h->d_pri_res; a.dua_res = h->d_dua_res;
     a.solved = h->d_solved; a.counter = h->d_counter + h->part;
+    a.trace = h->profiling == 3 ? h->d_trace : nullptr; a.trace_n = h->d_trace_n; a.trace_cap = h->trace_cap; a.part = h->part;
     a.cycles = h->profiling >= 2 ? h->d_cycles : nullptr;      // 1: stage timers only, 2: + in-kernel cycle counters
     cudaMemsetAsync(h->d_counter + h->part, 0, sizeof(int), h->stream);
     k_admm_order<<<1, 1024, 0, h->stream>>>(h->d_iters + h->v0, h->d_order + h->v0, h->nv, h->v0);
@@ -229,19 +231,24 @@ void launch_admm(pgn_handle* h) {
     if (grid > h->nv) grid = h->nv;
     // launches of different pipeline parts may overlap: every part owns a slice of the scratch
     a.scratch = h->admm_tmem ? h->d_admm_scratch + (size_t)h->part * full * tm_scratch_doubles(h->tab.Nk, h->tab.nnzA) : nullptr;
-    if (h->admm_tmem) {
-#define TM_LAUNCH(ns, nt)                                                                      \
-        if (a.cycles) ns::k_admm<true><<<grid, nt, h->admm_smem_bytes, h->stream>>>(a);       \
-        else ns::k_admm<false><<<grid, nt, h->admm_smem_bytes, h->stream>>>(a);
-        TM_LAUNCH(vtm, 256)
-#undef TM_LAUNCH
-    } else if (small) {
-        if (a.cycles) v256::k_admm<true><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
-        else v256::k_admm<false><<<grid, 256, h->admm_smem_bytes, h->stream>>>(a);
-    } else {
-        if (a.cycles) v512::k_admm<true><<<grid, 512, h->admm_smem_bytes, h->stream>>>(a);
-        else v512::k_admm<false><<<grid, 512, h->admm_smem_bytes, h->stream>>>(a);
-    }
+    // The pipeline parts run on high-priority streams and the ADMM kernel is launched at the lowest priority: two resident ADMM CTAs hold the
+    // whole register file of an SM, so without this the short kernels of the other parts (nodes, linearisation, HJI, propagation) queue behind
+    // every pending ADMM CTA instead of slipping into the slot an exiting one frees (pgn_set_pipeline_parts).
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.dynamicSmemBytes = h->admm_smem_bytes; cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority; attr[0].val.priority = h->prio_least;
+    cfg.attrs = attr; cfg.numAttrs = h->admm_low_priority ? 1 : 0;
+#define ADMM_LAUNCH(ns, nt)                                                                   \
+    do {                                                                                      \
+        cfg.blockDim = dim3(nt);                                                              \
+        if (a.cycles) cudaLaunchKernelEx(&cfg, ns::k_admm<true>, a);                          \
+        else cudaLaunchKernelEx(&cfg, ns::k_admm<false>, a);                                  \
+    } while (0)
+    if (h->admm_tmem) ADMM_LAUNCH(vtm, 256);
+    else if (small) ADMM_LAUNCH(v256, 256);
+    else ADMM_LAUNCH(v512, 512);
+#undef ADMM_LAUNCH
     h->launches++;
 }
 

@@ -53,11 +53,14 @@ struct DeviceGuard {
 #define ENTER_NODRAIN(h, msg)  REQUIRE(h, msg); DeviceGuard dev_guard__((h)->device)
 #define ENTER(h, msg)  ENTER_NODRAIN(h, msg); if ((h)->ring_count) drain_ring(h); if ((h)->sim_open) { int rc__ = finish_sim(h); if (rc__) return rc__; }
 
+// profiling: 1 = stage timers (the stages run serially, one part), 2 = + in-kernel cycle counters of the ADMM kernel, 3 = the cycle counters alone
+// (pipeline parts and graphs stay on: the counters then describe the free-running loop)
+static inline bool serial_profiling(const pgn_handle* h) { return h->profiling == 1 || h->profiling == 2; }
 struct StageTimer {
     pgn_handle* h; int idx;
-    StageTimer(pgn_handle* h_, int idx_) : h(h_), idx(idx_) { if (h->profiling) cudaEventRecord(h->ev[0], h->stream); }
+    StageTimer(pgn_handle* h_, int idx_) : h(h_), idx(idx_) { if (serial_profiling(h)) cudaEventRecord(h->ev[0], h->stream); }
     ~StageTimer() {
-        if (h->profiling) {
+        if (serial_profiling(h)) {
             cudaEventRecord(h->ev[1], h->stream);
             cudaEventSynchronize(h->ev[1]);
             float ms = 0;
@@ -183,7 +186,7 @@ int set_hji_internal(pgn_handle* h, const int32_t dims[7], const float* knots, c
 // stream continues after all parts.  One part (or stage timers on): `body` runs as is on the caller's stream.
 template <class F>
 int for_each_part(pgn_handle* h, F body) {
-    if (h->parts <= 1 || h->profiling) return body();
+    if (h->parts <= 1 || serial_profiling(h)) return body();
     cudaStream_t s0 = h->stream, side0 = h->side_stream;
     cudaEvent_t f0 = h->ev_fork, j0 = h->ev_join;
     int rc = PGN_OK;
@@ -269,6 +272,9 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     if (pgn::tail_segments(h->tab.tail_dim) > h->admm_threads) { delete h; return set_err(PGN_EINVAL, "dense tail of dimension %d needs more than %d ADMM threads", h->tab.tail_dim, h->admm_threads); }
     if (h->tab.Nk > (h->admm_threads >= 512 ? 3 : 5) * h->admm_threads) { delete h; return set_err(PGN_EINVAL, "QP too large: %d KKT rows for %d ADMM threads", h->tab.Nk, h->admm_threads); }
     auto bail = [&](int rc) { pgn_destroy(h); return rc; };
+    h->prio_least = 0; h->prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&h->prio_least, &h->prio_greatest);
+    { const char* ev = getenv("PGN_ADMM_PRIORITY"); h->admm_low_priority = ev ? atoi(ev) != 0 : 1; }
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return set_err(PGN_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
     h->stream = h->own_stream;
@@ -437,6 +443,8 @@ int pgn_destroy(pgn_handle* h) {
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_lag) cudaFreeHost(h->h_lag);
     if (h->d_hji_ws) cudaFree(h->d_hji_ws);
+    if (h->d_trace) cudaFree(h->d_trace);
+    if (h->d_trace_n) cudaFree(h->d_trace_n);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     if (h->ring_created)
         for (int sl = 0; sl < PGN_RING; sl++) { cudaEventDestroy(h->ring_h2d[sl]); for (int p = 0; p < PGN_MAX_PARTS; p++) cudaEventDestroy(h->ring_done[sl][p]); }
@@ -668,7 +676,7 @@ int pgn_step_submit(pgn_handle* h, const double* q, const double* u, const doubl
     const size_t lo = (flags & 1) ? 0 : (flags & 2) ? 6 * B : (flags & 4) ? 9 * B : 14 * B;
     CK(cudaMemcpyAsync(din + lo, hin + lo, (15 * B - lo) * 8, cudaMemcpyHostToDevice, s0));      // ONE copy of the span that holds the present fields
     CK(cudaEventRecord(h->ring_h2d[sl], s0));
-    const int P = (h->parts <= 1 || h->profiling) ? 1 : h->parts;
+    const int P = (h->parts <= 1 || serial_profiling(h)) ? 1 : h->parts;
     cudaStream_t side0 = h->side_stream;
     cudaEvent_t f0 = h->ev_fork, j0 = h->ev_join;
     for (int p = 0; p < P; p++) {
@@ -736,7 +744,7 @@ int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const doub
     if (other) memcpy(io + 1 + 9 * B, other, 4 * B * 8);
     memcpy(io + 1 + 13 * B, stamp, B * 8);
     int rc = PGN_OK;
-    if (h->profiling) {
+    if (serial_profiling(h)) {
         rc = callback_enqueue(h);          // stage timers synchronise: no capture
     } else {
         if (!h->cb_has_exec || h->cb_epoch != h->epoch || h->cb_stream != h->stream) {
@@ -766,11 +774,15 @@ int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const doub
 // one closed-loop step of the current vehicle range on the current stream: the step stages, the plant step on the side stream.
 // rec_slot >= 0: the history recorder keeps (state, control, node 1, params 1) of this step (pgn_set_history).
 static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt, int rec_slot) {
+    launch_stamp(h, 0);
     step_time_steps_dev(h, d_t0);
+    launch_stamp(h, 1);
     step_nodes(h);
     if (rec_slot >= 0) launch_record(h, rec_slot);
+    launch_stamp(h, 2);
     step_update(h);
-    if (h->profiling || !h->side_stream) {            // stage timers synchronise: serial order
+    launch_stamp(h, 3);
+    if (serial_profiling(h) || !h->side_stream) {            // stage timers synchronise: serial order
         step_solve(h);
         step_controls(h, h->d_controls);
         { StageTimer T(h, 5); launch_rollout(h, dt); }
@@ -782,9 +794,12 @@ static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt, int r
     launch_propagate_shadow(h, dt, h->side_stream);
     CK(cudaEventRecord(h->ev_join, h->side_stream));
     step_solve(h);
+    launch_stamp(h, 4);
     step_controls(h, h->d_controls);
+    launch_stamp(h, 5);
     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     launch_commit_rollout(h);
+    launch_stamp(h, 6);
     return PGN_OK;
 }
 // step + plant rollout of `simulate` (model_predictive_control.jl:87-98) with the plant step beside the QP solve
@@ -858,7 +873,7 @@ static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
     const int rec = h->hist_stride > 0;
     if (rec) { const int nrec = std::min(h->hist_cap, (h->sim_target + h->hist_stride - 1) / h->hist_stride); if (nrec > h->hist_n) h->hist_n = nrec; }
     h->hold_on = 1; h->round_cap = cap; h->sim_cap = cap;
-    const bool graphs = h->parts > 1 && !h->profiling && !getenv("PGN_NO_GRAPHS");
+    const bool graphs = h->parts > 1 && !serial_profiling(h) && !getenv("PGN_NO_GRAPHS");
     if (graphs) {
         // every part's graph is made ready BEFORE anything is launched: destroying / instantiating a graph synchronises with the device, and
         // done between the parts' launches it serialised the parts (measured: 101 cold steps 227 ms -> 553 ms after any re-capture)
@@ -948,7 +963,8 @@ int pgn_set_pipeline_parts(pgn_handle* h, int32_t parts) {
     if (parts > 1 && !h->parts_created) {
         CK(cudaEventCreateWithFlags(&h->part_begin, cudaEventDisableTiming));
         for (int p = 0; p < PGN_MAX_PARTS; p++) {
-            CK(cudaStreamCreateWithFlags(&h->part_stream[p], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->part_side[p], cudaStreamNonBlocking));
+            const int prio = h->admm_low_priority ? h->prio_greatest : h->prio_least;
+            CK(cudaStreamCreateWithPriority(&h->part_stream[p], cudaStreamNonBlocking, prio)); CK(cudaStreamCreateWithPriority(&h->part_side[p], cudaStreamNonBlocking, prio));
             CK(cudaEventCreateWithFlags(&h->part_done[p], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&h->part_evf[p], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->part_evj[p], cudaEventDisableTiming));
         }
@@ -1156,7 +1172,30 @@ int pgn_device_stats(pgn_handle* h, int32_t** d_iters, int32_t** d_status) {
     if (d_status) *d_status = h->d_status;
     return PGN_OK;
 }
-int pgn_set_profiling(pgn_handle* h, int32_t on) { ENTER(h, "NULL handle"); h->epoch++; h->profiling = on; return PGN_OK; }
+int pgn_set_profiling(pgn_handle* h, int32_t on) {
+    ENTER(h, "NULL handle");
+    if (on == 3 && !h->d_trace) {
+        h->trace_cap = 1 << 19;
+        CK(cudaMalloc(&h->d_trace, (size_t)h->trace_cap * 24)); CK(cudaMalloc(&h->d_trace_n, sizeof(int)));
+        CK(cudaMemset(h->d_trace_n, 0, sizeof(int)));
+    }
+    h->epoch++; h->profiling = on;
+    return PGN_OK;
+}
+// profiling 3: the (start ns, end ns, part | QPs << 8 | SM << 32) records of the ADMM CTAs launched since the last reset; returns the count through *n
+int pgn_get_admm_trace(pgn_handle* h, unsigned long long* out, int32_t max_entries, int32_t* n, int32_t reset) {
+    ENTER(h, "NULL handle"); REQUIRE(out && n && max_entries >= 0, "bad argument");
+    *n = 0;
+    if (!h->d_trace) return PGN_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    int cnt = 0;
+    CK(cudaMemcpy(&cnt, h->d_trace_n, sizeof(int), cudaMemcpyDeviceToHost));
+    cnt = std::min(std::min(cnt, h->trace_cap), (int)max_entries);
+    CK(cudaMemcpy(out, h->d_trace, (size_t)cnt * 24, cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (reset) CK(cudaMemset(h->d_trace_n, 0, sizeof(int)));
+    return PGN_OK;
+}
 int pgn_get_admm_cycles(pgn_handle* h, double* out, int32_t reset) {
     ENTER(h, "NULL handle"); REQUIRE(out, "NULL argument");
     unsigned long long c[512];

@@ -79,6 +79,7 @@ struct AdmmSettings {
 }  // namespace pgn
 
 struct pgn_handle {
+    int prio_least, prio_greatest, admm_low_priority;      // stream priority range of the device; 1 = part streams high, ADMM launches low
     pgn_config cfg;
     int device;
     cudaStream_t stream, own_stream;
@@ -123,6 +124,7 @@ struct pgn_handle {
     cudaGraph_t cb_graph; cudaGraphExec_t cb_exec; long long epoch, cb_epoch, cb_launches; cudaStream_t cb_stream; int cb_has_exec;
     int32_t* d_order;                                    // ticket -> vehicle order of the ADMM launch
     int* d_counter;                                      // work-queue ticket for the persistent ADMM kernel
+    unsigned long long* d_trace; int* d_trace_n; int trace_cap;      // profiling 3: (start ns, end ns, part | QPs << 8 | SM << 32) of every ADMM CTA
     unsigned long long* d_cycles;                        // [8] per-phase cycle counters of the ADMM kernel (profiling only)
     double* d_stage;                                     // AoS<->SoA staging
     size_t stage_bytes;
@@ -182,6 +184,7 @@ void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int 
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
 void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n);
 void launch_round_begin(pgn_handle* h, double dt);      // target step count: d_lag[1]
+void launch_stamp(pgn_handle* h, int stage);      // profiling 3: time stamp record between the stages of a round
 void launch_fill_i32(pgn_handle* h, int32_t* d, int value, int n);      // deferred solves: per-vehicle step time and hold flags of the current range
 void launch_count_lag(pgn_handle* h, int target);                   // vehicles with fewer than `target` completed steps -> d_lag
 void launch_unpack_range(pgn_handle* h, const double* d_in, int flags);   // the same for the current vehicle range, from a ring slot

@@ -659,6 +659,17 @@ __global__ void k_fill_i32(int32_t* __restrict__ d, int value, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = value;
 }
+// profiling 3: a time stamp between the stages of a round (record: %globaltimer, 0, part | stage << 8 | 1 << 63)
+__global__ void k_stamp(unsigned long long* __restrict__ trace, int* __restrict__ trace_n, int cap, unsigned long long meta) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const int slot = atomicAdd(trace_n, 1);
+    if (slot < cap) { trace[3 * slot] = t; trace[3 * slot + 1] = 0; trace[3 * slot + 2] = meta; }
+}
+void launch_stamp(pgn_handle* h, int stage) {
+    if (h->profiling != 3 || !h->d_trace) return;
+    k_stamp<<<1, 1, 0, h->stream>>>(h->d_trace, h->d_trace_n, h->trace_cap, (unsigned long long)h->part | ((unsigned long long)stage << 8) | (1ull << 63));
+}
 void launch_fill_i32(pgn_handle* h, int32_t* d, int value, int n) {
     k_fill_i32<<<(n + 255) / 256, 256, 0, h->stream>>>(d, value, n);
     h->launches++;

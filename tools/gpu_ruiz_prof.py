@@ -12,10 +12,13 @@ m.set_state(state, control, other)
 for k in range(35):
     m.step(t0 + 0.01 * k); m.rollout(0.01)
 m.set_profiling(2); m.admm_cycles(reset=True)
-m.step(t0 + 0.35)
+import time
+t_w = time.perf_counter(); m.step(t0 + 0.35); t_w = time.perf_counter() - t_w
 out = np.zeros(512); m._lib.pgn_get_admm_cycles(m._h, out.ctypes.data_as(__import__("ctypes").c_void_p), 1)
 tot = out[:8].sum()
+print("step (profiling build, joined): %.3f ms; ADMM CTA lifetimes fill %.2f of 296 slots x step time at 1.965 GHz" % (t_w * 1e3, out[15] / (296 * t_w * 1.965e9)))
 print("phases (gather, ruiz, factor, solve, update, check, store, ticket):", np.round(out[:8] / tot, 3), "cycles per QP:", tot / 1024)
+print("CTA lifetimes / sum of phases: %.3f  (prologue: tensor-memory allocation, static tables)" % (out[15] / tot))
 names = ["norms + sqrt/rcp", "barrier after norms", "scale A", "vector updates", "block reduce", "cost scaling"]
 rz = out[8:14]
 print("norm gathers (cycles per pass and QP): %.0f  sqrt / reciprocal / publish: %.0f" % (out[14] / 1024 / 10, out[8] / 1024 / 10))
