@@ -826,7 +826,7 @@ def finish(dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4], help="index into BASELINE.json `configs` (1 = the configuration the metric is quoted on)")
     ap.add_argument("--batch", type=int, default=0, help="vehicles per GPU (default: the config's per-GPU size)")
