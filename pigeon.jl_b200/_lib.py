@@ -51,6 +51,7 @@ def load():
     for name in SYMBOLS:
         getattr(lib, name)   # AttributeError if the library does not export a declared symbol
     lib.pgn_create.argtypes = [C.POINTER(PgnConfig), C.POINTER(C.c_void_p)]
+    lib.pgn_get_admm_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32]
     lib.pgn_simulate.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int32]
     lib.pgn_simulate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32]
     lib.pgn_set_pipeline_parts.argtypes = [C.c_void_p, C.c_int32]

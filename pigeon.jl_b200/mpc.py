@@ -415,6 +415,14 @@ class BatchedTrajectoryTrackingMPC:
         return dict(nodes=out[0], linearize=out[1], hji=out[2], admm=out[3], controls=out[4], rollout=out[5], launches=int(out[6]), catchup_rounds=int(out[7]))
 
 
+    def admm_trace(self, reset=True, max_entries=1 << 19):
+        """Records of profiling mode 3 (set_profiling(3)): an (n, 3) uint64 array of (start ns, end ns, meta) — meta = part | QPs solved << 8 | SM << 32
+        for an ADMM CTA, part | stage << 8 | 1 << 63 (end = 0) for a time stamp between the stages of a round."""
+        buf = np.zeros(3 * max_entries, dtype=np.uint64)
+        n = C.c_int32(0)
+        check(self._lib.pgn_get_admm_trace(self._h, dptr(buf), int(max_entries), C.byref(n), int(reset)))
+        return buf[:3 * n.value].reshape(n.value, 3)
+
     def admm_cycles(self, reset=True):
         out = np.zeros(512)
         check(self._lib.pgn_get_admm_cycles(self._h, dptr(out), int(reset)))

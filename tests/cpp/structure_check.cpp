@@ -12,7 +12,8 @@ using namespace pgn;
 
 int main(int argc, char** argv) {
     int kind = argc > 1 ? atoi(argv[1]) : 0, Ns = argc > 2 ? atoi(argv[2]) : 10, Nl = argc > 3 ? atoi(argv[3]) : 20, ord = argc > 4 ? atoi(argv[4]) : 0;
-    const int nwarps = argc > 6 ? atoi(argv[6]) : ADMM_THREADS / 32;      // argv[5]: verbose flag, argv[6]: warps the programs are scheduled for
+    // argv[5]: verbose flag, argv[6] (or the environment variable PGN_CHECK_NWARPS): warps the programs are scheduled for
+    const int nwarps = argc > 6 ? atoi(argv[6]) : (getenv("PGN_CHECK_NWARPS") ? atoi(getenv("PGN_CHECK_NWARPS")) : ADMM_THREADS / 32);
     QpTables Q; char err[256];
     if (!build_qp_tables(kind, Ns, Nl, ord, Q, err, 256, nwarps)) { printf("FAIL %s\n", err); return 1; }
     const int Nk = Q.Nk, n = Q.n, m = Q.m;
@@ -136,9 +137,29 @@ int main(int argc, char** argv) {
         for (int e = Q.kadj_ptr[r]; e < Q.kadj_ptr[r + 1]; e++) t += Aval[Q.kadj_e[e]] * x[Q.kadj_nb[e]];
         kadj_err = std::fmax(kadj_err, std::fabs(t - off));
     }
+    // Ruiz norm program (256-thread kernels): every position owned exactly once, and the maximum over its slots (pad slots read the always-zero
+    // double behind the A values) equals the maximum over its adjacency list
+    int rz_bad = 0;
+    if (Q.rz_prog) {
+        std::vector<double> Apad(Aval); Apad.push_back(0.0);
+        std::vector<int> owned(Nk, 0);
+        for (int u = 0, s0 = 0; u < RZP_U; s0 += rzp_k(u), u++)
+            for (int t = 0; t < RZP_NT; t++) {
+                const int p = Q.rz_pos[u * RZP_NT + t];
+                if (p == 0xFFFF) continue;
+                if (p >= Nk) { rz_bad++; continue; }
+                owned[p]++;
+                double a = 0, bref = 0;
+                for (int k = 0; k < rzp_k(u); k++) { const int sl = s0 + k; const uint32_t e = (Q.rz_idx[(sl >> 1) * RZP_NT + t] >> (16 * (sl & 1))) & 0xffffu; if ((int)e > Q.nnzA) { rz_bad++; continue; } a = std::fmax(a, std::fabs(Apad[e])); }
+                for (int e = Q.kadj_ptr[p]; e < Q.kadj_ptr[p + 1]; e++) bref = std::fmax(bref, std::fabs(Aval[Q.kadj_e[e]]));
+                if (a != bref) rz_bad++;
+            }
+        for (int p = 0; p < Nk; p++) if (owned[p] != 1) rz_bad++;
+    }
+    if (tail_segments(Q.tail_dim) > 32 * nwarps) rz_bad++;      // the dense-tail sweep gives every eight-element row segment its own thread
     int wmax = 0; for (int l = 0; l < Q.nlev; l++) wmax = std::max(wmax, (int)(Q.lvl_ptr[l + 1] - Q.lvl_ptr[l]));
-    printf("kind=%d N=%d n=%d m=%d Nk=%d nnzA=%d nnzL=%d nlev=%d maxwidth=%d pairs=%zu rec_len=%d tail_level=%d tail_dim=%d res=%.3e kadj_err=%.3e\n", kind, Q.N, n, m, Nk, Q.nnzA,
-           Q.nnzL, Q.nlev, wmax, npairs, Q.rec.rec_len, Q.tail_level, Q.tail_dim, res, kadj_err);
+    printf("kind=%d N=%d n=%d m=%d Nk=%d nnzA=%d nnzL=%d nlev=%d maxwidth=%d pairs=%zu rec_len=%d tail_level=%d tail_dim=%d rz_prog=%d rz_bad=%d res=%.3e kadj_err=%.3e\n", kind, Q.N, n, m, Nk, Q.nnzA,
+           Q.nnzL, Q.nlev, wmax, npairs, Q.rec.rec_len, Q.tail_level, Q.tail_dim, Q.rz_prog, rz_bad, res, kadj_err);
     printf("  ranges:"); for (size_t k = 0; k + 1 < Q.range_lvl.size(); k += 2) printf(" [%d,%d)", Q.range_lvl[k], Q.range_lvl[k + 1]);
     printf("  nslots %d  solve phases fwd %d bwd %d tasks %zu bent %zu  factor tasks %zu ents %zu  inverse levels %zu tasks %zu ents %zu max tasks/warp %d\n", Q.nslots, Q.n_fwd_ph, Q.n_bwd_ph,
            Q.sol_task.size() / 4, Q.bent.size(), Q.fac_task.size() / 4, Q.fac_ent.size(), Q.inv_lvl_ptr.size() - 1, Q.inv_task.size() / 4, Q.inv_ent.size(), Q.inv_max_tasks_per_warp);
@@ -154,5 +175,5 @@ int main(int argc, char** argv) {
             printf("\n");
         }
     }
-    return (res < 1e-8 && kadj_err < 1e-10) ? 0 : 2;
+    return (res < 1e-8 && kadj_err < 1e-10 && rz_bad == 0) ? 0 : 2;
 }

@@ -351,3 +351,43 @@ def test_cell_ordered_hji_lookup_is_bit_identical(p):
         Vs, gs = g.hji_lookup(x[:33])           # tiny sets work in cell order too
         assert np.array_equal(Vs, V0[:33]) and np.array_equal(gs, g0[:33])
     g.close()
+
+
+@pytest.mark.gpu
+def test_free_running_profile_records_every_admm_cta_and_changes_nothing(p):
+    """pgn_set_profiling(3): the counting build of the ADMM kernel inside the ordinary free-running loop (pipeline parts and graphs on).  One
+    record per ADMM CTA (start <= end on %globaltimer, its pipeline part, the QPs it solved) and seven time stamps per round and part; the
+    closed loop itself must come out bit-identical to the unprofiled one."""
+    import torch
+    B, n, parts = 96, 6, 3
+    trajs, tid, state, control, t0, other = batch(p, B, n_traj=4)
+
+    def run(prof):
+        g = p.BatchedCoupledTrajectoryTrackingMPC(p.X1(), trajs, B, trajectory_index=tid)
+        g.set_pipeline_parts(parts)
+        g.set_profiling(prof)
+        g.set_state(state, control, other)
+        d = torch.tensor(t0, dtype=torch.float64, device="cuda")
+        g.simulate_device_async(d.data_ptr(), 0.01, n)
+        q, u = g.get_state()
+        st = g.stats()
+        tr = g.admm_trace() if prof == 3 else None
+        cyc = g.admm_cycles() if prof == 3 else None
+        g.close()
+        return q, u, st["iters"], st["status"], tr, cyc
+    ref = run(0)
+    got = run(3)
+    for a, b in zip(ref[:4], got[:4]):
+        assert np.array_equal(a, b, equal_nan=True)
+    tr, cyc = got[4], got[5]
+    stamp = (tr[:, 2] >> np.uint64(63)) == 1
+    cta, st = tr[~stamp], tr[stamp]
+    assert len(cta) > 0 and (cta[:, 0] <= cta[:, 1]).all()
+    part = (cta[:, 2] & np.uint64(0xff)).astype(int)
+    nqp = ((cta[:, 2] >> np.uint64(8)) & np.uint64(0xffffff)).astype(int)
+    assert set(part) == set(range(parts))
+    assert nqp.sum() >= B * n                                     # every vehicle solved n QPs (deferred solves may add continuation launches)
+    assert len(st) % (7 * parts) == 0 and len(st) >= 7 * parts * n
+    stage = ((st[:, 2] >> np.uint64(8)) & np.uint64(0xff)).astype(int)
+    assert set(stage) == set(range(7))
+    assert sum(cyc.values()) > 0

@@ -56,17 +56,21 @@ def test_product_does_not_reference_the_oracle():
                 assert "oracle_py" not in src and "liboracle" not in src and '#include "../../oracle' not in src, f
 
 
-@pytest.mark.parametrize("args", ["0 10 20 0", "0 10 20 1", "0 5 10 0", "1 10 20 0", "1 10 20 1", "0 1 0 0", "1 3 2 0"])
+@pytest.mark.parametrize("args", ["0 10 20 0", "0 10 20 1", "0 5 10 0", "1 10 20 0", "1 10 20 1", "0 1 0 0", "1 3 2 0", "0 10 20 0 w8", "1 10 20 0 w8"])
 def test_static_qp_tables_factor_and_solve(args, tmp_path):
     exe = str(tmp_path / "structure_check")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "structure_check.cpp"),
                            os.path.join(ROOT, "pigeon.jl_b200", "csrc", "pgn_structure.cpp")])
-    r = subprocess.run([exe] + args.split(), capture_output=True, text=True)
+    env = dict(os.environ)
+    if args.endswith(" w8"):      # the programs of the 256-thread ADMM builds (8 warps)
+        args = args[:-3]; env["PGN_CHECK_NWARPS"] = "8"
+    r = subprocess.run([exe] + args.split(), capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     kv = dict(x.split("=") for x in r.stdout.splitlines()[0].split())
     kind, Ns, Nl = (int(a) for a in args.split()[:3])
     m = o.Mpc(kind, N_short=Ns, N_long=Nl)
     assert (int(kv["n"]), int(kv["m"]), int(kv["nnzA"])) == (m.n, m.m, m.nnzA)      # same canonical QP as the oracle
+    assert int(kv["rz_bad"]) == 0 and int(kv["rz_prog"]) == 1      # the Ruiz norm program covers every adjacency list of these QPs
 
 
 def test_nested_dissection_cuts_solve_depth(tmp_path):
