@@ -252,6 +252,11 @@ void launch_admm(pgn_handle* h) {
     h->launches++;
 }
 
+// graph kernel nodes do not take the priority of the stream they were captured on: ensure_round_graph sets it node by node and asks here
+bool admm_is_kernel(const void* f) {
+    return f == (const void*)vtm::k_admm<false> || f == (const void*)vtm::k_admm<true> || f == (const void*)v256::k_admm<false> || f == (const void*)v256::k_admm<true> ||
+           f == (const void*)v512::k_admm<false> || f == (const void*)v512::k_admm<true>;
+}
 int admm_orow_fwd(const QpTables& t) { return orow_fwd_count(t); }
 size_t admm_scratch_doubles(const pgn_handle* h) {
     return h->admm_tmem ? (size_t)PGN_MAX_PARTS * h->num_sms * 2 * tm_scratch_doubles(h->tab.Nk, h->tab.nnzA) : 0;

@@ -375,7 +375,8 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     h->in_callback = 0; h->cb_has_exec = 0; h->epoch = 1; h->cb_epoch = 0; h->cb_launches = 0; h->h_io = nullptr;
     CK(cudaMemset(h->d_tskip, 0, B)); CK(cudaMemset(h->d_se, 0, 2 * B * 8));
     h->hji_sort = getenv("PGN_HJI_SORT") ? atoi(getenv("PGN_HJI_SORT")) : -1; h->d_hji_ws = nullptr; h->hji_ws_bytes = 0; h->hji_tma_valid = 0;
-    for (int p = 0; p < PGN_MAX_PARTS; p++) h->rg_exec[p] = nullptr;
+    for (int p = 0; p < PGN_MAX_PARTS; p++) { h->rg_exec[p] = nullptr; h->rg_exec2[p] = nullptr; }
+    { const char* ev = getenv("PGN_SPLIT_ROUNDS"); h->split_rounds = ev ? atoi(ev) != 0 : 0; }      // measured: no gain (below), off by default
     h->sim_axis_valid = 0; h->catchup_rounds = 0;
     h->hold_on = 0; h->sim_open = 0; h->sim_target = 0; h->sim_dt = 0.0; h->round_cap = 0; h->h_lag = nullptr;
     h->solve_cap = -1; h->sim_cap = 0;      // deferred solves inside the simulate loops: automatic (effective_cap)
@@ -773,8 +774,24 @@ int pgn_from_autobox(pgn_handle* h, const double* q, const double* u, const doub
 }
 // one closed-loop step of the current vehicle range on the current stream: the step stages, the plant step on the side stream.
 // rec_slot >= 0: the history recorder keeps (state, control, node 1, params 1) of this step (pgn_set_history).
-static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt, int rec_slot) {
+// phase 0: the whole round.  Split rounds (simulate loop, graphs): phase 1 = everything before the QP solve, with the plant propagation forked at the
+// start and joined at the end (it then runs beside the nodes / linearisation stages instead of beside the solve); phase 2 = everything after it
+static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt, int rec_slot, int phase = 0) {
+    if (phase == 2) {
+        launch_stamp(h, 4);
+        step_controls(h, h->d_controls);
+        launch_stamp(h, 5);
+        launch_commit_rollout(h);
+        launch_stamp(h, 6);
+        return PGN_OK;
+    }
     launch_stamp(h, 0);
+    if (phase == 1) {    // fork: the propagation reads state / current control only (nothing on the main stream writes them before the commit)
+        CK(cudaEventRecord(h->ev_fork, h->stream));
+        CK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        launch_propagate_shadow(h, dt, h->side_stream);
+        CK(cudaEventRecord(h->ev_join, h->side_stream));
+    }
     step_time_steps_dev(h, d_t0);
     launch_stamp(h, 1);
     step_nodes(h);
@@ -782,6 +799,7 @@ static int step_rollout_body(pgn_handle* h, const double* d_t0, double dt, int r
     launch_stamp(h, 2);
     step_update(h);
     launch_stamp(h, 3);
+    if (phase == 1) { CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0)); return PGN_OK; }
     if (serial_profiling(h) || !h->side_stream) {            // stage timers synchronise: serial order
         step_solve(h);
         step_controls(h, h->d_controls);
@@ -837,22 +855,56 @@ static int effective_cap(const pgn_handle* h) {
 // launches and 4 event operations.  The loop was host-bound from 4 parts up (tools/gpu_parts_sweep.sh: 5 parts 401 k steps/s against 514 k with 4).
 static void drop_round_graph(pgn_handle* h, int p) {
     if (h->rg_exec[p]) { cudaGraphExecDestroy(h->rg_exec[p]); cudaGraphDestroy(h->rg_graph[p]); h->rg_exec[p] = nullptr; }
+    if (h->rg_exec2[p]) { cudaGraphExecDestroy(h->rg_exec2[p]); cudaGraphDestroy(h->rg_graph2[p]); h->rg_exec2[p] = nullptr; }
 }
-static int ensure_round_graph(pgn_handle* h, int p, double dt, int cap, int rec) {      // called with the part's streams / range swapped into the handle
-    if (h->rg_exec[p] && h->rg_epoch[p] == h->epoch && h->rg_dt[p] == dt && h->rg_cap[p] == cap && h->rg_rec[p] == rec && h->rg_v0[p] == h->v0 && h->rg_nv[p] == h->nv) return PGN_OK;
-    drop_round_graph(h, p);
+// kernel nodes do not inherit the priority of the capturing stream: every per-vehicle kernel gets the highest priority, the ADMM kernel the lowest
+static void set_node_priorities(pgn_handle* h, cudaGraph_t g) {
+    size_t nn = 0;
+    if (cudaGraphGetNodes(g, nullptr, &nn) != cudaSuccess || !nn) { cudaGetLastError(); return; }
+    std::vector<cudaGraphNode_t> nodes(nn);
+    cudaGraphGetNodes(g, nodes.data(), &nn);
+    for (size_t i = 0; i < nn; i++) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchAttributeValue v;
+        memset(&v, 0, sizeof(v));
+        v.priority = pgn::admm_is_kernel(kp.func) ? h->prio_least : h->prio_greatest;
+        if (cudaGraphKernelNodeSetAttribute(nodes[i], cudaLaunchAttributePriority, &v) != cudaSuccess) cudaGetLastError();
+    }
+}
+// Split rounds (PGN_SPLIT_ROUNDS=1): the graph of a round is cut in two around the QP solve and the ADMM kernel is launched between them as an
+// ordinary low-priority launch.  Measured (tools/gpu_admm_trace.py): inside ONE graph the node priorities are set and read back correctly but do
+// not change the order in which the block scheduler serves the kernels — `controls` (3.5 us of work) waits 46 us on average and 313 us at the 90th
+// percentile behind the pending ADMM CTAs of the other parts; with split rounds 16 / 50 us (time steps 79 -> 42, nodes 108 -> 89, commit + next round
+// 30 -> 21) — and the loop is exactly as fast as before (548 k against 547 k steps/s): what the short kernels gain, the linearisation (424 -> 453 us)
+// and the ADMM launches (1166 -> 1210 us) lose, because the step is bound by the SM time of those two kernels, not by the order they are served in.
+static int capture_round(pgn_handle* h, double dt, int rec, int phase, cudaGraph_t* g_out, cudaGraphExec_t* x_out, long long* n_launches) {
     const long long l0 = h->launches;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    launch_round_begin(h, dt);
-    int rc = step_rollout_body(h, h->d_t0, dt, rec ? 0 : -1);
+    if (phase != 2) launch_round_begin(h, dt);
+    int rc = step_rollout_body(h, h->d_t0, dt, rec ? 0 : -1, phase);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->stream, &g);
-    h->rg_launches[p] = h->launches - l0; h->launches = l0;
+    *n_launches += h->launches - l0; h->launches = l0;
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return set_err(PGN_ECUDA, "graph capture of a simulate round failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&h->rg_exec[p], g, 0);
-    if (e != cudaSuccess) { cudaGraphDestroy(g); h->rg_exec[p] = nullptr; return set_err(PGN_ECUDA, "graph instantiation failed: %s", cudaGetErrorString(e)); }
-    h->rg_graph[p] = g; h->rg_epoch[p] = h->epoch; h->rg_dt[p] = dt; h->rg_cap[p] = cap; h->rg_rec[p] = rec; h->rg_v0[p] = h->v0; h->rg_nv[p] = h->nv;
+    if (h->admm_low_priority) set_node_priorities(h, g);
+    e = cudaGraphInstantiate(x_out, g, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); *x_out = nullptr; return set_err(PGN_ECUDA, "graph instantiation failed: %s", cudaGetErrorString(e)); }
+    *g_out = g;
+    return PGN_OK;
+}
+static int ensure_round_graph(pgn_handle* h, int p, double dt, int cap, int rec) {      // called with the part's streams / range swapped into the handle
+    if (h->rg_exec[p] && h->rg_epoch[p] == h->epoch && h->rg_dt[p] == dt && h->rg_cap[p] == cap && h->rg_rec[p] == rec && h->rg_v0[p] == h->v0 && h->rg_nv[p] == h->nv &&
+        (h->rg_exec2[p] != nullptr) == (h->split_rounds != 0)) return PGN_OK;
+    drop_round_graph(h, p);
+    h->rg_launches[p] = 0;
+    int rc = capture_round(h, dt, rec, h->split_rounds ? 1 : 0, &h->rg_graph[p], &h->rg_exec[p], &h->rg_launches[p]);
+    if (rc) return rc;
+    if (h->split_rounds && (rc = capture_round(h, dt, rec, 2, &h->rg_graph2[p], &h->rg_exec2[p], &h->rg_launches[p]))) { drop_round_graph(h, p); return rc; }
+    h->rg_epoch[p] = h->epoch; h->rg_dt[p] = dt; h->rg_cap[p] = cap; h->rg_rec[p] = rec; h->rg_v0[p] = h->v0; h->rg_nv[p] = h->nv;
     return PGN_OK;
 }
 // The simulate loop in ROUNDS: a round = one step attempt of every vehicle of the range that is not held.  Every vehicle counts its own steps
@@ -891,7 +943,15 @@ static int simulate_enqueue(pgn_handle* h, double dt, int k0, int n_steps) {
     }
     int rc = for_each_part(h, [&]() {
         if (graphs) {
-            for (int k = 0; k < n_steps; k++) CK(cudaGraphLaunch(h->rg_exec[h->part], h->stream));
+            if (h->rg_exec2[h->part]) {
+                for (int k = 0; k < n_steps; k++) {
+                    CK(cudaGraphLaunch(h->rg_exec[h->part], h->stream));
+                    step_solve(h);                                   // counts its own launches
+                    CK(cudaGraphLaunch(h->rg_exec2[h->part], h->stream));
+                }
+            } else {
+                for (int k = 0; k < n_steps; k++) CK(cudaGraphLaunch(h->rg_exec[h->part], h->stream));
+            }
             h->launches += (long long)n_steps * h->rg_launches[h->part];
             return (int)PGN_OK;
         }

@@ -157,6 +157,7 @@ struct pgn_handle {
     // vehicle therefore counts its own steps.  d_hold: 0 steps normally, 1 solve continues, 2 reached the target step count.
     int solve_cap, sim_cap, round_cap, hold_on, sim_target, sim_open, sim_axis_valid; double sim_dt; long long catchup_rounds;
     // one simulate round per pipeline part as a CUDA graph (captured once, replayed every round)
+    cudaGraph_t rg_graph2[PGN_MAX_PARTS]; cudaGraphExec_t rg_exec2[PGN_MAX_PARTS]; int split_rounds;      // split rounds: the part of a round after the QP solve
     cudaGraph_t rg_graph[PGN_MAX_PARTS]; cudaGraphExec_t rg_exec[PGN_MAX_PARTS]; long long rg_epoch[PGN_MAX_PARTS], rg_launches[PGN_MAX_PARTS];
     double rg_dt[PGN_MAX_PARTS]; int rg_cap[PGN_MAX_PARTS], rg_rec[PGN_MAX_PARTS], rg_v0[PGN_MAX_PARTS], rg_nv[PGN_MAX_PARTS];
     uint8_t* d_hold; int32_t *d_kstep, *d_iters_acc; int *d_lag, *h_lag;
@@ -184,6 +185,7 @@ void launch_transpose_in(pgn_handle* h, const double* d_aos, double* d_soa, int 
 void launch_transpose_out(pgn_handle* h, const double* d_soa, double* d_aos, int k);   // [k][B] -> [B][k]
 void launch_time_axpy(pgn_handle* h, const double* d_base, double k, double dt, double* d_v, int n);
 void launch_round_begin(pgn_handle* h, double dt);      // target step count: d_lag[1]
+bool admm_is_kernel(const void* f);                   // is this device function one of the ADMM kernel instantiations? (graph node priorities)
 void launch_stamp(pgn_handle* h, int stage);      // profiling 3: time stamp record between the stages of a round
 void launch_fill_i32(pgn_handle* h, int32_t* d, int value, int n);      // deferred solves: per-vehicle step time and hold flags of the current range
 void launch_count_lag(pgn_handle* h, int target);                   // vehicles with fewer than `target` completed steps -> d_lag
