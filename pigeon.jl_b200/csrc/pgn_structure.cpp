@@ -479,12 +479,14 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         tasks.push_back((uint32_t)t.K | ((uint32_t)flags << 16));
         tasks.push_back(0u);
     };
-    auto fwd_phase = [&](int pa, int pb, int c_lo, int c_hi, int flags) {      // rows [pa, pb), CSR entries with c_lo <= col < c_hi
+    const bool skip_k0 = getenv("PGN_NO_K0_SKIP") == nullptr;
+    Q.fwd_k0_end = 0; Q.bwd_k0_phase = -1; Q.bwd_k0_warp0 = 0; Q.bwd_k0.clear();
+    auto fwd_phase = [&](int pa, int pb, int c_lo, int c_hi, int flags, int skip_below = 0) {      // rows [max(pa, skip_below), pb), CSR entries with c_lo <= col < c_hi
         std::vector<std::vector<int>> ents(pb - pa);
-        std::vector<int> len(pb - pa);
+        std::vector<int> len, keep;
         for (int r = pa; r < pb; r++) {
             for (int x = Q.lrow_ptr[r]; x < Q.lrow_ptr[r + 1]; x++) if (Q.lrow_col[x] >= c_lo && Q.lrow_col[x] < c_hi) ents[r - pa].push_back(x);
-            len[r - pa] = (int)ents[r - pa].size();
+            if (r >= skip_below) { keep.push_back(r - pa); len.push_back((int)ents[r - pa].size()); }
         }
         size_t tip = 0;
         for (const SchedTask& t : place_tasks(schedule_phase(len, SCHED_NW))) {
@@ -492,8 +494,8 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
             const int g = 1 << t.sh, ebase = nslots, rbase = (int)Q.sol_orow.size();
             Q.fidx.resize(ebase + 32 * t.K, (uint16_t)Nk);
             for (size_t rr = 0; rr < t.rows.size(); rr++) {
-                Q.sol_orow.push_back((uint16_t)(pa + t.rows[rr]));
-                const auto& E = ents[t.rows[rr]];
+                Q.sol_orow.push_back((uint16_t)(pa + keep[t.rows[rr]]));
+                const auto& E = ents[keep[t.rows[rr]]];
                 for (size_t x = 0; x < E.size(); x++) {
                     const int lane = (int)(rr << t.sh) + (int)(x % g), k = (int)(x / g), sl = ebase + k * 32 + lane;
                     slot[E[x]] = sl;
@@ -507,7 +509,13 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     };
     for (int k = 0; k < nr; k++) {
         if (k > 0) fwd_phase(range_pa[k], range_pb[k], 0, range_pa[k], TASK_DST_TMP);                                         // t = b - W_ext y^           (sol -> tmp)
-        fwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD | TASK_SCALE_OUT);   // y^ = (t + M t) / d         (tmp -> sol)
+        int skip_below = 0;
+        if (k == 0 && skip_k0) {      // level 0 of the first range: no predecessors at all, y^ = t / d is formed with the right-hand side
+            int e = 0;
+            while (e < range_pb[0] && Q.lrow_ptr[e + 1] == Q.lrow_ptr[e]) e++;
+            Q.fwd_k0_end = skip_below = e;
+        }
+        fwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD | TASK_SCALE_OUT, skip_below);   // y^ = (t + M t) / d         (tmp -> sol)
     }
     if (Q.tail_dim > 0) fwd_phase(Q.tail_start, Nk, 0, Q.tail_start, TASK_DST_TMP);                               // tail stage 1               (sol -> tmp)
     Q.n_fwd_ph = (int)Q.sol_ph_ptr.size() - 1;
@@ -517,12 +525,16 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
     Q.fidx.resize(nslots, (uint16_t)Nk);
     if (nslots + Nk >= 65535) return fail("L slots exceed the 16-bit index range of the device tables");
     // -- backward solve: (L slot, source) pairs in program order
-    auto bwd_phase = [&](int pa, int pb, int r_lo, int r_hi, int flags) {      // columns [pa, pb), CSC entries with r_lo <= row < r_hi
-        std::vector<std::vector<int>> ents(pb - pa);
-        std::vector<int> len(pb - pa);
+    // mode 0: every column gets a task row; 1: the columns without entries go to `dropped` instead; 2: columns without entries that are in `drop_if` get none
+    auto bwd_phase = [&](int pa, int pb, int r_lo, int r_hi, int flags, int mode = 0, std::vector<uint16_t>* dropped = nullptr, const std::vector<char>* drop_if = nullptr) {
+        std::vector<std::vector<int>> ents(pb - pa);       // columns [pa, pb), CSC entries with r_lo <= row < r_hi
+        std::vector<int> len, keep;
         for (int c = pa; c < pb; c++) {
             for (int x = Q.lcol_ptr[c]; x < Q.lcol_ptr[c + 1]; x++) if (Q.lcol_row[x] >= r_lo && Q.lcol_row[x] < r_hi) ents[c - pa].push_back(x);
-            len[c - pa] = (int)ents[c - pa].size();
+            const bool empty = ents[c - pa].empty();
+            if (mode == 1 && empty) { dropped->push_back((uint16_t)c); continue; }
+            if (mode == 2 && empty && (*drop_if)[c]) continue;
+            keep.push_back(c - pa); len.push_back((int)ents[c - pa].size());
         }
         size_t tip = 0;
         for (const SchedTask& t : place_tasks(schedule_phase(len, SCHED_NW))) {
@@ -530,8 +542,8 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
             const int g = 1 << t.sh, ebase = (int)Q.bent.size(), rbase = (int)Q.sol_orow.size();
             Q.bent.resize(ebase + 32 * t.K, (uint32_t)Q.zslot | ((uint32_t)Nk << 16));
             for (size_t rr = 0; rr < t.rows.size(); rr++) {
-                Q.sol_orow.push_back((uint16_t)(pa + t.rows[rr]));
-                const auto& E = ents[t.rows[rr]];
+                Q.sol_orow.push_back((uint16_t)(pa + keep[t.rows[rr]]));
+                const auto& E = ents[keep[t.rows[rr]]];
                 for (size_t x = 0; x < E.size(); x++) {
                     const int lane = (int)(rr << t.sh) + (int)(x % g), k = (int)(x / g);
                     Q.bent[ebase + k * 32 + lane] = (uint32_t)slot[Q.lcol_val[E[x]]] | ((uint32_t)Q.lcol_row[E[x]] << 16);
@@ -541,7 +553,24 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         }
         Q.sol_ph_ptr.push_back((uint16_t)(Q.sol_task.size() / 4));
     };
+    // the copies of the task-less columns of the first range run beside the tasks of the phase (after the first forward phase, which still
+    // reads the scratch vector as right-hand side, and before the last backward phase, which reads the copies) that leaves the most warps idle
+    int host_phase = -1, host_tasks = 1 << 30;
+    const int n_ph_total = Q.n_fwd_ph + 2 * nr;
+    for (int ph = 1; ph + 1 < n_ph_total && ph < Q.n_fwd_ph; ph++) {        // forward phases are final here; the backward ones are not built yet
+        const int nt = Q.sol_ph_ptr[ph + 1] - Q.sol_ph_ptr[ph];
+        if (nt < host_tasks) { host_tasks = nt; host_phase = ph; }
+    }
+    const bool k0_bwd = skip_k0 && host_phase >= 1 && nr >= 1;
     for (int k = nr - 1; k >= 0; k--) {
+        if (k == 0 && k0_bwd) {
+            bwd_phase(range_pa[k], range_pb[k], range_pb[k], Nk, TASK_DST_TMP | TASK_SCALE_ACC, 1, &Q.bwd_k0);     // v = y^ - (W_below' x) / d  (sol -> tmp)
+            std::vector<char> isk0(Nk, 0);
+            for (uint16_t c : Q.bwd_k0) isk0[c] = 1;
+            bwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD, 2, nullptr, &isk0);   // x = v + M' v           (tmp -> sol)
+            Q.bwd_k0_phase = host_phase; Q.bwd_k0_warp0 = host_tasks;      // tasks of the host phase: warps >= this count are idle in it (all warps copy if there is none)
+            continue;
+        }
         bwd_phase(range_pa[k], range_pb[k], range_pb[k], Nk, TASK_DST_TMP | TASK_SCALE_ACC);                       // v = y^ - (W_below' x) / d  (sol -> tmp)
         bwd_phase(range_pa[k], range_pb[k], range_pa[k], range_pb[k], TASK_SRC_TMP | TASK_ADD);                    // x = v + M' v               (tmp -> sol)
     }

@@ -110,6 +110,12 @@ struct QpTables {
     std::vector<uint16_t> fidx;                        // forward: source position per L slot (size nslots)
     std::vector<uint32_t> bent;                        // backward entries in program order: L slot | source position << 16
     int rhs_tmp_end;                                   // positions [0, rhs_tmp_end) = first range: their right-hand side goes to the scratch vector
+    // Rows without entries are kept out of the biggest phases (they are 13 + 15 + 7 of the 28 + 28 + 27 tasks of the first range of the coupled
+    // N = 31 QP):  positions [0, fwd_k0_end) — level 0: y^ = t / d — are written by whoever forms the right-hand side;  the columns bwd_k0 of the
+    // first range have nothing below the range (v = y^): they are copied sol -> scratch by the warps that phase bwd_k0_phase leaves idle
+    // (bwd_k0_warp0 = number of tasks of that phase), and those among them without in-range successors either (x = v = y^) need no task at all
+    int fwd_k0_end, bwd_k0_phase, bwd_k0_warp0;
+    std::vector<uint16_t> bwd_k0;
     // Tensor-memory layout of the L values (tmem_layout = 1, the two-QPs-per-SM variant for QPs whose factor does not fit shared memory twice):
     // task t of a phase runs on warp (t - first task of the phase) % nwarps, and a warp reaches only the 32 TMEM lanes of quadrant warp % 4; the
     // K slot rows of task t occupy the 2 K 32-bit columns [sol_tcol[t], sol_tcol[t] + 2 K) of that quadrant — lane l, slot k of the task is the

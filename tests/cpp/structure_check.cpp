@@ -123,9 +123,17 @@ int main(int argc, char** argv) {
         }
         for (auto& o : outs) { (dst_tmp ? tmp : x)[o.first] = o.second; if (!dst_tmp) written[o.first]++; }
     };
-    for (int ph = 0; ph < Q.n_fwd_ph; ph++) run_phase(ph, false);
+    for (int p = 0; p < Q.fwd_k0_end; p++) { x[p] = tmp[p] * Dinv[p]; written[p]++; }      // level 0 is formed with the right-hand side
+    if (!Q.bwd_k0.empty() && !(Q.bwd_k0_phase >= 1 && Q.bwd_k0_phase + 1 < Q.n_fwd_ph + Q.n_bwd_ph)) { printf("FAIL host phase of the task-less columns\n"); return 3; }
+    for (int ph = 0; ph < Q.n_fwd_ph; ph++) {
+        if (ph == Q.bwd_k0_phase) for (uint16_t c : Q.bwd_k0) tmp[c] = x[c];
+        run_phase(ph, false);
+    }
     for (int i = 0; i < Dm; i++) { double acc = 0; for (int k = 0; k < Dm; k++) acc += S[PK(i, k)] * tmp[ts + k]; x[ts + i] = -acc; }
-    for (int ph = Q.n_fwd_ph; ph < Q.n_fwd_ph + Q.n_bwd_ph; ph++) run_phase(ph, true);
+    for (int ph = Q.n_fwd_ph; ph < Q.n_fwd_ph + Q.n_bwd_ph; ph++) {
+        if (ph == Q.bwd_k0_phase) for (uint16_t c : Q.bwd_k0) tmp[c] = x[c];
+        run_phase(ph, true);
+    }
     if (x[Nk] != 0.0 || tmp[Nk] != 0.0) { printf("FAIL zero element written\n"); return 3; }
     // residual ||K x - b||_inf and the kadj product against the dense one
     double res = 0, kadj_err = 0;
