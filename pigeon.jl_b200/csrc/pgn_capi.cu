@@ -303,7 +303,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
     UP(q_hji_t); UP(pos_var); UP(pos_con); UP(pos2idx); UP(is_con); UP(kadj_ptr); UP(kadj_e); UP(kadj_nb);
     UP(fac_lvl_ptr); UP(fac_tgt); UP(inv_lvl_ptr); UP(inv_tgt);
     { std::vector<uint16_t> k0(t.bwd_k0); k0.resize(k0.size() + 64, 0); if ((rc = dev_upload(h, k0, &q.bwd_k0))) return bail(rc); }
-    q.n_bwd_k0 = (int)t.bwd_k0.size(); q.bwd_k0_phase = t.bwd_k0_phase; q.bwd_k0_warp0 = t.bwd_k0_warp0; q.fwd_k0_end = t.fwd_k0_end;
+    q.n_bwd_k0 = (int)t.bwd_k0.size(); q.bwd_k0_phase = t.bwd_k0_phase; q.bwd_k0_warp0 = t.bwd_k0_warp0; q.fwd_k0_end = t.fwd_k0_end; q.fac_k0_end = t.fac_k0_end;
     UP(rz_pos); UP(rz_idx); q.rz_prog = (t.rz_prog && h->admm_threads == RZP_NT) ? 1 : 0;
     {   // the solve tables are read in batches of four slot rows with the surplus masked AFTER the load: the device copies carry four slot
         // rows of padding (zero entries) so that the variant that reads them from global memory never leaves its allocations

@@ -63,7 +63,7 @@ struct QpDev {
     const uint32_t* bent;
     const uint32_t *fac_lvl_ptr, *fac_tgt, *inv_lvl_ptr, *inv_tgt;
     const unsigned long long *fac_ent, *inv_ent;
-    const uint16_t* bwd_k0; int n_bwd_k0, bwd_k0_phase, bwd_k0_warp0, fwd_k0_end;      // task-less rows of the first range (pgn_structure.h)
+    const uint16_t* bwd_k0; int n_bwd_k0, bwd_k0_phase, bwd_k0_warp0, fwd_k0_end, fac_k0_end;      // task-less rows of the first range (pgn_structure.h)
     int nslots, zslot, rhs_tmp_end, n_fwd_ph, n_bwd_ph, n_sol_task, n_fac_task, n_inv_task, n_bent, n_orow, n_orow_fwd, n_fac_lvl, n_inv_levels;
     int tail_level, tail_start, tail_dim;
     const double* ctab;      // [CT_LEN]

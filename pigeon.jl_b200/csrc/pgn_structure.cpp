@@ -480,7 +480,7 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
         tasks.push_back(0u);
     };
     const bool skip_k0 = getenv("PGN_NO_K0_SKIP") == nullptr;
-    Q.fwd_k0_end = 0; Q.bwd_k0_phase = -1; Q.bwd_k0_warp0 = 0; Q.bwd_k0.clear();
+    Q.fwd_k0_end = 0; Q.bwd_k0_phase = -1; Q.bwd_k0_warp0 = 0; Q.bwd_k0.clear(); Q.fac_k0_end = 0;
     auto fwd_phase = [&](int pa, int pb, int c_lo, int c_hi, int flags, int skip_below = 0) {      // rows [max(pa, skip_below), pb), CSR entries with c_lo <= col < c_hi
         std::vector<std::vector<int>> ents(pb - pa);
         std::vector<int> len, keep;
@@ -632,6 +632,11 @@ bool build_qp_tables(int kind, int N_short, int N_long, int ordering, QpTables& 
                 }
                 if (!o.ents.empty()) tg.push_back(std::move(o));      // W_ij = K_ij needs no work
             }
+        }
+        if (l == 0 && skip_k0 && Q.tail_level > 1) {      // level 0: pivots without a single update, d_j = K_jj — inverted where K_jj is written
+            bool all_empty = true;
+            for (const Tgt& t : tg) all_empty = all_empty && t.ents.empty() && (t.tgt & FAC_TGT_PIVOT);
+            if (all_empty) { Q.fac_k0_end = Q.lvl_ptr[1]; continue; }
         }
         emit_level(tg, Q.fac_task, Q.fac_lvl_ptr, Q.fac_tgt, Q.fac_ent);
     }

@@ -114,6 +114,8 @@ struct QpTables {
     // N = 31 QP):  positions [0, fwd_k0_end) — level 0: y^ = t / d — are written by whoever forms the right-hand side;  the columns bwd_k0 of the
     // first range have nothing below the range (v = y^): they are copied sol -> scratch by the warps that phase bwd_k0_phase leaves idle
     // (bwd_k0_warp0 = number of tasks of that phase), and those among them without in-range successors either (x = v = y^) need no task at all
+    // likewise the factorisation: the pivots of level 0 have no update terms, [0, fac_k0_end) are inverted where K_jj is written and level 0 has no pass
+    int fac_k0_end;
     int fwd_k0_end, bwd_k0_phase, bwd_k0_warp0;
     std::vector<uint16_t> bwd_k0;
     // Tensor-memory layout of the L values (tmem_layout = 1, the two-QPs-per-SM variant for QPs whose factor does not fit shared memory twice):

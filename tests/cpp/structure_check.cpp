@@ -36,7 +36,7 @@ int main(int argc, char** argv) {
     for (int p = 0; p < Nk; p++) {
         const double kpp = Q.is_con[p] ? -rhoinv[Q.pos2idx[p]] : Pd[Q.pos2idx[p]];
         if (p >= ts && Dm > 0) { const int i = p - ts; L[NS + i * (i + 1) / 2 + i] = kpp; Dinv[p] = 0.0; }
-        else Dinv[p] = kpp;                                              // holds K_pp until the pivot is formed
+        else Dinv[p] = p < Q.fac_k0_end ? 1.0 / kpp : kpp;               // holds K_pp until the pivot is formed (level 0: formed here)
     }
     size_t npairs = 0;
     // a task list executed the way the warps do: every lane accumulates its K slots, the lanes of a row are summed, lane 0 of the row applies the result
@@ -177,8 +177,8 @@ int main(int argc, char** argv) {
             for (int t = Q.sol_ph_ptr[ph]; t < Q.sol_ph_ptr[ph + 1]; t++) printf(" %ux%d/K%u", (Q.sol_task[4 * t + 1] >> 16) & 0xff, 1 << (Q.sol_task[4 * t + 1] >> 24), Q.sol_task[4 * t + 2] & 0xffff);
             printf("\n");
         }
-        for (int l = 0; l < Q.nlev; l++) {
-            printf("  factor level %2d:", l);
+        for (int l = 0; l + 1 < (int)Q.fac_lvl_ptr.size(); l++) {
+            printf("  factor pass %2d:", l);
             for (uint32_t t = Q.fac_lvl_ptr[l]; t < Q.fac_lvl_ptr[l + 1]; t++) printf(" %ux%d/K%u", (Q.fac_task[4 * t + 1] >> 16) & 0xff, 1 << (Q.fac_task[4 * t + 1] >> 24), Q.fac_task[4 * t + 2] & 0xffff);
             printf("\n");
         }
