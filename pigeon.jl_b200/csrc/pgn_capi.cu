@@ -269,6 +269,7 @@ int pgn_create(const pgn_config* cfg, pgn_handle** out) {
         if (h->admm_threads == 512 && !h->admm_tmem &&
             !build_qp_tables(cfg->kind, cfg->N_short, cfg->N_long, cfg->kkt_ordering, h->tab, err, sizeof(err), 16)) { delete h; return set_err(PGN_EINVAL, "QP analysis failed: %s", err); }
     }
+    if (4 * ((h->tab.tail_dim + 7) & ~7) + 2 > 2 * ((h->tab.Nk + 2) & ~1)) { delete h; return set_err(PGN_EINVAL, "dense tail of dimension %d: the pivot-column buffer of its sweep does not fit two vectors of %d KKT rows", h->tab.tail_dim, h->tab.Nk); }
     if (pgn::tail_segments(h->tab.tail_dim) > h->admm_threads) { delete h; return set_err(PGN_EINVAL, "dense tail of dimension %d needs more than %d ADMM threads", h->tab.tail_dim, h->admm_threads); }
     if (h->tab.Nk > (h->admm_threads >= 512 ? 3 : 5) * h->admm_threads) { delete h; return set_err(PGN_EINVAL, "QP too large: %d KKT rows for %d ADMM threads", h->tab.Nk, h->admm_threads); }
     auto bail = [&](int rc) { pgn_destroy(h); return rc; };
