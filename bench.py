@@ -290,6 +290,16 @@ def run_settled(cx, p, cfg_idx, B, K, W, seed_shift, want_stage=True, trajs=None
     mpc.set_state(state, control, other)
     d_base = torch.tensor(t0, dtype=torch.float64, device=cx.dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    # one-time costs stay outside the cold-start region (it is about cold SOLVER state, not a cold driver): CUDA loads a kernel's module at its
+    # first launch (a throwaway 64-vehicle handle runs two steps) and this handle's round graphs are captured and instantiated by a simulate
+    # call of zero steps.  Measured: the region read 203 k steps/s on one box and 300 k on another before this, for the same 30 steps.
+    nw = min(64, B)
+    warm = make_mpc(p, cfg_idx, trajs, tid[:nw], nw, cx.local)
+    warm.set_state(state[:nw], control[:nw], other[:nw] if other is not None else None)
+    warm.simulate_device(t0[:nw], DT, 2)
+    warm.close()
+    mpc.simulate_device_async(d_base.data_ptr(), DT, 0, k0=0)
+    mpc.synchronize()
     cx.barrier()
     ev[0].record(cx.stream)
     mpc.simulate_device_async(d_base.data_ptr(), DT, 1, k0=0)
