@@ -306,3 +306,47 @@ def test_jld2_hji_cache_round_trip_and_structure(p, tmp_path):
     jld2.write_jld2(f, {"grid_knots": tuple(knots), "V_raw": V, "∇V_raw": gV})
     r2 = p.load_hji_cache(f)
     assert np.array_equal(r2.gradV, c.gradV)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 7, 12, 36, 59])
+def test_two_pivot_sweep_formulas_give_minus_inverse(dim):
+    """The dense-tail sweep of k_admm (pgn_admm_kernel.inc, factor()) restated on a full symmetric matrix: block pivot {p, p+1} with
+    B^-1 = [e1 e2; e2 e3]; ordinary rows use w = U_i B^-1, the two pivot rows count as zero and use w = -(row of B^-1); every element becomes
+    S_ik - w1 c1_k - w2 c2_k and the two pivot columns receive w1, w2; an odd dimension ends with one scalar pivot.  On a quasi-definite
+    matrix (positive and negative pivots, as the Schur complement of the KKT top separators) the result must be -S^-1."""
+    rng = np.random.default_rng(dim)
+    npos = (dim + 1) // 2
+    G = rng.standard_normal((dim, dim))
+    S = np.zeros((dim, dim))
+    S[:npos, :npos] = G[:npos, :npos] @ G[:npos, :npos].T + npos * np.eye(npos)
+    S[npos:, npos:] = -(G[npos:, npos:] @ G[npos:, npos:].T + (dim - npos + 1) * np.eye(dim - npos))
+    S[npos:, :npos] = 0.3 * G[npos:, :npos]; S[:npos, npos:] = S[npos:, :npos].T
+    perm = rng.permutation(dim)                      # interleave the signs as the elimination order does
+    S = S[np.ix_(perm, perm)]
+    ref = -np.linalg.inv(S)
+    A = S.copy()
+    p = 0
+    while p + 1 < dim:
+        c1, c2 = A[:, p].copy(), A[:, p + 1].copy()
+        a, b, c = c1[p], c1[p + 1], c2[p + 1]
+        dinv = 1.0 / (a * c - b * b)
+        e1, e2, e3 = c * dinv, -(b * dinv), a * dinv
+        new = np.empty_like(A)
+        for i in range(dim):
+            w1, w2 = c1[i] * e1 + c2[i] * e2, c1[i] * e2 + c2[i] * e3
+            base = A[i].copy()
+            if i == p: w1, w2, base = -e1, -e2, np.zeros(dim)
+            if i == p + 1: w1, w2, base = -e2, -e3, np.zeros(dim)
+            row = base - w1 * c1 - w2 * c2
+            row[p], row[p + 1] = w1, w2
+            new[i] = row
+        A = new
+        p += 2
+    if p < dim:
+        cc = A[:, p].copy()
+        dinv = 1.0 / cc[p]
+        new = A - np.outer(cc * dinv, cc)
+        new[:, p] = cc * dinv; new[p, :] = cc * dinv; new[p, p] = -dinv
+        A = new
+    assert np.allclose(A, A.T, rtol=0, atol=1e-9 * np.abs(ref).max())
+    assert np.allclose(A, ref, rtol=1e-9, atol=1e-10 * np.abs(ref).max())
